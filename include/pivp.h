@@ -1,0 +1,130 @@
+/* libpivp.so -- C-ABI of the B200-native video-prediction training path.
+ *
+ * The reference (kristofbc/physical-interaction-video-prediction) has NO plugin / FFI layer: its hot
+ * path is pure-Python Chainer links (src/models/train_model.py).  This header therefore defines the
+ * boundary a maintainer would bind with ctypes + CuPy device pointers (INTEGRATION.md shows the stub);
+ * every entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - All pointers are CALLER-OWNED DEVICE pointers (cupy `arr.data.ptr`, torch `t.data_ptr()`); the
+ *    library never allocates or frees.  Scratch is passed in as `workspace` (+ `*_workspace_bytes`).
+ *  - `stream` is a cudaStream_t passed as void*; every launch goes to it, nothing synchronises.
+ *  - Return 0 on success, a negative PIVP_E* code otherwise; pivp_last_error() returns a thread-local
+ *    message.  Shape / pointer violations are errors, not undefined behaviour.
+ *  - Trunk activations are NHWC "views": element (row m = b*H*W + y*W + x, channel c) lives at
+ *    p[m*cs + co + c] (cs = row stride in elements, co = channel offset) so that the channel
+ *    concatenations of the reference (F.concat, train_model.py:262,565,575) are free.
+ *    Image-space tensors (frames, enc7 / mask logits) are NCHW planes exactly like the reference's.
+ *  - Convolution weights are stored [N][KH][KW][C] (OHWI); a Chainer Deconvolution2D weight
+ *    (in,out,kh,kw) is stored [in][KH][KW][out].  ConvLSTM gate rows are ordered
+ *    [32-channel block][gate j,i,f,o][channel] (private layout; see layout.py for the bijection).
+ *  - fp32 everywhere in this header; `*_bf16` pointers are optional bf16 shadows (may be NULL).
+ */
+#ifndef PIVP_H_
+#define PIVP_H_
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PIVP_OK 0
+#define PIVP_EINVAL (-1)
+#define PIVP_ECUDA (-2)
+#define PIVP_EUNSUPPORTED (-3)
+
+const char* pivp_last_error(void);
+int pivp_abi_version(void);
+int pivp_device_sync_check(void);
+
+/* ---- Convolution2D / Deconvolution2D (train_model.py:224,500-507,527; Chainer A.2/A.3) --------------- */
+/* y = conv(x, w) + bias [, relu]  -- L.Convolution2D forward; Deconvolution2D input-gradient */
+int pivp_conv2d_fwd(const float* x, int x_cs, int x_co, int B, int H, int W, int C,
+                    const float* w, const float* bias, int N, int KH, int KW, int stride, int pad,
+                    float* y, int y_cs, int y_co, int Ho, int Wo, int relu, int accumulate, void* stream);
+/* dx = conv^T(dy, w) [+ bias, relu]  -- Convolution2D input-gradient; L.Deconvolution2D forward (outsize = H,W) */
+int pivp_conv2d_dgrad(const float* dy, int dy_cs, int dy_co, int B, int Ho, int Wo, int N,
+                      const float* w, const float* bias, int KH, int KW, int stride, int pad,
+                      float* dx, int dx_cs, int dx_co, int H, int W, int C, int relu, int accumulate, void* stream);
+/* dw += x (*) dy ; dbias += sum dy   (dbias may be NULL) */
+int pivp_conv2d_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, int C,
+                      const float* dy, int dy_cs, int dy_co, int Ho, int Wo, int N,
+                      int KH, int KW, int stride, int pad, float* dw, float* dbias, void* stream);
+int pivp_colsum(const float* v, int v_cs, int v_co, int P, int N, float* out, void* stream);
+
+/* ---- BasicConvLSTMCell gate math (train_model.py:269-272; D.5) ---------------------------------------- */
+/* gates: (M, 4C) pre-activations in, activated gates out (saved for backward). c_prev may be NULL (zeros). */
+int pivp_lstm_gates_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, int h_cs, int h_co,
+                        void* h_bf16, int hb_cs, int hb_co, long M, int C, float forget_bias, void* stream);
+/* dh = dh_a (dense, may be NULL) + dh_b (view, may be NULL); dc in/out (dc_valid=0: treat incoming dc as 0);
+ * gates: activated gates in, d(pre-activation) out. */
+int pivp_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh_a,
+                        const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* dg_bf16,
+                        long M, int C, void* stream);
+
+/* ---- LayerNormalizationConv2D (train_model.py:186-208; A.4, D.4) -------------------------------------- */
+size_t pivp_layernorm_workspace_bytes(int B, int n);
+/* per-sample LN over HW*C with per-element gamma/beta (HWC order); stats (B,2) = mean, rstd saved for bwd */
+int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
+                       float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
+                       int relu, float* stats, void* workspace, size_t ws_bytes, void* stream);
+/* g = g1 + g2 (g2 may be NULL), masked by [y>0] when relu; dgamma/dbeta are accumulated into */
+int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+                       const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
+                       float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream);
+
+/* ---- small view ops (F.relu backward :698, F.concat copies, layout packing) --------------------------- */
+int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,
+                  float* dst, int d_cs, int d_co, long M, int C, void* stream);
+int pivp_copy_view(const float* src, int s_cs, int s_co, float* dst, int d_cs, int d_co, void* dst_bf16, int db_cs, int db_co,
+                   long M, int C, void* stream);
+int pivp_nchw_to_nhwc(const float* src, float* dst, int d_cs, int d_co, int B, int C, int HW, void* stream);
+int pivp_nhwc_to_nchw(const float* src, int s_cs, int s_co, float* dst, int B, int C, int HW, int accumulate, void* stream);
+int pivp_axpy(const float* x, float* y, long n, void* stream);
+int pivp_relu_mask(const float* y, float* g, long n, void* stream);
+int pivp_fill(float* p, float value, long n, void* stream);
+
+/* ---- state predictor + smear (train_model.py:563-565,676,730-731) ------------------------------------- */
+int pivp_state_fwd(const float* action, const float* cur, const float* Wc, const float* bc, float* sa, float* next,
+                   float* smear, int sm_cs, int sm_co, int npix, int B, void* stream);
+int pivp_state_bwd(const float* dn_a, const float* dn_b, const float* sa, const float* Wc, const float* dsmear, int ds_cs, int ds_co,
+                   int npix, int B, float* d_cur_prev, float* dWc, float* dbc, void* stream);
+
+/* ---- L.Linear (train_model.py:289,321-322,430-431,457-466) -------------------------------------------- */
+int pivp_linear_fwd(const float* x, int xs, const float* W, const float* bias, float* y, int B, int K, int N, int relu, void* stream);
+int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, float* dx, int dxs, int accumulate_dx,
+                    float* dW, float* db, int B, int K, int N, void* stream);
+
+/* ---- loss, scheduled sampling, optimizer --------------------------------------------------------------- */
+/* F.mean_squared_error pieces (train_model.py:741,751): *loss_slot += sum (gen-target)^2 ; dgen = gscale*(gen-target) */
+int pivp_mse(const float* gen, const float* target, long n, float gscale, float* dgen, float* loss_slot, void* stream);
+/* scheduled_sample (train_model.py:73-122) as the per-sample select it reduces to */
+int pivp_sched_select(const float* gt, const float* gen, const int* take, float* out, int B, int per_sample, void* stream);
+/* Chainer 2.0.1 AdamRule (train_model.py:860-861; A.8). step[0] = number of updates done so far (device int, incremented). */
+int pivp_adam_step(float* p, const float* g, float* m, float* v, long n, int* step, float alpha, float beta1, float beta2, float eps,
+                   float gscale, void* stream);
+
+/* ---- fused transform + mask softmax + composite (train_model.py:315-349 / 388-415 / 454-471 + 719-728) - */
+int pivp_cdna_fused_fwd(const float* prev, const float* enc7_pre, const float* mask_pre, const float* kern_raw, float* out,
+                        int B, int H, int W, int num_masks, void* stream);
+size_t pivp_cdna_fused_bwd_workspace_bytes(int B, int H, int W, int num_masks);
+int pivp_cdna_fused_bwd(const float* g_out, const float* prev, const float* enc7_pre, const float* mask_pre, const float* kern_raw,
+                        float* d_enc7_pre, float* d_mask_pre, float* d_kern_raw, float* d_prev, int accumulate_dprev,
+                        int B, int H, int W, int num_masks, void* workspace, size_t ws_bytes, void* stream);
+int pivp_dna_fused_fwd(const float* prev, const float* enc7_pre, const float* mask_pre, float* out, int B, int H, int W, void* stream);
+size_t pivp_dna_fused_bwd_workspace_bytes(int B, int H, int W);
+int pivp_dna_fused_bwd(const float* g_out, const float* prev, const float* enc7_pre, const float* mask_pre,
+                       float* d_enc7_pre, float* d_mask_pre, float* d_prev, int accumulate_dprev,
+                       int B, int H, int W, void* workspace, size_t ws_bytes, void* stream);
+int pivp_stp_fused_fwd(const float* prev, const float* enc7_pre, const float* mask_pre, const float* theta_raw, float* out,
+                       int B, int H, int W, int num_masks, int oob_border, void* stream);
+size_t pivp_stp_fused_bwd_workspace_bytes(int B, int H, int W, int num_masks);
+int pivp_stp_fused_bwd(const float* g_out, const float* prev, const float* enc7_pre, const float* mask_pre, const float* theta_raw,
+                       float* d_enc7_pre, float* d_mask_pre, float* d_theta, float* d_prev,
+                       int B, int H, int W, int num_masks, int oob_border, void* workspace, size_t ws_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PIVP_H_ */

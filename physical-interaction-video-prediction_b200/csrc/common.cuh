@@ -1,0 +1,70 @@
+// Shared helpers for libpivp.so (sm_100a only).  See include/pivp.h for the C-ABI contract.
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#define PIVP_OK 0
+#define PIVP_EINVAL (-1)     // bad shape / alignment / null pointer
+#define PIVP_ECUDA (-2)      // CUDA runtime error at launch
+#define PIVP_EUNSUPPORTED (-3)
+
+namespace pivp {
+
+void set_error(const char* fmt, ...);
+
+// 2-D strided view of an NHWC tensor slice: element (row m, channel ch) lives at p[m*cs + co + ch].
+struct View {
+    float* p;
+    int cs;   // row (pixel) stride in elements
+    int co;   // channel offset of the slice inside the row
+};
+struct CView {
+    const float* p;
+    int cs;
+    int co;
+};
+
+static inline int check_launch(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("%s: %s", what, cudaGetErrorString(e));
+        return PIVP_ECUDA;
+    }
+    return PIVP_OK;
+}
+
+#define PIVP_REQUIRE(cond, ...)                  \
+    do {                                         \
+        if (!(cond)) {                           \
+            pivp::set_error(__VA_ARGS__);        \
+            return PIVP_EINVAL;                  \
+        }                                        \
+    } while (0)
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum for blockDim.x <= 1024 (multiple of 32).  `red` must hold 32 floats.  Result valid in all threads.
+__device__ __forceinline__ float block_sum(float v, float* red) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();                 // protect `red` from a previous use
+    if (lane == 0) red[wid] = v;
+    __syncthreads();
+    const int nw = (blockDim.x + 31) >> 5;
+    float r = (lane < nw) ? red[lane] : 0.f;
+    r = warp_sum(r);
+    return r;
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + __expf(-x)); }
+// accurate variants used by the fp32 parity path
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.f / (1.f + expf(-x)); }
+
+}  // namespace pivp

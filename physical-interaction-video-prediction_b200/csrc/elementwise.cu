@@ -1,0 +1,584 @@
+// Bandwidth-bound pieces of the training step over NHWC views / NCHW planes:
+// ConvLSTM gate math (train_model.py:269-272), LayerNormalizationConv2D (:203-208) fwd/bwd,
+// ReLU backward (:698), layout packing, the state predictor (:676,730-731) with the smear (:563-565),
+// Linear layers (:321-322,457-466), MSE (:741,751), scheduled-sampling select (:73-122) and Adam (A.8).
+#include "common.cuh"
+
+namespace pivp {
+
+// ----------------------------------------------------------------------------- ConvLSTM gates
+// Gate buffer layout: row m holds 4*C values ordered [block of 32 channels][gate j,i,f,o][32 channels].
+__device__ __forceinline__ int gate_col(int ch, int gate) { return (ch >> 5) * 128 + gate * 32 + (ch & 31); }
+
+__global__ void lstm_gates_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_out,
+                                      View h_out, __nv_bfloat16* __restrict__ h_bf16, int hb_cs, int hb_co,
+                                      long M, int C, float forget_bias) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C) return;
+    const long m = idx / C;
+    const int ch = (int)(idx - m * C);
+    float* g = gates + m * 4 * C;
+    const float j = tanhf(g[gate_col(ch, 0)]);
+    const float i = sigmoid_acc(g[gate_col(ch, 1)]);
+    const float f = sigmoid_acc(g[gate_col(ch, 2)] + forget_bias);
+    const float o = sigmoid_acc(g[gate_col(ch, 3)]);
+    const float cp = c_prev ? c_prev[idx] : 0.f;
+    const float c = cp * f + i * j;
+    const float h = tanhf(c) * o;
+    g[gate_col(ch, 0)] = j; g[gate_col(ch, 1)] = i; g[gate_col(ch, 2)] = f; g[gate_col(ch, 3)] = o;
+    c_out[idx] = c;
+    h_out.p[m * h_out.cs + h_out.co + ch] = h;
+    if (h_bf16) h_bf16[m * hb_cs + hb_co + ch] = __float2bfloat16(h);
+}
+
+// dh = dh_a[m][ch] (+ dh_b view), dc_next (nullable) -> d(pre-activations) written over the saved gates, dc_prev over dc.
+__global__ void lstm_gates_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
+                                      const float* __restrict__ dh_a, CView dh_b, float* __restrict__ dc, int dc_valid,
+                                      __nv_bfloat16* __restrict__ dg_bf16, long M, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C) return;
+    const long m = idx / C;
+    const int ch = (int)(idx - m * C);
+    float* g = gates + m * 4 * C;
+    const float j = g[gate_col(ch, 0)], i = g[gate_col(ch, 1)], f = g[gate_col(ch, 2)], o = g[gate_col(ch, 3)];
+    float dh = dh_a ? dh_a[idx] : 0.f;
+    if (dh_b.p) dh += dh_b.p[m * dh_b.cs + dh_b.co + ch];
+    const float tc = tanhf(c_cur[idx]);
+    const float d_o = dh * tc * o * (1.f - o);
+    float dcv = dh * o * (1.f - tc * tc);
+    if (dc_valid) dcv += dc[idx];
+    const float cp = c_prev ? c_prev[idx] : 0.f;
+    const float d_f = dcv * cp * f * (1.f - f);
+    const float d_i = dcv * j * i * (1.f - i);
+    const float d_j = dcv * i * (1.f - j * j);
+    dc[idx] = dcv * f;
+    g[gate_col(ch, 0)] = d_j; g[gate_col(ch, 1)] = d_i; g[gate_col(ch, 2)] = d_f; g[gate_col(ch, 3)] = d_o;
+    if (dg_bf16) {
+        __nv_bfloat16* gb = dg_bf16 + m * 4 * C;
+        gb[gate_col(ch, 0)] = __float2bfloat16(d_j); gb[gate_col(ch, 1)] = __float2bfloat16(d_i);
+        gb[gate_col(ch, 2)] = __float2bfloat16(d_f); gb[gate_col(ch, 3)] = __float2bfloat16(d_o);
+    }
+}
+
+// ----------------------------------------------------------------------------- LayerNorm over (H*W*C) per sample
+constexpr int LN_T = 256, LN_E = 16;        // a stats CTA keeps LN_T*LN_E elements in registers
+
+__device__ __forceinline__ long ln_addr(const CView& v, long b, int HW, int C, int e) {
+    const int pix = e / C, ch = e - pix * C;
+    return (b * HW + pix) * v.cs + v.co + ch;
+}
+
+__global__ void __launch_bounds__(LN_T) ln_stats_kernel(CView x, int n, int C, int chunk, float2* __restrict__ partial) {
+    __shared__ float red[32];
+    const int s = blockIdx.x, S = gridDim.x;
+    const long b = blockIdx.y;
+    const int HW = n / C;
+    const int e0 = s * chunk, e1 = min(n, e0 + chunk);
+    float v[LN_E];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_E; ++i) {
+        const int e = e0 + i * LN_T + threadIdx.x;
+        v[i] = (e < e1) ? __ldg(x.p + ln_addr(x, b, HW, C, e)) : 0.f;
+        sum += v[i];
+    }
+    const float cnt = (float)(e1 - e0);
+    const float mean = block_sum(sum, red) / cnt;
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < LN_E; ++i) {
+        const int e = e0 + i * LN_T + threadIdx.x;
+        const float d = v[i] - mean;
+        if (e < e1) m2 += d * d;
+    }
+    m2 = block_sum(m2, red);
+    if (threadIdx.x == 0) partial[b * S + s] = make_float2(mean, m2);
+}
+
+__device__ __forceinline__ float2 ln_combine(const float2* __restrict__ partial, long b, int S, int n, int chunk, float eps) {
+    float mu = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float cnt = (float)(min(n, (s + 1) * chunk) - s * chunk);
+        mu += partial[b * S + s].x * cnt;
+    }
+    mu /= (float)n;
+    float m2 = 0.f;
+    for (int s = 0; s < S; ++s) {
+        const float cnt = (float)(min(n, (s + 1) * chunk) - s * chunk);
+        const float2 p = partial[b * S + s];
+        const float d = p.x - mu;
+        m2 += p.y + cnt * d * d;
+    }
+    return make_float2(mu, 1.f / sqrtf(m2 / (float)n + eps));
+}
+
+__global__ void __launch_bounds__(LN_T) ln_apply_kernel(CView x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                        int n, int C, const float2* __restrict__ partial, int S, int chunk, float eps,
+                                                        View y, View y2, __nv_bfloat16* __restrict__ y_bf16, int yb_cs, int yb_co,
+                                                        int relu, float2* __restrict__ stats) {
+    const long b = blockIdx.y;
+    const int HW = n / C;
+    const float2 st = ln_combine(partial, b, S, n, chunk, eps);
+    if (blockIdx.x == 0 && threadIdx.x == 0) stats[b] = st;
+    for (int e = blockIdx.x * LN_T + threadIdx.x; e < n; e += gridDim.x * LN_T) {
+        const int pix = e / C, ch = e - pix * C;
+        const long row = b * HW + pix;
+        float v = (__ldg(x.p + row * x.cs + x.co + ch) - st.x) * st.y * __ldg(gamma + e) + __ldg(beta + e);
+        if (relu) v = fmaxf(v, 0.f);
+        y.p[row * y.cs + y.co + ch] = v;
+        if (y2.p) y2.p[row * y2.cs + y2.co + ch] = v;
+        if (y_bf16) y_bf16[row * yb_cs + yb_co + ch] = __float2bfloat16(v);
+    }
+}
+
+// partial sums of q = g*gamma and q*xhat per sample  (g = (g1+g2) * [y>0] when relu)
+__global__ void __launch_bounds__(LN_T) ln_bwd_stats_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float2* __restrict__ stats,
+                                                            int n, int C, int chunk, int relu, float2* __restrict__ partial) {
+    __shared__ float red[32];
+    const int s = blockIdx.x, S = gridDim.x;
+    const long b = blockIdx.y;
+    const int HW = n / C;
+    const int e0 = s * chunk, e1 = min(n, e0 + chunk);
+    const float2 st = stats[b];
+    float s1 = 0.f, s2 = 0.f;
+    for (int e = e0 + threadIdx.x; e < e1; e += LN_T) {
+        const int pix = e / C, ch = e - pix * C;
+        const long row = b * HW + pix;
+        const float xh = (__ldg(x.p + row * x.cs + x.co + ch) - st.x) * st.y;
+        float g = __ldg(g1.p + row * g1.cs + g1.co + ch);
+        if (g2.p) g += __ldg(g2.p + row * g2.cs + g2.co + ch);
+        const float ga = __ldg(gamma + e);
+        if (relu && xh * ga + __ldg(beta + e) <= 0.f) g = 0.f;
+        const float q = g * ga;
+        s1 += q;
+        s2 += q * xh;
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) partial[b * S + s] = make_float2(s1, s2);
+}
+
+// thread per element e, loop over the batch: dx, and dgamma[e] += sum_b g*xhat, dbeta[e] += sum_b g
+__global__ void __launch_bounds__(LN_T) ln_bwd_apply_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, const float2* __restrict__ stats,
+                                                            const float2* __restrict__ partial, int S, int B, int n, int C, int relu,
+                                                            View dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ float2 tot[];      // [B] : (mean q, mean q*xhat)
+    for (int b = threadIdx.x; b < B; b += LN_T) {
+        float a = 0.f, c = 0.f;
+        for (int s = 0; s < S; ++s) { const float2 p = partial[(long)b * S + s]; a += p.x; c += p.y; }
+        tot[b] = make_float2(a / (float)n, c / (float)n);
+    }
+    __syncthreads();
+    const int e = blockIdx.x * LN_T + threadIdx.x;
+    if (e >= n) return;
+    const int HW = n / C;
+    const int pix = e / C, ch = e - pix * C;
+    const float ga = __ldg(gamma + e), be = relu ? __ldg(beta + e) : 0.f;
+    float dg = 0.f, db = 0.f;
+    for (int b = 0; b < B; ++b) {
+        const long row = (long)b * HW + pix;
+        const float2 st = stats[b];
+        const float xh = (__ldg(x.p + row * x.cs + x.co + ch) - st.x) * st.y;
+        float g = __ldg(g1.p + row * g1.cs + g1.co + ch);
+        if (g2.p) g += __ldg(g2.p + row * g2.cs + g2.co + ch);
+        if (relu && xh * ga + be <= 0.f) g = 0.f;
+        dg += g * xh;
+        db += g;
+        const float2 t2 = tot[b];
+        dx.p[row * dx.cs + dx.co + ch] = (g * ga - t2.x - xh * t2.y) * st.y;
+    }
+    dgamma[e] += dg;
+    dbeta[e] += db;
+}
+
+// ----------------------------------------------------------------------------- small view kernels
+// dst = (ga + gb) * [out > 0]
+__global__ void relu_bwd_kernel(CView out, CView ga, CView gb, View dst, long M, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C) return;
+    const long m = idx / C;
+    const int ch = (int)(idx - m * C);
+    float g = ga.p[m * ga.cs + ga.co + ch];
+    if (gb.p) g += gb.p[m * gb.cs + gb.co + ch];
+    dst.p[m * dst.cs + dst.co + ch] = out.p[m * out.cs + out.co + ch] > 0.f ? g : 0.f;
+}
+
+__global__ void copy_view_kernel(CView src, View dst, __nv_bfloat16* __restrict__ dst_bf16, int db_cs, int db_co, long M, int C) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C) return;
+    const long m = idx / C;
+    const int ch = (int)(idx - m * C);
+    const float v = src.p[m * src.cs + src.co + ch];
+    if (dst.p) dst.p[m * dst.cs + dst.co + ch] = v;
+    if (dst_bf16) dst_bf16[m * db_cs + db_co + ch] = __float2bfloat16(v);
+}
+
+// planar (B,C,HW) <-> NHWC view rows (b*HW + pix)
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, View dst, int B, int C, int HW) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*HW pixels
+    if (idx >= (long)B * HW) return;
+    const long b = idx / HW;
+    const int pix = (int)(idx - b * HW);
+    for (int c = 0; c < C; ++c) dst.p[idx * dst.cs + dst.co + c] = __ldg(src + (b * C + c) * HW + pix);
+}
+
+__global__ void nhwc_to_nchw_kernel(CView src, float* __restrict__ dst, int B, int C, int HW, int accumulate) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long)B * HW) return;
+    const long b = idx / HW;
+    const int pix = (int)(idx - b * HW);
+    for (int c = 0; c < C; ++c) {
+        const float v = src.p[idx * src.cs + src.co + c];
+        float* d = dst + (b * C + c) * HW + pix;
+        *d = accumulate ? (*d + v) : v;
+    }
+}
+
+__global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] += x[i];
+}
+
+// ----------------------------------------------------------------------------- state predictor + smear
+// one block per sample: sa = [action, cur]; next = Wc sa + bc; smear sa over npix rows of `smear`.
+__global__ void state_fwd_kernel(const float* __restrict__ action, const float* __restrict__ cur, const float* __restrict__ Wc,
+                                 const float* __restrict__ bc, float* __restrict__ sa, float* __restrict__ next, View smear, int npix) {
+    __shared__ float s[10];
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t < 5) s[t] = action[b * 5 + t];
+    else if (t < 10) s[t] = cur[b * 5 + t - 5];
+    __syncthreads();
+    if (t < 10) sa[b * 10 + t] = s[t];
+    if (t < 5) {
+        float a = bc[t];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) a = fmaf(Wc[t * 10 + k], s[k], a);
+        next[b * 5 + t] = a;
+    }
+    if (smear.p)
+        for (int i = t; i < npix * 10; i += blockDim.x) {
+            const int p = i / 10, k = i - p * 10;
+            smear.p[((long)b * npix + p) * smear.cs + smear.co + k] = s[k];
+        }
+}
+
+// single block. d_next = dn_a + dn_b (either may be null); d_sa = Wc^T d_next + smear-sum; d_cur_prev = d_sa[5:10].
+__global__ void state_bwd_kernel(const float* __restrict__ dn_a, const float* __restrict__ dn_b, const float* __restrict__ sa,
+                                 const float* __restrict__ Wc, CView dsmear, int npix, int B,
+                                 float* __restrict__ d_cur_prev, float* __restrict__ dWc, float* __restrict__ dbc) {
+    __shared__ float accW[50], accb[5];
+    const int t = threadIdx.x;
+    if (t < 50) accW[t] = 0.f;
+    if (t < 5) accb[t] = 0.f;
+    __syncthreads();
+    for (int b = t; b < B; b += blockDim.x) {
+        float dn[5];
+#pragma unroll
+        for (int j = 0; j < 5; ++j) dn[j] = (dn_a ? dn_a[b * 5 + j] : 0.f) + (dn_b ? dn_b[b * 5 + j] : 0.f);
+#pragma unroll
+        for (int j = 0; j < 5; ++j) {
+            atomicAdd(&accb[j], dn[j]);
+#pragma unroll
+            for (int k = 0; k < 10; ++k) atomicAdd(&accW[j * 10 + k], dn[j] * sa[b * 10 + k]);
+        }
+        for (int k = 5; k < 10; ++k) {
+            float d = 0.f;
+#pragma unroll
+            for (int j = 0; j < 5; ++j) d = fmaf(Wc[j * 10 + k], dn[j], d);
+            if (dsmear.p)
+                for (int p = 0; p < npix; ++p) d += dsmear.p[((long)b * npix + p) * dsmear.cs + dsmear.co + k];
+            d_cur_prev[b * 5 + k - 5] = d;
+        }
+    }
+    __syncthreads();
+    if (t < 50) dWc[t] += accW[t];
+    if (t < 5) dbc[t] += accb[t];
+}
+
+// ----------------------------------------------------------------------------- Linear
+constexpr int LIN_BB = 8;
+__global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, int xs, const float* __restrict__ W,
+                                                         const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N, int relu) {
+    __shared__ float red[32];
+    const int n = blockIdx.x, b0 = blockIdx.y * LIN_BB;
+    float acc[LIN_BB] = {};
+    for (int k = threadIdx.x; k < K; k += 256) {
+        const float wv = __ldg(W + (long)n * K + k);
+#pragma unroll
+        for (int bb = 0; bb < LIN_BB; ++bb)
+            if (b0 + bb < B) acc[bb] = fmaf(wv, __ldg(x + (long)(b0 + bb) * xs + k), acc[bb]);
+    }
+#pragma unroll
+    for (int bb = 0; bb < LIN_BB; ++bb) {
+        const float v = block_sum(acc[bb], red);
+        if (threadIdx.x == 0 && b0 + bb < B) {
+            float o = v + (bias ? bias[n] : 0.f);
+            y[(long)(b0 + bb) * N + n] = relu ? fmaxf(o, 0.f) : o;
+        }
+    }
+}
+
+// dx[b][k] (+)= sum_n dy[b][n] W[n][k]
+__global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx, int dxs,
+                                     int B, int K, int N, int accumulate) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
+    if (k >= K) return;
+    float a = 0.f;
+    for (int n = 0; n < N; ++n) a = fmaf(__ldg(dy + (long)b * N + n), __ldg(W + (long)n * K + k), a);
+    float* d = dx + (long)b * dxs + k;
+    *d = accumulate ? (*d + a) : a;
+}
+
+// dW[n][k] += sum_b dy[b][n] x[b][k];  db[n] += sum_b dy[b][n]
+__global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, int xs, float* __restrict__ dW,
+                                     float* __restrict__ db, int B, int K, int N) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
+    if (k < K) {
+        float a = 0.f;
+        for (int b = 0; b < B; ++b) a = fmaf(__ldg(dy + (long)b * N + n), __ldg(x + (long)b * xs + k), a);
+        dW[(long)n * K + k] += a;
+    }
+    if (db && blockIdx.x == 0 && threadIdx.x == 0) {
+        float s = 0.f;
+        for (int b = 0; b < B; ++b) s += dy[(long)b * N + n];
+        db[n] += s;
+    }
+}
+
+// relu'(y) applied in place to a dense gradient (y is the saved post-ReLU output)
+__global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict__ g, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && y[i] <= 0.f) g[i] = 0.f;
+}
+
+// ----------------------------------------------------------------------------- loss, select, Adam
+// *loss_slot += sum (a-b)^2 ; dgen = gscale * (a-b)   (a = generated, b = target)
+__global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, float gscale,
+                                                  float* __restrict__ dgen, float* __restrict__ loss_slot) {
+    __shared__ float red[32];
+    float s = 0.f;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+        const float d = a[i] - b[i];
+        s += d * d;
+        if (dgen) dgen[i] = gscale * d;
+    }
+    s = block_sum(s, red);
+    if (threadIdx.x == 0) atomicAdd(loss_slot, s);
+}
+
+// out[b] = take[b] ? gt[b] : gen[b]   (train_model.py:73-122 reduces to this select)
+__global__ void sched_select_kernel(const float* __restrict__ gt, const float* __restrict__ gen, const int* __restrict__ take,
+                                    float* __restrict__ out, int per_sample, long n) {
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[i] = take[i / per_sample] ? gt[i] : gen[i];
+}
+
+// Chainer 2.0.1 AdamRule.  step[0] holds t-1 on entry; lr computed once per block.
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                                   float* __restrict__ v, long n, const int* __restrict__ step, float alpha, float b1,
+                                                   float b2, float eps, float gscale) {
+    __shared__ float lr_s;
+    if (threadIdx.x == 0) {
+        const double t = (double)(step[0] + 1);
+        lr_s = (float)((double)alpha * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+    }
+    __syncthreads();
+    const float lr = lr_s;
+    for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
+        const float gi = g[i] * gscale;
+        const float mi = m[i] + (1.f - b1) * (gi - m[i]);
+        const float vi = v[i] + (1.f - b2) * (gi * gi - v[i]);
+        m[i] = mi;
+        v[i] = vi;
+        p[i] -= lr * mi / (sqrtf(vi) + eps);
+    }
+}
+
+__global__ void counter_inc_kernel(int* c) { c[0] += 1; }
+
+__global__ void fill_kernel(float* __restrict__ p, float v, long n) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+static inline unsigned nblk(long n, int t) { return (unsigned)((n + t - 1) / t); }
+
+}  // namespace pivp
+
+using namespace pivp;
+
+extern "C" {
+
+int pivp_lstm_gates_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, int h_cs, int h_co,
+                        void* h_bf16, int hb_cs, int hb_co, long M, int C, float forget_bias, void* stream) {
+    PIVP_REQUIRE(gates && c_out && h_out && M > 0 && C > 0 && C % 32 == 0, "lstm_gates_fwd: bad argument (C must be a multiple of 32)");
+    lstm_gates_fwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_out, View{h_out, h_cs, h_co},
+                                                                              (__nv_bfloat16*)h_bf16, hb_cs, hb_co, M, C, forget_bias);
+    return check_launch("lstm_gates_fwd");
+}
+
+int pivp_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh_a,
+                        const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* dg_bf16,
+                        long M, int C, void* stream) {
+    PIVP_REQUIRE(gates && c_cur && dc && (dh_a || dh_b) && M > 0 && C % 32 == 0, "lstm_gates_bwd: bad argument");
+    lstm_gates_bwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_cur, dh_a, CView{dh_b, dhb_cs, dhb_co},
+                                                                              dc, dc_valid, (__nv_bfloat16*)dg_bf16, M, C);
+    return check_launch("lstm_gates_bwd");
+}
+
+static int ln_split(int n, int* chunk) {
+    int S = (n + LN_T * LN_E - 1) / (LN_T * LN_E);
+    *chunk = (n + S - 1) / S;
+    return S;
+}
+
+size_t pivp_layernorm_workspace_bytes(int B, int n) {
+    int chunk;
+    const int S = ln_split(n, &chunk);
+    return (size_t)B * S * sizeof(float2);
+}
+
+int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
+                       float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
+                       int relu, float* stats, void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(x && gamma && beta && y && stats && workspace, "layernorm_fwd: null pointer");
+    PIVP_REQUIRE(B > 0 && HW > 0 && C > 0, "layernorm_fwd: bad shape");
+    const int n = HW * C;
+    int chunk;
+    const int S = ln_split(n, &chunk);
+    PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_fwd: workspace too small");
+    ln_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, n, C, chunk, (float2*)workspace);
+    if (int e = check_launch("layernorm_fwd(stats)")) return e;
+    int gx = (n + LN_T * 4 - 1) / (LN_T * 4);
+    ln_apply_kernel<<<dim3(gx, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, gamma, beta, n, C, (const float2*)workspace, S, chunk,
+                                                                     eps, View{y, y_cs, y_co}, View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16,
+                                                                     yb_cs, yb_co, relu, (float2*)stats);
+    return check_launch("layernorm_fwd(apply)");
+}
+
+int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+                       const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
+                       float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(x && g1 && gamma && beta && stats && dx && dgamma && dbeta && workspace, "layernorm_bwd: null pointer");
+    const int n = HW * C;
+    int chunk;
+    const int S = ln_split(n, &chunk);
+    PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_bwd: workspace too small");
+    PIVP_REQUIRE(B <= 4096, "layernorm_bwd: batch too large for the shared-memory totals");
+    ln_bwd_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co},
+                                                                        gamma, beta, (const float2*)stats, n, C, chunk, relu, (float2*)workspace);
+    if (int e = check_launch("layernorm_bwd(stats)")) return e;
+    ln_bwd_apply_kernel<<<nblk(n, LN_T), LN_T, (size_t)B * sizeof(float2), (cudaStream_t)stream>>>(
+        CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
+        (const float2*)workspace, S, B, n, C, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta);
+    return check_launch("layernorm_bwd(apply)");
+}
+
+int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,
+                  float* dst, int d_cs, int d_co, long M, int C, void* stream) {
+    PIVP_REQUIRE(out && ga && dst && M > 0 && C > 0, "relu_bwd: bad argument");
+    relu_bwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
+                                                                        View{dst, d_cs, d_co}, M, C);
+    return check_launch("relu_bwd");
+}
+
+int pivp_copy_view(const float* src, int s_cs, int s_co, float* dst, int d_cs, int d_co, void* dst_bf16, int db_cs, int db_co,
+                   long M, int C, void* stream) {
+    PIVP_REQUIRE(src && (dst || dst_bf16) && M > 0 && C > 0, "copy_view: bad argument");
+    copy_view_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, View{dst, d_cs, d_co},
+                                                                         (__nv_bfloat16*)dst_bf16, db_cs, db_co, M, C);
+    return check_launch("copy_view");
+}
+
+int pivp_nchw_to_nhwc(const float* src, float* dst, int d_cs, int d_co, int B, int C, int HW, void* stream) {
+    PIVP_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad argument");
+    nchw_to_nhwc_kernel<<<nblk((long)B * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, View{dst, d_cs, d_co}, B, C, HW);
+    return check_launch("nchw_to_nhwc");
+}
+
+int pivp_nhwc_to_nchw(const float* src, int s_cs, int s_co, float* dst, int B, int C, int HW, int accumulate, void* stream) {
+    PIVP_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad argument");
+    nhwc_to_nchw_kernel<<<nblk((long)B * HW, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, dst, B, C, HW, accumulate);
+    return check_launch("nhwc_to_nchw");
+}
+
+int pivp_axpy(const float* x, float* y, long n, void* stream) {
+    PIVP_REQUIRE(x && y && n > 0, "axpy: bad argument");
+    axpy_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    return check_launch("axpy");
+}
+
+int pivp_state_fwd(const float* action, const float* cur, const float* Wc, const float* bc, float* sa, float* next,
+                   float* smear, int sm_cs, int sm_co, int npix, int B, void* stream) {
+    PIVP_REQUIRE(action && cur && Wc && bc && sa && next && B > 0, "state_fwd: bad argument");
+    state_fwd_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(action, cur, Wc, bc, sa, next, View{smear, sm_cs, sm_co}, npix);
+    return check_launch("state_fwd");
+}
+
+int pivp_state_bwd(const float* dn_a, const float* dn_b, const float* sa, const float* Wc, const float* dsmear, int ds_cs, int ds_co,
+                   int npix, int B, float* d_cur_prev, float* dWc, float* dbc, void* stream) {
+    PIVP_REQUIRE(sa && Wc && d_cur_prev && dWc && dbc && B > 0, "state_bwd: bad argument");
+    state_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dn_a, dn_b, sa, Wc, CView{dsmear, ds_cs, ds_co}, npix, B, d_cur_prev, dWc, dbc);
+    return check_launch("state_bwd");
+}
+
+int pivp_linear_fwd(const float* x, int xs, const float* W, const float* bias, float* y, int B, int K, int N, int relu, void* stream) {
+    PIVP_REQUIRE(x && W && y && B > 0 && K > 0 && N > 0 && xs >= K, "linear_fwd: bad argument");
+    linear_fwd_kernel<<<dim3(N, (B + LIN_BB - 1) / LIN_BB), 256, 0, (cudaStream_t)stream>>>(x, xs, W, bias, y, B, K, N, relu);
+    return check_launch("linear_fwd");
+}
+
+int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, float* dx, int dxs, int accumulate_dx,
+                    float* dW, float* db, int B, int K, int N, void* stream) {
+    PIVP_REQUIRE(dy && x && W && dW && B > 0 && K > 0 && N > 0, "linear_bwd: bad argument");
+    if (dx) {
+        linear_bwd_dx_kernel<<<dim3((K + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(dy, W, dx, dxs, B, K, N, accumulate_dx);
+        if (int e = check_launch("linear_bwd(dx)")) return e;
+    }
+    linear_bwd_dw_kernel<<<dim3((K + 255) / 256, N), 256, 0, (cudaStream_t)stream>>>(dy, x, xs, dW, db, B, K, N);
+    return check_launch("linear_bwd(dw)");
+}
+
+int pivp_relu_mask(const float* y, float* g, long n, void* stream) {
+    PIVP_REQUIRE(y && g && n > 0, "relu_mask: bad argument");
+    relu_mask_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(y, g, n);
+    return check_launch("relu_mask");
+}
+
+int pivp_mse(const float* gen, const float* target, long n, float gscale, float* dgen, float* loss_slot, void* stream) {
+    PIVP_REQUIRE(gen && target && loss_slot && n > 0, "mse: bad argument");
+    unsigned g = nblk(n, 256 * 4);
+    if (g > 592) g = 592;
+    mse_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(gen, target, n, gscale, dgen, loss_slot);
+    return check_launch("mse");
+}
+
+int pivp_sched_select(const float* gt, const float* gen, const int* take, float* out, int B, int per_sample, void* stream) {
+    PIVP_REQUIRE(gt && gen && take && out && B > 0 && per_sample > 0, "sched_select: bad argument");
+    const long n = (long)B * per_sample;
+    sched_select_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(gt, gen, take, out, per_sample, n);
+    return check_launch("sched_select");
+}
+
+int pivp_adam_step(float* p, const float* g, float* m, float* v, long n, int* step, float alpha, float beta1, float beta2, float eps,
+                   float gscale, void* stream) {
+    PIVP_REQUIRE(p && g && m && v && step && n > 0, "adam_step: bad argument");
+    unsigned gb = nblk(n, 256 * 4);
+    if (gb > 148 * 8) gb = 148 * 8;
+    adam_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step, alpha, beta1, beta2, eps, gscale);
+    if (int e = check_launch("adam_step")) return e;
+    counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+    return check_launch("adam_step(counter)");
+}
+
+int pivp_fill(float* p, float value, long n, void* stream) {
+    PIVP_REQUIRE(p && n > 0, "fill: bad argument");
+    unsigned gb = nblk(n, 256 * 4);
+    if (gb > 148 * 8) gb = 148 * 8;
+    fill_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(p, value, n);
+    return check_launch("fill");
+}
+
+}  // extern "C"

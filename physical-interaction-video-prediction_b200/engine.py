@@ -1,0 +1,528 @@
+"""Forward / backward orchestration of the training step over libpivp.so.
+
+This is the host side of ``Model.__call__`` (train_model.py:620-764) and of ``loss.backward()``
+(train_model.py:950): an explicit time loop forward that keeps every activation the reverse sweep needs,
+and an explicit reverse-time loop (BPTT) that launches the backward kernels.  torch is used ONLY to own
+device memory and to provide the CUDA stream; every arithmetic operation is a libpivp.so kernel.
+There is no CPU / PyTorch fallback: if the library is missing, construction fails.
+
+Buffers (NHWC views, see include/pivp.h).  ``xhL[t]`` holds the concatenated ConvLSTM input of layer L at
+time t: channels [0,Cin) = layer input x_t, channels [Cin,Cin+C) = h_{t-1}; the gate kernel of step t writes
+h_t straight into ``xhL[t+1]``, so the reference's F.concat (train_model.py:262) never materialises.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import layout
+from ._lib import lib, PivpError
+
+LSTM_SIZES = layout.LSTM_SIZES
+LSTM_IN = layout.LSTM_IN
+# spatial level of each ConvLSTM layer (divisor of H, W)
+LSTM_LEVEL = (2, 2, 4, 4, 8, 4, 2)
+LN_OF_LSTM = ("hidden1", "hidden2", "hidden3", "hidden4", "hidden5", "hidden6", "hidden7")
+
+
+class View(object):
+    """(tensor, row stride, channel offset, channels) -- an NHWC slice."""
+    __slots__ = ("t", "cs", "co", "C")
+
+    def __init__(self, t, cs, co, C):
+        self.t, self.cs, self.co, self.C = t, cs, co, C
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+def _ptr(t):
+    return 0 if t is None else t.data_ptr()
+
+
+class Engine(object):
+    def __init__(self, model_type="CDNA", num_masks=10, use_state=True, height=64, width=64, context_frames=2,
+                 device="cuda", compute="f32", stp_oob="zeros"):
+        if model_type not in ("CDNA", "DNA", "STP"):
+            raise ValueError("No network specified")
+        if model_type == "DNA" and num_masks != 1:
+            raise ValueError("Only one mask is supported for DNA model.")          # train_model.py:389-390
+        if height % 8 or width % 8:
+            raise ValueError("height and width must be multiples of 8")
+        if compute not in ("f32", "bf16"):
+            raise ValueError("compute must be 'f32' or 'bf16'")
+        self.L = lib()                                   # raises if libpivp.so is absent: no fallback
+        if not torch.cuda.is_available():
+            raise PivpError("a CUDA device is required: this path has no CPU fallback")
+        self.model_type, self.M, self.use_state = model_type, int(num_masks), bool(use_state)
+        self.H, self.W, self.ctx = int(height), int(width), int(context_frames)
+        self.dev = torch.device(device)
+        self.compute = compute
+        self.oob = 1 if stp_oob == "border" else 0
+        self.Ne = {"CDNA": 3, "DNA": 25, "STP": 3}[model_type]
+        self.M1 = self.M + 1
+        self.Nh = self.Ne + self.M1
+        self.sa = 10 if self.use_state else 0
+        self.specs, self.nparam = layout.param_specs(model_type, self.M, self.use_state, self.H, self.W)
+        self.spec = {s.name: s for s in self.specs}
+        self.flat_p = torch.zeros(self.nparam, dtype=torch.float32, device=self.dev)
+        self.flat_g = torch.zeros(self.nparam, dtype=torch.float32, device=self.dev)
+        self.p = {s.name: self.flat_p[s.offset:s.offset + s.size] for s in self.specs}
+        self.g = {s.name: self.flat_g[s.offset:s.offset + s.size] for s in self.specs}
+        self.ws = None
+        self.tc = None                                   # tensor-core (bf16) plan, created lazily
+        self.load_chainer_params(layout.lecun_normal_init(self.specs))
+
+    # ------------------------------------------------------------------ parameters
+    def load_chainer_params(self, params):
+        """params: dict Chainer path -> ndarray in Chainer layout (A.9)."""
+        host = np.zeros(self.nparam, np.float32)
+        for s in self.specs:
+            if s.name not in params:
+                raise KeyError("missing parameter %s" % s.name)
+            host[s.offset:s.offset + s.size] = s.to_internal(params[s.name]).reshape(-1)
+        self.flat_p.copy_(torch.from_numpy(host))
+        self.params_changed()
+
+    def export_chainer(self, flat):
+        host = flat.detach().cpu().numpy()
+        return {s.name: s.to_chainer(host[s.offset:s.offset + s.size]) for s in self.specs}
+
+    def chainer_params(self):
+        return self.export_chainer(self.flat_p)
+
+    def chainer_grads(self):
+        return self.export_chainer(self.flat_g)
+
+    def params_changed(self):
+        if self.tc is not None:
+            self.tc.refresh_weights()
+
+    # ------------------------------------------------------------------ workspace
+    def _alloc(self, *shape, zero=False, dtype=torch.float32):
+        f = torch.zeros if zero else torch.empty
+        return f(*shape, dtype=dtype, device=self.dev)
+
+    def _workspace(self, B, T):
+        if self.ws is not None and self.ws["B"] == B and self.ws["T"] == T:
+            return self.ws
+        H, W = self.H, self.W
+        ws = {"B": B, "T": T}
+        HW = {1: H * W, 2: (H // 2) * (W // 2), 4: (H // 4) * (W // 4), 8: (H // 8) * (W // 8)}
+        Mr = {k: B * v for k, v in HW.items()}
+        ws["HW"], ws["Mr"] = HW, Mr
+        A = self._alloc
+        S = T - 1
+        ws["img_nhwc"] = [A(Mr[1], 3) for _ in range(S)]
+        ws["enc0_pre"] = [A(Mr[2], 32) for _ in range(S)]
+        ws["xh"], ws["G"], ws["c"] = [], [], []
+        for cin, c, lv in zip(LSTM_IN, LSTM_SIZES, LSTM_LEVEL):
+            ws["xh"].append([A(Mr[lv], cin + c, zero=(t == 0)) for t in range(T)])     # xh[.][0] h-slot = zeros
+            ws["G"].append([A(Mr[lv], 4 * c) for _ in range(S)])
+            ws["c"].append([A(Mr[lv], c) for _ in range(S)])
+        ws["hid2"] = [A(Mr[2], 32) for _ in range(S)]
+        ws["hid4"] = [A(Mr[4], 64) for _ in range(S)]
+        ws["in3"] = [A(Mr[8], 64 + self.sa) for _ in range(S)]
+        ws["hid5"] = [A(Mr[8], 128) for _ in range(S)]
+        ws["cat5"] = [A(Mr[4], 96) for _ in range(S)]
+        ws["cat6"] = [A(Mr[2], 64) for _ in range(S)]
+        ws["e6pre"] = [A(Mr[1], 64) for _ in range(S)]
+        ws["e6"] = [A(Mr[1], 64) for _ in range(S)]
+        ws["head"] = [A(Mr[1], self.Nh) for _ in range(S)]
+        ws["enc7_pre"] = [A(B, self.Ne, H, W) for _ in range(S)]
+        ws["mask_pre"] = [A(B, self.M1, H, W) for _ in range(S)]
+        ws["gen"] = [A(B, 3, H, W) for _ in range(S)]
+        ws["prev_buf"] = [A(B, 3, H, W) for _ in range(S)]
+        ws["sa"] = [A(B, 10) for _ in range(S)]
+        ws["cur"] = [A(B, 5) for _ in range(T)]
+        ws["ln_stats"] = {name: [A(B, 2) for _ in range(S)] for name in
+                          ("norm_enc0", "norm_enc6") + LN_OF_LSTM}
+        if self.model_type == "CDNA":
+            ws["kern_raw"] = [A(B, 25 * self.M) for _ in range(S)]
+        elif self.model_type == "STP":
+            ws["stp_s"] = [A(B, 100) for _ in range(S)]
+            ws["theta_raw"] = [A(B, 6) for _ in range(S)]
+        ws["take"] = torch.zeros(S, B, dtype=torch.int32, device=self.dev)
+        ws["take_host"] = torch.zeros(S, B, dtype=torch.int32).pin_memory()
+        ws["loss_slots"] = A(2 * S, zero=True)
+        # ---- backward temporaries
+        ws["dxh"] = [A(Mr[lv], cin + c) for cin, c, lv in zip(LSTM_IN, LSTM_SIZES, LSTM_LEVEL)]
+        ws["dln"] = [A(Mr[lv], c) for c, lv in zip(LSTM_SIZES, LSTM_LEVEL)]
+        ws["dc"] = [A(Mr[lv], c) for c, lv in zip(LSTM_SIZES, LSTM_LEVEL)]
+        ws["d_gen"] = [A(B, 3, H, W, zero=True) for _ in range(S)]
+        ws["d_gs"] = [A(B, 5, zero=True) for _ in range(S)]
+        ws["d_cur"] = [A(B, 5), A(B, 5)]
+        ws["d_e6"] = A(Mr[1], 64)
+        ws["d_e6pre"] = A(Mr[1], 64)
+        ws["d_head"] = A(Mr[1], self.Nh)
+        ws["d_enc7_pre"] = A(B, self.Ne, H, W)
+        ws["d_mask_pre"] = A(B, self.M1, H, W)
+        ws["d_prev"] = A(B, 3, H, W)
+        ws["d_img_nhwc"] = A(Mr[1], 3)
+        ws["d_hid5"] = A(Mr[8], 128)
+        ws["d_cat6"] = A(Mr[2], 64)
+        ws["d_cat5"] = A(Mr[4], 96)
+        ws["d_e5pre"] = A(Mr[2], 96)
+        ws["d_e4pre"] = A(Mr[4], 128)
+        ws["d_e3pre"] = A(Mr[8], 64)
+        ws["d_in3"] = A(Mr[8], 64 + self.sa)
+        ws["d_e2pre"] = A(Mr[8], 64)
+        ws["d_hid4"] = A(Mr[4], 64)
+        ws["d_e1pre"] = A(Mr[4], 32)
+        ws["d_hid2"] = A(Mr[2], 32)
+        ws["d_enc0pre"] = A(Mr[2], 32)
+        if self.model_type == "CDNA":
+            ws["d_kern_raw"] = A(B, 25 * self.M)
+            nb = self.L.query("pivp_cdna_fused_bwd_workspace_bytes", B, H, W, self.M)
+        elif self.model_type == "DNA":
+            nb = self.L.query("pivp_dna_fused_bwd_workspace_bytes", B, H, W)
+        else:
+            ws["d_theta"] = A(B, 6)
+            ws["d_stp_s"] = A(B, 100)
+            nb = self.L.query("pivp_stp_fused_bwd_workspace_bytes", B, H, W, self.M)
+        ws["fused_ws"] = torch.empty(nb, dtype=torch.uint8, device=self.dev)
+        nb = self.L.query("pivp_layernorm_workspace_bytes", B, 64 * H * W)
+        ws["ln_ws"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)
+        self.ws = ws
+        if self.compute == "bf16":
+            from .tensorcore import TensorCorePlan
+            self.tc = TensorCorePlan(self, ws)
+        return ws
+
+    # ------------------------------------------------------------------ thin kernel wrappers
+    def _s(self):
+        return torch.cuda.current_stream(self.dev).cuda_stream
+
+    def _conv_fwd(self, x, B, H, W, w, b, N, k, stride, pad, y, relu=0, acc=0):
+        Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+        self.L.call("pivp_conv2d_fwd", x.ptr, x.cs, x.co, B, H, W, x.C, _ptr(w), _ptr(b), N, k, k, stride, pad,
+                    y.ptr, y.cs, y.co, Ho, Wo, relu, acc, self._s())
+
+    def _conv_dgrad(self, dy, B, Ho, Wo, w, b, k, stride, pad, dx, H, W, relu=0, acc=0):
+        self.L.call("pivp_conv2d_dgrad", dy.ptr, dy.cs, dy.co, B, Ho, Wo, dy.C, _ptr(w), _ptr(b), k, k, stride, pad,
+                    dx.ptr, dx.cs, dx.co, H, W, dx.C, relu, acc, self._s())
+
+    def _conv_wgrad(self, x, B, H, W, dy, Ho, Wo, k, stride, pad, dw, db):
+        self.L.call("pivp_conv2d_wgrad", x.ptr, x.cs, x.co, B, H, W, x.C, dy.ptr, dy.cs, dy.co, Ho, Wo, dy.C,
+                    k, k, stride, pad, _ptr(dw), _ptr(db), self._s())
+
+    def _ln_fwd(self, name, x, B, HW, y, y2, relu, stats, y_bf16=None):
+        ws = self.ws
+        self.L.call("pivp_layernorm_fwd", x.ptr, x.cs, x.co, _ptr(self.p[name + "/norm/gamma"]), _ptr(self.p[name + "/norm/beta"]),
+                    B, HW, x.C, 1e-6, y.ptr, y.cs, y.co, 0 if y2 is None else y2.ptr, 0 if y2 is None else y2.cs,
+                    0 if y2 is None else y2.co, 0 if y_bf16 is None else y_bf16.ptr, 0 if y_bf16 is None else y_bf16.cs,
+                    0 if y_bf16 is None else y_bf16.co, relu, _ptr(stats), _ptr(ws["ln_ws"]), ws["ln_ws"].numel(), self._s())
+
+    def _ln_bwd(self, name, x, g1, g2, B, HW, relu, stats, dx):
+        ws = self.ws
+        self.L.call("pivp_layernorm_bwd", x.ptr, x.cs, x.co, g1.ptr, g1.cs, g1.co, 0 if g2 is None else g2.ptr,
+                    0 if g2 is None else g2.cs, 0 if g2 is None else g2.co, _ptr(self.p[name + "/norm/gamma"]),
+                    _ptr(self.p[name + "/norm/beta"]), _ptr(stats), B, HW, x.C, relu, dx.ptr, dx.cs, dx.co,
+                    _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(ws["ln_ws"]),
+                    ws["ln_ws"].numel(), self._s())
+
+    def _relu_bwd(self, out, ga, gb, dst, M):
+        self.L.call("pivp_relu_bwd", out.ptr, out.cs, out.co, ga.ptr, ga.cs, ga.co, 0 if gb is None else gb.ptr,
+                    0 if gb is None else gb.cs, 0 if gb is None else gb.co, dst.ptr, dst.cs, dst.co, M, dst.C, self._s())
+
+    # ------------------------------------------------------------------ ConvLSTM layer (fwd / bwd)
+    def _lstm_fwd(self, li, t, B):
+        ws = self.ws
+        cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
+        h, w = self.H // lv, self.W // lv
+        name = "lstm%d/conv" % (li + 1)
+        xh, Gt = ws["xh"][li][t], ws["G"][li][t]
+        if self.tc is not None:
+            self.tc.lstm_conv_fwd(li, t)
+        else:
+            self._conv_fwd(View(xh, cin + C, 0, cin + C), B, h, w, self.p[name + "/W"], self.p[name + "/b"], 4 * C, 5, 1, 2,
+                           View(Gt, 4 * C, 0, 4 * C))
+        hb = None if self.tc is None else self.tc.xh_bf16[li][t + 1]
+        self.L.call("pivp_lstm_gates_fwd", _ptr(Gt), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
+                    _ptr(ws["xh"][li][t + 1]), cin + C, cin, _ptr(hb), cin + C, cin, ws["Mr"][lv], C, 1.0, self._s())
+
+    def _lstm_bwd(self, li, t, B, last):
+        """dln[li] holds the LN-path gradient of h_t; dxh[li] (from step t+1) holds d h_t via the recurrent input."""
+        ws = self.ws
+        cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
+        h, w = self.H // lv, self.W // lv
+        name = "lstm%d/conv" % (li + 1)
+        Gt, dxh = ws["G"][li][t], ws["dxh"][li]
+        dg_bf16 = None if self.tc is None else self.tc.dg_bf16[li]
+        self.L.call("pivp_lstm_gates_bwd", _ptr(Gt), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
+                    _ptr(ws["dln"][li]), 0 if last else _ptr(dxh), cin + C, cin, _ptr(ws["dc"][li]), 0 if last else 1,
+                    _ptr(dg_bf16), ws["Mr"][lv], C, self._s())
+        dG = View(Gt, 4 * C, 0, 4 * C)
+        xh = View(ws["xh"][li][t], cin + C, 0, cin + C)
+        if self.tc is not None and self.tc.has_bwd:
+            self.tc.lstm_conv_bwd(li, t)
+        else:
+            self._conv_wgrad(xh, B, h, w, dG, h, w, 5, 1, 2, self.g[name + "/W"], self.g[name + "/b"])
+            self._conv_dgrad(dG, B, h, w, self.p[name + "/W"], None, 5, 1, 2, View(dxh, cin + C, 0, cin + C), h, w)
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, images, actions, states, take_gt=None, feedself=True):
+        """images (T,B,3,H,W), actions/states (T,B,5) fp32 CUDA tensors.  ``take_gt``: int32 (T-1,B) host array with the
+        scheduled-sampling select for steps t >= ctx (rows before are ignored) or None when ``feedself``."""
+        T, B = int(images.shape[0]), int(images.shape[1])
+        H, W = self.H, self.W
+        assert images.shape[2:] == (3, H, W) and images.dtype == torch.float32 and images.is_contiguous()
+        ws = self._workspace(B, T)
+        L, s = self.L, self._s()
+        HW, Mr = ws["HW"], ws["Mr"]
+        self.feedself = bool(feedself)
+        self.images, self.states = images, states
+        if not feedself:
+            ws["take_host"].copy_(torch.from_numpy(np.ascontiguousarray(take_gt, dtype=np.int32)))
+            ws["take"].copy_(ws["take_host"], non_blocking=True)
+        ws["cur"][0].copy_(states[0])
+        ws["loss_slots"].zero_()
+        self.prev = []
+        p = self.p
+        for t in range(T - 1):
+            # ---- previous frame (train_model.py:663-673)
+            if t < self.ctx:
+                prev = images[t]
+            elif feedself:
+                prev = ws["gen"][t - 1]
+            else:
+                prev = ws["prev_buf"][t]
+                L.call("pivp_sched_select", _ptr(images[t]), _ptr(ws["gen"][t - 1]), _ptr(ws["take"][t]), _ptr(prev), B, 3 * H * W, s)
+            self.prev.append(prev)
+            L.call("pivp_nchw_to_nhwc", _ptr(prev), _ptr(ws["img_nhwc"][t]), 3, 0, B, 3, HW[1], s)
+            # ---- group 0: enc0 -> LN -> relu  (goes to lstm1's x slot and to the enc6 skip slot)
+            self._conv_fwd(View(ws["img_nhwc"][t], 3, 0, 3), B, H, W, p["enc0/W"], p["enc0/b"], 32, 5, 2, 2,
+                           View(ws["enc0_pre"][t], 32, 0, 32))
+            self._ln_fwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), B, HW[2], View(ws["xh"][0][t], 64, 0, 32),
+                         View(ws["cat6"][t], 64, 32, 32), 1, ws["ln_stats"]["norm_enc0"][t],
+                         None if self.tc is None else self.tc.xview(0, t))
+            # ---- group 1
+            self._lstm_fwd(0, t, B)
+            self._ln_fwd("hidden1", View(ws["xh"][0][t + 1], 64, 32, 32), B, HW[2], View(ws["xh"][1][t], 64, 0, 32), None, 0,
+                         ws["ln_stats"]["hidden1"][t], None if self.tc is None else self.tc.xview(1, t))
+            self._lstm_fwd(1, t, B)
+            self._ln_fwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), B, HW[2], View(ws["hid2"][t], 32, 0, 32), None, 0,
+                         ws["ln_stats"]["hidden2"][t])
+            self._conv_fwd(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, p["enc1/W"], p["enc1/b"], 32, 3, 2, 1,
+                           View(ws["xh"][2][t], 96, 0, 32), relu=1)
+            L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64,
+                   0 if self.tc is None else self.tc.xview(2, t).ptr, 96, 0, Mr[4], 32, s)
+            # ---- group 2
+            self._lstm_fwd(2, t, B)
+            self._ln_fwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), B, HW[4], View(ws["xh"][3][t], 128, 0, 64), None, 0,
+                         ws["ln_stats"]["hidden3"][t], None if self.tc is None else self.tc.xview(3, t))
+            self._lstm_fwd(3, t, B)
+            self._ln_fwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), B, HW[4], View(ws["hid4"][t], 64, 0, 64), None, 0,
+                         ws["ln_stats"]["hidden4"][t])
+            self._conv_fwd(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, p["enc2/W"], p["enc2/b"], 64, 3, 2, 1,
+                           View(ws["in3"][t], 64 + self.sa, 0, 64), relu=1)
+            # ---- group 3: smear + enc3; state predictor (train_model.py:676,730)
+            L.call("pivp_state_fwd", _ptr(actions[t]), _ptr(ws["cur"][t]), _ptr(p["current_state/W"]), _ptr(p["current_state/b"]),
+                   _ptr(ws["sa"][t]), _ptr(ws["cur"][t + 1]), _ptr(ws["in3"][t]) if self.use_state else 0, 64 + self.sa, 64,
+                   HW[8], B, s)
+            self._conv_fwd(View(ws["in3"][t], 64 + self.sa, 0, 64 + self.sa), B, H // 8, W // 8, p["enc3/W"], p["enc3/b"], 64, 1, 1, 0,
+                           View(ws["xh"][4][t], 192, 0, 64), relu=1)
+            if self.tc is not None:
+                L.call("pivp_copy_view", _ptr(ws["xh"][4][t]), 192, 0, 0, 0, 0, self.tc.xview(4, t).ptr, 192, 0, Mr[8], 64, s)
+            # ---- group 4
+            self._lstm_fwd(4, t, B)
+            self._ln_fwd("hidden5", View(ws["xh"][4][t + 1], 192, 64, 128), B, HW[8], View(ws["hid5"][t], 128, 0, 128), None, 0,
+                         ws["ln_stats"]["hidden5"][t])
+            self._conv_dgrad(View(ws["hid5"][t], 128, 0, 128), B, H // 8, W // 8, p["enc4/W"], p["enc4/b"], 3, 2, 1,
+                             View(ws["xh"][5][t], 192, 0, 128), H // 4, W // 4, relu=1)
+            if self.tc is not None:
+                L.call("pivp_copy_view", _ptr(ws["xh"][5][t]), 192, 0, 0, 0, 0, self.tc.xview(5, t).ptr, 192, 0, Mr[4], 128, s)
+            # ---- group 5
+            self._lstm_fwd(5, t, B)
+            self._ln_fwd("hidden6", View(ws["xh"][5][t + 1], 192, 128, 64), B, HW[4], View(ws["cat5"][t], 96, 0, 64), None, 0,
+                         ws["ln_stats"]["hidden6"][t])
+            self._conv_dgrad(View(ws["cat5"][t], 96, 0, 96), B, H // 4, W // 4, p["enc5/W"], p["enc5/b"], 3, 2, 1,
+                             View(ws["xh"][6][t], 128, 0, 96), H // 2, W // 2, relu=1)
+            if self.tc is not None:
+                L.call("pivp_copy_view", _ptr(ws["xh"][6][t]), 128, 0, 0, 0, 0, self.tc.xview(6, t).ptr, 128, 0, Mr[2], 96, s)
+            # ---- group 6
+            self._lstm_fwd(6, t, B)
+            self._ln_fwd("hidden7", View(ws["xh"][6][t + 1], 128, 96, 32), B, HW[2], View(ws["cat6"][t], 64, 0, 32), None, 0,
+                         ws["ln_stats"]["hidden7"][t])
+            self._conv_dgrad(View(ws["cat6"][t], 64, 0, 64), B, H // 2, W // 2, p["enc6/W"], p["enc6/b"], 3, 2, 1,
+                             View(ws["e6pre"][t], 64, 0, 64), H, W, relu=0)
+            self._ln_fwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), B, HW[1], View(ws["e6"][t], 64, 0, 64), None, 1,
+                         ws["ln_stats"]["norm_enc6"][t])
+            # ---- heads (enc7 + masks 1x1), NCHW planes out
+            self._conv_fwd(View(ws["e6"][t], 64, 0, 64), B, H, W, p["model/enc7/W"], p["model/enc7/b"], self.Nh, 1, 1, 0,
+                           View(ws["head"][t], self.Nh, 0, self.Nh))
+            L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, 0, _ptr(ws["enc7_pre"][t]), B, self.Ne, HW[1], 0, s)
+            L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, self.Ne, _ptr(ws["mask_pre"][t]), B, self.M1, HW[1], 0, s)
+            # ---- transform + masks + composite
+            K5 = 128 * HW[8]
+            if self.model_type == "CDNA":
+                L.call("pivp_linear_fwd", _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]), _ptr(p["model/cdna_kerns/b"]),
+                       _ptr(ws["kern_raw"][t]), B, K5, 25 * self.M, 0, s)
+                L.call("pivp_cdna_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["kern_raw"][t]),
+                       _ptr(ws["gen"][t]), B, H, W, self.M, s)
+            elif self.model_type == "DNA":
+                L.call("pivp_dna_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["gen"][t]), B, H, W, s)
+            else:
+                L.call("pivp_linear_fwd", _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]), _ptr(p["model/stp_input/b"]),
+                       _ptr(ws["stp_s"][t]), B, K5, 100, 1, s)
+                L.call("pivp_linear_fwd", _ptr(ws["stp_s"][t]), 100, _ptr(p["model/identity_params/W"]),
+                       _ptr(p["model/identity_params/b"]), _ptr(ws["theta_raw"][t]), B, 100, 6, 0, s)
+                L.call("pivp_stp_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["theta_raw"][t]),
+                       _ptr(ws["gen"][t]), B, H, W, self.M, self.oob, s)
+        # ---- loss (train_model.py:737-758): sums go to loss_slots, the loss gradients to d_gen / d_gs
+        n_img, n_sta = B * 3 * H * W, B * 5
+        div = float(T - self.ctx)
+        for t in range(T - 1):
+            if t >= self.ctx - 1:
+                L.call("pivp_mse", _ptr(ws["gen"][t]), _ptr(images[t + 1]), n_img, 2.0 / (n_img * div), _ptr(ws["d_gen"][t]),
+                       ws["loss_slots"][t:].data_ptr(), s)
+                L.call("pivp_mse", _ptr(ws["cur"][t + 1]), _ptr(states[t + 1]), n_sta, 1e-4 * 2.0 / (n_sta * div), _ptr(ws["d_gs"][t]),
+                       ws["loss_slots"][T - 1 + t:].data_ptr(), s)
+            else:
+                ws["d_gen"][t].zero_()
+                ws["d_gs"][t].zero_()
+        self.T, self.B = T, B
+        return ws["gen"]
+
+    def loss_values(self):
+        """Host-side finish of train_model.py:739-758 (forces a D2H sync, like ref:955-956).  Returns (loss, psnr_all, recon)."""
+        ws, T, B = self.ws, self.T, self.B
+        slots = ws["loss_slots"].cpu().numpy()
+        n_img, n_sta = np.float32(B * 3 * self.H * self.W), np.float32(B * 5)
+        loss, psnr, recon = np.float32(0), 0.0, []
+        for t in range(self.ctx - 1, T - 1):
+            c = np.float32(slots[t]) / n_img
+            recon.append(float(c))
+            psnr += 10.0 * math.log(1.0 / float(c)) / math.log(10.0)
+            loss = np.float32(loss + c)
+        for t in range(self.ctx - 1, T - 1):
+            loss = np.float32(loss + np.float32(slots[T - 1 + t]) / n_sta * np.float32(1e-4))
+        loss = np.float32(loss / np.float32(T - self.ctx))
+        return float(loss), psnr, recon
+
+    # ------------------------------------------------------------------ backward (BPTT)
+    def cleargrads(self):
+        self.flat_g.zero_()
+
+    def backward(self):
+        ws, L, s = self.ws, self.L, self._s()
+        T, B, H, W = self.T, self.B, self.H, self.W
+        HW, Mr = ws["HW"], ws["Mr"]
+        p, g = self.p, self.g
+        K5 = 128 * HW[8]
+        d_cur_in = None                       # gradient w.r.t. cur[t+1] arriving from step t+1's state_action
+        for t in range(T - 2, -1, -1):
+            last = (t == T - 2)
+            prev = self.prev[t]
+            need_dprev = self.feedself and t >= self.ctx          # prev_t = gen_{t-1} keeps the graph (ref:664-666)
+            d_prev = ws["d_prev"] if need_dprev else None
+            # ---- fused transform backward
+            if self.model_type == "CDNA":
+                L.call("pivp_cdna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
+                       _ptr(ws["kern_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_kern_raw"]),
+                       _ptr(d_prev), 0, B, H, W, self.M, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
+                L.call("pivp_linear_bwd", _ptr(ws["d_kern_raw"]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]),
+                       _ptr(ws["d_hid5"]), K5, 0, _ptr(g["model/cdna_kerns/W"]), _ptr(g["model/cdna_kerns/b"]), B, K5, 25 * self.M, s)
+                hid5_has_grad = True
+            elif self.model_type == "DNA":
+                L.call("pivp_dna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
+                       _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(d_prev), 0, B, H, W, _ptr(ws["fused_ws"]),
+                       ws["fused_ws"].numel(), s)
+                hid5_has_grad = False
+            else:
+                if need_dprev:
+                    d_prev.zero_()
+                L.call("pivp_stp_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
+                       _ptr(ws["theta_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_theta"]), _ptr(d_prev),
+                       B, H, W, self.M, self.oob, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
+                L.call("pivp_linear_bwd", _ptr(ws["d_theta"]), _ptr(ws["stp_s"][t]), 100, _ptr(p["model/identity_params/W"]),
+                       _ptr(ws["d_stp_s"]), 100, 0, _ptr(g["model/identity_params/W"]), _ptr(g["model/identity_params/b"]), B, 100, 6, s)
+                L.call("pivp_relu_mask", _ptr(ws["stp_s"][t]), _ptr(ws["d_stp_s"]), B * 100, s)
+                L.call("pivp_linear_bwd", _ptr(ws["d_stp_s"]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]),
+                       _ptr(ws["d_hid5"]), K5, 0, _ptr(g["model/stp_input/W"]), _ptr(g["model/stp_input/b"]), B, K5, 100, s)
+                hid5_has_grad = True
+            # ---- heads backward: planes -> NHWC, then 1x1 conv dgrad / wgrad
+            L.call("pivp_nchw_to_nhwc", _ptr(ws["d_enc7_pre"]), _ptr(ws["d_head"]), self.Nh, 0, B, self.Ne, HW[1], s)
+            L.call("pivp_nchw_to_nhwc", _ptr(ws["d_mask_pre"]), _ptr(ws["d_head"]), self.Nh, self.Ne, B, self.M1, HW[1], s)
+            dhead = View(ws["d_head"], self.Nh, 0, self.Nh)
+            self._conv_wgrad(View(ws["e6"][t], 64, 0, 64), B, H, W, dhead, H, W, 1, 1, 0, g["model/enc7/W"], g["model/enc7/b"])
+            self._conv_dgrad(dhead, B, H, W, p["model/enc7/W"], None, 1, 1, 0, View(ws["d_e6"], 64, 0, 64), H, W)
+            # ---- norm_enc6 (+relu) and enc6 deconv
+            self._ln_bwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), View(ws["d_e6"], 64, 0, 64), None, B, HW[1], 1,
+                         ws["ln_stats"]["norm_enc6"][t], View(ws["d_e6pre"], 64, 0, 64))
+            de6 = View(ws["d_e6pre"], 64, 0, 64)
+            self._conv_wgrad(de6, B, H, W, View(ws["cat6"][t], 64, 0, 64), H // 2, W // 2, 3, 2, 1, g["enc6/W"], None)
+            L.call("pivp_colsum", de6.ptr, 64, 0, Mr[1], 64, _ptr(g["enc6/b"]), s)
+            self._conv_fwd(de6, B, H, W, p["enc6/W"], None, 64, 3, 2, 1, View(ws["d_cat6"], 64, 0, 64))
+            # ---- lstm7
+            self._ln_bwd("hidden7", View(ws["xh"][6][t + 1], 128, 96, 32), View(ws["d_cat6"], 64, 0, 32), None, B, HW[2], 0,
+                         ws["ln_stats"]["hidden7"][t], View(ws["dln"][6], 32, 0, 32))
+            self._lstm_bwd(6, t, B, last)
+            # ---- enc5 deconv (input concat(hidden6, encs[1]))
+            self._relu_bwd(View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, View(ws["d_e5pre"], 96, 0, 96), Mr[2])
+            de5 = View(ws["d_e5pre"], 96, 0, 96)
+            self._conv_wgrad(de5, B, H // 2, W // 2, View(ws["cat5"][t], 96, 0, 96), H // 4, W // 4, 3, 2, 1, g["enc5/W"], None)
+            L.call("pivp_colsum", de5.ptr, 96, 0, Mr[2], 96, _ptr(g["enc5/b"]), s)
+            self._conv_fwd(de5, B, H // 2, W // 2, p["enc5/W"], None, 96, 3, 2, 1, View(ws["d_cat5"], 96, 0, 96))
+            # ---- lstm6
+            self._ln_bwd("hidden6", View(ws["xh"][5][t + 1], 192, 128, 64), View(ws["d_cat5"], 96, 0, 64), None, B, HW[4], 0,
+                         ws["ln_stats"]["hidden6"][t], View(ws["dln"][5], 64, 0, 64))
+            self._lstm_bwd(5, t, B, last)
+            # ---- enc4 deconv (input hidden5); d_hid5 may already hold the kernel-Linear contribution
+            self._relu_bwd(View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, View(ws["d_e4pre"], 128, 0, 128), Mr[4])
+            de4 = View(ws["d_e4pre"], 128, 0, 128)
+            self._conv_wgrad(de4, B, H // 4, W // 4, View(ws["hid5"][t], 128, 0, 128), H // 8, W // 8, 3, 2, 1, g["enc4/W"], None)
+            L.call("pivp_colsum", de4.ptr, 128, 0, Mr[4], 128, _ptr(g["enc4/b"]), s)
+            self._conv_fwd(de4, B, H // 4, W // 4, p["enc4/W"], None, 128, 3, 2, 1, View(ws["d_hid5"], 128, 0, 128),
+                           acc=1 if hid5_has_grad else 0)
+            # ---- lstm5
+            self._ln_bwd("hidden5", View(ws["xh"][4][t + 1], 192, 64, 128), View(ws["d_hid5"], 128, 0, 128), None, B, HW[8], 0,
+                         ws["ln_stats"]["hidden5"][t], View(ws["dln"][4], 128, 0, 128))
+            self._lstm_bwd(4, t, B, last)
+            # ---- enc3 (1x1 on concat(enc2 out, smear))
+            self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"], 64, 0, 64), Mr[8])
+            de3 = View(ws["d_e3pre"], 64, 0, 64)
+            cin3 = 64 + self.sa
+            self._conv_wgrad(View(ws["in3"][t], cin3, 0, cin3), B, H // 8, W // 8, de3, H // 8, W // 8, 1, 1, 0, g["enc3/W"], g["enc3/b"])
+            self._conv_dgrad(de3, B, H // 8, W // 8, p["enc3/W"], None, 1, 1, 0, View(ws["d_in3"], cin3, 0, cin3), H // 8, W // 8)
+            # ---- state predictor + smear backward; produces d cur[t] for step t-1
+            d_cur_out = ws["d_cur"][t & 1]
+            L.call("pivp_state_bwd", _ptr(ws["d_gs"][t]), _ptr(d_cur_in), _ptr(ws["sa"][t]), _ptr(p["current_state/W"]),
+                   _ptr(ws["d_in3"]) if self.use_state else 0, cin3, 64, HW[8], B, _ptr(d_cur_out),
+                   _ptr(g["current_state/W"]), _ptr(g["current_state/b"]), s)
+            d_cur_in = d_cur_out
+            # ---- enc2
+            self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, View(ws["d_e2pre"], 64, 0, 64), Mr[8])
+            de2 = View(ws["d_e2pre"], 64, 0, 64)
+            self._conv_wgrad(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, de2, H // 8, W // 8, 3, 2, 1, g["enc2/W"], g["enc2/b"])
+            self._conv_dgrad(de2, B, H // 8, W // 8, p["enc2/W"], None, 3, 2, 1, View(ws["d_hid4"], 64, 0, 64), H // 4, W // 4)
+            # ---- lstm4, lstm3
+            self._ln_bwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), View(ws["d_hid4"], 64, 0, 64), None, B, HW[4], 0,
+                         ws["ln_stats"]["hidden4"][t], View(ws["dln"][3], 64, 0, 64))
+            self._lstm_bwd(3, t, B, last)
+            self._ln_bwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), View(ws["dxh"][3], 128, 0, 64), None, B, HW[4], 0,
+                         ws["ln_stats"]["hidden3"][t], View(ws["dln"][2], 64, 0, 64))
+            self._lstm_bwd(2, t, B, last)
+            # ---- enc1: encs[1] feeds lstm3 (x slot) and the enc5 skip slot
+            self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32),
+                           View(ws["d_e1pre"], 32, 0, 32), Mr[4])
+            de1 = View(ws["d_e1pre"], 32, 0, 32)
+            self._conv_wgrad(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, de1, H // 4, W // 4, 3, 2, 1, g["enc1/W"], g["enc1/b"])
+            self._conv_dgrad(de1, B, H // 4, W // 4, p["enc1/W"], None, 3, 2, 1, View(ws["d_hid2"], 32, 0, 32), H // 2, W // 2)
+            # ---- lstm2, lstm1
+            self._ln_bwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), View(ws["d_hid2"], 32, 0, 32), None, B, HW[2], 0,
+                         ws["ln_stats"]["hidden2"][t], View(ws["dln"][1], 32, 0, 32))
+            self._lstm_bwd(1, t, B, last)
+            self._ln_bwd("hidden1", View(ws["xh"][0][t + 1], 64, 32, 32), View(ws["dxh"][1], 64, 0, 32), None, B, HW[2], 0,
+                         ws["ln_stats"]["hidden1"][t], View(ws["dln"][0], 32, 0, 32))
+            self._lstm_bwd(0, t, B, last)
+            # ---- norm_enc0 (+relu): encs[0] feeds lstm1 (x slot) and the enc6 skip slot; enc0
+            self._ln_bwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), View(ws["dxh"][0], 64, 0, 32), View(ws["d_cat6"], 64, 32, 32),
+                         B, HW[2], 1, ws["ln_stats"]["norm_enc0"][t], View(ws["d_enc0pre"], 32, 0, 32))
+            de0 = View(ws["d_enc0pre"], 32, 0, 32)
+            self._conv_wgrad(View(ws["img_nhwc"][t], 3, 0, 3), B, H, W, de0, H // 2, W // 2, 5, 2, 2, g["enc0/W"], g["enc0/b"])
+            if need_dprev:
+                self._conv_dgrad(de0, B, H // 2, W // 2, p["enc0/W"], None, 5, 2, 2, View(ws["d_img_nhwc"], 3, 0, 3), H, W)
+                L.call("pivp_nhwc_to_nchw", _ptr(ws["d_img_nhwc"]), 3, 0, _ptr(d_prev), B, 3, HW[1], 1, s)
+                L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)

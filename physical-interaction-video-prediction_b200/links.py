@@ -1,0 +1,297 @@
+"""The reference's link surface (src/models/train_model.py) over the CUDA path.
+
+Same class names, constructor arguments, call signatures and attributes as the reference:
+``LayerNormalizationConv2D`` (:186-208), ``BasicConvLSTMCell`` (:216-276), ``StatelessCDNA/DNA/STP``
+(:278-475), ``Model`` (:478-764) and the helpers ``concat_examples`` (:51-71), ``scheduled_sample`` (:73-122),
+``peak_signal_to_noise_ratio`` (:124-134).  Tensors are torch CUDA fp32 in the reference's NCHW layout.
+``Model`` runs the whole step through ``engine.Engine``; the small links run the same kernels stand-alone so
+that they can be dropped into a Chainer graph one at a time.
+"""
+import math
+
+import numpy as np
+import torch
+
+from . import functions as Fn
+from .engine import Engine
+from ._lib import lib, PivpError
+
+RELU_SHIFT = 1e-12      # train_model.py:42
+DNA_KERN_SIZE = 5       # train_model.py:45
+
+
+# ----------------------------------------------------------------------------- helpers
+def concat_examples(batch):
+    """train_model.py:51-71 (host side, NumPy): list of [img (T,H,W,3), act (T,5), sta (T,5)] -> time-major, channel-first."""
+    img = np.array([b[0] for b in batch])
+    act = np.array([b[1] for b in batch])
+    sta = np.array([b[2] for b in batch])
+    return (np.ascontiguousarray(img.transpose(1, 0, 4, 2, 3)), np.ascontiguousarray(act.transpose(1, 0, 2)),
+            np.ascontiguousarray(sta.transpose(1, 0, 2)))
+
+
+from .parallel import num_ground_truth, scheduled_sample_mask, schedule_plan, allreduce_sum_   # noqa: E402,F401
+
+
+def scheduled_sample(ground_truth_x, generated_x, batch_size, num_ground_truth):
+    """train_model.py:73-122: batch with ``num_ground_truth`` samples from the ground truth and the rest generated.
+    Same RNG consumption as the reference; the gather/stitch runs as one select kernel on the device (no D2H round trip)."""
+    take = torch.from_numpy(scheduled_sample_mask(batch_size, num_ground_truth)).to(generated_x.device)
+    out = torch.empty_like(generated_x)
+    per = int(generated_x.numel() // int(batch_size))
+    lib().call("pivp_sched_select", ground_truth_x.data_ptr(), generated_x.data_ptr(), take.data_ptr(), out.data_ptr(),
+               int(batch_size), per, torch.cuda.current_stream(out.device).cuda_stream)
+    return out
+
+
+def peak_signal_to_noise_ratio(true, pred):
+    """train_model.py:124-134: 10 log10(1 / MSE) with the batch-level MSE (computed by the mse kernel)."""
+    slot = torch.zeros(1, dtype=torch.float32, device=pred.device)
+    lib().call("pivp_mse", pred.data_ptr(), true.data_ptr(), pred.numel(), 0.0, 0, slot.data_ptr(),
+               torch.cuda.current_stream(pred.device).cuda_stream)
+    mse = float(slot.item()) / pred.numel()
+    return 10.0 * math.log(1.0 / mse) / math.log(10.0)
+
+
+class _Scalar(object):
+    """Stands in for the 0-d ``chainer.Variable`` the reference returns as loss: ``.data`` / ``float()`` force the D2H read."""
+
+    def __init__(self, getter):
+        self._get, self._v = getter, None
+
+    @property
+    def data(self):
+        if self._v is None:
+            self._v = np.float32(self._get())
+        return self._v
+
+    def __float__(self):
+        return float(self.data)
+
+    def __repr__(self):
+        return "loss(%r)" % float(self)
+
+
+# ----------------------------------------------------------------------------- small links (stand-alone use)
+class LayerNormalizationConv2D(object):
+    """train_model.py:186-208.  gamma/beta are created lazily from the first input (size C*H*W), like L.LayerNormalization()."""
+
+    def __init__(self):
+        self.gamma = self.beta = None
+        self._f = Fn.LayerNormalizationFunction()
+
+    def __call__(self, inputs):
+        n = inputs[0].numel()
+        if self.gamma is None:
+            self.gamma = torch.ones(n, dtype=torch.float32, device=inputs.device)
+            self.beta = torch.zeros(n, dtype=torch.float32, device=inputs.device)
+        self._x = inputs
+        return self._f.forward((inputs, self.gamma, self.beta))[0]
+
+    def backward(self, gy):
+        gx, self.ggamma, self.gbeta = self._f.backward((self._x, self.gamma, self.beta), (gy,))
+        return gx
+
+
+class BasicConvLSTMCell(object):
+    """train_model.py:216-276.  ``W`` (4*out, in+out, k, k) / ``b`` in Chainer layout, created on first call (LeCunNormal)."""
+
+    def __init__(self, out_size=None, filter_size=5):
+        self.out_size, self.filter_size = out_size, filter_size
+        self.W = self.b = None
+        self.reset_state()
+
+    def reset_state(self):
+        self.c = None
+        self.h = None
+
+    def __call__(self, inputs, forget_bias=1.0):
+        B, Cin, H, W = inputs.shape
+        C, k = self.out_size, self.filter_size
+        dev = inputs.device
+        if self.W is None:
+            fan_in = (Cin + C) * k * k
+            self.W = (torch.randn(4 * C, Cin + C, k, k, device=dev) * math.sqrt(1.0 / fan_in)).float()
+            self.b = torch.zeros(4 * C, device=dev)
+        if self.c is None:
+            self.c = torch.zeros(B, C, H, W, device=dev)
+        if self.h is None:
+            self.h = torch.zeros(B, C, H, W, device=dev)
+        from .layout import gate_perm
+        L = lib()
+        s = torch.cuda.current_stream(dev).cuda_stream
+        M = B * H * W
+        xh = torch.empty(M, Cin + C, device=dev)
+        L.call("pivp_nchw_to_nhwc", inputs.data_ptr(), xh.data_ptr(), Cin + C, 0, B, Cin, H * W, s)
+        L.call("pivp_nchw_to_nhwc", self.h.data_ptr(), xh.data_ptr(), Cin + C, Cin, B, C, H * W, s)
+        perm = torch.from_numpy(gate_perm(C)).to(dev)
+        wi = torch.empty_like(self.W)
+        wi[perm] = self.W
+        wi = wi.permute(0, 2, 3, 1).contiguous()
+        bi = torch.empty_like(self.b)
+        bi[perm] = self.b
+        G = torch.empty(M, 4 * C, device=dev)
+        L.call("pivp_conv2d_fwd", xh.data_ptr(), Cin + C, 0, B, H, W, Cin + C, wi.data_ptr(), bi.data_ptr(), 4 * C, k, k, 1, k // 2,
+               G.data_ptr(), 4 * C, 0, H, W, 0, 0, s)
+        cp = Fn.nchw_to_nhwc(self.c)
+        cn, hn = torch.empty(M, C, device=dev), torch.empty(M, C, device=dev)
+        L.call("pivp_lstm_gates_fwd", G.data_ptr(), cp.data_ptr(), cn.data_ptr(), hn.data_ptr(), C, 0, 0, 0, 0, M, C, float(forget_bias), s)
+        self.c = Fn.nhwc_to_nchw(cn, B, C, H, W)
+        self.h = Fn.nhwc_to_nchw(hn, B, C, H, W)
+        return self.h
+
+
+class _Stateless(object):
+    def __init__(self, num_masks):
+        self.num_masks = num_masks
+
+
+class StatelessCDNA(_Stateless):
+    """train_model.py:278-351 as a fused op: call with the 1x1 outputs and the kernel Linear output."""
+
+    def __call__(self, prev_image, enc7_pre, mask_pre, kern_raw):
+        return Fn.CDNACompositeFunction(self.num_masks).forward((prev_image, enc7_pre, mask_pre, kern_raw))[0]
+
+
+class StatelessDNA(_Stateless):
+    """train_model.py:354-417."""
+
+    def __call__(self, prev_image, enc7_pre, mask_pre):
+        if self.num_masks != 1:
+            raise ValueError("Only one mask is supported for DNA model.")
+        return Fn.DNACompositeFunction().forward((prev_image, enc7_pre, mask_pre))[0]
+
+
+class StatelessSTP(_Stateless):
+    """train_model.py:419-475."""
+
+    def __call__(self, prev_image, enc7_pre, mask_pre, theta_raw, oob="zeros"):
+        return Fn.STPCompositeFunction(self.num_masks, oob).forward((prev_image, enc7_pre, mask_pre, theta_raw))[0]
+
+
+# ----------------------------------------------------------------------------- Model
+class Model(object):
+    """train_model.py:478-764.  Same constructor arguments; extra keyword-only geometry / device options.
+
+    ``__call__(x, iter_num)`` runs the forward pass and returns the loss; ``backward()`` runs BPTT into ``.grads``;
+    ``.loss .psnr_all .summaries .gen_images .conv_res .reset_state()`` exist as in the reference.
+    """
+
+    def __init__(self, num_masks, is_cdna=True, is_dna=False, is_stp=False, use_state=True, scheduled_sampling_k=-1,
+                 num_frame_before_prediction=2, prefix=None, height=64, width=64, device="cuda", compute="f32",
+                 stp_oob="zeros", rank=0, world_size=1):
+        model_type = "CDNA" if is_cdna else ("STP" if is_stp else ("DNA" if is_dna else None))   # precedence as ref:532-537
+        if model_type is None:
+            raise ValueError("No network specified")
+        self.engine = Engine(model_type, num_masks, use_state, height, width, num_frame_before_prediction, device, compute, stp_oob)
+        self.num_masks, self.use_state = num_masks, use_state
+        self.scheduled_sampling_k = scheduled_sampling_k
+        self.num_frame_before_prediction = num_frame_before_prediction
+        self.prefix = prefix
+        self.train = True                      # stands in for chainer.config.train (ref:649)
+        self.rank, self.world_size = rank, world_size
+        self.reset_state()
+
+    def reset_state(self):
+        """ref:604-618.  The recurrent state lives in per-step buffers that every forward overwrites, so this only resets the report."""
+        self.loss = 0.0
+        self.psnr_all = 0.0
+        self.summaries = []
+        self.conv_res = []
+
+    # parameters in Chainer layout (npz-compatible, A.9)
+    def params(self):
+        return self.engine.chainer_params()
+
+    def load_params(self, params):
+        self.engine.load_chainer_params(params)
+
+    @property
+    def grads(self):
+        return self.engine.chainer_grads()
+
+    def cleargrads(self):
+        self.engine.cleargrads()
+
+    def schedule(self, batch_size_global, T, iter_num):
+        """Scheduled-sampling plan for one step (ref:649-657, 663-673): returns (feedself, take[T-1, B_local], n_gt).
+        Every rank draws the SAME global permutations and keeps its slice."""
+        return schedule_plan(batch_size_global, T, iter_num, self.scheduled_sampling_k, self.num_frame_before_prediction,
+                             self.train, self.rank, self.world_size)
+
+    def __call__(self, x, iter_num=-1.0):
+        images, actions, states = x
+        dev = self.engine.dev
+        images, actions, states = [torch.as_tensor(a, dtype=torch.float32).to(dev).contiguous() for a in (images, actions, states)]
+        T, B = images.shape[0], images.shape[1]
+        feedself, take, self.num_ground_truth = self.schedule(B * self.world_size, T, iter_num)
+        self.take_gt = take
+        gen = self.engine.forward(images, actions, states, take, feedself)
+        self.gen_images = gen
+        self.gen_states = self.engine.ws["cur"][1:]
+        self.conv_res = [self.engine.ws["xh"][0][T - 2], self.engine.ws["e6"][T - 2]]
+        cache = {}
+
+        def values():
+            if not cache:
+                cache["v"] = self.engine.loss_values()
+            return cache["v"]
+        self.loss = _Scalar(lambda: values()[0])
+        self.psnr_all = _Scalar(lambda: values()[1])
+        self._values = values
+        return self.loss
+
+    def make_summaries(self):
+        """ref:744-759 strings (forces the D2H read)."""
+        loss, psnr, recon = self._values()
+        p = self.prefix or ""
+        out = []
+        for i, c in enumerate(recon):
+            out.append("%s_recon_cost%d: %s" % (p, i, c))
+            out.append("%s_psnr%d: %s" % (p, i, 10.0 * math.log(1.0 / c) / math.log(10.0)))
+        out.append("%s_psnr_all: %s" % (p, psnr))
+        out.append("%s_loss: %s" % (p, loss))
+        self.summaries = out
+        return out
+
+    def backward(self):
+        self.engine.backward()
+
+
+class Adam(object):
+    """chainer.optimizers.Adam as used at train_model.py:860-861,950 (Chainer 2.0.1 AdamRule)."""
+
+    def __init__(self, alpha=0.001, beta1=0.9, beta2=0.999, eps=1e-8):
+        self.alpha, self.beta1, self.beta2, self.eps = alpha, beta1, beta2, eps
+        self.target = None
+
+    def setup(self, model):
+        self.target = model
+        e = model.engine
+        self.m = torch.zeros_like(e.flat_p)
+        self.v = torch.zeros_like(e.flat_p)
+        self.step = torch.zeros(1, dtype=torch.int32, device=e.dev)
+        return self
+
+    @property
+    def t(self):
+        return int(self.step.item())
+
+    def apply(self):
+        """All-reduce (data parallel) + fused 1/N scale + Adam on the flat buffers."""
+        e = self.target.engine
+        ws = self.target.world_size
+        if ws > 1:
+            allreduce_sum_(e.flat_g)                          # NCCL sum over NVLink
+        lib().call("pivp_adam_step", e.flat_p.data_ptr(), e.flat_g.data_ptr(), self.m.data_ptr(), self.v.data_ptr(), e.nparam,
+                   self.step.data_ptr(), self.alpha, self.beta1, self.beta2, self.eps, 1.0 / ws,
+                   torch.cuda.current_stream(e.dev).cuda_stream)
+        e.params_changed()
+
+    def update(self, lossfun, *args):
+        """ref:950 ``optimizer.update(training_model, [imgs, acts, stas], itr)``: forward, cleargrads, backward, update."""
+        loss = lossfun(*args)
+        self.target.cleargrads()
+        self.target.backward()
+        self.apply()
+        return loss

@@ -1,0 +1,181 @@
+"""Whole-step GPU parity: Model.__call__ + backward + Adam through libpivp.so against the NumPy oracle.
+
+fp32 path tolerances: loss / frames / masks 1e-4 relative (north_star); per-tensor gradients: max-abs error
+<= 2e-3 of the tensor's max-abs against the float64 oracle (the float32 oracle itself sits at ~1e-3 on the
+smallest tensors, see test_oracle_float32_close_to_float64); scheduled-sampling masks bit-exact.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as OM
+from oracle import npgrad as G
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a = a.detach().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    return float(np.abs(a.astype(np.float64) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def perturbed(cfg, seed=7, scale=0.05):
+    p = OM.init_params(cfg)
+    rs = np.random.RandomState(seed)
+    for k in sorted(p):
+        if not k.endswith("/W"):
+            p[k] = (p[k] + scale * rs.standard_normal(p[k].shape)).astype(np.float32)
+    return p
+
+
+def make_model(pk, mt, nm, k, H, W, oob="zeros", compute="f32", use_state=True):
+    return pk.Model(nm, is_cdna=(mt == "CDNA"), is_dna=(mt == "DNA"), is_stp=(mt == "STP"), use_state=use_state,
+                    scheduled_sampling_k=k, prefix="t", height=H, width=W, stp_oob=oob, compute=compute)
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import pivp_b200
+    pivp_b200.lib()
+    return pivp_b200
+
+
+CASES = [
+    ("CDNA", 10, 900.0, 32, 32, 3, 5, "zeros", True),
+    ("CDNA", 10, -1.0, 32, 32, 2, 4, "zeros", True),
+    ("CDNA", 4, 900.0, 16, 24, 3, 4, "zeros", False),
+    ("DNA", 1, 900.0, 32, 32, 3, 4, "zeros", True),
+    ("DNA", 1, -1.0, 16, 16, 2, 4, "zeros", True),
+    ("STP", 10, 900.0, 32, 32, 3, 4, "zeros", True),
+    ("STP", 5, -1.0, 16, 16, 2, 4, "border", True),
+    ("CDNA", 10, 900.0, 64, 64, 2, 4, "zeros", True),
+]
+
+
+@pytest.mark.parametrize("mt,nm,k,H,W,B,T,oob,use_state", CASES)
+def test_model_step_matches_oracle(pk, mt, nm, k, H, W, B, T, oob, use_state):
+    cfg64 = OM.Config(mt, nm, use_state=use_state, schedsamp_k=k, height=H, width=W, stp_oob=oob, dtype=np.float64)
+    params = perturbed(cfg64)
+    batch = OM.concat_examples(OM.synthetic_sequences(B, T, cfg64))
+    np.random.seed(99)
+    take = []
+    ref = OM.forward(params, batch, 6000, cfg64, take_gt_log=take)
+    G.backward(ref["loss"])
+    model = make_model(pk, mt, nm, k, H, W, oob, use_state=use_state)
+    model.load_params(params)
+    np.random.seed(99)
+    loss = model([torch.from_numpy(a) for a in batch], 6000)
+    model.cleargrads()
+    model.backward()
+    torch.cuda.synchronize()
+    # index work: bit-exact
+    if k != -1.0:
+        assert int(model.num_ground_truth) == int(ref["n_gt"])
+        got_take = model.take_gt[cfg64.context_frames:T - 1].astype(bool)
+        assert np.array_equal(got_take, np.array(take).reshape(got_take.shape))
+    # values
+    assert abs(float(loss) - float(ref["loss"].data)) <= 1e-4 * abs(float(ref["loss"].data))
+    for t in range(T - 1):
+        assert rel(model.gen_images[t], ref["gen_images"][t].data) < 1e-4, t
+        assert rel(model.engine.ws["mask_pre"][t], ref["trace"][t]["mask_pre"].data) < 1e-4, t
+        assert rel(model.gen_states[t], ref["gen_states"][t].data) < 1e-4, t
+    assert abs(float(model.psnr_all) - ref["psnr_all"]) < 1e-2
+    grads = model.grads
+    worst = {}
+    for key, v in ref["P"].items():
+        r = np.zeros_like(v.data) if v.grad is None else v.grad
+        worst[key] = np.abs(grads[key].astype(np.float64) - r).max() / (np.abs(r).max() + 1e-20)
+    bad = {k_: e for k_, e in worst.items() if e > 2e-3}
+    assert not bad, bad
+
+
+def test_train_steps_follow_oracle_adam(pk):
+    """Three optimizer.update() calls (train_model.py:950): parameters track the oracle's Chainer-Adam trajectory."""
+    cfg = OM.Config("CDNA", 10, schedsamp_k=900.0, height=32, width=32)
+    params = perturbed(cfg)
+    oparams = {k: v.copy() for k, v in params.items()}
+    batch = OM.concat_examples(OM.synthetic_sequences(2, 4, cfg))
+    model = make_model(pk, "CDNA", 10, 900.0, 32, 32)
+    model.load_params(params)
+    opt = pk.Adam(alpha=1e-3).setup(model)
+    adam = OM.Adam(alpha=1e-3)
+    np.random.seed(3)
+    losses = [float(opt.update(model, [torch.from_numpy(a) for a in batch], 6000 + i)) for i in range(3)]
+    np.random.seed(3)
+    olosses = [float(OM.train_step(oparams, adam, batch, 6000 + i, cfg)["loss"].data) for i in range(3)]
+    assert opt.t == 3
+    # Adam's m/sqrt(v) normalisation turns tiny gradient differences into O(alpha) parameter differences,
+    # so parameters are compared on an absolute scale of a few alpha, losses at 1e-3 relative.
+    for a, b in zip(losses, olosses):
+        assert abs(a - b) <= 2e-3 * abs(b), (losses, olosses)
+    got = model.params()
+    for key in ("lstm5/conv/W", "enc0/W", "masks/W", "hidden3/norm/gamma"):
+        assert np.abs(got[key] - oparams[key]).max() < 3.5e-3, key
+
+
+@pytest.mark.parametrize("name", ["cdna_sched", "cdna_feedself", "dna_sched", "stp_sched"])
+def test_model_matches_golden_vectors(pk, name):
+    sys.path.insert(0, GOLD)
+    import make_golden
+    mt, nm, k, it, B, T, H = make_golden.CASES[name]
+    gold = np.load(os.path.join(GOLD, name + ".npz"))
+    cfg = OM.Config(mt, nm, schedsamp_k=k, height=H, width=H)
+    params = OM.init_params(cfg, seed=4321)
+    rs = np.random.RandomState(7)
+    for key in sorted(params):
+        if not key.endswith("/W"):
+            params[key] = (params[key] + 0.05 * rs.standard_normal(params[key].shape)).astype(np.float32)
+    batch = OM.concat_examples(OM.synthetic_sequences(B, T, cfg, seed=1234))
+    model = make_model(pk, mt, nm, k, H, H)
+    model.load_params(params)
+    np.random.seed(99)
+    loss = model([torch.from_numpy(a) for a in batch], it)
+    model.cleargrads()
+    model.backward()
+    torch.cuda.synchronize()
+    if k != -1.0:
+        assert int(model.num_ground_truth) == int(gold["n_gt"])
+        assert np.array_equal(model.take_gt[2:T - 1].astype(bool), gold["take_gt"])
+    assert abs(float(loss) - float(gold["loss"])) <= 1e-4 * float(gold["loss"])
+    assert rel(model.gen_images[-1], gold["gen_last"].astype(np.float64)) < 1e-4
+    assert rel(model.gen_states[-1], gold["gen_state_last"].astype(np.float64)) < 1e-4
+    grads = model.grads
+    for key in grads:
+        l2 = np.sqrt((grads[key].astype(np.float64) ** 2).sum())
+        np.testing.assert_allclose(l2, gold["gl2/" + key], rtol=5e-3, atol=1e-9, err_msg=key)
+
+
+def test_data_parallel_shards_equal_full_batch(pk):
+    """two ranks' shard gradients, summed and scaled by 1/N, equal the single-process full-batch gradient,
+    and both ranks slice ONE global scheduled-sampling permutation (emulated on one GPU, no collective needed)."""
+    cfg = OM.Config("CDNA", 10, schedsamp_k=900.0, height=32, width=32)
+    params = perturbed(cfg)
+    B, T = 4, 4
+    batch = OM.concat_examples(OM.synthetic_sequences(B, T, cfg))
+    full = make_model(pk, "CDNA", 10, 900.0, 32, 32)
+    full.load_params(params)
+    np.random.seed(11)
+    lf = float(full([torch.from_numpy(a) for a in batch], 6000))
+    full.cleargrads(); full.backward()
+    gfull = full.engine.flat_g.clone()
+    acc = torch.zeros_like(gfull)
+    losses = []
+    takes = []
+    for r in range(2):
+        m = pk.Model(10, is_cdna=True, scheduled_sampling_k=900.0, prefix="r", height=32, width=32, rank=r, world_size=2)
+        m.load_params(params)
+        shard = [torch.from_numpy(np.ascontiguousarray(a[:, r * 2:(r + 1) * 2])) for a in batch]
+        np.random.seed(11)
+        losses.append(float(m(shard, 6000)))
+        takes.append(m.take_gt)
+        m.cleargrads(); m.backward()
+        acc += m.engine.flat_g
+    acc /= 2
+    assert np.array_equal(np.concatenate(takes, axis=1), full.take_gt)
+    assert abs(0.5 * (losses[0] + losses[1]) - lf) < 1e-5 * lf
+    den = float(gfull.abs().max())
+    assert float((acc - gfull).abs().max()) / den < 1e-4
