@@ -124,6 +124,23 @@ int pivp_stp_fused_bwd(const float* g_out, const float* prev, const float* enc7_
                        float* d_enc7_pre, float* d_mask_pre, float* d_theta, float* d_prev,
                        int B, int H, int W, int num_masks, int oob_border, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- tcgen05 / TMEM / TMA path for the seven ConvLSTM 5x5 convolutions (bf16 operands, fp32 accumulate) ---------- */
+/* fp32 master W[n][tap][c] -> bf16 forward operand Wf[n][tap][Kpad] and tap-flipped dgrad operand Wd[c][tap'][n] */
+int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream);
+/* D[m,n] = sum_{tap,c} In[pixel(m)+tap-2, c] * Wt[n][tap][c]  (In bf16 NHWC with row stride in_cs; Wt bf16 [N][25][Kc]).
+ * mode 0: out[m*out_cs+out_co+n] = D (+bias)                      -- Convolution2D input-gradient (D.5) with Wd
+ * mode 1: bias + gates + cell + h fused (train_model.py:262-272)  -- BN must be 128, N = 4C in the gate-interleaved order;
+ *         writes activated gates (M,4C), c_out, h (fp32 view + optional bf16 view + optional channel-major bf16 copy).
+ * Returns PIVP_EUNSUPPORTED when B*H*W cannot be cut into 128-pixel TMA boxes. */
+int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
+                    const void* wt_bf16, int N, int BN,
+                    int mode, const float* bias,
+                    float* out, int out_cs, int out_co,
+                    float* gates, const float* c_prev, float* c_out,
+                    float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
+                    void* h_t, long h_t_ld, int hT_co,
+                    int C, float forget_bias, int accurate, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

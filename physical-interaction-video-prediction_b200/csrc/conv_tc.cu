@@ -1,0 +1,427 @@
+// tcgen05 / TMEM / TMA implicit-GEMM 5x5 convolution for the seven ConvLSTM layers (bf16 operands, fp32 accumulate).
+//
+// Replaces the `self.conv(inputs_h)` + gate math of BasicConvLSTMCell (train_model.py:262-272) in the forward pass,
+// and Chainer's Convolution2D input-gradient in the backward pass.  Both are the same stride-1 "same"
+// convolution over an NHWC bf16 tensor:
+//      D[m, n] = sum_{tap=(dy,dx), c} In[pixel(m) + (dy-2, dx-2), c] * Wt[n][tap][c]
+// (for the input gradient the caller passes dG as `In` and a tap-flipped, transposed weight -- see pivp_tc_prep_weights).
+//
+// GEMM view: M = B*H*W pixels (128 per CTA), N = output channels (BN <= 256 per CTA), K = 25 taps x Kc channels.
+//  * A tile: one 4-D TMA box {64 ch, TW, TH, TB} (TW*TH*TB = 128 pixels) per (tap, 64-channel block), fetched at the
+//    tap-shifted coordinate; out-of-image pixels are zero-filled by TMA, which IS the convolution's zero padding.
+//    The box lands in shared memory as 128 rows x 128 B with the 128-byte swizzle = the canonical K-major UMMA layout.
+//  * B tile: 2-D TMA box {64, BN} of the K-major weight matrix [N][25*Kc].
+//  * tcgen05.mma (cta_group::1, kind::f16, M=128, N=BN, K=16) issued by one elected thread, accumulator in TMEM.
+//  * Warp roles: warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer, warps 2..5 = epilogue (one TMEM lane
+//    quarter each).  smem ring of `stages` slots with full/empty mbarriers; tcgen05.commit frees slots.
+//  * Epilogue mode 1 (ConvLSTM forward): bias + gates + cell update + h fused -- the pre-activations never reach HBM.
+//    N is ordered [32-channel block][gate j,i,f,o][channel], so one 128-column tile holds all four gates of 32 channels.
+//  * Two CTAs are resident per SM (<= 110 KB smem, <= 256 TMEM columns each), so one CTA's epilogue overlaps the other's
+//    main loop without an in-kernel tile scheduler.
+#include "common.cuh"
+#include <cuda.h>
+
+namespace pivp {
+
+constexpr int TC_BM = 128;          // pixels per CTA (TMEM lanes)
+constexpr int TC_BK = 64;           // bf16 elements per k-block row = 128 B = one swizzle span
+constexpr int TC_THREADS = 192;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\ntcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, float v[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr));
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (SM100): start>>4 | LBO(ignored)=1 | SBO=1024>>4 | version=1 | SW128
+__device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+
+struct TcEpilogue {
+    int mode;                    // 0: plain fp32 store (+bias), 1: ConvLSTM gates
+    const float* bias;           // [N] (may be null in mode 0)
+    float* out; int out_cs, out_co;              // mode 0: D -> out[m*out_cs + out_co + n]
+    float* gates;                                // mode 1: activated gates [M][N] (saved for backward)
+    const float* c_prev; float* c_out;           // [M][C]  (c_prev may be null)
+    float* h_out; int h_cs, h_co;                // fp32 h view (next step's xh h-slot)
+    __nv_bfloat16* h_bf16; int hb_cs, hb_co;     // bf16 shadow (GEMM operand of the next step)
+    __nv_bfloat16* h_t; long h_t_ld;             // optional channel-major bf16 copy  h_t[(hT_co + ch) * h_t_ld + m]  (wgrad operand)
+    int hT_co;
+    int C;                                       // LSTM channels (N = 4C)
+    float forget_bias;
+    int accurate;                                // 1: expf/tanhf, 0: tanh.approx
+};
+
+struct TcGeom {
+    int H, W, TW, TH, TB;        // image size at this level, pixel box of one M tile
+    int Kc;                      // contracted channels per tap (multiple of 64)
+    int N, BN;                   // output channels, tile width
+    int stages;
+    int tmem_cols;
+};
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+conv5x5_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom g, TcEpilogue ep) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // carve: [stages][A 16 KB | B BN*128] then barriers
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)g.BN * 128, stage_bytes = a_bytes + b_bytes;
+    uint64_t* bars = (uint64_t*)(smem + (size_t)g.stages * stage_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + g.stages;
+    uint64_t* accum_full = bars + 2 * g.stages;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * g.stages + 1);
+    float* bias_s = (float*)(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x, n_tile = blockIdx.y;
+    const int n0 = n_tile * g.BN;
+    const int kblocks_per_tap = g.Kc / TC_BK;
+    const int num_kb = 25 * kblocks_per_tap;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
+        mbar_init(smem_u32(accum_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2 && ep.bias) {
+        for (int i = threadIdx.x - 64; i < g.BN; i += 128) bias_s[i] = ep.bias[n0 + i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            // first pixel of this M tile: tiles walk x fastest, then y, then batch
+            const int tiles_x = g.W / g.TW, tiles_y = g.H / g.TH;
+            const int tx = m_tile % tiles_x, ty = (m_tile / tiles_x) % tiles_y, tb = m_tile / (tiles_x * tiles_y);
+            const int x0 = tx * g.TW, y0 = ty * g.TH, b0 = tb * g.TB;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % g.stages;
+                const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+                mbar_wait(smem_u32(empty + s), ph ^ 1u);
+                const int tap = kb / kblocks_per_tap, cb = kb - tap * kblocks_per_tap;
+                const int dy = tap / 5, dx = tap - dy * 5;
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+                mbar_expect_tx(smem_u32(full + s), stage_bytes);
+                tma_load_4d(sa, &map_a, smem_u32(full + s), cb * TC_BK, x0 + dx - 2, y0 + dy - 2, b0);
+                tma_load_2d(sb, &map_b, smem_u32(full + s), tap * g.Kc + cb * TC_BK, n0);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % g.stages;
+            const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
+            mbar_wait(smem_u32(full + s), ph);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
+                const uint64_t ad = make_kmajor_sw128_desc(sa), bd = make_kmajor_sw128_desc(sb);
+#pragma unroll
+                for (int k = 0; k < TC_BK / 16; ++k)      // advance 16 bf16 = 32 B = 2 (>>4 units) inside the swizzle span
+                    tc_mma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
+                tc_commit(smem_u32(empty + s));           // frees the smem slot when these MMAs retire
+                if (kb == num_kb - 1) tc_commit(smem_u32(accum_full));
+            }
+            __syncwarp();
+        }
+    } else {
+        // ===================== epilogue (warps 2..5) =====================
+        const int q = warp & 3;                            // TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const long m = (long)m_tile * TC_BM + row;
+        mbar_wait(smem_u32(accum_full), 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (ep.mode == 0) {
+            for (int c0 = 0; c0 < g.BN; c0 += 8) {
+                float v[8];
+                tc_ld8(trow + (uint32_t)c0, v);
+                tc_ld_wait();
+                float* dst = ep.out + m * ep.out_cs + ep.out_co + n0 + c0;
+                if (ep.bias) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] += bias_s[c0 + i];
+                }
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        } else {
+            // tile = 32 channels x 4 gates: columns [0,32) j, [32,64) i, [64,96) f, [96,128) o
+            const int ch0 = n_tile * 32;
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+                float gj[8], gi[8], gf[8], go[8];
+                tc_ld8(trow + (uint32_t)(c0), gj);
+                tc_ld8(trow + (uint32_t)(32 + c0), gi);
+                tc_ld8(trow + (uint32_t)(64 + c0), gf);
+                tc_ld8(trow + (uint32_t)(96 + c0), go);
+                tc_ld_wait();
+                float cp[8], cn[8], hn[8];
+                if (ep.c_prev) {
+                    const float4 a = *reinterpret_cast<const float4*>(ep.c_prev + m * ep.C + ch0 + c0);
+                    const float4 b = *reinterpret_cast<const float4*>(ep.c_prev + m * ep.C + ch0 + c0 + 4);
+                    cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
+                } else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) cp[i] = 0.f;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float j = gj[i] + bias_s[c0 + i], ii = gi[i] + bias_s[32 + c0 + i];
+                    float f = gf[i] + bias_s[64 + c0 + i] + ep.forget_bias, o = go[i] + bias_s[96 + c0 + i];
+                    if (ep.accurate) { j = tanhf(j); ii = sigmoid_acc(ii); f = sigmoid_acc(f); o = sigmoid_acc(o); }
+                    else { j = tanh_fast(j); ii = sigmoid_fast(ii); f = sigmoid_fast(f); o = sigmoid_fast(o); }
+                    cn[i] = cp[i] * f + ii * j;
+                    hn[i] = (ep.accurate ? tanhf(cn[i]) : tanh_fast(cn[i])) * o;
+                    gj[i] = j; gi[i] = ii; gf[i] = f; go[i] = o;
+                }
+                float* gp = ep.gates + m * (4 * ep.C) + n0 + c0;
+                *reinterpret_cast<float4*>(gp) = make_float4(gj[0], gj[1], gj[2], gj[3]);
+                *reinterpret_cast<float4*>(gp + 4) = make_float4(gj[4], gj[5], gj[6], gj[7]);
+                *reinterpret_cast<float4*>(gp + 32) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+                *reinterpret_cast<float4*>(gp + 36) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+                *reinterpret_cast<float4*>(gp + 64) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+                *reinterpret_cast<float4*>(gp + 68) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+                *reinterpret_cast<float4*>(gp + 96) = make_float4(go[0], go[1], go[2], go[3]);
+                *reinterpret_cast<float4*>(gp + 100) = make_float4(go[4], go[5], go[6], go[7]);
+                float* cdst = ep.c_out + m * ep.C + ch0 + c0;
+                *reinterpret_cast<float4*>(cdst) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                *reinterpret_cast<float4*>(cdst + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                float* hdst = ep.h_out + m * ep.h_cs + ep.h_co + ch0 + c0;
+                *reinterpret_cast<float4*>(hdst) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(hdst + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+                if (ep.h_bf16) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(hn[4], hn[5]), p3 = __floats2bfloat162_rn(hn[6], hn[7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                    *reinterpret_cast<uint4*>(ep.h_bf16 + m * ep.hb_cs + ep.hb_co + ch0 + c0) = pk;
+                }
+                if (ep.h_t) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) ep.h_t[(long)(ep.hT_co + ch0 + c0 + i) * ep.h_t_ld + m] = __float2bfloat16(hn[i]);
+                }
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------------------------------ weight preparation
+// fp32 master W[n][tap][c] (c < Cx)  ->  bf16 forward operand  Wf[n][tap][Kpad]  (zero padded to Kpad channels)
+//                                    ->  bf16 dgrad operand    Wd[c][tap'][n] = W[n][24 - tap'][c]
+__global__ void tc_prep_weights_kernel(const float* __restrict__ W, int N, int Cx, int Kpad, __nv_bfloat16* __restrict__ Wf,
+                                       __nv_bfloat16* __restrict__ Wd) {
+    const long total_f = (long)N * 25 * Kpad;
+    const long total_d = (long)Cx * 25 * N;
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_f + total_d; i += (long)gridDim.x * blockDim.x) {
+        if (i < total_f) {
+            if (!Wf) continue;
+            const int c = (int)(i % Kpad);
+            const long r = i / Kpad;                    // n*25 + tap
+            Wf[i] = __float2bfloat16(c < Cx ? W[r * Cx + c] : 0.f);
+        } else {
+            if (!Wd) continue;
+            const long jx = i - total_f;
+            const int n = (int)(jx % N);
+            const long r = jx / N;                      // c*25 + tap'
+            const int tp = (int)(r % 25), c = (int)(r / 25);
+            Wd[jx] = __float2bfloat16(W[((long)n * 25 + (24 - tp)) * Cx + c]);
+        }
+    }
+}
+
+// libpivp.so must load on machines without a driver (the build check runs on a CPU box), so the driver entry point is
+// resolved at first use through the runtime instead of linking libcuda.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)p;
+    }
+    return fn;
+}
+
+static CUresult encode_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+                            const cuuint32_t* box) {
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    EncodeTiledFn enc = get_encode_fn();
+    if (!enc) return CUDA_ERROR_NOT_FOUND;
+    return enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides_bytes, box,
+                                  estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+
+static int pick_pixel_box(int B, int H, int W, int* TW, int* TH, int* TB) {
+    // 128 consecutive NHWC pixels that form a box: full rows (TW = W), then rows, then whole images
+    if (W > 128 || 128 % W) return -1;
+    *TW = W;
+    int th = 128 / W;
+    if (th > H) th = H;
+    if (H % th) return -1;
+    *TH = th;
+    const int tb = 128 / (W * th);
+    if (tb > 1 && th != H) return -1;
+    if (B % tb) return -1;
+    *TB = tb;
+    return 0;
+}
+
+}  // namespace pivp
+
+using namespace pivp;
+
+extern "C" {
+
+int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream) {
+    PIVP_REQUIRE(W && N > 0 && Cx > 0 && Kpad >= Cx && (w_fwd_bf16 || w_dgrad_bf16), "tc_prep_weights: bad argument");
+    tc_prep_weights_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(W, N, Cx, Kpad, (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
+    return check_launch("tc_prep_weights");
+}
+
+// Returns PIVP_EUNSUPPORTED (without launching) when the shape cannot be tiled: callers fall back to nothing -- they must
+// pick shapes the path supports (the ConvLSTM layers of the model at even batch sizes all do).
+int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
+                    const void* wt_bf16, int N, int BN,
+                    int mode, const float* bias,
+                    float* out, int out_cs, int out_co,
+                    float* gates, const float* c_prev, float* c_out,
+                    float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
+                    void* h_t, long h_t_ld, int hT_co,
+                    int C, float forget_bias, int accurate, void* stream) {
+    PIVP_REQUIRE(in_bf16 && wt_bf16, "tc_conv5x5: null operand");
+    PIVP_REQUIRE(Kc > 0 && Kc % TC_BK == 0 && in_cs >= Kc && in_cs % 8 == 0, "tc_conv5x5: Kc must be a multiple of 64 and rows 16-byte aligned");
+    PIVP_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && N % BN == 0, "tc_conv5x5: BN must be a multiple of 16 <= 256 dividing N");
+    if (mode == 1) {
+        PIVP_REQUIRE(BN == 128 && N == 4 * C && C % 32 == 0 && gates && c_out && h_out && bias, "tc_conv5x5: gate epilogue needs BN=128, N=4C, bias");
+        PIVP_REQUIRE(h_cs % 4 == 0 && h_co % 4 == 0 && (!h_bf16 || (hb_cs % 8 == 0 && hb_co % 8 == 0)), "tc_conv5x5: h views must be 16-byte aligned");
+    } else {
+        PIVP_REQUIRE(mode == 0 && out && out_cs % 4 == 0 && out_co % 4 == 0, "tc_conv5x5: plain epilogue needs a 16-byte aligned fp32 view");
+    }
+    int TW, TH, TB;
+    if (pick_pixel_box(B, H, W, &TW, &TH, &TB) != 0) {
+        set_error("tc_conv5x5: cannot tile B=%d H=%d W=%d into 128-pixel boxes", B, H, W);
+        return PIVP_EUNSUPPORTED;
+    }
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)in_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, (cuuint64_t)H * W * in_cs * 2};
+        cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+        CUresult r = encode_tmap(&map_a, in_bf16, 4, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("tc_conv5x5: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return PIVP_ECUDA; }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)25 * Kc, (cuuint64_t)N};
+        cuuint64_t str[1] = {(cuuint64_t)25 * Kc * 2};
+        cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+        CUresult r = encode_tmap(&map_b, wt_bf16, 2, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("tc_conv5x5: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return PIVP_ECUDA; }
+    }
+    TcGeom g;
+    g.H = H; g.W = W; g.TW = TW; g.TH = TH; g.TB = TB; g.Kc = Kc; g.N = N; g.BN = BN;
+    const int stage_bytes = TC_BM * 128 + BN * 128;
+    int stages = (100 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    g.stages = stages;
+    g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)BN * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv5x5_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { set_error("tc_conv5x5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PIVP_ECUDA; }
+        attr_set = true;
+    }
+    TcEpilogue ep;
+    ep.mode = mode; ep.bias = bias; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co; ep.gates = gates; ep.c_prev = c_prev;
+    ep.c_out = c_out; ep.h_out = h_out; ep.h_cs = h_cs; ep.h_co = h_co; ep.h_bf16 = (__nv_bfloat16*)h_bf16; ep.hb_cs = hb_cs; ep.hb_co = hb_co;
+    ep.h_t = (__nv_bfloat16*)h_t; ep.h_t_ld = h_t_ld; ep.hT_co = hT_co;
+    ep.C = C; ep.forget_bias = forget_bias; ep.accurate = accurate;
+    const long M = (long)B * H * W;
+    dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN));
+    conv5x5_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
+    return check_launch("tc_conv5x5");
+}
+
+}  // extern "C"

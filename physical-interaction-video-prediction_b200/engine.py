@@ -234,13 +234,12 @@ class Engine(object):
         name = "lstm%d/conv" % (li + 1)
         xh, Gt = ws["xh"][li][t], ws["G"][li][t]
         if self.tc is not None:
-            self.tc.lstm_conv_fwd(li, t)
-        else:
-            self._conv_fwd(View(xh, cin + C, 0, cin + C), B, h, w, self.p[name + "/W"], self.p[name + "/b"], 4 * C, 5, 1, 2,
-                           View(Gt, 4 * C, 0, 4 * C))
-        hb = None if self.tc is None else self.tc.xh_bf16[li][t + 1]
+            self.tc.lstm_fwd(li, t)            # conv + bias + gates + cell + h in ONE tcgen05 kernel
+            return
+        self._conv_fwd(View(xh, cin + C, 0, cin + C), B, h, w, self.p[name + "/W"], self.p[name + "/b"], 4 * C, 5, 1, 2,
+                       View(Gt, 4 * C, 0, 4 * C))
         self.L.call("pivp_lstm_gates_fwd", _ptr(Gt), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
-                    _ptr(ws["xh"][li][t + 1]), cin + C, cin, _ptr(hb), cin + C, cin, ws["Mr"][lv], C, 1.0, self._s())
+                    _ptr(ws["xh"][li][t + 1]), cin + C, cin, 0, 0, 0, ws["Mr"][lv], C, 1.0, self._s())
 
     def _lstm_bwd(self, li, t, B, last):
         """dln[li] holds the LN-path gradient of h_t; dxh[li] (from step t+1) holds d h_t via the recurrent input."""
@@ -255,10 +254,10 @@ class Engine(object):
                     _ptr(dg_bf16), ws["Mr"][lv], C, self._s())
         dG = View(Gt, 4 * C, 0, 4 * C)
         xh = View(ws["xh"][li][t], cin + C, 0, cin + C)
-        if self.tc is not None and self.tc.has_bwd:
-            self.tc.lstm_conv_bwd(li, t)
+        self._conv_wgrad(xh, B, h, w, dG, h, w, 5, 1, 2, self.g[name + "/W"], self.g[name + "/b"])
+        if self.tc is not None:
+            self.tc.lstm_dgrad(li, t)          # dxh = conv(dG_bf16, tap-flipped W) on tcgen05
         else:
-            self._conv_wgrad(xh, B, h, w, dG, h, w, 5, 1, 2, self.g[name + "/W"], self.g[name + "/b"])
             self._conv_dgrad(dG, B, h, w, self.p[name + "/W"], None, 5, 1, 2, View(dxh, cin + C, 0, cin + C), h, w)
 
     # ------------------------------------------------------------------ forward

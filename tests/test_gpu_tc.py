@@ -1,0 +1,153 @@
+"""GPU parity of the tcgen05/TMEM/TMA ConvLSTM kernels (bf16 operands, fp32 accumulation).
+
+Kernel-level: against the fp32 SIMT kernels of the same library fed the SAME bf16-rounded operands (differences are
+then accumulation order only -> 2e-3 of max-abs), and against the NumPy oracle's convolution.
+Model-level (bf16 mode): frames and masks within 2e-2 relative of the fp32/float64 oracle (north_star tolerance).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import model as OM
+from oracle import npgrad as G
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pk():
+    import pivp_b200
+    pivp_b200.lib()
+    return pivp_b200
+
+
+def rel(a, b):
+    a = a.detach().float().cpu().numpy() if isinstance(a, torch.Tensor) else np.asarray(a)
+    b = b.detach().float().cpu().numpy() if isinstance(b, torch.Tensor) else np.asarray(b)
+    return float(np.abs(a.astype(np.float64) - b).max() / (np.abs(b).max() + 1e-30))
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("B,H,W,Kc,N,BN", [
+    (2, 32, 32, 64, 128, 128),     # lstm1/2 forward shape
+    (2, 16, 16, 128, 256, 128),    # lstm4 forward
+    (2, 8, 8, 192, 512, 128),      # lstm5 forward (two images per 128-pixel tile)
+    (4, 32, 32, 128, 64, 64),      # lstm1 input-gradient shape (N = Cin + C)
+    (2, 16, 16, 256, 96, 96),      # lstm3 input-gradient
+    (2, 16, 16, 256, 192, 192),    # lstm6 input-gradient
+    (2, 64, 64, 64, 128, 128),     # 128x128 images, level 2
+])
+def test_tc_conv5x5_plain_matches_simt(pk, B, H, W, Kc, N, BN):
+    L = pk.lib()
+    rs = np.random.RandomState(0)
+    M = B * H * W
+    x = torch.from_numpy(rs.standard_normal((M, Kc)).astype(np.float32)).cuda().bfloat16()
+    w = torch.from_numpy((rs.standard_normal((N, 25, Kc)) / np.sqrt(25 * Kc)).astype(np.float32)).cuda().bfloat16()
+    bias = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).cuda()
+    out = torch.zeros(M, N, device="cuda")
+    L.call("pivp_tc_conv5x5", x.data_ptr(), Kc, B, H, W, Kc, w.data_ptr(), N, BN, 0, bias.data_ptr(),
+           out.data_ptr(), N, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0, stream())
+    ref = torch.zeros(M, N, device="cuda")
+    xf, wf = x.float().contiguous(), w.float().contiguous()
+    L.call("pivp_conv2d_fwd", xf.data_ptr(), Kc, 0, B, H, W, Kc, wf.data_ptr(), bias.data_ptr(), N, 5, 5, 1, 2,
+           ref.data_ptr(), N, 0, H, W, 0, 0, stream())
+    torch.cuda.synchronize()
+    assert rel(out, ref) < 2e-3
+    # and against the oracle's convolution on a slice of the batch (NCHW, Chainer weight layout)
+    xo = xf[:H * W].cpu().numpy().reshape(1, H, W, Kc).transpose(0, 3, 1, 2).astype(np.float64)
+    wo = wf.cpu().numpy().reshape(N, 5, 5, Kc).transpose(0, 3, 1, 2).astype(np.float64)
+    yo = G.convolution_2d(G.Var(xo), G.Var(wo), G.Var(bias.cpu().numpy().astype(np.float64)), 1, 2).data
+    got = out[:H * W].reshape(1, H, W, N).permute(0, 3, 1, 2)
+    assert rel(got, yo) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,W,cin,C,t0", [(2, 32, 32, 32, 32, True), (2, 16, 16, 64, 64, False), (2, 8, 8, 64, 128, False)])
+def test_tc_convlstm_fused_matches_simt_and_gate_kernel(pk, B, H, W, cin, C, t0):
+    L = pk.lib()
+    rs = np.random.RandomState(1)
+    M, cx = B * H * W, cin + C
+    Kp = (cx + 63) // 64 * 64
+    xh = torch.zeros(M, Kp, device="cuda")
+    xh[:, :cx] = torch.from_numpy(rs.standard_normal((M, cx)).astype(np.float32)).cuda()
+    xh_b = xh.bfloat16()
+    Wm = torch.from_numpy((rs.standard_normal((4 * C, 25, cx)) / np.sqrt(25 * cx)).astype(np.float32)).cuda()
+    bias = torch.from_numpy((0.1 * rs.standard_normal(4 * C)).astype(np.float32)).cuda()
+    Wf = torch.empty(4 * C, 25, Kp, dtype=torch.bfloat16, device="cuda")
+    Wd = torch.empty(cx, 25, 4 * C, dtype=torch.bfloat16, device="cuda")
+    L.call("pivp_tc_prep_weights", Wm.data_ptr(), 4 * C, cx, Kp, Wf.data_ptr(), Wd.data_ptr(), stream())
+    # prepared weights: forward copy is a zero-padded cast, dgrad copy is tap-flipped and transposed
+    assert torch.equal(Wf[:, :, :cx], Wm.bfloat16()) and (Kp == cx or float(Wf[:, :, cx:].abs().max()) == 0.0)
+    assert torch.equal(Wd, Wm.bfloat16().flip(1).permute(2, 1, 0).contiguous())
+    c_prev = None if t0 else torch.from_numpy(rs.standard_normal((M, C)).astype(np.float32)).cuda()
+    gates, c_out = torch.empty(M, 4 * C, device="cuda"), torch.empty(M, C, device="cuda")
+    h_out = torch.zeros(M, cx, device="cuda")
+    h_b = torch.zeros(M, Kp, dtype=torch.bfloat16, device="cuda")
+    for accurate in (1, 0):
+        L.call("pivp_tc_conv5x5", xh_b.data_ptr(), Kp, B, H, W, Kp, Wf.data_ptr(), 4 * C, 128, 1, bias.data_ptr(),
+               0, 0, 0, gates.data_ptr(), 0 if c_prev is None else c_prev.data_ptr(), c_out.data_ptr(),
+               h_out.data_ptr(), cx, cin, h_b.data_ptr(), Kp, cin, 0, 0, 0, C, 1.0, accurate, stream())
+        # reference: SIMT conv on the bf16-rounded operands + the fp32 gate kernel
+        G_ref = torch.empty(M, 4 * C, device="cuda")
+        xf, wf = xh_b.float().contiguous(), Wf.float().contiguous()
+        L.call("pivp_conv2d_fwd", xf.data_ptr(), Kp, 0, B, H, W, Kp, wf.data_ptr(), bias.data_ptr(), 4 * C, 5, 5, 1, 2,
+               G_ref.data_ptr(), 4 * C, 0, H, W, 0, 0, stream())
+        c_ref, h_ref = torch.empty(M, C, device="cuda"), torch.zeros(M, cx, device="cuda")
+        L.call("pivp_lstm_gates_fwd", G_ref.data_ptr(), 0 if c_prev is None else c_prev.data_ptr(), c_ref.data_ptr(),
+               h_ref.data_ptr(), cx, cin, 0, 0, 0, M, C, 1.0, stream())
+        torch.cuda.synchronize()
+        tol = 2e-3 if accurate else 4e-3          # tanh.approx.f32 has ~2^-11 relative error
+        assert rel(gates, G_ref) < tol and rel(c_out, c_ref) < tol and rel(h_out, h_ref) < tol
+        assert float(h_out[:, :cin].abs().max()) == 0.0                       # only the h slot is written
+        assert rel(h_b[:, cin:cx], h_out[:, cin:cx]) < 1e-2                   # bf16 shadow of h
+
+
+def test_tc_unsupported_shapes_are_reported(pk):
+    L = pk.lib()
+    x = torch.zeros(3 * 8 * 8, 64, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(64, 25, 64, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(3 * 8 * 8, 64, device="cuda")
+    with pytest.raises(pk.PivpError) as ei:       # 3 images of 8x8 cannot form 128-pixel boxes
+        L.call("pivp_tc_conv5x5", x.data_ptr(), 64, 3, 8, 8, 64, w.data_ptr(), 64, 64, 0, 0, out.data_ptr(), 64, 0,
+               0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0, stream())
+    assert "cannot tile" in str(ei.value)
+
+
+@pytest.mark.parametrize("mt,nm,k", [("CDNA", 10, 900.0), ("CDNA", 10, -1.0), ("DNA", 1, 900.0), ("STP", 10, 900.0)])
+def test_model_bf16_within_tolerance_of_oracle(pk, mt, nm, k):
+    """bf16 compute mode end to end (64x64, B=2): north_star tolerance 2e-2 relative on frames and masks;
+    per-tensor gradient tolerance: max-abs error <= 6e-2 of the tensor's max-abs."""
+    H = W = 64
+    B, T = 2, 4
+    cfg = OM.Config(mt, nm, schedsamp_k=k, height=H, width=W, dtype=np.float64)
+    params = OM.init_params(cfg)
+    rs = np.random.RandomState(7)
+    for key in sorted(params):
+        if not key.endswith("/W"):
+            params[key] = params[key] + 0.05 * rs.standard_normal(params[key].shape)
+    batch = OM.concat_examples(OM.synthetic_sequences(B, T, cfg))
+    np.random.seed(99)
+    ref = OM.forward(params, batch, 6000, cfg)
+    G.backward(ref["loss"])
+    model = pk.Model(nm, is_cdna=(mt == "CDNA"), is_dna=(mt == "DNA"), is_stp=(mt == "STP"), scheduled_sampling_k=k,
+                     prefix="t", height=H, width=W, compute="bf16")
+    model.load_params(params)
+    np.random.seed(99)
+    loss = model([torch.from_numpy(a) for a in batch], 6000)
+    model.cleargrads()
+    model.backward()
+    torch.cuda.synchronize()
+    assert abs(float(loss) - float(ref["loss"].data)) <= 2e-2 * abs(float(ref["loss"].data))
+    for t in range(T - 1):
+        assert rel(model.gen_images[t], ref["gen_images"][t].data) < 2e-2, t
+        assert rel(model.engine.ws["mask_pre"][t], ref["trace"][t]["mask_pre"].data) < 2e-2, t
+    grads = model.grads
+    bad = {}
+    for key, v in ref["P"].items():
+        r = np.zeros_like(v.data) if v.grad is None else v.grad
+        e = np.abs(grads[key].astype(np.float64) - r).max() / (np.abs(r).max() + 1e-20)
+        if e > 6e-2:
+            bad[key] = e
+    assert not bad, bad
