@@ -37,6 +37,8 @@ extern "C" {
 const char* pivp_last_error(void);
 int pivp_abi_version(void);
 int pivp_device_sync_check(void);
+/* number of CUDA kernels this library has launched in this process (every successful launch is counted once) */
+long pivp_launch_count(void);
 
 /* ---- Convolution2D / Deconvolution2D (train_model.py:224,500-507,527; Chainer A.2/A.3) --------------- */
 /* y = conv(x, w) + bias [, relu]  -- L.Convolution2D forward; Deconvolution2D input-gradient */

@@ -9,7 +9,7 @@ from . import layout                                                      # noqa
 
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import pivp_b200` works in a build-only environment
-    if name in ("functions", "links", "engine", "tensorcore", "parallel"):
+    if name in ("functions", "links", "engine", "tensorcore", "parallel", "train", "data"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name in ("Model", "Adam", "BasicConvLSTMCell", "LayerNormalizationConv2D", "StatelessCDNA", "StatelessDNA",
@@ -17,4 +17,7 @@ def __getattr__(name):
                 "num_ground_truth", "scheduled_sample_mask"):
         from . import links
         return getattr(links, name)
+    if name == "TrainStep":
+        from .train import TrainStep
+        return TrainStep
     raise AttributeError(name)

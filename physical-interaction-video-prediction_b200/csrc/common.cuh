@@ -14,6 +14,7 @@
 namespace pivp {
 
 void set_error(const char* fmt, ...);
+void note_launch();          // bumps the process-wide kernel-launch counter (pivp_launch_count)
 
 // 2-D strided view of an NHWC tensor slice: element (row m, channel ch) lives at p[m*cs + co + ch].
 struct View {
@@ -33,6 +34,7 @@ static inline int check_launch(const char* what) {
         set_error("%s: %s", what, cudaGetErrorString(e));
         return PIVP_ECUDA;
     }
+    note_launch();
     return PIVP_OK;
 }
 

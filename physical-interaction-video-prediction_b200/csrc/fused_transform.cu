@@ -448,11 +448,15 @@ static int make_band(int H, int W, int M1, int extra_rows, Band* bd) {
     return PIVP_OK;
 }
 
+// Raises the dynamic shared-memory limit of `kernel` once per (kernel type, size) so that steady-state calls -- and CUDA-graph
+// capture -- issue no attribute call.  Every kernel in this file has a distinct signature, hence a distinct instantiation.
 template <typename K>
 static int allow_smem(K kernel, size_t bytes) {
-    if (bytes > 48 * 1024) {
+    static size_t granted = 48 * 1024;
+    if (bytes > granted) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e)); return PIVP_ECUDA; }
+        granted = bytes;
     }
     return PIVP_OK;
 }

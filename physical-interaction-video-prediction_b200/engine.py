@@ -261,9 +261,20 @@ class Engine(object):
             self._conv_dgrad(dG, B, h, w, self.p[name + "/W"], None, 5, 1, 2, View(dxh, cin + C, 0, cin + C), h, w)
 
     # ------------------------------------------------------------------ forward
+    def stage_schedule(self, take_gt):
+        """Host part of a step: put the scheduled-sampling select (int32 (T-1,B)) into the pinned staging buffer."""
+        self.ws["take_host"].copy_(torch.from_numpy(np.ascontiguousarray(take_gt, dtype=np.int32)))
+
     def forward(self, images, actions, states, take_gt=None, feedself=True):
         """images (T,B,3,H,W), actions/states (T,B,5) fp32 CUDA tensors.  ``take_gt``: int32 (T-1,B) host array with the
         scheduled-sampling select for steps t >= ctx (rows before are ignored) or None when ``feedself``."""
+        self._workspace(int(images.shape[1]), int(images.shape[0]))
+        if not feedself:
+            self.stage_schedule(take_gt)
+        return self.forward_device(images, actions, states, feedself)
+
+    def forward_device(self, images, actions, states, feedself=True):
+        """Device part of the forward pass: stream-ordered work only (CUDA-graph capturable)."""
         T, B = int(images.shape[0]), int(images.shape[1])
         H, W = self.H, self.W
         assert images.shape[2:] == (3, H, W) and images.dtype == torch.float32 and images.is_contiguous()
@@ -273,7 +284,6 @@ class Engine(object):
         self.feedself = bool(feedself)
         self.images, self.states = images, states
         if not feedself:
-            ws["take_host"].copy_(torch.from_numpy(np.ascontiguousarray(take_gt, dtype=np.int32)))
             ws["take"].copy_(ws["take_host"], non_blocking=True)
         ws["cur"][0].copy_(states[0])
         ws["loss_slots"].zero_()
@@ -306,7 +316,7 @@ class Engine(object):
             self._conv_fwd(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, p["enc1/W"], p["enc1/b"], 32, 3, 2, 1,
                            View(ws["xh"][2][t], 96, 0, 32), relu=1)
             L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64,
-                   0 if self.tc is None else self.tc.xview(2, t).ptr, 96, 0, Mr[4], 32, s)
+                   0 if self.tc is None else self.tc.xview(2, t).ptr, 0 if self.tc is None else self.tc.Kpad[2], 0, Mr[4], 32, s)
             # ---- group 2
             self._lstm_fwd(2, t, B)
             self._ln_fwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), B, HW[4], View(ws["xh"][3][t], 128, 0, 64), None, 0,
@@ -323,7 +333,7 @@ class Engine(object):
             self._conv_fwd(View(ws["in3"][t], 64 + self.sa, 0, 64 + self.sa), B, H // 8, W // 8, p["enc3/W"], p["enc3/b"], 64, 1, 1, 0,
                            View(ws["xh"][4][t], 192, 0, 64), relu=1)
             if self.tc is not None:
-                L.call("pivp_copy_view", _ptr(ws["xh"][4][t]), 192, 0, 0, 0, 0, self.tc.xview(4, t).ptr, 192, 0, Mr[8], 64, s)
+                L.call("pivp_copy_view", _ptr(ws["xh"][4][t]), 192, 0, 0, 0, 0, self.tc.xview(4, t).ptr, self.tc.Kpad[4], 0, Mr[8], 64, s)
             # ---- group 4
             self._lstm_fwd(4, t, B)
             self._ln_fwd("hidden5", View(ws["xh"][4][t + 1], 192, 64, 128), B, HW[8], View(ws["hid5"][t], 128, 0, 128), None, 0,
@@ -331,7 +341,7 @@ class Engine(object):
             self._conv_dgrad(View(ws["hid5"][t], 128, 0, 128), B, H // 8, W // 8, p["enc4/W"], p["enc4/b"], 3, 2, 1,
                              View(ws["xh"][5][t], 192, 0, 128), H // 4, W // 4, relu=1)
             if self.tc is not None:
-                L.call("pivp_copy_view", _ptr(ws["xh"][5][t]), 192, 0, 0, 0, 0, self.tc.xview(5, t).ptr, 192, 0, Mr[4], 128, s)
+                L.call("pivp_copy_view", _ptr(ws["xh"][5][t]), 192, 0, 0, 0, 0, self.tc.xview(5, t).ptr, self.tc.Kpad[5], 0, Mr[4], 128, s)
             # ---- group 5
             self._lstm_fwd(5, t, B)
             self._ln_fwd("hidden6", View(ws["xh"][5][t + 1], 192, 128, 64), B, HW[4], View(ws["cat5"][t], 96, 0, 64), None, 0,
@@ -339,7 +349,7 @@ class Engine(object):
             self._conv_dgrad(View(ws["cat5"][t], 96, 0, 96), B, H // 4, W // 4, p["enc5/W"], p["enc5/b"], 3, 2, 1,
                              View(ws["xh"][6][t], 128, 0, 96), H // 2, W // 2, relu=1)
             if self.tc is not None:
-                L.call("pivp_copy_view", _ptr(ws["xh"][6][t]), 128, 0, 0, 0, 0, self.tc.xview(6, t).ptr, 128, 0, Mr[2], 96, s)
+                L.call("pivp_copy_view", _ptr(ws["xh"][6][t]), 128, 0, 0, 0, 0, self.tc.xview(6, t).ptr, self.tc.Kpad[6], 0, Mr[2], 96, s)
             # ---- group 6
             self._lstm_fwd(6, t, B)
             self._ln_fwd("hidden7", View(ws["xh"][6][t + 1], 128, 96, 32), B, HW[2], View(ws["cat6"][t], 64, 0, 32), None, 0,

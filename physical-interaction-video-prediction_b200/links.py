@@ -228,18 +228,24 @@ class Model(object):
         self.take_gt = take
         gen = self.engine.forward(images, actions, states, take, feedself)
         self.gen_images = gen
-        self.gen_states = self.engine.ws["cur"][1:]
-        self.conv_res = [self.engine.ws["xh"][0][T - 2], self.engine.ws["e6"][T - 2]]
+        self._bind_loss()
+        return self.loss
+
+    def _bind_loss(self):
+        """Lazy handles for .loss / .psnr_all: the D2H read (ref:955-956) happens when they are first looked at."""
+        e = self.engine
+        T = e.T
+        self.gen_states = e.ws["cur"][1:]
+        self.conv_res = [e.ws["xh"][0][T - 2], e.ws["e6"][T - 2]]
         cache = {}
 
         def values():
             if not cache:
-                cache["v"] = self.engine.loss_values()
+                cache["v"] = e.loss_values()
             return cache["v"]
         self.loss = _Scalar(lambda: values()[0])
         self.psnr_all = _Scalar(lambda: values()[1])
         self._values = values
-        return self.loss
 
     def make_summaries(self):
         """ref:744-759 strings (forces the D2H read)."""
