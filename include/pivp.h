@@ -143,6 +143,14 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     void* h_t, long h_t_ld, int hT_co,
                     int C, float forget_bias, int accurate, void* stream);
 
+/* dst[c][p] = src[p][c] (bf16, c < C); optional colsum[c] += sum_p src[p][c] (fp32) -- builds the pixel-major operands of the
+ * weight-gradient GEMM and, for dG, the ConvLSTM bias gradient. */
+int pivp_tc_transpose(const void* src_bf16, int src_ld, long P, int C, void* dst_bf16, long dst_ld, float* colsum, void* stream);
+size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4);
+/* dW[n][tap][c] += sum over all SB images (time steps x batch) of dG^T (N4, SB*H*W) x shifted XH^T (Cx, SB, H, W)   (D.5) */
+int pivp_tc_wgrad5x5(const void* dgT_bf16, const void* xhT_bf16, int SB, int H, int W, int Cx, int N4, float* dW,
+                     void* workspace, size_t ws_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

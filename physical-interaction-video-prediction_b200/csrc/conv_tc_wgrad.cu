@@ -1,0 +1,279 @@
+// tcgen05 weight-gradient of the ConvLSTM 5x5 convolutions, deferred to the end of BPTT and batched over ALL time steps:
+//      dW[n][tap][c] += sum_{t} sum_{p} dG_t[p][n] * XH_t[p + (dy-2, dx-2)][c]             (train_model.py:950)
+// One launch per layer contracts over K = S*B*H*W pixels (S = T-1 steps) instead of 9 launches of K = B*H*W:
+// long K loops, 9x fewer launches, and the split-K partials are written once.
+//
+// GEMM view per CTA: D[128 n-rows][ntaps x Cx columns] in TMEM (<= 512 fp32 columns), K = pixels.
+//  * A = dG^T  [4C][S*P]  bf16, K(pixel)-major   -> 2-D TMA box {64 px, 128 rows}
+//  * B = XH^T  [Cx][S*B][H][W] bf16, pixel-major -> 4-D TMA box {bw, bh, 1, Cx} (bw*bh = 64 px) fetched at the tap-shifted
+//    coordinate; pixels outside the image are zero-filled by TMA (= the convolution's zero padding).
+//  Both land as rows of 128 B with the 128-byte swizzle = canonical K-major UMMA operands.
+//  * A ring (3 x 16 KB) and B ring (up to 8 x Cx*128 B) with full/empty mbarriers; one A tile feeds ntaps*4 MMAs.
+//  * grid = (4C/128, tap groups, K splits); every CTA stores its fp32 partial tile, a second kernel sums the splits into dW.
+// The channel-major operands are produced by transpose_bf16_kernel (which also yields the bias gradient as column sums).
+#include "tc_common.cuh"
+
+namespace pivp {
+
+constexpr int WG_THREADS = 192;
+constexpr int WG_ASTAGES = 3;
+
+struct WgGeom {
+    int H, W, bw, bh;        // image size at this level, pixel box (bw*bh = 64)
+    int Cx, N4;              // channels of XH (B rows / accumulator width per tap), 4C
+    int tpg;                 // taps per group
+    int kb_total, kb_per_split;
+    int b_stages;
+};
+
+__global__ void __launch_bounds__(WG_THREADS, 1)
+conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, WgGeom g, float* __restrict__ part) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)g.Cx * 128;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + WG_ASTAGES * a_bytes;
+    uint64_t* bars = (uint64_t*)(smem_b + (size_t)g.b_stages * b_bytes);
+    uint64_t* a_full = bars;
+    uint64_t* a_empty = a_full + WG_ASTAGES;
+    uint64_t* b_full = a_empty + WG_ASTAGES;
+    uint64_t* b_empty = b_full + g.b_stages;
+    uint64_t* accum_full = b_empty + g.b_stages;
+    uint32_t* tmem_slot = (uint32_t*)(accum_full + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n0 = blockIdx.x * 128;
+    const int tap0 = blockIdx.y * g.tpg;
+    const int ntaps = min(g.tpg, 25 - tap0);
+    const int split = blockIdx.z;
+    const int kb0 = split * g.kb_per_split, kb1 = min(g.kb_total, kb0 + g.kb_per_split);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < WG_ASTAGES; ++s) { mbar_init(smem_u32(a_full + s), 1); mbar_init(smem_u32(a_empty + s), 1); }
+        for (int s = 0; s < g.b_stages; ++s) { mbar_init(smem_u32(b_full + s), 1); mbar_init(smem_u32(b_empty + s), 1); }
+        mbar_init(smem_u32(accum_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            const int hw = g.H * g.W;
+            uint32_t ai = 0, bi = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const uint32_t sa = ai % WG_ASTAGES;
+                mbar_wait(smem_u32(a_empty + sa), ((ai / WG_ASTAGES) & 1u) ^ 1u);
+                mbar_expect_tx(smem_u32(a_full + sa), a_bytes);
+                tma_load_2d(smem_u32(smem_a + sa * a_bytes), &map_a, smem_u32(a_full + sa), kb * 64, n0);
+                ++ai;
+                const long p = (long)kb * 64;
+                const int bimg = (int)(p / hw), rem = (int)(p - (long)bimg * hw);
+                const int y0 = rem / g.W, x0 = rem - y0 * g.W;
+                for (int tl = 0; tl < ntaps; ++tl) {
+                    const int tap = tap0 + tl, dy = tap / 5, dx = tap - dy * 5;
+                    const uint32_t sb = bi % (uint32_t)g.b_stages;
+                    mbar_wait(smem_u32(b_empty + sb), ((bi / (uint32_t)g.b_stages) & 1u) ^ 1u);
+                    mbar_expect_tx(smem_u32(b_full + sb), b_bytes);
+                    tma_load_4d(smem_u32(smem_b + (size_t)sb * b_bytes), &map_b, smem_u32(b_full + sb), x0 + dx - 2, y0 + dy - 2, bimg, 0);
+                    ++bi;
+                }
+            }
+        }
+    } else if (warp == 1) {
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.Cx >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        uint32_t ai = 0, bi = 0;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            const uint32_t sa = ai % WG_ASTAGES;
+            mbar_wait(smem_u32(a_full + sa), (ai / WG_ASTAGES) & 1u);
+            const uint64_t ad = make_kmajor_sw128_desc(smem_u32(smem_a + sa * a_bytes));
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const uint32_t sb = bi % (uint32_t)g.b_stages;
+                mbar_wait(smem_u32(b_full + sb), (bi / (uint32_t)g.b_stages) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint64_t bd = make_kmajor_sw128_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        tc_mma_bf16(tmem_base + (uint32_t)(tl * g.Cx), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
+                                    (kb > kb0 || k > 0) ? 1u : 0u);
+                    tc_commit(smem_u32(b_empty + sb));
+                }
+                __syncwarp();
+                ++bi;
+            }
+            if (lane == 0) {
+                tc_commit(smem_u32(a_empty + sa));
+                if (kb == kb1 - 1) tc_commit(smem_u32(accum_full));
+            }
+            __syncwarp();
+            ++ai;
+        }
+    } else {
+        const int q = warp & 3;
+        const int n = n0 + q * 32 + lane;
+        mbar_wait(smem_u32(accum_full), 0);
+        tc_fence_after();
+        const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        float* dst_row = part + ((size_t)split * g.N4 + n) * 25 * g.Cx;
+        for (int tl = 0; tl < ntaps; ++tl) {
+            float* dst = dst_row + (size_t)(tap0 + tl) * g.Cx;
+            for (int c0 = 0; c0 < g.Cx; c0 += 8) {
+                float v[8];
+                tc_ld8(trow + (uint32_t)(tl * g.Cx + c0), v);
+                tc_ld_wait();
+                *reinterpret_cast<float4*>(dst + c0) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + c0 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+        }
+        tc_fence_before();
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    }
+}
+
+// dW[i] += sum_s part[s][i]
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int splits) {
+    const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i4 >= n) return;
+    float4 acc = *reinterpret_cast<const float4*>(out + i4);
+    for (int s = 0; s < splits; ++s) {
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)s * n + i4);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    *reinterpret_cast<float4*>(out + i4) = acc;
+}
+
+// dst[c][p] = src[p][c] for c < C (bf16); optional colsum[c] += sum_p src[p][c] (fp32).  Tiles of 64 x 64.
+__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, long P, int C,
+                                                             __nv_bfloat16* __restrict__ dst, long dst_ld, float* __restrict__ colsum) {
+    __shared__ unsigned short tile[64][66];
+    const long p0 = (long)blockIdx.x * 64;
+    const int c0 = blockIdx.y * 64;
+    const int t = threadIdx.x;
+    {   // load: 64 rows x 32 words, coalesced along c
+        const int wcol = t & 31, r0 = t >> 5;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int r = r0 + 8 * i;
+            const long p = p0 + r;
+            unsigned int w = 0;
+            const int c = c0 + 2 * wcol;
+            if (p < P && c < C) w = *reinterpret_cast<const unsigned int*>(src + p * src_ld + c);     // C, src_ld even
+            tile[r][2 * wcol] = (unsigned short)(w & 0xffffu);
+            tile[r][2 * wcol + 1] = (unsigned short)(w >> 16);
+        }
+    }
+    __syncthreads();
+    const int w = t & 31, cg = t >> 5;          // w: pixel pair (2w, 2w+1); cg: channel phase
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int cl = cg + 8 * j, c = c0 + cl;
+        const unsigned short lo = tile[2 * w][cl], hi = tile[2 * w + 1][cl];
+        if (c < C && p0 + 2 * w < P)
+            *reinterpret_cast<unsigned int*>(dst + (long)c * dst_ld + p0 + 2 * w) = (unsigned int)lo | ((unsigned int)hi << 16);
+        if (colsum) {
+            float s = __bfloat162float(__ushort_as_bfloat16(lo)) + __bfloat162float(__ushort_as_bfloat16(hi));
+            s = warp_sum(s);
+            if (w == 0 && c < C) atomicAdd(colsum + c, s);
+        }
+    }
+}
+
+}  // namespace pivp
+
+using namespace pivp;
+
+extern "C" {
+
+int pivp_tc_transpose(const void* src_bf16, int src_ld, long P, int C, void* dst_bf16, long dst_ld, float* colsum, void* stream) {
+    PIVP_REQUIRE(src_bf16 && dst_bf16 && P > 0 && C > 0 && (C % 2) == 0 && (src_ld % 2) == 0 && (P % 2) == 0 && dst_ld >= P && (dst_ld % 2) == 0,
+                 "tc_transpose: bad argument (C, P and leading dimensions must be even)");
+    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64));
+    transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_bf16, src_ld, P, C, (__nv_bfloat16*)dst_bf16, dst_ld, colsum);
+    return check_launch("tc_transpose");
+}
+
+static void wgrad_plan(int Cx, int N4, int kb_total, int* tpg, int* groups, int* splits, int* kbps) {
+    int tmax = 512 / Cx;
+    if (tmax > 25) tmax = 25;
+    *groups = (25 + tmax - 1) / tmax;
+    *tpg = (25 + *groups - 1) / *groups;
+    *groups = (25 + *tpg - 1) / *tpg;
+    const int tiles = (N4 / 128) * (*groups);
+    int s = (2 * 148 + tiles - 1) / tiles;
+    int smax = kb_total / 8;
+    if (smax < 1) smax = 1;
+    if (s > smax) s = smax;
+    if (s < 1) s = 1;
+    *kbps = (kb_total + s - 1) / s;
+    *splits = (kb_total + *kbps - 1) / *kbps;
+}
+
+size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4) {
+    const long ptot = (long)SB * H * W;
+    int tpg, groups, splits, kbps;
+    wgrad_plan(Cx, N4, (int)(ptot / 64), &tpg, &groups, &splits, &kbps);
+    return (size_t)splits * N4 * 25 * Cx * sizeof(float);
+}
+
+// dgT: [N4][SB*H*W] bf16 (pixel-major), xhT: [Cx][SB][H][W] bf16, dW: fp32 [N4][25][Cx] accumulated into.
+int pivp_tc_wgrad5x5(const void* dgT_bf16, const void* xhT_bf16, int SB, int H, int W, int Cx, int N4, float* dW,
+                     void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(dgT_bf16 && xhT_bf16 && dW && workspace, "tc_wgrad5x5: null pointer");
+    PIVP_REQUIRE(Cx >= 16 && Cx <= 256 && Cx % 16 == 0 && N4 % 128 == 0, "tc_wgrad5x5: Cx must be a multiple of 16 <= 256, 4C a multiple of 128");
+    const long ptot = (long)SB * H * W;
+    if ((H * W) % 64 || W < 8 || (W < 64 && 64 % W) || (W > 64 && W % 64)) {
+        set_error("tc_wgrad5x5: cannot cut %dx%d images into 64-pixel TMA boxes", H, W);
+        return PIVP_EUNSUPPORTED;
+    }
+    WgGeom g;
+    g.H = H; g.W = W; g.bw = W < 64 ? W : 64; g.bh = 64 / g.bw; g.Cx = Cx; g.N4 = N4;
+    int groups, splits;
+    g.kb_total = (int)(ptot / 64);
+    wgrad_plan(Cx, N4, g.kb_total, &g.tpg, &groups, &splits, &g.kb_per_split);
+    PIVP_REQUIRE(ws_bytes >= (size_t)splits * N4 * 25 * Cx * sizeof(float), "tc_wgrad5x5: workspace too small");
+    int bst = (150 * 1024) / (Cx * 128);
+    if (bst > 8) bst = 8;
+    if (bst < 2) bst = 2;
+    g.b_stages = bst;
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ptot, (cuuint64_t)N4};
+        cuuint64_t str[1] = {(cuuint64_t)ptot * 2};
+        cuuint32_t box[2] = {64, 128};
+        CUresult r = encode_tmap(&map_a, dgT_bf16, 2, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("tc_wgrad5x5: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return PIVP_ECUDA; }
+    }
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)SB, (cuuint64_t)Cx};
+        cuuint64_t str[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)ptot * 2};
+        cuuint32_t box[4] = {(cuuint32_t)g.bw, (cuuint32_t)g.bh, 1, (cuuint32_t)Cx};
+        CUresult r = encode_tmap(&map_b, xhT_bf16, 4, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("tc_wgrad5x5: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return PIVP_ECUDA; }
+    }
+    const size_t smem = 1024 + (size_t)WG_ASTAGES * 16384 + (size_t)bst * Cx * 128 + (2 * WG_ASTAGES + 2 * bst + 1) * 8 + 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv5x5_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+        if (e != cudaSuccess) { set_error("tc_wgrad5x5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PIVP_ECUDA; }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(N4 / 128), (unsigned)groups, (unsigned)splits);
+    conv5x5_wgrad_tc_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, (float*)workspace);
+    if (int e = check_launch("tc_wgrad5x5")) return e;
+    const long n = (long)N4 * 25 * Cx;
+    splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dW, n, splits);
+    return check_launch("tc_wgrad5x5(reduce)");
+}
+
+}  // extern "C"

@@ -248,16 +248,16 @@ class Engine(object):
         h, w = self.H // lv, self.W // lv
         name = "lstm%d/conv" % (li + 1)
         Gt, dxh = ws["G"][li][t], ws["dxh"][li]
-        dg_bf16 = None if self.tc is None else self.tc.dg_bf16[li]
+        dg_bf16 = None if self.tc is None else self.tc.dg_bf16[li][t]
         self.L.call("pivp_lstm_gates_bwd", _ptr(Gt), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
                     _ptr(ws["dln"][li]), 0 if last else _ptr(dxh), cin + C, cin, _ptr(ws["dc"][li]), 0 if last else 1,
                     _ptr(dg_bf16), ws["Mr"][lv], C, self._s())
         dG = View(Gt, 4 * C, 0, 4 * C)
         xh = View(ws["xh"][li][t], cin + C, 0, cin + C)
-        self._conv_wgrad(xh, B, h, w, dG, h, w, 5, 1, 2, self.g[name + "/W"], self.g[name + "/b"])
         if self.tc is not None:
-            self.tc.lstm_dgrad(li, t)          # dxh = conv(dG_bf16, tap-flipped W) on tcgen05
+            self.tc.lstm_dgrad(li, t)          # dxh = conv(dG_bf16, tap-flipped W) on tcgen05; wgrad is deferred (wgrad_all)
         else:
+            self._conv_wgrad(xh, B, h, w, dG, h, w, 5, 1, 2, self.g[name + "/W"], self.g[name + "/b"])
             self._conv_dgrad(dG, B, h, w, self.p[name + "/W"], None, 5, 1, 2, View(dxh, cin + C, 0, cin + C), h, w)
 
     # ------------------------------------------------------------------ forward
@@ -535,3 +535,5 @@ class Engine(object):
                 self._conv_dgrad(de0, B, H // 2, W // 2, p["enc0/W"], None, 5, 2, 2, View(ws["d_img_nhwc"], 3, 0, 3), H, W)
                 L.call("pivp_nhwc_to_nchw", _ptr(ws["d_img_nhwc"]), 3, 0, _ptr(d_prev), B, 3, HW[1], 1, s)
                 L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)
+        if self.tc is not None:
+            self.tc.wgrad_all()                # ConvLSTM weight/bias gradients: one tcgen05 GEMM per layer over all time steps

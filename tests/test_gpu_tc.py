@@ -151,3 +151,38 @@ def test_model_bf16_within_tolerance_of_oracle(pk, mt, nm, k):
         if e > 6e-2:
             bad[key] = e
     assert not bad, bad
+
+
+@pytest.mark.parametrize("SB,H,W,Cx,N4", [
+    (4, 32, 32, 64, 128),      # lstm1/2 (2 steps x batch 2)
+    (6, 16, 16, 96, 256),      # lstm3
+    (4, 8, 8, 192, 512),       # lstm5: one 8x8 image per 64-pixel box
+    (2, 16, 16, 128, 256),     # lstm4
+    (2, 64, 64, 64, 128),      # 128x128 images, level 2
+])
+def test_tc_wgrad_matches_simt(pk, SB, H, W, Cx, N4):
+    """Deferred weight gradient: transposes + tcgen05 GEMM + split-K reduce == SIMT fp32 wgrad on the same bf16 operands."""
+    L = pk.lib()
+    rs = np.random.RandomState(3)
+    P = SB * H * W
+    Kp = (Cx + 63) // 64 * 64
+    xh = torch.zeros(P, Kp, device="cuda")
+    xh[:, :Cx] = torch.from_numpy(rs.standard_normal((P, Cx)).astype(np.float32)).cuda()
+    xh_b = xh.bfloat16()
+    dg_b = torch.from_numpy((rs.standard_normal((P, N4)) * 0.1).astype(np.float32)).cuda().bfloat16()
+    xhT = torch.empty(Cx, P, dtype=torch.bfloat16, device="cuda")
+    dgT = torch.empty(N4, P, dtype=torch.bfloat16, device="cuda")
+    db = torch.zeros(N4, device="cuda")
+    L.call("pivp_tc_transpose", xh_b.data_ptr(), Kp, P, Cx, xhT.data_ptr(), P, 0, stream())
+    L.call("pivp_tc_transpose", dg_b.data_ptr(), N4, P, N4, dgT.data_ptr(), P, db.data_ptr(), stream())
+    assert torch.equal(xhT, xh_b[:, :Cx].t().contiguous()) and torch.equal(dgT, dg_b.t().contiguous())
+    assert rel(db, dg_b.float().sum(0)) < 1e-4
+    nb = L.query("pivp_tc_wgrad_workspace_bytes", SB, H, W, Cx, N4)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    dW = torch.full((N4, 25, Cx), 0.5, device="cuda")                 # accumulated into
+    L.call("pivp_tc_wgrad5x5", dgT.data_ptr(), xhT.data_ptr(), SB, H, W, Cx, N4, dW.data_ptr(), ws.data_ptr(), nb, stream())
+    ref = torch.full((N4, 25, Cx), 0.5, device="cuda")
+    xf, gf = xh_b[:, :Cx].float().contiguous(), dg_b.float().contiguous()
+    L.call("pivp_conv2d_wgrad", xf.data_ptr(), Cx, 0, SB, H, W, Cx, gf.data_ptr(), N4, 0, H, W, N4, 5, 5, 1, 2, ref.data_ptr(), 0, stream())
+    torch.cuda.synchronize()
+    assert rel(dW, ref) < 2e-3
