@@ -143,12 +143,13 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     void* h_t, long h_t_ld, int hT_co,
                     int C, float forget_bias, int accurate, void* stream);
 
-/* dst[c][p] = src[p][c] (bf16, c < C); optional colsum[c] += sum_p src[p][c] (fp32) -- builds the pixel-major operands of the
- * weight-gradient GEMM and, for dG, the ConvLSTM bias gradient. */
-int pivp_tc_transpose(const void* src_bf16, int src_ld, long P, int C, void* dst_bf16, long dst_ld, float* colsum, void* stream);
+/* out[c] += sum_p src[p][c] over a bf16 (P, ld) matrix -- the ConvLSTM bias gradient from the stacked dG of all time steps */
+int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out, void* stream);
 size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4);
-/* dW[n][tap][c] += sum over all SB images (time steps x batch) of dG^T (N4, SB*H*W) x shifted XH^T (Cx, SB, H, W)   (D.5) */
-int pivp_tc_wgrad5x5(const void* dgT_bf16, const void* xhT_bf16, int SB, int H, int W, int Cx, int N4, float* dW,
+/* dW[n][tap][c] += sum over all SB images (time steps x batch) and pixels p of dG[p][n] * XH[p + tap - 2][c]   (D.5).
+ * dg: (SB*H*W, N4) bf16; xh: NHWC bf16 with row stride xh_cs >= ceil(Cx/64)*64 (pad channels are ignored). Both operands are
+ * read MN-major by tcgen05.mma straight from these NHWC tensors. */
+int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* dW,
                      void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -4,14 +4,18 @@
 // long K loops, 9x fewer launches, and the split-K partials are written once.
 //
 // GEMM view per CTA: D[128 n-rows][ntaps x Cx columns] in TMEM (<= 512 fp32 columns), K = pixels.
-//  * A = dG^T  [4C][S*P]  bf16, K(pixel)-major   -> 2-D TMA box {64 px, 128 rows}
-//  * B = XH^T  [Cx][S*B][H][W] bf16, pixel-major -> 4-D TMA box {bw, bh, 1, Cx} (bw*bh = 64 px) fetched at the tap-shifted
-//    coordinate; pixels outside the image are zero-filled by TMA (= the convolution's zero padding).
-//  Both land as rows of 128 B with the 128-byte swizzle = canonical K-major UMMA operands.
-//  * A ring (3 x 16 KB) and B ring (up to 8 x Cx*128 B) with full/empty mbarriers; one A tile feeds ntaps*4 MMAs.
+// Both operands are consumed MN-MAJOR, straight from the NHWC bf16 tensors the forward / input-gradient kernels already use
+// (no transposed copies): a TMA box of 64 pixels x 64 channels lands as 64 rows (K) of 128 B (64 MN elements) with the
+// 128-byte swizzle, which is the canonical MN-major SWIZZLE_128B UMMA layout (8 K-rows x 128 B atoms; SBO = 1024 B between
+// 8-row K groups, LBO = 8192 B between 64-element MN chunks).
+//  * A = dG   [S*P][4C] bf16 -> two 2-D boxes {64 ch, 64 px} (128 n-rows)
+//  * B = XH   [T*B][H][W][Kpad] bf16 -> ceil(Cx/64) 4-D boxes {64 ch, bw, bh, 1} (bw*bh = 64 px) at the tap-shifted pixel
+//    coordinate; out-of-image pixels are zero-filled by TMA (= the convolution's zero padding).  TMA cannot shift along the
+//    contiguous dimension by less than 16 B, which is why the pixel shift must be on an outer dimension, i.e. NHWC.
+//  * A ring (3 x 16 KB) and B ring (up to 8 slots) with full/empty mbarriers; one A tile feeds ntaps*4 MMAs.
 //  * grid = (4C/128, tap groups, K splits); every CTA stores its fp32 partial tile, a second kernel sums the splits into dW.
-// The channel-major operands are produced by transpose_bf16_kernel (which also yields the bias gradient as column sums).
 #include "tc_common.cuh"
+#include <stdlib.h>
 
 namespace pivp {
 
@@ -20,17 +24,31 @@ constexpr int WG_ASTAGES = 3;
 
 struct WgGeom {
     int H, W, bw, bh;        // image size at this level, pixel box (bw*bh = 64)
-    int Cx, N4;              // channels of XH (B rows / accumulator width per tap), 4C
+    int Cx, N4;              // channels of XH (accumulator width per tap), 4C
+    int chunks;              // 64-channel chunks of XH covering Cx
     int tpg;                 // taps per group
     int kb_total, kb_per_split;
     int b_stages;
 };
 
+// MN-major, 128-byte swizzle shared-memory matrix descriptor: LBO = byte distance between 64-element MN chunks,
+// SBO = 1024 B between groups of 8 K-rows.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, WgGeom g, float* __restrict__ part) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    const uint32_t a_bytes = 128 * 128, b_bytes = (uint32_t)g.Cx * 128;
+    const uint32_t chunk_bytes = 64 * 128;                        // 64 pixel rows x 128 B
+    const uint32_t a_bytes = 2 * chunk_bytes, b_bytes = (uint32_t)g.chunks * chunk_bytes;
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + WG_ASTAGES * a_bytes;
     uint64_t* bars = (uint64_t*)(smem_b + (size_t)g.b_stages * b_bytes);
@@ -71,7 +89,9 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 const uint32_t sa = ai % WG_ASTAGES;
                 mbar_wait(smem_u32(a_empty + sa), ((ai / WG_ASTAGES) & 1u) ^ 1u);
                 mbar_expect_tx(smem_u32(a_full + sa), a_bytes);
-                tma_load_2d(smem_u32(smem_a + sa * a_bytes), &map_a, smem_u32(a_full + sa), kb * 64, n0);
+                const uint32_t adst = smem_u32(smem_a + sa * a_bytes);
+                tma_load_2d(adst, &map_a, smem_u32(a_full + sa), n0, kb * 64);
+                tma_load_2d(adst + chunk_bytes, &map_a, smem_u32(a_full + sa), n0 + 64, kb * 64);
                 ++ai;
                 const long p = (long)kb * 64;
                 const int bimg = (int)(p / hw), rem = (int)(p - (long)bimg * hw);
@@ -81,28 +101,32 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                     const uint32_t sb = bi % (uint32_t)g.b_stages;
                     mbar_wait(smem_u32(b_empty + sb), ((bi / (uint32_t)g.b_stages) & 1u) ^ 1u);
                     mbar_expect_tx(smem_u32(b_full + sb), b_bytes);
-                    tma_load_4d(smem_u32(smem_b + (size_t)sb * b_bytes), &map_b, smem_u32(b_full + sb), x0 + dx - 2, y0 + dy - 2, bimg, 0);
+                    const uint32_t bdst = smem_u32(smem_b + (size_t)sb * b_bytes);
+                    for (int ch = 0; ch < g.chunks; ++ch)
+                        tma_load_4d(bdst + ch * chunk_bytes, &map_b, smem_u32(b_full + sb), ch * 64, x0 + dx - 2, y0 + dy - 2, bimg);
                     ++bi;
                 }
             }
         }
     } else if (warp == 1) {
-        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.Cx >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        // D=f32, A=B=bf16, BOTH MN-major (bits 15, 16), N>>3 at [17,23), M>>4 at [24,29)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(g.Cx >> 3) << 17) |
+                               ((uint32_t)(128 >> 4) << 24);
         uint32_t ai = 0, bi = 0;
         for (int kb = kb0; kb < kb1; ++kb) {
             const uint32_t sa = ai % WG_ASTAGES;
             mbar_wait(smem_u32(a_full + sa), (ai / WG_ASTAGES) & 1u);
-            const uint64_t ad = make_kmajor_sw128_desc(smem_u32(smem_a + sa * a_bytes));
+            const uint32_t abase = smem_u32(smem_a + sa * a_bytes);
             for (int tl = 0; tl < ntaps; ++tl) {
                 const uint32_t sb = bi % (uint32_t)g.b_stages;
                 mbar_wait(smem_u32(b_full + sb), (bi / (uint32_t)g.b_stages) & 1u);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint64_t bd = make_kmajor_sw128_desc(smem_u32(smem_b + (size_t)sb * b_bytes));
+                    const uint32_t bbase = smem_u32(smem_b + (size_t)sb * b_bytes);
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        tc_mma_bf16(tmem_base + (uint32_t)(tl * g.Cx), ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc,
-                                    (kb > kb0 || k > 0) ? 1u : 0u);
+                    for (int k = 0; k < 4; ++k)        // 16 pixels (K) = 16 rows x 128 B = 2048 B per MMA
+                        tc_mma_bf16(tmem_base + (uint32_t)(tl * g.Cx), make_mnmajor_sw128_desc(abase + k * 2048, chunk_bytes),
+                                    make_mnmajor_sw128_desc(bbase + k * 2048, chunk_bytes), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
                     tc_commit(smem_u32(b_empty + sb));
                 }
                 __syncwarp();
@@ -153,39 +177,28 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
     *reinterpret_cast<float4*>(out + i4) = acc;
 }
 
-// dst[c][p] = src[p][c] for c < C (bf16); optional colsum[c] += sum_p src[p][c] (fp32).  Tiles of 64 x 64.
-__global__ void __launch_bounds__(256) transpose_bf16_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, long P, int C,
-                                                             __nv_bfloat16* __restrict__ dst, long dst_ld, float* __restrict__ colsum) {
-    __shared__ unsigned short tile[64][66];
-    const long p0 = (long)blockIdx.x * 64;
-    const int c0 = blockIdx.y * 64;
-    const int t = threadIdx.x;
-    {   // load: 64 rows x 32 words, coalesced along c
-        const int wcol = t & 31, r0 = t >> 5;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int r = r0 + 8 * i;
-            const long p = p0 + r;
-            unsigned int w = 0;
-            const int c = c0 + 2 * wcol;
-            if (p < P && c < C) w = *reinterpret_cast<const unsigned int*>(src + p * src_ld + c);     // C, src_ld even
-            tile[r][2 * wcol] = (unsigned short)(w & 0xffffu);
-            tile[r][2 * wcol + 1] = (unsigned short)(w >> 16);
+// out[c] += sum_p src[p][c]  (bf16 in, fp32 accumulate): the ConvLSTM bias gradient over all time steps.
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int ld, long P, int C, long pchunk,
+                                                          float* __restrict__ out) {
+    __shared__ float red[8][66];
+    const int cp = threadIdx.x & 31, row = threadIdx.x >> 5;          // channel pair, row phase
+    const int c = blockIdx.x * 64 + 2 * cp;
+    const long p0 = (long)blockIdx.y * pchunk, p1 = min(P, p0 + pchunk);
+    float s0 = 0.f, s1 = 0.f;
+    if (c < C)
+        for (long p = p0 + row; p < p1; p += 8) {
+            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + p * ld + c);
+            s0 += __low2float(v);
+            s1 += __high2float(v);
         }
-    }
+    red[row][2 * cp] = s0;
+    red[row][2 * cp + 1] = s1;
     __syncthreads();
-    const int w = t & 31, cg = t >> 5;          // w: pixel pair (2w, 2w+1); cg: channel phase
+    if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
+        float t = 0.f;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const int cl = cg + 8 * j, c = c0 + cl;
-        const unsigned short lo = tile[2 * w][cl], hi = tile[2 * w + 1][cl];
-        if (c < C && p0 + 2 * w < P)
-            *reinterpret_cast<unsigned int*>(dst + (long)c * dst_ld + p0 + 2 * w) = (unsigned int)lo | ((unsigned int)hi << 16);
-        if (colsum) {
-            float s = __bfloat162float(__ushort_as_bfloat16(lo)) + __bfloat162float(__ushort_as_bfloat16(hi));
-            s = warp_sum(s);
-            if (w == 0 && c < C) atomicAdd(colsum + c, s);
-        }
+        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
+        atomicAdd(out + blockIdx.x * 64 + threadIdx.x, t);
     }
 }
 
@@ -195,12 +208,14 @@ using namespace pivp;
 
 extern "C" {
 
-int pivp_tc_transpose(const void* src_bf16, int src_ld, long P, int C, void* dst_bf16, long dst_ld, float* colsum, void* stream) {
-    PIVP_REQUIRE(src_bf16 && dst_bf16 && P > 0 && C > 0 && (C % 2) == 0 && (src_ld % 2) == 0 && (P % 2) == 0 && dst_ld >= P && (dst_ld % 2) == 0,
-                 "tc_transpose: bad argument (C, P and leading dimensions must be even)");
-    dim3 grid((unsigned)((P + 63) / 64), (unsigned)((C + 63) / 64));
-    transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_bf16, src_ld, P, C, (__nv_bfloat16*)dst_bf16, dst_ld, colsum);
-    return check_launch("tc_transpose");
+int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out, void* stream) {
+    PIVP_REQUIRE(src_bf16 && out && P > 0 && C > 0 && (C % 2) == 0 && (ld % 2) == 0, "tc_colsum_bf16: bad argument (C and ld must be even)");
+    int splits = (int)((P + 4095) / 4096);
+    if (splits > 148 * 4) splits = 148 * 4;
+    const long pchunk = (P + splits - 1) / splits;
+    dim3 grid((unsigned)((C + 63) / 64), (unsigned)splits);
+    colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_bf16, ld, P, C, pchunk, out);
+    return check_launch("tc_colsum_bf16");
 }
 
 static void wgrad_plan(int Cx, int N4, int kb_total, int* tpg, int* groups, int* splits, int* kbps) {
@@ -226,42 +241,44 @@ size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4) {
     return (size_t)splits * N4 * 25 * Cx * sizeof(float);
 }
 
-// dgT: [N4][SB*H*W] bf16 (pixel-major), xhT: [Cx][SB][H][W] bf16, dW: fp32 [N4][25][Cx] accumulated into.
-int pivp_tc_wgrad5x5(const void* dgT_bf16, const void* xhT_bf16, int SB, int H, int W, int Cx, int N4, float* dW,
+// dg: [SB*H*W][N4] bf16 (NHWC, all time steps stacked), xh: [>=SB][H][W][xh_cs] bf16 (NHWC), dW: fp32 [N4][25][Cx] accumulated into.
+int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* dW,
                      void* workspace, size_t ws_bytes, void* stream) {
-    PIVP_REQUIRE(dgT_bf16 && xhT_bf16 && dW && workspace, "tc_wgrad5x5: null pointer");
+    PIVP_REQUIRE(dg_bf16 && xh_bf16 && dW && workspace, "tc_wgrad5x5: null pointer");
     PIVP_REQUIRE(Cx >= 16 && Cx <= 256 && Cx % 16 == 0 && N4 % 128 == 0, "tc_wgrad5x5: Cx must be a multiple of 16 <= 256, 4C a multiple of 128");
+    const int chunks = (Cx + 63) / 64;
+    PIVP_REQUIRE(xh_cs >= chunks * 64 && xh_cs % 8 == 0, "tc_wgrad5x5: XH rows must hold ceil(Cx/64)*64 channels and be 16-byte aligned");
     const long ptot = (long)SB * H * W;
-    if ((H * W) % 64 || W < 8 || (W < 64 && 64 % W) || (W > 64 && W % 64)) {
+    if ((H * W) % 64 || (W < 64 && 64 % W) || (W > 64 && W % 64)) {
         set_error("tc_wgrad5x5: cannot cut %dx%d images into 64-pixel TMA boxes", H, W);
         return PIVP_EUNSUPPORTED;
     }
     WgGeom g;
-    g.H = H; g.W = W; g.bw = W < 64 ? W : 64; g.bh = 64 / g.bw; g.Cx = Cx; g.N4 = N4;
+    g.H = H; g.W = W; g.bw = W < 64 ? W : 64; g.bh = 64 / g.bw; g.Cx = Cx; g.N4 = N4; g.chunks = chunks;
     int groups, splits;
     g.kb_total = (int)(ptot / 64);
     wgrad_plan(Cx, N4, g.kb_total, &g.tpg, &groups, &splits, &g.kb_per_split);
     PIVP_REQUIRE(ws_bytes >= (size_t)splits * N4 * 25 * Cx * sizeof(float), "tc_wgrad5x5: workspace too small");
-    int bst = (150 * 1024) / (Cx * 128);
+    int bst = (150 * 1024) / (chunks * 8192);
     if (bst > 8) bst = 8;
     if (bst < 2) bst = 2;
     g.b_stages = bst;
     CUtensorMap map_a, map_b;
     {
-        cuuint64_t dims[2] = {(cuuint64_t)ptot, (cuuint64_t)N4};
-        cuuint64_t str[1] = {(cuuint64_t)ptot * 2};
-        cuuint32_t box[2] = {64, 128};
-        CUresult r = encode_tmap(&map_a, dgT_bf16, 2, dims, str, box);
+        cuuint64_t dims[2] = {(cuuint64_t)N4, (cuuint64_t)ptot};
+        cuuint64_t str[1] = {(cuuint64_t)N4 * 2};
+        cuuint32_t box[2] = {64, 64};
+        CUresult r = encode_tmap(&map_a, dg_bf16, 2, dims, str, box);
         if (r != CUDA_SUCCESS) { set_error("tc_wgrad5x5: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return PIVP_ECUDA; }
     }
     {
-        cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)SB, (cuuint64_t)Cx};
-        cuuint64_t str[3] = {(cuuint64_t)W * 2, (cuuint64_t)H * W * 2, (cuuint64_t)ptot * 2};
-        cuuint32_t box[4] = {(cuuint32_t)g.bw, (cuuint32_t)g.bh, 1, (cuuint32_t)Cx};
-        CUresult r = encode_tmap(&map_b, xhT_bf16, 4, dims, str, box);
+        cuuint64_t dims[4] = {(cuuint64_t)xh_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)SB};
+        cuuint64_t str[3] = {(cuuint64_t)xh_cs * 2, (cuuint64_t)W * xh_cs * 2, (cuuint64_t)H * W * xh_cs * 2};
+        cuuint32_t box[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, 1};
+        CUresult r = encode_tmap(&map_b, xh_bf16, 4, dims, str, box);
         if (r != CUDA_SUCCESS) { set_error("tc_wgrad5x5: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return PIVP_ECUDA; }
     }
-    const size_t smem = 1024 + (size_t)WG_ASTAGES * 16384 + (size_t)bst * Cx * 128 + (2 * WG_ASTAGES + 2 * bst + 1) * 8 + 16;
+    const size_t smem = 1024 + (size_t)WG_ASTAGES * 16384 + (size_t)bst * chunks * 8192 + (2 * WG_ASTAGES + 2 * bst + 1) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv5x5_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);

@@ -4,7 +4,7 @@ Created by ``Engine`` when ``compute="bf16"``.  fp32 stays the master format of 
 bandwidth-bound kernels consume (cell state, LayerNorm input, gradients); this class only adds the bf16 GEMM operands:
   xh_bf16[l][t]  (M, Kpad)   concatenated layer input [x | h_{t-1}], channels padded to a multiple of 64 (fwd GEMM A operand)
   dg_bf16[l][t]  (M, 4C)     gate pre-activation gradients (input-gradient GEMM A operand)
-  xhT[l], dgT[l]             channel-major copies over ALL time steps (weight-gradient GEMM operands, built after BPTT)
+  (the weight-gradient GEMM reads xh_bf16 / dg_bf16 of ALL time steps MN-major, straight from these NHWC tensors)
   Wf[l], Wd[l]               K-major bf16 weights (forward / tap-flipped input-gradient), refreshed after every Adam step
 """
 import torch
@@ -23,7 +23,7 @@ class TensorCorePlan(object):
         self.S = S
         self.Kpad = [(cin + c + 63) // 64 * 64 for cin, c in zip(LSTM_IN, LSTM_SIZES)]
         self.xh_all, self.dg_all, self.xh_bf16, self.dg_bf16 = [], [], [], []
-        self.xhT, self.dgT, self.Wf, self.Wd = [], [], [], []
+        self.Wf, self.Wd = [], []
         wsb = 16
         for li, (cin, c, lv) in enumerate(zip(LSTM_IN, LSTM_SIZES, LSTM_LEVEL)):
             M = ws["Mr"][lv]
@@ -38,8 +38,6 @@ class TensorCorePlan(object):
             self.dg_all.append(da)
             self.xh_bf16.append([xa[t] for t in range(T)])
             self.dg_bf16.append([da[t] for t in range(S)])
-            self.xhT.append(torch.empty(cin + c, S * M, dtype=torch.bfloat16, device=dev))
-            self.dgT.append(torch.empty(4 * c, S * M, dtype=torch.bfloat16, device=dev))
             self.Wf.append(torch.empty(4 * c, 25, self.Kpad[li], dtype=torch.bfloat16, device=dev))
             self.Wd.append(torch.empty(cin + c, 25, 4 * c, dtype=torch.bfloat16, device=dev))
             wsb = max(wsb, eng.L.query("pivp_tc_wgrad_workspace_bytes", S * B, h, w, cin + c, 4 * c))
@@ -91,8 +89,6 @@ class TensorCorePlan(object):
             h, w = e.H // lv, e.W // lv
             cx = cin + C
             name = "lstm%d/conv" % (li + 1)
-            e.L.call("pivp_tc_transpose", _ptr(self.xh_all[li]), self.Kpad[li], S * M, cx, _ptr(self.xhT[li]), S * M, 0, e._s())
-            e.L.call("pivp_tc_transpose", _ptr(self.dg_all[li]), 4 * C, S * M, 4 * C, _ptr(self.dgT[li]), S * M,
-                     _ptr(e.g[name + "/b"]), e._s())
-            e.L.call("pivp_tc_wgrad5x5", _ptr(self.dgT[li]), _ptr(self.xhT[li]), S * B, h, w, cx, 4 * C, _ptr(e.g[name + "/W"]),
-                     _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
+            e.L.call("pivp_tc_colsum_bf16", _ptr(self.dg_all[li]), 4 * C, S * M, 4 * C, _ptr(e.g[name + "/b"]), e._s())
+            e.L.call("pivp_tc_wgrad5x5", _ptr(self.dg_all[li]), _ptr(self.xh_all[li]), self.Kpad[li], S * B, h, w, cx, 4 * C,
+                     _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
