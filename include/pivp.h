@@ -143,6 +143,16 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     void* h_t, long h_t_ld, int hT_co,
                     int C, float forget_bias, int accurate, void* stream);
 
+/* dst[i] = bf16(src[idx[i]]) (idx < 0 -> 0): builds permuted / zero-padded bf16 weight operands from the fp32 master parameters */
+int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, void* stream);
+/* General tap-list implicit GEMM on tcgen05: D[m,n] = sum_t sum_c In[pixel(m)+(dy_t,dx_t), coff_t+c] * Wt[n][t*Kc+c];
+ * out[row(m)] = relu?(D + bias) to an fp32 view and/or a bf16 view, row(m) = ((b*OH + i*os + oa)*OW + j*os + ob).
+ * One call = one output phase of a stride-2 Deconvolution2D (train_model.py:505-507), a 1x1 convolution, ...
+ * dy/dx/coff are HOST int arrays of length ntaps (<= 25). */
+int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int ntaps, const int* dy, const int* dx, const int* coff,
+                      const void* wt_bf16, int N, int BN, const float* bias, int relu,
+                      float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
+                      int OH, int OW, int os, int oa, int ob, void* stream);
 /* out[c] += sum_p src[p][c] over a bf16 (P, ld) matrix -- the ConvLSTM bias gradient from the stacked dG of all time steps */
 int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out, void* stream);
 size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4);

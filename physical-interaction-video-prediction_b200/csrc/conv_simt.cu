@@ -316,7 +316,7 @@ int pivp_conv2d_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, i
     conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, pchunk);
     if (int e = check_launch("conv2d_wgrad")) return e;
     if (dbias) {
-        int s2 = (P + 2047) / 2048;
+        int s2 = (P + 255) / 256;
         int pc = (P + s2 - 1) / s2;
         dim3 g2((unsigned)((N + 31) / 32), (unsigned)s2);
         colsum_kernel<<<g2, dim3(32, 8), 0, (cudaStream_t)stream>>>(CView{dy, dy_cs, dy_co}, P, N, dbias, pc);
@@ -327,7 +327,7 @@ int pivp_conv2d_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, i
 
 int pivp_colsum(const float* v, int v_cs, int v_co, int P, int N, float* out, void* stream) {
     PIVP_REQUIRE(v && out && P > 0 && N > 0, "colsum: bad argument");
-    int s2 = (P + 2047) / 2048;
+    int s2 = (P + 255) / 256;
     int pc = (P + s2 - 1) / s2;
     dim3 g2((unsigned)((N + 31) / 32), (unsigned)s2);
     colsum_kernel<<<g2, dim3(32, 8), 0, (cudaStream_t)stream>>>(CView{v, v_cs, v_co}, P, N, out, pc);

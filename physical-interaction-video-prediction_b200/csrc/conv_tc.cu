@@ -36,7 +36,9 @@ __device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0
 struct TcEpilogue {
     int mode;                    // 0: plain fp32 store (+bias), 1: ConvLSTM gates
     const float* bias;           // [N] (may be null in mode 0)
-    float* out; int out_cs, out_co;              // mode 0: D -> out[m*out_cs + out_co + n]
+    float* out; int out_cs, out_co;              // mode 0: D -> out[row(m)*out_cs + out_co + n]  (may be null)
+    __nv_bfloat16* out_bf16; int ob_cs, ob_co;   // mode 0: optional bf16 copy (next GEMM's operand), same row mapping
+    int relu;                                    // mode 0: ReLU after bias
     float* gates;                                // mode 1: activated gates [M][N] (saved for backward)
     const float* c_prev; float* c_out;           // [M][C]  (c_prev may be null)
     float* h_out; int h_cs, h_co;                // fp32 h view (next step's xh h-slot)
@@ -48,16 +50,22 @@ struct TcEpilogue {
     int accurate;                                // 1: expf/tanhf, 0: tanh.approx
 };
 
+constexpr int TC_MAXTAPS = 25;
 struct TcGeom {
-    int H, W, TW, TH, TB;        // image size at this level, pixel box of one M tile
+    int H, W, TW, TH, TB;        // pixel grid the M tiles walk (A-operand grid), pixel box of one M tile
     int Kc;                      // contracted channels per tap (multiple of 64)
     int N, BN;                   // output channels, tile width
     int stages;
     int tmem_cols;
+    int ntaps;                   // K = ntaps * Kc
+    signed char dy[TC_MAXTAPS], dx[TC_MAXTAPS];   // pixel offset of each tap on the A grid
+    short coff[TC_MAXTAPS];                       // channel offset of each tap inside the A rows
+    // plain-epilogue row mapping: A-grid pixel (b,i,j) -> output row ((b*OH + i*os + oa)*OW + j*os + ob)
+    int OH, OW, os, oa, ob;
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
-conv5x5_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom g, TcEpilogue ep) {
+conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom g, TcEpilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][A 16 KB | B BN*128] then barriers
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -73,7 +81,7 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
     const int m_tile = blockIdx.x, n_tile = blockIdx.y;
     const int n0 = n_tile * g.BN;
     const int kblocks_per_tap = g.Kc / TC_BK;
-    const int num_kb = 25 * kblocks_per_tap;
+    const int num_kb = g.ntaps * kblocks_per_tap;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
@@ -104,10 +112,9 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
                 const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
                 mbar_wait(smem_u32(empty + s), ph ^ 1u);
                 const int tap = kb / kblocks_per_tap, cb = kb - tap * kblocks_per_tap;
-                const int dy = tap / 5, dx = tap - dy * 5;
                 const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
                 mbar_expect_tx(smem_u32(full + s), stage_bytes);
-                tma_load_4d(sa, &map_a, smem_u32(full + s), cb * TC_BK, x0 + dx - 2, y0 + dy - 2, b0);
+                tma_load_4d(sa, &map_a, smem_u32(full + s), g.coff[tap] + cb * TC_BK, x0 + g.dx[tap], y0 + g.dy[tap], b0);
                 tma_load_2d(sb, &map_b, smem_u32(full + s), tap * g.Kc + cb * TC_BK, n0);
             }
         }
@@ -140,17 +147,36 @@ conv5x5_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_consta
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         if (ep.mode == 0) {
+            // output row of this A-grid pixel (identity for stride-1 convs, phase scatter for transposed convs)
+            const int hw = g.H * g.W;
+            const int bi = (int)(m / hw), rem = (int)(m - (long)bi * hw);
+            const int iy = rem / g.W, ix = rem - iy * g.W;
+            const long orow = ((long)bi * g.OH + iy * g.os + g.oa) * g.OW + ix * g.os + g.ob;
             for (int c0 = 0; c0 < g.BN; c0 += 8) {
                 float v[8];
                 tc_ld8(trow + (uint32_t)c0, v);
                 tc_ld_wait();
-                float* dst = ep.out + m * ep.out_cs + ep.out_co + n0 + c0;
                 if (ep.bias) {
 #pragma unroll
                     for (int i = 0; i < 8; ++i) v[i] += bias_s[c0 + i];
                 }
-                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                if (ep.relu) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+                }
+                if (ep.out) {
+                    float* dst = ep.out + orow * ep.out_cs + ep.out_co + n0 + c0;
+                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+                }
+                if (ep.out_bf16) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+                    uint4 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                    *reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ob_cs + ep.ob_co + n0 + c0) = pk;
+                }
             }
         } else {
             // tile = 32 channels x 4 gates: columns [0,32) j, [32,64) i, [64,96) f, [96,128) o
@@ -258,6 +284,68 @@ static int pick_pixel_box(int B, int H, int W, int* TW, int* TH, int* TB) {
     return 0;
 }
 
+// dst[i] = bf16(src[idx[i]]), idx < 0 -> 0.  Builds any permuted / zero-padded bf16 weight operand from the fp32 master.
+__global__ void gather_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, long n, __nv_bfloat16* __restrict__ dst) {
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int j = idx[i];
+        dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
+    }
+}
+
+static int launch_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int ntaps, const int* dy, const int* dx, const int* coff,
+                            const void* wt_bf16, int N, int BN, TcEpilogue ep, int OH, int OW, int os, int oa, int ob, void* stream,
+                            const char* who) {
+    PIVP_REQUIRE(in_bf16 && wt_bf16, "%s: null operand", who);
+    PIVP_REQUIRE(ntaps >= 1 && ntaps <= TC_MAXTAPS, "%s: 1..25 taps", who);
+    PIVP_REQUIRE(Kc > 0 && Kc % TC_BK == 0 && in_cs % 8 == 0, "%s: Kc must be a multiple of 64 and rows 16-byte aligned", who);
+    PIVP_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && N % BN == 0, "%s: BN must be a multiple of 16 <= 256 dividing N", who);
+    int TW, TH, TB;
+    if (pick_pixel_box(B, H, W, &TW, &TH, &TB) != 0) {
+        set_error("%s: cannot tile B=%d H=%d W=%d into 128-pixel boxes", who, B, H, W);
+        return PIVP_EUNSUPPORTED;
+    }
+    TcGeom g;
+    g.H = H; g.W = W; g.TW = TW; g.TH = TH; g.TB = TB; g.Kc = Kc; g.N = N; g.BN = BN; g.ntaps = ntaps;
+    for (int t = 0; t < ntaps; ++t) {
+        PIVP_REQUIRE(dy[t] >= -64 && dy[t] <= 64 && dx[t] >= -64 && dx[t] <= 64 && coff[t] >= 0 && coff[t] + Kc <= in_cs && coff[t] % 8 == 0,
+                     "%s: tap %d out of range", who, t);
+        g.dy[t] = (signed char)dy[t]; g.dx[t] = (signed char)dx[t]; g.coff[t] = (short)coff[t];
+    }
+    g.OH = OH; g.OW = OW; g.os = os; g.oa = oa; g.ob = ob;
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)in_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, (cuuint64_t)H * W * in_cs * 2};
+        cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+        CUresult r = encode_tmap(&map_a, in_bf16, 4, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(A) failed (%d)", who, (int)r); return PIVP_ECUDA; }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)ntaps * Kc, (cuuint64_t)N};
+        cuuint64_t str[1] = {(cuuint64_t)ntaps * Kc * 2};
+        cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
+        CUresult r = encode_tmap(&map_b, wt_bf16, 2, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B) failed (%d)", who, (int)r); return PIVP_ECUDA; }
+    }
+    const int stage_bytes = TC_BM * 128 + BN * 128;
+    int stages = (100 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    g.stages = stages;
+    g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)BN * 4;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+        if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
+        attr_set = true;
+    }
+    const long M = (long)B * H * W;
+    dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN));
+    conv_taps_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
+    return check_launch(who);
+}
+
 }  // namespace pivp
 
 using namespace pivp;
@@ -270,8 +358,14 @@ int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf
     return check_launch("tc_prep_weights");
 }
 
-// Returns PIVP_EUNSUPPORTED (without launching) when the shape cannot be tiled: callers fall back to nothing -- they must
-// pick shapes the path supports (the ConvLSTM layers of the model at even batch sizes all do).
+int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, void* stream) {
+    PIVP_REQUIRE(src && idx && dst_bf16 && n > 0, "gather_bf16: bad argument");
+    unsigned gb = (unsigned)((n + 255) / 256);
+    if (gb > 148 * 8) gb = 148 * 8;
+    gather_bf16_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)dst_bf16);
+    return check_launch("gather_bf16");
+}
+
 int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     const void* wt_bf16, int N, int BN,
                     int mode, const float* bias,
@@ -280,59 +374,41 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
                     void* h_t, long h_t_ld, int hT_co,
                     int C, float forget_bias, int accurate, void* stream) {
-    PIVP_REQUIRE(in_bf16 && wt_bf16, "tc_conv5x5: null operand");
-    PIVP_REQUIRE(Kc > 0 && Kc % TC_BK == 0 && in_cs >= Kc && in_cs % 8 == 0, "tc_conv5x5: Kc must be a multiple of 64 and rows 16-byte aligned");
-    PIVP_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && N % BN == 0, "tc_conv5x5: BN must be a multiple of 16 <= 256 dividing N");
+    PIVP_REQUIRE(in_cs >= Kc, "tc_conv5x5: row stride smaller than Kc");
     if (mode == 1) {
         PIVP_REQUIRE(BN == 128 && N == 4 * C && C % 32 == 0 && gates && c_out && h_out && bias, "tc_conv5x5: gate epilogue needs BN=128, N=4C, bias");
         PIVP_REQUIRE(h_cs % 4 == 0 && h_co % 4 == 0 && (!h_bf16 || (hb_cs % 8 == 0 && hb_co % 8 == 0)), "tc_conv5x5: h views must be 16-byte aligned");
     } else {
         PIVP_REQUIRE(mode == 0 && out && out_cs % 4 == 0 && out_co % 4 == 0, "tc_conv5x5: plain epilogue needs a 16-byte aligned fp32 view");
     }
-    int TW, TH, TB;
-    if (pick_pixel_box(B, H, W, &TW, &TH, &TB) != 0) {
-        set_error("tc_conv5x5: cannot tile B=%d H=%d W=%d into 128-pixel boxes", B, H, W);
-        return PIVP_EUNSUPPORTED;
-    }
-    CUtensorMap map_a, map_b;
-    {
-        cuuint64_t dims[4] = {(cuuint64_t)in_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
-        cuuint64_t str[3] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, (cuuint64_t)H * W * in_cs * 2};
-        cuuint32_t box[4] = {(cuuint32_t)TC_BK, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
-        CUresult r = encode_tmap(&map_a, in_bf16, 4, dims, str, box);
-        if (r != CUDA_SUCCESS) { set_error("tc_conv5x5: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return PIVP_ECUDA; }
-    }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)25 * Kc, (cuuint64_t)N};
-        cuuint64_t str[1] = {(cuuint64_t)25 * Kc * 2};
-        cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
-        CUresult r = encode_tmap(&map_b, wt_bf16, 2, dims, str, box);
-        if (r != CUDA_SUCCESS) { set_error("tc_conv5x5: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return PIVP_ECUDA; }
-    }
-    TcGeom g;
-    g.H = H; g.W = W; g.TW = TW; g.TH = TH; g.TB = TB; g.Kc = Kc; g.N = N; g.BN = BN;
-    const int stage_bytes = TC_BM * 128 + BN * 128;
-    int stages = (100 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
-    if (stages < 2) stages = 2;
-    g.stages = stages;
-    g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)BN * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv5x5_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-        if (e != cudaSuccess) { set_error("tc_conv5x5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PIVP_ECUDA; }
-        attr_set = true;
-    }
+    int dy[25], dx[25], co[25];
+    for (int t = 0; t < 25; ++t) { dy[t] = t / 5 - 2; dx[t] = t % 5 - 2; co[t] = 0; }
     TcEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
     ep.mode = mode; ep.bias = bias; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co; ep.gates = gates; ep.c_prev = c_prev;
     ep.c_out = c_out; ep.h_out = h_out; ep.h_cs = h_cs; ep.h_co = h_co; ep.h_bf16 = (__nv_bfloat16*)h_bf16; ep.hb_cs = hb_cs; ep.hb_co = hb_co;
     ep.h_t = (__nv_bfloat16*)h_t; ep.h_t_ld = h_t_ld; ep.hT_co = hT_co;
     ep.C = C; ep.forget_bias = forget_bias; ep.accurate = accurate;
-    const long M = (long)B * H * W;
-    dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN));
-    conv5x5_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
-    return check_launch("tc_conv5x5");
+    return launch_conv_taps(in_bf16, in_cs, B, H, W, Kc, 25, dy, dx, co, wt_bf16, N, BN, ep, H, W, 1, 0, 0, stream, "tc_conv5x5");
+}
+
+// General tap-list convolution with a plain epilogue:  D[m,n] = sum_t sum_c In[pixel(m)+(dy_t,dx_t), coff_t + c] * Wt[n][t*Kc + c],
+// out[row(m)] = relu?(D + bias) written to an fp32 view and/or a bf16 view, row(m) = ((b*OH + i*os + oa)*OW + j*os + ob).
+// One call = one output phase of a stride-2 Deconvolution2D (train_model.py:505-507), a 1x1 convolution, ...
+int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int ntaps, const int* dy, const int* dx, const int* coff,
+                      const void* wt_bf16, int N, int BN, const float* bias, int relu,
+                      float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
+                      int OH, int OW, int os, int oa, int ob, void* stream) {
+    PIVP_REQUIRE(dy && dx && coff, "tc_conv_taps: null tap list (host arrays)");
+    PIVP_REQUIRE(out || out_bf16, "tc_conv_taps: no output");
+    PIVP_REQUIRE((!out || (out_cs % 4 == 0 && out_co % 4 == 0)) && (!out_bf16 || (ob_cs % 8 == 0 && ob_co % 8 == 0)),
+                 "tc_conv_taps: output views must be 16-byte aligned");
+    PIVP_REQUIRE(os >= 1 && oa >= 0 && ob >= 0 && OH >= (H - 1) * os + oa + 1 && OW >= (W - 1) * os + ob + 1, "tc_conv_taps: bad output mapping");
+    TcEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.mode = 0; ep.bias = bias; ep.relu = relu; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co;
+    ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ob_cs = ob_cs; ep.ob_co = ob_co;
+    return launch_conv_taps(in_bf16, in_cs, B, H, W, Kc, ntaps, dy, dx, coff, wt_bf16, N, BN, ep, OH, OW, os, oa, ob, stream, "tc_conv_taps");
 }
 
 }  // extern "C"

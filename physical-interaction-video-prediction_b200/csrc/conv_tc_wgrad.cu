@@ -210,8 +210,8 @@ extern "C" {
 
 int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out, void* stream) {
     PIVP_REQUIRE(src_bf16 && out && P > 0 && C > 0 && (C % 2) == 0 && (ld % 2) == 0, "tc_colsum_bf16: bad argument (C and ld must be even)");
-    int splits = (int)((P + 4095) / 4096);
-    if (splits > 148 * 4) splits = 148 * 4;
+    int splits = (int)((P + 511) / 512);
+    if (splits > 148 * 8) splits = 148 * 8;
     const long pchunk = (P + splits - 1) / splits;
     dim3 grid((unsigned)((C + 63) / 64), (unsigned)splits);
     colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_bf16, ld, P, C, pchunk, out);

@@ -264,60 +264,65 @@ __global__ void state_fwd_kernel(const float* __restrict__ action, const float* 
         }
 }
 
-// single block. d_next = dn_a + dn_b (either may be null); d_sa = Wc^T d_next + smear-sum; d_cur_prev = d_sa[5:10].
+// one block (64 threads) per sample: d_next = dn_a + dn_b (either may be null); d_sa = Wc^T d_next + smear-sum;
+// d_cur_prev = d_sa[5:10]; dWc / dbc accumulated with atomics (50 + 5 values per sample).
 __global__ void state_bwd_kernel(const float* __restrict__ dn_a, const float* __restrict__ dn_b, const float* __restrict__ sa,
                                  const float* __restrict__ Wc, CView dsmear, int npix, int B,
                                  float* __restrict__ d_cur_prev, float* __restrict__ dWc, float* __restrict__ dbc) {
-    __shared__ float accW[50], accb[5];
-    const int t = threadIdx.x;
-    if (t < 50) accW[t] = 0.f;
-    if (t < 5) accb[t] = 0.f;
+    __shared__ float dn[5];
+    __shared__ float sm[5][64];
+    const int b = blockIdx.x, t = threadIdx.x;
+    if (t < 5) dn[t] = (dn_a ? dn_a[b * 5 + t] : 0.f) + (dn_b ? dn_b[b * 5 + t] : 0.f);
+    // smear gradient: sum over pixels of channels 5..9 of the state_action slice
+    float acc[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    if (dsmear.p)
+        for (int p = t; p < npix; p += 64) {
+            const float* row = dsmear.p + ((long)b * npix + p) * dsmear.cs + dsmear.co + 5;
+#pragma unroll
+            for (int k = 0; k < 5; ++k) acc[k] += row[k];
+        }
+#pragma unroll
+    for (int k = 0; k < 5; ++k) sm[k][t] = acc[k];
     __syncthreads();
-    for (int b = t; b < B; b += blockDim.x) {
-        float dn[5];
+    if (t < 5) {
+        float d = 0.f;
+        for (int i = 0; i < 64; ++i) d += sm[t][i];
 #pragma unroll
-        for (int j = 0; j < 5; ++j) dn[j] = (dn_a ? dn_a[b * 5 + j] : 0.f) + (dn_b ? dn_b[b * 5 + j] : 0.f);
-#pragma unroll
-        for (int j = 0; j < 5; ++j) {
-            atomicAdd(&accb[j], dn[j]);
-#pragma unroll
-            for (int k = 0; k < 10; ++k) atomicAdd(&accW[j * 10 + k], dn[j] * sa[b * 10 + k]);
-        }
-        for (int k = 5; k < 10; ++k) {
-            float d = 0.f;
-#pragma unroll
-            for (int j = 0; j < 5; ++j) d = fmaf(Wc[j * 10 + k], dn[j], d);
-            if (dsmear.p)
-                for (int p = 0; p < npix; ++p) d += dsmear.p[((long)b * npix + p) * dsmear.cs + dsmear.co + k];
-            d_cur_prev[b * 5 + k - 5] = d;
-        }
+        for (int j = 0; j < 5; ++j) d = fmaf(Wc[j * 10 + 5 + t], dn[j], d);
+        d_cur_prev[b * 5 + t] = d;
+        atomicAdd(dbc + t, dn[t]);
     }
-    __syncthreads();
-    if (t < 50) dWc[t] += accW[t];
-    if (t < 5) dbc[t] += accb[t];
+    if (t < 50) atomicAdd(dWc + t, dn[t / 10] * sa[b * 10 + t % 10]);
 }
 
 // ----------------------------------------------------------------------------- Linear
-constexpr int LIN_BB = 8;
+constexpr int LIN_BB = 8, LIN_NN = 4;
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, int xs, const float* __restrict__ W,
                                                          const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N, int relu) {
     __shared__ float red[32];
-    const int n = blockIdx.x, b0 = blockIdx.y * LIN_BB;
-    float acc[LIN_BB] = {};
+    const int n0 = blockIdx.x * LIN_NN, b0 = blockIdx.y * LIN_BB;
+    float acc[LIN_NN][LIN_BB] = {};
     for (int k = threadIdx.x; k < K; k += 256) {
-        const float wv = __ldg(W + (long)n * K + k);
+        float wv[LIN_NN], xv[LIN_BB];
 #pragma unroll
-        for (int bb = 0; bb < LIN_BB; ++bb)
-            if (b0 + bb < B) acc[bb] = fmaf(wv, __ldg(x + (long)(b0 + bb) * xs + k), acc[bb]);
+        for (int nn = 0; nn < LIN_NN; ++nn) wv[nn] = (n0 + nn < N) ? __ldg(W + (long)(n0 + nn) * K + k) : 0.f;
+#pragma unroll
+        for (int bb = 0; bb < LIN_BB; ++bb) xv[bb] = (b0 + bb < B) ? __ldg(x + (long)(b0 + bb) * xs + k) : 0.f;
+#pragma unroll
+        for (int nn = 0; nn < LIN_NN; ++nn)
+#pragma unroll
+            for (int bb = 0; bb < LIN_BB; ++bb) acc[nn][bb] = fmaf(wv[nn], xv[bb], acc[nn][bb]);
     }
 #pragma unroll
-    for (int bb = 0; bb < LIN_BB; ++bb) {
-        const float v = block_sum(acc[bb], red);
-        if (threadIdx.x == 0 && b0 + bb < B) {
-            float o = v + (bias ? bias[n] : 0.f);
-            y[(long)(b0 + bb) * N + n] = relu ? fmaxf(o, 0.f) : o;
+    for (int nn = 0; nn < LIN_NN; ++nn)
+#pragma unroll
+        for (int bb = 0; bb < LIN_BB; ++bb) {
+            const float v = block_sum(acc[nn][bb], red);
+            if (threadIdx.x == 0 && b0 + bb < B && n0 + nn < N) {
+                float o = v + (bias ? bias[n0 + nn] : 0.f);
+                y[(long)(b0 + bb) * N + n0 + nn] = relu ? fmaxf(o, 0.f) : o;
+            }
         }
-    }
 }
 
 // dx[b][k] (+)= sum_n dy[b][n] W[n][k]
@@ -520,13 +525,13 @@ int pivp_state_fwd(const float* action, const float* cur, const float* Wc, const
 int pivp_state_bwd(const float* dn_a, const float* dn_b, const float* sa, const float* Wc, const float* dsmear, int ds_cs, int ds_co,
                    int npix, int B, float* d_cur_prev, float* dWc, float* dbc, void* stream) {
     PIVP_REQUIRE(sa && Wc && d_cur_prev && dWc && dbc && B > 0, "state_bwd: bad argument");
-    state_bwd_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dn_a, dn_b, sa, Wc, CView{dsmear, ds_cs, ds_co}, npix, B, d_cur_prev, dWc, dbc);
+    state_bwd_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(dn_a, dn_b, sa, Wc, CView{dsmear, ds_cs, ds_co}, npix, B, d_cur_prev, dWc, dbc);
     return check_launch("state_bwd");
 }
 
 int pivp_linear_fwd(const float* x, int xs, const float* W, const float* bias, float* y, int B, int K, int N, int relu, void* stream) {
     PIVP_REQUIRE(x && W && y && B > 0 && K > 0 && N > 0 && xs >= K, "linear_fwd: bad argument");
-    linear_fwd_kernel<<<dim3(N, (B + LIN_BB - 1) / LIN_BB), 256, 0, (cudaStream_t)stream>>>(x, xs, W, bias, y, B, K, N, relu);
+    linear_fwd_kernel<<<dim3((N + LIN_NN - 1) / LIN_NN, (B + LIN_BB - 1) / LIN_BB), 256, 0, (cudaStream_t)stream>>>(x, xs, W, bias, y, B, K, N, relu);
     return check_launch("linear_fwd");
 }
 

@@ -306,6 +306,8 @@ class Engine(object):
             self._ln_fwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), B, HW[2], View(ws["xh"][0][t], 64, 0, 32),
                          View(ws["cat6"][t], 64, 32, 32), 1, ws["ln_stats"]["norm_enc0"][t],
                          None if self.tc is None else self.tc.xview(0, t))
+            if self.tc is not None:
+                L.call("pivp_copy_view", _ptr(ws["cat6"][t]), 64, 32, 0, 0, 0, _ptr(self.tc.cat6_b[t]), 64, 32, Mr[2], 32, s)
             # ---- group 1
             self._lstm_fwd(0, t, B)
             self._ln_fwd("hidden1", View(ws["xh"][0][t + 1], 64, 32, 32), B, HW[2], View(ws["xh"][1][t], 64, 0, 32), None, 0,
@@ -317,6 +319,8 @@ class Engine(object):
                            View(ws["xh"][2][t], 96, 0, 32), relu=1)
             L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64,
                    0 if self.tc is None else self.tc.xview(2, t).ptr, 0 if self.tc is None else self.tc.Kpad[2], 0, Mr[4], 32, s)
+            if self.tc is not None:
+                L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, 0, 0, 0, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, s)
             # ---- group 2
             self._lstm_fwd(2, t, B)
             self._ln_fwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), B, HW[4], View(ws["xh"][3][t], 128, 0, 64), None, 0,
@@ -337,25 +341,30 @@ class Engine(object):
             # ---- group 4
             self._lstm_fwd(4, t, B)
             self._ln_fwd("hidden5", View(ws["xh"][4][t + 1], 192, 64, 128), B, HW[8], View(ws["hid5"][t], 128, 0, 128), None, 0,
-                         ws["ln_stats"]["hidden5"][t])
-            self._conv_dgrad(View(ws["hid5"][t], 128, 0, 128), B, H // 8, W // 8, p["enc4/W"], p["enc4/b"], 3, 2, 1,
-                             View(ws["xh"][5][t], 192, 0, 128), H // 4, W // 4, relu=1)
+                         ws["ln_stats"]["hidden5"][t], None if self.tc is None else View(self.tc.hid5_b[t], 128, 0, 128))
             if self.tc is not None:
-                L.call("pivp_copy_view", _ptr(ws["xh"][5][t]), 192, 0, 0, 0, 0, self.tc.xview(5, t).ptr, self.tc.Kpad[5], 0, Mr[4], 128, s)
+                self.tc.deconv_fwd("enc4", self.tc.hid5_b[t], ws["xh"][5][t], 192, self.tc.xh_bf16[5][t], self.tc.Kpad[5], 1)
+            else:
+                self._conv_dgrad(View(ws["hid5"][t], 128, 0, 128), B, H // 8, W // 8, p["enc4/W"], p["enc4/b"], 3, 2, 1,
+                                 View(ws["xh"][5][t], 192, 0, 128), H // 4, W // 4, relu=1)
             # ---- group 5
             self._lstm_fwd(5, t, B)
             self._ln_fwd("hidden6", View(ws["xh"][5][t + 1], 192, 128, 64), B, HW[4], View(ws["cat5"][t], 96, 0, 64), None, 0,
-                         ws["ln_stats"]["hidden6"][t])
-            self._conv_dgrad(View(ws["cat5"][t], 96, 0, 96), B, H // 4, W // 4, p["enc5/W"], p["enc5/b"], 3, 2, 1,
-                             View(ws["xh"][6][t], 128, 0, 96), H // 2, W // 2, relu=1)
+                         ws["ln_stats"]["hidden6"][t], None if self.tc is None else View(self.tc.cat5_b[t], 128, 0, 64))
             if self.tc is not None:
-                L.call("pivp_copy_view", _ptr(ws["xh"][6][t]), 128, 0, 0, 0, 0, self.tc.xview(6, t).ptr, self.tc.Kpad[6], 0, Mr[2], 96, s)
+                self.tc.deconv_fwd("enc5", self.tc.cat5_b[t], ws["xh"][6][t], 128, self.tc.xh_bf16[6][t], self.tc.Kpad[6], 1)
+            else:
+                self._conv_dgrad(View(ws["cat5"][t], 96, 0, 96), B, H // 4, W // 4, p["enc5/W"], p["enc5/b"], 3, 2, 1,
+                                 View(ws["xh"][6][t], 128, 0, 96), H // 2, W // 2, relu=1)
             # ---- group 6
             self._lstm_fwd(6, t, B)
             self._ln_fwd("hidden7", View(ws["xh"][6][t + 1], 128, 96, 32), B, HW[2], View(ws["cat6"][t], 64, 0, 32), None, 0,
-                         ws["ln_stats"]["hidden7"][t])
-            self._conv_dgrad(View(ws["cat6"][t], 64, 0, 64), B, H // 2, W // 2, p["enc6/W"], p["enc6/b"], 3, 2, 1,
-                             View(ws["e6pre"][t], 64, 0, 64), H, W, relu=0)
+                         ws["ln_stats"]["hidden7"][t], None if self.tc is None else View(self.tc.cat6_b[t], 64, 0, 32))
+            if self.tc is not None:
+                self.tc.deconv_fwd("enc6", self.tc.cat6_b[t], ws["e6pre"][t], 64, None, 0, 0)
+            else:
+                self._conv_dgrad(View(ws["cat6"][t], 64, 0, 64), B, H // 2, W // 2, p["enc6/W"], p["enc6/b"], 3, 2, 1,
+                                 View(ws["e6pre"][t], 64, 0, 64), H, W, relu=0)
             self._ln_fwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), B, HW[1], View(ws["e6"][t], 64, 0, 64), None, 1,
                          ws["ln_stats"]["norm_enc6"][t])
             # ---- heads (enc7 + masks 1x1), NCHW planes out

@@ -7,6 +7,9 @@ bandwidth-bound kernels consume (cell state, LayerNorm input, gradients); this c
   (the weight-gradient GEMM reads xh_bf16 / dg_bf16 of ALL time steps MN-major, straight from these NHWC tensors)
   Wf[l], Wd[l]               K-major bf16 weights (forward / tap-flipped input-gradient), refreshed after every Adam step
 """
+import ctypes
+
+import numpy as np
 import torch
 
 from .engine import LSTM_IN, LSTM_SIZES, LSTM_LEVEL, View, _ptr
@@ -43,13 +46,60 @@ class TensorCorePlan(object):
             wsb = max(wsb, eng.L.query("pivp_tc_wgrad_workspace_bytes", S * B, h, w, cin + c, 4 * c))
         self.wgrad_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         self.accurate = 0
+        # ---- stride-2 Deconvolution2D layers enc4/enc5/enc6 (train_model.py:505-507) as 4 output phases each
+        M8, M4, M2 = ws["Mr"][8], ws["Mr"][4], ws["Mr"][2]
+        self.hid5_b = [torch.zeros(M8, 128, dtype=torch.bfloat16, device=dev) for _ in range(S)]
+        self.cat5_b = [torch.zeros(M4, 128, dtype=torch.bfloat16, device=dev) for _ in range(S)]     # 96 used, 32 zero pad
+        self.cat6_b = [torch.zeros(M2, 64, dtype=torch.bfloat16, device=dev) for _ in range(S)]
+        self.dec = {}
+        for name, cin, cout, lv in (("enc4", 128, 128, 8), ("enc5", 96, 96, 4), ("enc6", 64, 64, 2)):
+            self.dec[name] = self._plan_deconv(name, cin, cout, lv)
         self.refresh_weights()
+
+    def _plan_deconv(self, name, cin, cout, lv):
+        """Sub-pixel decomposition: output pixel (2i+a, 2j+b) only sees taps ky = a+1 (mod 2), kx = b+1 (mod 2):
+        1 / 2 / 2 / 4 taps for the four phases, each a stride-1 implicit GEMM on the INPUT grid (oy = 2*iy + ky - 1)."""
+        e = self.eng
+        dev = e.dev
+        kc = (cin + 63) // 64 * 64
+        base = e.spec[name + "/W"].offset                 # internal layout [cin][ky][kx][cout]
+        sel = {0: [(0, 1)], 1: [(1, 0), (0, 2)]}          # phase -> [(pixel offset, kernel index)]
+        phases = []
+        for a in (0, 1):
+            for b in (0, 1):
+                taps = [(dy, dx, ky, kx) for (dy, ky) in sel[a] for (dx, kx) in sel[b]]
+                idx = np.full((cout, len(taps), kc), -1, np.int32)
+                ci = np.arange(cin)
+                for t, (dy, dx, ky, kx) in enumerate(taps):
+                    for co in range(cout):
+                        idx[co, t, :cin] = base + ((ci * 3 + ky) * 3 + kx) * cout + co
+                arr = lambda v: (ctypes.c_int * len(taps))(*v)
+                phases.append(dict(a=a, b=b, n=len(taps), dy=arr([t[0] for t in taps]), dx=arr([t[1] for t in taps]),
+                                   co=arr([0] * len(taps)), idx=torch.from_numpy(idx.reshape(-1)).to(dev),
+                                   wt=torch.empty(cout, len(taps) * kc, dtype=torch.bfloat16, device=dev)))
+        bn = cout if cout <= 128 else 128
+        if (self.ws["Mr"][lv] // 128) * (cout // bn) < 64 and cout % 64 == 0:
+            bn = 64
+        return dict(cin=cin, cout=cout, kc=kc, lv=lv, phases=phases, bn=bn)
 
     def refresh_weights(self):
         e = self.eng
         for li, (cin, c) in enumerate(zip(LSTM_IN, LSTM_SIZES)):
             e.L.call("pivp_tc_prep_weights", _ptr(e.p["lstm%d/conv/W" % (li + 1)]), 4 * c, cin + c, self.Kpad[li],
                      _ptr(self.Wf[li]), _ptr(self.Wd[li]), e._s())
+        for d in getattr(self, "dec", {}).values():
+            for ph in d["phases"]:
+                e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(ph["idx"]), ph["idx"].numel(), _ptr(ph["wt"]), e._s())
+
+    def deconv_fwd(self, name, x_bf16, out, out_cs, out_bf16, ob_cs, relu):
+        """Deconvolution2D forward (+bias, optional ReLU) -> fp32 view `out` (row stride out_cs, channel offset 0) and an
+        optional bf16 copy (the next ConvLSTM's x slot): four tcgen05 launches, one per output phase."""
+        e, d = self.eng, self.dec[name]
+        h, w = e.H // d["lv"], e.W // d["lv"]
+        for ph in d["phases"]:
+            e.L.call("pivp_tc_conv_taps", _ptr(x_bf16), d["kc"], self.ws["B"], h, w, d["kc"], ph["n"], ph["dy"], ph["dx"], ph["co"],
+                     _ptr(ph["wt"]), d["cout"], d["bn"], _ptr(e.p[name + "/b"]), relu,
+                     _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, 2 * h, 2 * w, 2, ph["a"], ph["b"], e._s())
 
     def xview(self, li, t):
         """bf16 x-slot of layer li at time t (what the producer of the layer input also writes)."""
@@ -74,8 +124,15 @@ class TensorCorePlan(object):
         cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
         h, w = e.H // lv, e.W // lv
         cx = cin + C
+        bn = cx                                # one N tile if that already fills the GPU, else the largest split reaching ~1 wave
+        mt = ws["Mr"][lv] // 128
+        for cand in (cx, cx // 2, cx // 3, cx // 4, cx // 6):
+            if cand >= 16 and cand % 16 == 0 and cx % cand == 0:
+                bn = cand
+                if mt * (cx // cand) >= 120:
+                    break
         e.L.call("pivp_tc_conv5x5", _ptr(self.dg_bf16[li][t]), 4 * C, ws["B"], h, w, 4 * C,
-                 _ptr(self.Wd[li]), cx, cx, 0, 0,
+                 _ptr(self.Wd[li]), cx, bn, 0, 0,
                  _ptr(ws["dxh"][li]), cx, 0,
                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
                  C, 0.0, 0, e._s())

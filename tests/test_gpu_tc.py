@@ -200,3 +200,42 @@ def test_tc_wgrad_matches_simt(pk, SB, H, W, Cx, N4):
     L.call("pivp_conv2d_wgrad", xf.data_ptr(), Cx, 0, SB, H, W, Cx, gf.data_ptr(), N4, 0, H, W, N4, 5, 5, 1, 2, ref.data_ptr(), 0, stream())
     torch.cuda.synchronize()
     assert rel(dW, ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,ih,iw,cin,cout,bn,relu", [(2, 8, 8, 128, 128, 64, 1), (2, 16, 16, 96, 96, 96, 1), (2, 32, 32, 64, 64, 64, 0)])
+def test_tc_deconv_phases_match_simt(pk, B, ih, iw, cin, cout, bn, relu):
+    """Stride-2 Deconvolution2D forward (enc4/5/6, train_model.py:505-507) as four tcgen05 phase launches == SIMT kernel."""
+    import ctypes
+    L = pk.lib()
+    rs = np.random.RandomState(4)
+    kc = (cin + 63) // 64 * 64
+    M = B * ih * iw
+    x = torch.zeros(M, kc, device="cuda")
+    x[:, :cin] = torch.from_numpy(rs.standard_normal((M, cin)).astype(np.float32)).cuda()
+    xb = x.bfloat16()
+    Wi = torch.from_numpy((rs.standard_normal((cin, 3, 3, cout)) / np.sqrt(9 * cout)).astype(np.float32)).cuda().bfloat16().float()
+    bias = torch.from_numpy(rs.standard_normal(cout).astype(np.float32)).cuda()
+    out = torch.full((B * 4 * ih * iw, cout + 8), -5.0, device="cuda")           # row stride cout+8: slice view
+    out_b = torch.zeros(B * 4 * ih * iw, cout, dtype=torch.bfloat16, device="cuda")
+    sel = {0: [(0, 1)], 1: [(1, 0), (0, 2)]}
+    keep = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = [(dy, dx, ky, kx) for (dy, ky) in sel[a] for (dx, kx) in sel[b]]
+            wt = torch.zeros(cout, len(taps), kc, device="cuda")
+            for t, (dy, dx, ky, kx) in enumerate(taps):
+                wt[:, t, :cin] = Wi[:, ky, kx, :].t()
+            wt = wt.bfloat16().contiguous()
+            arr = lambda v: (ctypes.c_int * len(taps))(*v)
+            keep.append(wt)
+            L.call("pivp_tc_conv_taps", xb.data_ptr(), kc, B, ih, iw, kc, len(taps), arr([t[0] for t in taps]), arr([t[1] for t in taps]),
+                   arr([0] * len(taps)), wt.data_ptr(), cout, bn, bias.data_ptr(), relu, out.data_ptr(), cout + 8, 0,
+                   out_b.data_ptr(), cout, 0, 2 * ih, 2 * iw, 2, a, b, stream())
+    ref = torch.zeros(B * 4 * ih * iw, cout, device="cuda")
+    xf = xb[:, :cin].float().contiguous()
+    L.call("pivp_conv2d_dgrad", xf.data_ptr(), cin, 0, B, ih, iw, cin, Wi.data_ptr(), bias.data_ptr(), 3, 3, 2, 1,
+           ref.data_ptr(), cout, 0, 2 * ih, 2 * iw, cout, relu, 0, stream())
+    torch.cuda.synchronize()
+    assert rel(out[:, :cout], ref) < 2e-3
+    assert torch.all(out[:, cout:] == -5.0)
+    assert rel(out_b, ref) < 1e-2
