@@ -150,9 +150,17 @@ int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, v
  * One call = one output phase of a stride-2 Deconvolution2D (train_model.py:505-507), a 1x1 convolution, ...
  * dy/dx/coff are HOST int arrays of length ntaps (<= 25). */
 int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int ntaps, const int* dy, const int* dx, const int* coff,
-                      const void* wt_bf16, int N, int BN, const float* bias, int relu,
+                      const void* wt_bf16, int N, int BN, const float* bias, int relu, int accumulate,
                       float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
                       int OH, int OW, int os, int oa, int ob, void* stream);
+/* fp32 NHWC view -> bf16 copy; s2d=1 writes the space-to-depth layout the stride-2 layers contract over
+ * (row = (b, y/2, x/2), channel = d_co + ((y&1)*2 + (x&1))*cblk + ch) */
+int pivp_cast_bf16(const float* src, int s_cs, int s_co, void* dst_bf16, int d_cs, int d_co, long M, int C, int H, int W, int s2d, int cblk,
+                   void* stream);
+size_t pivp_tc_wgrad_taps_workspace_bytes(int SB, int H, int W, int Cx, int N4, int ntaps);
+/* general weight-gradient GEMM: dW[n][t][c] += sum_p A[p][n] * X[p + (dy_t,dx_t)][coff_t + c]  (n < N4, t < ntaps, c < Cx) */
+int pivp_tc_wgrad_taps(const void* a_bf16, int a_cs, const void* x_bf16, int x_cs, int SB, int H, int W, int Cx, int N4, int ntaps,
+                       const int* dy, const int* dx, const int* coff, float* dW, void* workspace, size_t ws_bytes, void* stream);
 /* out[c] += sum_p src[p][c] over a bf16 (P, ld) matrix -- the ConvLSTM bias gradient from the stacked dG of all time steps */
 int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out, void* stream);
 size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4);

@@ -39,6 +39,7 @@ struct TcEpilogue {
     float* out; int out_cs, out_co;              // mode 0: D -> out[row(m)*out_cs + out_co + n]  (may be null)
     __nv_bfloat16* out_bf16; int ob_cs, ob_co;   // mode 0: optional bf16 copy (next GEMM's operand), same row mapping
     int relu;                                    // mode 0: ReLU after bias
+    int accumulate;                              // mode 0: out += D (fp32 view only)
     float* gates;                                // mode 1: activated gates [M][N] (saved for backward)
     const float* c_prev; float* c_out;           // [M][C]  (c_prev may be null)
     float* h_out; int h_cs, h_co;                // fp32 h view (next step's xh h-slot)
@@ -166,6 +167,10 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 }
                 if (ep.out) {
                     float* dst = ep.out + orow * ep.out_cs + ep.out_co + n0 + c0;
+                    if (ep.accumulate) {
+                        const float4 o0 = *reinterpret_cast<const float4*>(dst), o1 = *reinterpret_cast<const float4*>(dst + 4);
+                        v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
+                    }
                     *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
                     *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
                 }
@@ -396,7 +401,7 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
 // out[row(m)] = relu?(D + bias) written to an fp32 view and/or a bf16 view, row(m) = ((b*OH + i*os + oa)*OW + j*os + ob).
 // One call = one output phase of a stride-2 Deconvolution2D (train_model.py:505-507), a 1x1 convolution, ...
 int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int ntaps, const int* dy, const int* dx, const int* coff,
-                      const void* wt_bf16, int N, int BN, const float* bias, int relu,
+                      const void* wt_bf16, int N, int BN, const float* bias, int relu, int accumulate,
                       float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
                       int OH, int OW, int os, int oa, int ob, void* stream) {
     PIVP_REQUIRE(dy && dx && coff, "tc_conv_taps: null tap list (host arrays)");
@@ -406,7 +411,7 @@ int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int K
     PIVP_REQUIRE(os >= 1 && oa >= 0 && ob >= 0 && OH >= (H - 1) * os + oa + 1 && OW >= (W - 1) * os + ob + 1, "tc_conv_taps: bad output mapping");
     TcEpilogue ep;
     memset(&ep, 0, sizeof(ep));
-    ep.mode = 0; ep.bias = bias; ep.relu = relu; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co;
+    ep.mode = 0; ep.bias = bias; ep.relu = relu; ep.accumulate = accumulate; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co;
     ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ob_cs = ob_cs; ep.ob_co = ob_co;
     return launch_conv_taps(in_bf16, in_cs, B, H, W, Kc, ntaps, dy, dx, coff, wt_bf16, N, BN, ep, OH, OW, os, oa, ob, stream, "tc_conv_taps");
 }

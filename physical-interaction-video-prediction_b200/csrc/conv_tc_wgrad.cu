@@ -29,6 +29,10 @@ struct WgGeom {
     int tpg;                 // taps per group
     int kb_total, kb_per_split;
     int b_stages;
+    int ntaps;               // total taps of the layer (25 for the ConvLSTM 5x5, 9 for the 3x3 stride-2 layers, 1 for 1x1)
+    int Mrows;               // accumulator rows = ceil(N4/128)*128 (rows >= N4 are zero: TMA fills out-of-range channels)
+    signed char dy[25], dx[25];
+    short coff[25];          // channel offset of each tap inside the XH rows (space-to-depth phases)
 };
 
 // MN-major, 128-byte swizzle shared-memory matrix descriptor: LBO = byte distance between 64-element MN chunks,
@@ -62,7 +66,7 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * 128;
     const int tap0 = blockIdx.y * g.tpg;
-    const int ntaps = min(g.tpg, 25 - tap0);
+    const int ntaps = min(g.tpg, g.ntaps - tap0);
     const int split = blockIdx.z;
     const int kb0 = split * g.kb_per_split, kb1 = min(g.kb_total, kb0 + g.kb_per_split);
 
@@ -97,13 +101,13 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
                 const int bimg = (int)(p / hw), rem = (int)(p - (long)bimg * hw);
                 const int y0 = rem / g.W, x0 = rem - y0 * g.W;
                 for (int tl = 0; tl < ntaps; ++tl) {
-                    const int tap = tap0 + tl, dy = tap / 5, dx = tap - dy * 5;
+                    const int tap = tap0 + tl;
                     const uint32_t sb = bi % (uint32_t)g.b_stages;
                     mbar_wait(smem_u32(b_empty + sb), ((bi / (uint32_t)g.b_stages) & 1u) ^ 1u);
                     mbar_expect_tx(smem_u32(b_full + sb), b_bytes);
                     const uint32_t bdst = smem_u32(smem_b + (size_t)sb * b_bytes);
                     for (int ch = 0; ch < g.chunks; ++ch)
-                        tma_load_4d(bdst + ch * chunk_bytes, &map_b, smem_u32(b_full + sb), ch * 64, x0 + dx - 2, y0 + dy - 2, bimg);
+                        tma_load_4d(bdst + ch * chunk_bytes, &map_b, smem_u32(b_full + sb), g.coff[tap] + ch * 64, x0 + g.dx[tap], y0 + g.dy[tap], bimg);
                     ++bi;
                 }
             }
@@ -145,7 +149,7 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         mbar_wait(smem_u32(accum_full), 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        float* dst_row = part + ((size_t)split * g.N4 + n) * 25 * g.Cx;
+        float* dst_row = part + ((size_t)split * g.Mrows + n) * g.ntaps * g.Cx;
         for (int tl = 0; tl < ntaps; ++tl) {
             float* dst = dst_row + (size_t)(tap0 + tl) * g.Cx;
             for (int c0 = 0; c0 < g.Cx; c0 += 8) {
@@ -165,13 +169,13 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     }
 }
 
-// dW[i] += sum_s part[s][i]
-__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, int splits) {
+// dW[i] += sum_s part[s*stride + i]   (i < n: the valid rows of every split's partial tile come first)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, long stride, int splits) {
     const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i4 >= n) return;
     float4 acc = *reinterpret_cast<const float4*>(out + i4);
     for (int s = 0; s < splits; ++s) {
-        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)s * n + i4);
+        const float4 v = *reinterpret_cast<const float4*>(part + (size_t)s * stride + i4);
         acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
     *reinterpret_cast<float4*>(out + i4) = acc;
@@ -218,13 +222,13 @@ int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out,
     return check_launch("tc_colsum_bf16");
 }
 
-static void wgrad_plan(int Cx, int N4, int kb_total, int* tpg, int* groups, int* splits, int* kbps) {
+static void wgrad_plan(int Cx, int Mrows, int ntaps_total, int kb_total, int* tpg, int* groups, int* splits, int* kbps) {
     int tmax = 512 / Cx;
-    if (tmax > 25) tmax = 25;
-    *groups = (25 + tmax - 1) / tmax;
-    *tpg = (25 + *groups - 1) / *groups;
-    *groups = (25 + *tpg - 1) / *tpg;
-    const int tiles = (N4 / 128) * (*groups);
+    if (tmax > ntaps_total) tmax = ntaps_total;
+    *groups = (ntaps_total + tmax - 1) / tmax;
+    *tpg = (ntaps_total + *groups - 1) / *groups;
+    *groups = (ntaps_total + *tpg - 1) / *tpg;
+    const int tiles = (Mrows / 128) * (*groups);
     int s = (2 * 148 + tiles - 1) / tiles;
     int smax = kb_total / 8;
     if (smax < 1) smax = 1;
@@ -234,31 +238,41 @@ static void wgrad_plan(int Cx, int N4, int kb_total, int* tpg, int* groups, int*
     *splits = (kb_total + *kbps - 1) / *kbps;
 }
 
-size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4) {
+static size_t wgrad_ws_bytes(int SB, int H, int W, int Cx, int N4, int ntaps) {
     const long ptot = (long)SB * H * W;
+    const int Mrows = (N4 + 127) / 128 * 128;
     int tpg, groups, splits, kbps;
-    wgrad_plan(Cx, N4, (int)(ptot / 64), &tpg, &groups, &splits, &kbps);
-    return (size_t)splits * N4 * 25 * Cx * sizeof(float);
+    wgrad_plan(Cx, Mrows, ntaps, (int)(ptot / 64), &tpg, &groups, &splits, &kbps);
+    return (size_t)splits * Mrows * ntaps * Cx * sizeof(float);
 }
 
-// dg: [SB*H*W][N4] bf16 (NHWC, all time steps stacked), xh: [>=SB][H][W][xh_cs] bf16 (NHWC), dW: fp32 [N4][25][Cx] accumulated into.
-int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* dW,
-                     void* workspace, size_t ws_bytes, void* stream) {
-    PIVP_REQUIRE(dg_bf16 && xh_bf16 && dW && workspace, "tc_wgrad5x5: null pointer");
-    PIVP_REQUIRE(Cx >= 16 && Cx <= 256 && Cx % 16 == 0 && N4 % 128 == 0, "tc_wgrad5x5: Cx must be a multiple of 16 <= 256, 4C a multiple of 128");
+size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4) { return wgrad_ws_bytes(SB, H, W, Cx, N4, 25); }
+size_t pivp_tc_wgrad_taps_workspace_bytes(int SB, int H, int W, int Cx, int N4, int ntaps) { return wgrad_ws_bytes(SB, H, W, Cx, N4, ntaps); }
+
+static int launch_wgrad(const void* dg_bf16, int dg_cs, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, int ntaps,
+                        const int* dy, const int* dx, const int* coff, float* dW, void* workspace, size_t ws_bytes, void* stream, const char* who) {
+    PIVP_REQUIRE(dg_bf16 && xh_bf16 && dW && workspace, "%s: null pointer", who);
+    PIVP_REQUIRE(ntaps >= 1 && ntaps <= 25, "%s: 1..25 taps", who);
+    PIVP_REQUIRE(Cx >= 16 && Cx <= 256 && Cx % 16 == 0 && N4 >= 8 && N4 % 8 == 0 && dg_cs >= N4 && dg_cs % 8 == 0,
+                 "%s: Cx must be a multiple of 16 <= 256, N4 a multiple of 8, rows 16-byte aligned", who);
     const int chunks = (Cx + 63) / 64;
-    PIVP_REQUIRE(xh_cs >= chunks * 64 && xh_cs % 8 == 0, "tc_wgrad5x5: XH rows must hold ceil(Cx/64)*64 channels and be 16-byte aligned");
+    PIVP_REQUIRE(xh_cs % 8 == 0, "%s: XH rows must be 16-byte aligned", who);
     const long ptot = (long)SB * H * W;
     if ((H * W) % 64 || (W < 64 && 64 % W) || (W > 64 && W % 64)) {
-        set_error("tc_wgrad5x5: cannot cut %dx%d images into 64-pixel TMA boxes", H, W);
+        set_error("%s: cannot cut %dx%d images into 64-pixel TMA boxes", who, H, W);
         return PIVP_EUNSUPPORTED;
     }
     WgGeom g;
-    g.H = H; g.W = W; g.bw = W < 64 ? W : 64; g.bh = 64 / g.bw; g.Cx = Cx; g.N4 = N4; g.chunks = chunks;
+    g.H = H; g.W = W; g.bw = W < 64 ? W : 64; g.bh = 64 / g.bw; g.Cx = Cx; g.N4 = N4; g.chunks = chunks; g.ntaps = ntaps;
+    g.Mrows = (N4 + 127) / 128 * 128;
+    for (int t = 0; t < ntaps; ++t) {
+        PIVP_REQUIRE(coff[t] >= 0 && coff[t] % 8 == 0 && coff[t] + chunks * 64 <= xh_cs + 56, "%s: tap %d channel offset out of range", who, t);
+        g.dy[t] = (signed char)dy[t]; g.dx[t] = (signed char)dx[t]; g.coff[t] = (short)coff[t];
+    }
     int groups, splits;
     g.kb_total = (int)(ptot / 64);
-    wgrad_plan(Cx, N4, g.kb_total, &g.tpg, &groups, &splits, &g.kb_per_split);
-    PIVP_REQUIRE(ws_bytes >= (size_t)splits * N4 * 25 * Cx * sizeof(float), "tc_wgrad5x5: workspace too small");
+    wgrad_plan(Cx, g.Mrows, ntaps, g.kb_total, &g.tpg, &groups, &splits, &g.kb_per_split);
+    PIVP_REQUIRE(ws_bytes >= (size_t)splits * g.Mrows * ntaps * Cx * sizeof(float), "%s: workspace too small", who);
     int bst = (150 * 1024) / (chunks * 8192);
     if (bst > 8) bst = 8;
     if (bst < 2) bst = 2;
@@ -266,31 +280,48 @@ int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB
     CUtensorMap map_a, map_b;
     {
         cuuint64_t dims[2] = {(cuuint64_t)N4, (cuuint64_t)ptot};
-        cuuint64_t str[1] = {(cuuint64_t)N4 * 2};
+        cuuint64_t str[1] = {(cuuint64_t)dg_cs * 2};
         cuuint32_t box[2] = {64, 64};
         CUresult r = encode_tmap(&map_a, dg_bf16, 2, dims, str, box);
-        if (r != CUDA_SUCCESS) { set_error("tc_wgrad5x5: cuTensorMapEncodeTiled(A) failed (%d)", (int)r); return PIVP_ECUDA; }
+        if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(A) failed (%d)", who, (int)r); return PIVP_ECUDA; }
     }
     {
         cuuint64_t dims[4] = {(cuuint64_t)xh_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)SB};
         cuuint64_t str[3] = {(cuuint64_t)xh_cs * 2, (cuuint64_t)W * xh_cs * 2, (cuuint64_t)H * W * xh_cs * 2};
         cuuint32_t box[4] = {64, (cuuint32_t)g.bw, (cuuint32_t)g.bh, 1};
         CUresult r = encode_tmap(&map_b, xh_bf16, 4, dims, str, box);
-        if (r != CUDA_SUCCESS) { set_error("tc_wgrad5x5: cuTensorMapEncodeTiled(B) failed (%d)", (int)r); return PIVP_ECUDA; }
+        if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B) failed (%d)", who, (int)r); return PIVP_ECUDA; }
     }
     const size_t smem = 1024 + (size_t)WG_ASTAGES * 16384 + (size_t)bst * chunks * 8192 + (2 * WG_ASTAGES + 2 * bst + 1) * 8 + 16;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv5x5_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
-        if (e != cudaSuccess) { set_error("tc_wgrad5x5: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return PIVP_ECUDA; }
+        if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
         attr_set = true;
     }
-    dim3 grid((unsigned)(N4 / 128), (unsigned)groups, (unsigned)splits);
+    dim3 grid((unsigned)(g.Mrows / 128), (unsigned)groups, (unsigned)splits);
     conv5x5_wgrad_tc_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, (float*)workspace);
-    if (int e = check_launch("tc_wgrad5x5")) return e;
-    const long n = (long)N4 * 25 * Cx;
-    splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dW, n, splits);
-    return check_launch("tc_wgrad5x5(reduce)");
+    if (int e = check_launch(who)) return e;
+    const long n = (long)N4 * ntaps * Cx;
+    const long stride = (long)g.Mrows * ntaps * Cx;
+    splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dW, n, stride, splits);
+    return check_launch(who);
+}
+
+// dg: [SB*H*W][N4] bf16 (NHWC, all time steps stacked), xh: [>=SB][H][W][xh_cs] bf16 (NHWC), dW: fp32 [N4][25][Cx] accumulated into.
+int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* dW,
+                     void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(N4 % 128 == 0 && xh_cs >= (Cx + 63) / 64 * 64, "tc_wgrad5x5: 4C must be a multiple of 128 and XH rows hold ceil(Cx/64)*64 channels");
+    int dy[25], dx[25], co[25];
+    for (int t = 0; t < 25; ++t) { dy[t] = t / 5 - 2; dx[t] = t % 5 - 2; co[t] = 0; }
+    return launch_wgrad(dg_bf16, N4, xh_bf16, xh_cs, SB, H, W, Cx, N4, 25, dy, dx, co, dW, workspace, ws_bytes, stream, "tc_wgrad5x5");
+}
+
+// General form: dW[n][t][c] += sum_p A[p][n] * X[p + (dy_t,dx_t)][coff_t + c]  for n < N4 (A rows of stride a_cs), t < ntaps, c < Cx.
+int pivp_tc_wgrad_taps(const void* a_bf16, int a_cs, const void* x_bf16, int x_cs, int SB, int H, int W, int Cx, int N4, int ntaps,
+                       const int* dy, const int* dx, const int* coff, float* dW, void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(dy && dx && coff, "tc_wgrad_taps: null tap list (host arrays)");
+    return launch_wgrad(a_bf16, a_cs, x_bf16, x_cs, SB, H, W, Cx, N4, ntaps, dy, dx, coff, dW, workspace, ws_bytes, stream, "tc_wgrad_taps");
 }
 
 }  // extern "C"

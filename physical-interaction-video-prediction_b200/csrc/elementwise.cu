@@ -236,6 +236,26 @@ __global__ void nhwc_to_nchw_kernel(CView src, float* __restrict__ dst, int B, i
     }
 }
 
+// fp32 NHWC view (rows on a B x H x W grid) -> bf16.  s2d = 0: dst[m][co + ch].  s2d = 1: space-to-depth for the stride-2
+// layers: dst row = (b, y/2, x/2) on the half grid, channel = co + ((y&1)*2 + (x&1))*cblk + ch  (cblk >= C, pad stays untouched).
+__global__ void cast_bf16_kernel(CView src, __nv_bfloat16* __restrict__ dst, int d_cs, int d_co, long M, int C, int H, int W, int s2d, int cblk) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C) return;
+    const long m = idx / C;
+    const int ch = (int)(idx - m * C);
+    const float v = src.p[m * src.cs + src.co + ch];
+    long row = m;
+    int cc = d_co + ch;
+    if (s2d) {
+        const long hw = (long)H * W;
+        const long b = m / hw;
+        const int r = (int)(m - b * hw), y = r / W, x = r - y * W;
+        row = (b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+        cc += ((y & 1) * 2 + (x & 1)) * cblk;
+    }
+    dst[row * d_cs + cc] = __float2bfloat16(v);
+}
+
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
@@ -507,6 +527,14 @@ int pivp_nhwc_to_nchw(const float* src, int s_cs, int s_co, float* dst, int B, i
     PIVP_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad argument");
     nhwc_to_nchw_kernel<<<nblk((long)B * HW, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, dst, B, C, HW, accumulate);
     return check_launch("nhwc_to_nchw");
+}
+
+int pivp_cast_bf16(const float* src, int s_cs, int s_co, void* dst_bf16, int d_cs, int d_co, long M, int C, int H, int W, int s2d, int cblk,
+                   void* stream) {
+    PIVP_REQUIRE(src && dst_bf16 && M > 0 && C > 0, "cast_bf16: bad argument");
+    PIVP_REQUIRE(!s2d || (H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && M % ((long)H * W) == 0 && cblk >= C), "cast_bf16: bad space-to-depth geometry");
+    cast_bf16_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, (__nv_bfloat16*)dst_bf16, d_cs, d_co, M, C, H, W, s2d, cblk);
+    return check_launch("cast_bf16");
 }
 
 int pivp_axpy(const float* x, float* y, long n, void* stream) {

@@ -54,7 +54,57 @@ class TensorCorePlan(object):
         self.dec = {}
         for name, cin, cout, lv in (("enc4", 128, 128, 8), ("enc5", 96, 96, 4), ("enc6", 64, 64, 2)):
             self.dec[name] = self._plan_deconv(name, cin, cout, lv)
+        # input gradients of the stride-2 convolutions enc1 / enc2 are transposed convolutions too: same phase decomposition
+        # (conv weight [N][ky][kx][C] has the deconv form with in := N, out := C)
+        self.dec["enc1"] = self._plan_deconv("enc1", 32, 32, 4)
+        self.dec["enc2"] = self._plan_deconv("enc2", 64, 64, 8)
+        self.de1_b = torch.zeros(M4, 64, dtype=torch.bfloat16, device=dev)      # bf16 d(enc1 pre-activation), 32 used
+        self.de2_b = torch.zeros(M8, 64, dtype=torch.bfloat16, device=dev)
+        # ---- deconvolution backward: dY in space-to-depth bf16 (all time steps kept for the deferred weight gradient)
+        self.dbw = {}
+        wsb2 = 16
+        for name, cin, cout, lv, xs in (("enc4", 128, 128, 8, self.hid5_b), ("enc5", 96, 96, 4, self.cat5_b), ("enc6", 64, 64, 2, self.cat6_b)):
+            self.dbw[name] = self._plan_deconv_bwd(name, cin, cout, lv)
+            wsb2 = max(wsb2, eng.L.query("pivp_tc_wgrad_taps_workspace_bytes", S * B, eng.H // lv, eng.W // lv, cout, cin, 9))
+        if wsb2 > self.wgrad_ws.numel():
+            self.wgrad_ws = torch.empty(wsb2, dtype=torch.uint8, device=dev)
+        # the deferred weight gradient needs the deconv inputs of all time steps stacked: re-home them in one tensor each
+        for nm in ("hid5_b", "cat5_b", "cat6_b"):
+            old = getattr(self, nm)
+            allt = torch.zeros(S, old[0].shape[0], old[0].shape[1], dtype=torch.bfloat16, device=dev)
+            setattr(self, nm + "_all", allt)
+            setattr(self, nm, [allt[t] for t in range(S)])
         self.refresh_weights()
+
+    def _plan_deconv_bwd(self, name, cin, cout, lv):
+        """Backward of a stride-2 deconvolution on the tensor cores.  dY (big grid) is cast to space-to-depth bf16
+        [B][h][w][4*cb]; then d_in[i,j][ci] = sum_{ky,kx,co} dY[2i+ky-1, 2j+kx-1][co] W[ci][ky][kx][co] is a 9-tap stride-1
+        implicit GEMM on the small grid (tap -> pixel offset {-1,0} and phase channel block), and dW[ci][ky][kx][co] is the
+        MN-major weight-gradient GEMM with the same taps (its output layout IS the internal [ci][ky][kx][co] layout)."""
+        e = self.eng
+        dev = e.dev
+        cb = (cout + 63) // 64 * 64
+        S, M = self.S, self.ws["Mr"][lv]
+        tapdef = {0: (-1, 1), 1: (0, 0), 2: (0, 1)}                     # k -> (pixel offset, phase)
+        taps = []
+        for ky in range(3):
+            for kx in range(3):
+                (dy, py), (dx, px) = tapdef[ky], tapdef[kx]
+                taps.append((dy, dx, (py * 2 + px) * cb))
+        base = e.spec[name + "/W"].offset
+        idx = np.full((cin, 9, cb), -1, np.int32)
+        co = np.arange(cout)
+        for ci in range(cin):
+            for t in range(9):
+                idx[ci, t, :cout] = base + (ci * 9 + t) * cout + co
+        arr = lambda v: (ctypes.c_int * 9)(*v)
+        bn = cin if cin <= 128 else 128
+        if (M // 128) * (cin // bn) < 64 and cin % 64 == 0:
+            bn = 64
+        return dict(cin=cin, cout=cout, cb=cb, lv=lv, bn=bn, dy=arr([t[0] for t in taps]), dx=arr([t[1] for t in taps]),
+                    co=arr([t[2] for t in taps]), idx=torch.from_numpy(idx.reshape(-1)).to(dev),
+                    wt=torch.empty(cin, 9 * cb, dtype=torch.bfloat16, device=dev),
+                    dys=torch.zeros(S, M, 4 * cb, dtype=torch.bfloat16, device=dev))
 
     def _plan_deconv(self, name, cin, cout, lv):
         """Sub-pixel decomposition: output pixel (2i+a, 2j+b) only sees taps ky = a+1 (mod 2), kx = b+1 (mod 2):
@@ -90,15 +140,42 @@ class TensorCorePlan(object):
         for d in getattr(self, "dec", {}).values():
             for ph in d["phases"]:
                 e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(ph["idx"]), ph["idx"].numel(), _ptr(ph["wt"]), e._s())
+        for d in getattr(self, "dbw", {}).values():
+            e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(d["idx"]), d["idx"].numel(), _ptr(d["wt"]), e._s())
 
-    def deconv_fwd(self, name, x_bf16, out, out_cs, out_bf16, ob_cs, relu):
+    def deconv_bwd_data(self, name, t, dy_f32, out, accumulate):
+        """dY (fp32, big grid, dense rows of cout) -> space-to-depth bf16 (kept for wgrad) -> d_in (fp32, dense rows of cin)."""
+        e, d = self.eng, self.dbw[name]
+        h, w = e.H // d["lv"], e.W // d["lv"]
+        B = self.ws["B"]
+        e.L.call("pivp_cast_bf16", _ptr(dy_f32), d["cout"], 0, _ptr(d["dys"][t]), 4 * d["cb"], 0, B * 4 * h * w, d["cout"], 2 * h, 2 * w, 1,
+                 d["cb"], e._s())
+        e.L.call("pivp_tc_conv_taps", _ptr(d["dys"][t]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
+                 d["cin"], d["bn"], 0, 0, accumulate, _ptr(out), d["cin"], 0, 0, 0, 0, h, w, 1, 0, 0, e._s())
+
+    def deconv_wgrad_all(self):
+        """Deferred weight gradients of enc4/5/6 over all time steps (one MN-major GEMM each)."""
+        e, S, B = self.eng, self.S, self.ws["B"]
+        for name, xall in (("enc4", self.hid5_b_all), ("enc5", self.cat5_b_all), ("enc6", self.cat6_b_all)):
+            d = self.dbw[name]
+            h, w = e.H // d["lv"], e.W // d["lv"]
+            e.L.call("pivp_tc_wgrad_taps", _ptr(xall), xall.shape[2], _ptr(d["dys"]), 4 * d["cb"], S * B, h, w, d["cout"], d["cin"], 9,
+                     d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
+
+    def conv_s2_dgrad(self, name, dy_f32, dy_b, M, C, out, out_cs):
+        """Input gradient of the stride-2 convolutions enc1 / enc2: cast d(pre-activation) to bf16, four phase launches."""
+        e = self.eng
+        e.L.call("pivp_cast_bf16", _ptr(dy_f32), C, 0, _ptr(dy_b), dy_b.shape[1], 0, M, C, 0, 0, 0, 0, e._s())
+        self.deconv_fwd(name, dy_b, out, out_cs, None, 0, 0, bias=False)
+
+    def deconv_fwd(self, name, x_bf16, out, out_cs, out_bf16, ob_cs, relu, bias=True):
         """Deconvolution2D forward (+bias, optional ReLU) -> fp32 view `out` (row stride out_cs, channel offset 0) and an
         optional bf16 copy (the next ConvLSTM's x slot): four tcgen05 launches, one per output phase."""
         e, d = self.eng, self.dec[name]
         h, w = e.H // d["lv"], e.W // d["lv"]
         for ph in d["phases"]:
             e.L.call("pivp_tc_conv_taps", _ptr(x_bf16), d["kc"], self.ws["B"], h, w, d["kc"], ph["n"], ph["dy"], ph["dx"], ph["co"],
-                     _ptr(ph["wt"]), d["cout"], d["bn"], _ptr(e.p[name + "/b"]), relu,
+                     _ptr(ph["wt"]), d["cout"], d["bn"], _ptr(e.p[name + "/b"]) if bias else 0, relu, 0,
                      _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, 2 * h, 2 * w, 2, ph["a"], ph["b"], e._s())
 
     def xview(self, li, t):
@@ -149,3 +226,4 @@ class TensorCorePlan(object):
             e.L.call("pivp_tc_colsum_bf16", _ptr(self.dg_all[li]), 4 * C, S * M, 4 * C, _ptr(e.g[name + "/b"]), e._s())
             e.L.call("pivp_tc_wgrad5x5", _ptr(self.dg_all[li]), _ptr(self.xh_all[li]), self.Kpad[li], S * B, h, w, cx, 4 * C,
                      _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
+        self.deconv_wgrad_all()

@@ -230,7 +230,7 @@ def test_tc_deconv_phases_match_simt(pk, B, ih, iw, cin, cout, bn, relu):
             arr = lambda v: (ctypes.c_int * len(taps))(*v)
             keep.append(wt)
             L.call("pivp_tc_conv_taps", xb.data_ptr(), kc, B, ih, iw, kc, len(taps), arr([t[0] for t in taps]), arr([t[1] for t in taps]),
-                   arr([0] * len(taps)), wt.data_ptr(), cout, bn, bias.data_ptr(), relu, out.data_ptr(), cout + 8, 0,
+                   arr([0] * len(taps)), wt.data_ptr(), cout, bn, bias.data_ptr(), relu, 0, out.data_ptr(), cout + 8, 0,
                    out_b.data_ptr(), cout, 0, 2 * ih, 2 * iw, 2, a, b, stream())
     ref = torch.zeros(B * 4 * ih * iw, cout, device="cuda")
     xf = xb[:, :cin].float().contiguous()
