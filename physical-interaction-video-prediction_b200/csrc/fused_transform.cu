@@ -461,6 +461,13 @@ static int allow_smem(K kernel, size_t bytes) {
     return PIVP_OK;
 }
 
+// fast path for the BASELINE geometry (cdna_band.cu)
+bool cdna_band_supported(int H, int W, int num_masks, const void* p0, const void* p1, const void* p2, const void* p3);
+int cdna_band_fwd(const float* prev, const float* e_pre, const float* a_pre, const float* kraw, float* out, int B, int H, cudaStream_t st);
+size_t cdna_band_bwd_workspace_floats(int B, int H);
+int cdna_band_bwd(const float* gout, const float* prev, const float* e_pre, const float* a_pre, const float* kraw, float* d_e,
+                  float* d_a, float* d_kraw, float* dKp, int B, int H, cudaStream_t st);
+
 }  // namespace pivp
 
 using namespace pivp;
@@ -470,6 +477,8 @@ extern "C" {
 int pivp_cdna_fused_fwd(const float* prev, const float* enc7_pre, const float* mask_pre, const float* kern_raw, float* out,
                         int B, int H, int W, int num_masks, void* stream) {
     PIVP_REQUIRE(prev && enc7_pre && mask_pre && kern_raw && out && B > 0 && num_masks >= 1, "cdna_fused_fwd: bad argument");
+    if (cdna_band_supported(H, W, num_masks, prev, enc7_pre, mask_pre, out) && cdna_band_supported(H, W, num_masks, kern_raw, out, out, out))
+        return cdna_band_fwd(prev, enc7_pre, mask_pre, kern_raw, out, B, H, (cudaStream_t)stream);
     Band bd;
     if (int e = make_band(H, W, num_masks + 1, 0, &bd)) return e;
     const size_t smem = sizeof(float) * ((size_t)bd.M1 * bd.L + 3 * (bd.R + 4) * (W + 4) + num_masks * 25);
@@ -492,6 +501,21 @@ int pivp_cdna_fused_bwd(const float* g_out, const float* prev, const float* enc7
     Band bd;
     if (int e = make_band(H, W, num_masks + 1, 0, &bd)) return e;
     cudaStream_t st = (cudaStream_t)stream;
+    if (cdna_band_supported(H, W, num_masks, prev, enc7_pre, mask_pre, g_out) &&
+        cdna_band_supported(H, W, num_masks, d_enc7_pre, d_mask_pre, workspace, workspace)) {
+        // one pass: every input read once, every output written once; workspace holds the per-band kernel-gradient partials
+        if (int e = cdna_band_bwd(g_out, prev, enc7_pre, mask_pre, kern_raw, d_enc7_pre, d_mask_pre, d_kern_raw, (float*)workspace, B, H, st))
+            return e;
+        if (d_prev) {
+            Band be;
+            if (int e = make_band(H, W, num_masks + 1, 4, &be)) return e;
+            const size_t sm2 = sizeof(float) * ((size_t)be.M1 * be.L + 3 * (be.R + 8) * (W + 4) + num_masks * 25);
+            if (int e = allow_smem(cdna_dprev_kernel, sm2)) return e;
+            cdna_dprev_kernel<<<dim3((H + be.R - 1) / be.R, B), FT, sm2, st>>>(g_out, mask_pre, kern_raw, d_prev, be, num_masks, accumulate_dprev);
+            return check_launch("cdna_fused_bwd(dprev)");
+        }
+        return PIVP_OK;
+    }
     float* wq = (float*)workspace;
     float* dK = wq + (size_t)B * (num_masks + 1) * H * W;
     cudaMemsetAsync(dK, 0, sizeof(float) * (size_t)B * num_masks * 25, st);
