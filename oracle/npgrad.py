@@ -15,7 +15,7 @@ from numpy.lib.stride_tricks import sliding_window_view
 
 class Var(object):
     """Array + graph node (stands in for ``chainer.Variable``)."""
-    __slots__ = ("data", "grad", "parents", "bwd", "name")
+    __slots__ = ("data", "grad", "parents", "bwd", "name", "saved_grad")
 
     def __init__(self, data, parents=(), bwd=None, name=None):
         self.data = data
@@ -53,6 +53,9 @@ def detach(x):
     return Var(as_var(x).data)
 
 
+KEEP_INTERMEDIATE = False
+
+
 def backward(loss, seed=None):
     """Reverse sweep (``loss.backward()`` inside ``optimizer.update``, train_model.py:950)."""
     order, seen = [], set()
@@ -79,6 +82,8 @@ def backward(loss, seed=None):
                 continue
             p.grad = g if p.grad is None else p.grad + g
         if v.parents:
+            if KEEP_INTERMEDIATE:
+                v.saved_grad = v.grad                    # debugging aid (scripts/dbg_bwd_stage.py): keep d(loss)/d(intermediate)
             v.grad = None if v is not loss else v.grad   # free intermediate grads
 
 

@@ -652,6 +652,8 @@ static int launch_bwd(const float* gout, const float* prev, const float* e_pre, 
 }  // namespace cb
 
 bool cdna_band_supported(int H, int W, int num_masks, const void* p0, const void* p1, const void* p2, const void* p3) {
+    const char* off = getenv("PIVP_CDNA_GENERIC");            // debugging switch: force the generic kernels of fused_transform.cu
+    if (off && atoi(off) != 0) return false;
     return W == cb::W && H % cb::R == 0 && num_masks == cb::M && cb::aligned16(p0) && cb::aligned16(p1) && cb::aligned16(p2) &&
            cb::aligned16(p3);
 }

@@ -430,6 +430,14 @@ __global__ void fill_kernel(float* __restrict__ p, float v, long n) {
 
 static inline unsigned nblk(long n, int t) { return (unsigned)((n + t - 1) / t); }
 
+// 128-bit vectorised LayerNorm kernels (layernorm_vec.cu): 1 = done, 0 = not applicable, < 0 = error
+int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
+               float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co, int relu,
+               float* stats, void* workspace, int S, int chunk, cudaStream_t st);
+int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+               const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu, float* dx, int dx_cs,
+               int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st);
+
 }  // namespace pivp
 
 using namespace pivp;
@@ -474,6 +482,9 @@ int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, c
     int chunk;
     const int S = ln_split(n, &chunk);
     PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_fwd: workspace too small");
+    if (int r = ln_vec_fwd(x, x_cs, x_co, gamma, beta, B, HW, C, eps, y, y_cs, y_co, y2, y2_cs, y2_co, y_bf16, yb_cs, yb_co, relu, stats,
+                           workspace, S, chunk, (cudaStream_t)stream))
+        return r < 0 ? r : PIVP_OK;
     ln_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, n, C, chunk, (float2*)workspace);
     if (int e = check_launch("layernorm_fwd(stats)")) return e;
     int gx = (n + LN_T * 4 - 1) / (LN_T * 4);
@@ -492,6 +503,9 @@ int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int 
     const int S = ln_split(n, &chunk);
     PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_bwd: workspace too small");
     PIVP_REQUIRE(B <= 4096, "layernorm_bwd: batch too large for the shared-memory totals");
+    if (int r = ln_vec_bwd(x, x_cs, x_co, g1, g1_cs, g1_co, g2, g2_cs, g2_co, gamma, beta, stats, B, HW, C, relu, dx, dx_cs, dx_co, dgamma,
+                           dbeta, workspace, S, chunk, (cudaStream_t)stream))
+        return r < 0 ? r : PIVP_OK;
     ln_bwd_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co},
                                                                         gamma, beta, (const float2*)stats, n, C, chunk, relu, (float2*)workspace);
     if (int e = check_launch("layernorm_bwd(stats)")) return e;

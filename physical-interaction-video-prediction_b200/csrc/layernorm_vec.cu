@@ -1,0 +1,254 @@
+// LayerNormalizationConv2D (train_model.py:186-208; D.4): 128-bit vectorised kernels for NHWC views whose channel count, row stride
+// and channel offset are multiples of 4 (every LayerNorm of the model).  Same algorithm and workspace layout as the scalar kernels in
+// elementwise.cu (Chan-merged per-chunk (mean, M2) partials, two launches forward, two backward); those remain the generic fallback.
+//
+// HBM-bound: forward reads x once per pass (second pass from L2), backward reads x, g twice; gamma/beta (per-element, shared by the
+// batch) stay in L2.  dgamma/dbeta are accumulated with 128-bit red.global.add (one per 4 elements per batch chunk).
+#include "common.cuh"
+#include <stdlib.h>
+
+namespace pivp {
+namespace lnv {
+
+constexpr int T = 256, E4 = 4;               // a stats CTA keeps T * E4 float4 = 4096 elements in registers
+constexpr int TB = 128;                      // backward-apply threads
+
+struct Geo {
+    int HW, C, cshift;                        // cshift = log2(C) when C is a power of two, else -1
+};
+__device__ __forceinline__ long row_addr(const Geo& g, long b, int e, int cs, int co) {
+    const int pix = g.cshift >= 0 ? (e >> g.cshift) : (e / g.C);
+    return (b * g.HW + pix) * cs + co + (e - pix * g.C);
+}
+__device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float hsum(float4 v) { return (v.x + v.y) + (v.z + v.w); }
+
+__global__ void __launch_bounds__(T) stats_kernel(CView x, Geo g, int n, int chunk, float2* __restrict__ partial) {
+    __shared__ float red[32];
+    const int s = blockIdx.x, S = gridDim.x;
+    const long b = blockIdx.y;
+    const int e0 = s * chunk, e1 = min(n, e0 + chunk);
+    float4 v[E4];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < E4; ++i) {
+        const int e = e0 + (i * T + threadIdx.x) * 4;
+        v[i] = (e < e1) ? ld4(x.p + row_addr(g, b, e, x.cs, x.co)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        sum += hsum(v[i]);
+    }
+    const float mean = block_sum(sum, red) / (float)(e1 - e0);
+    float m2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < E4; ++i) {
+        const int e = e0 + (i * T + threadIdx.x) * 4;
+        if (e < e1) {
+            const float a = v[i].x - mean, bb = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            m2 += (a * a + bb * bb) + (c * c + d * d);
+        }
+    }
+    m2 = block_sum(m2, red);
+    if (threadIdx.x == 0) partial[b * S + s] = make_float2(mean, m2);
+}
+
+// Chan merge of the S chunk partials of sample b by one warp; result (mean, rstd) valid in every lane.
+__device__ __forceinline__ float2 combine_warp(const float2* __restrict__ partial, long b, int S, int n, int chunk, float eps, int lane) {
+    float wsum = 0.f;
+    for (int s = lane; s < S; s += 32) wsum += partial[b * S + s].x * (float)(min(n, (s + 1) * chunk) - s * chunk);
+    const float mu = warp_sum(wsum) / (float)n;
+    float m2 = 0.f;
+    for (int s = lane; s < S; s += 32) {
+        const float2 p = partial[b * S + s];
+        const float d = p.x - mu;
+        m2 += p.y + (float)(min(n, (s + 1) * chunk) - s * chunk) * d * d;
+    }
+    m2 = warp_sum(m2);
+    return make_float2(mu, 1.f / sqrtf(m2 / (float)n + eps));
+}
+
+__global__ void __launch_bounds__(T) apply_kernel(CView x, const float* __restrict__ gamma, const float* __restrict__ beta, Geo g, int n,
+                                                  const float2* __restrict__ partial, int S, int chunk, float eps, View y, View y2,
+                                                  __nv_bfloat16* __restrict__ y_bf16, int yb_cs, int yb_co, int relu,
+                                                  float2* __restrict__ stats) {
+    __shared__ float2 st_s;
+    const long b = blockIdx.y;
+    if (threadIdx.x < 32) {
+        const float2 st = combine_warp(partial, b, S, n, chunk, eps, threadIdx.x);
+        if (threadIdx.x == 0) {
+            st_s = st;
+            if (blockIdx.x == 0) stats[b] = st;
+        }
+    }
+    __syncthreads();
+    const float2 st = st_s;
+    for (int e = (blockIdx.x * T + threadIdx.x) * 4; e < n; e += gridDim.x * T * 4) {
+        const int pix = g.cshift >= 0 ? (e >> g.cshift) : (e / g.C);
+        const int ch = e - pix * g.C;
+        const long row = b * g.HW + pix;
+        const float4 xv = ld4(x.p + row * x.cs + x.co + ch), ga = ld4(gamma + e), be = ld4(beta + e);
+        float4 v;
+        v.x = (xv.x - st.x) * st.y * ga.x + be.x;
+        v.y = (xv.y - st.x) * st.y * ga.y + be.y;
+        v.z = (xv.z - st.x) * st.y * ga.z + be.z;
+        v.w = (xv.w - st.x) * st.y * ga.w + be.w;
+        if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+        *reinterpret_cast<float4*>(y.p + row * y.cs + y.co + ch) = v;
+        if (y2.p) *reinterpret_cast<float4*>(y2.p + row * y2.cs + y2.co + ch) = v;
+        if (y_bf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned*>(&lo);
+            pk.y = *reinterpret_cast<unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(y_bf16 + row * yb_cs + yb_co + ch) = pk;
+        }
+    }
+}
+
+// g = (g1 + g2) * [y > 0 when relu];  xh = (x - mean) * rstd
+__device__ __forceinline__ void load_g_xh(const CView& x, const CView& g1, const CView& g2, long row, int ch, const float4& ga,
+                                          const float4& be, float2 st, int relu, float4& gq, float4& xh) {
+    const float4 xv = ld4(x.p + row * x.cs + x.co + ch);
+    gq = ld4(g1.p + row * g1.cs + g1.co + ch);
+    if (g2.p) {
+        const float4 t = ld4(g2.p + row * g2.cs + g2.co + ch);
+        gq.x += t.x; gq.y += t.y; gq.z += t.z; gq.w += t.w;
+    }
+    xh.x = (xv.x - st.x) * st.y; xh.y = (xv.y - st.x) * st.y; xh.z = (xv.z - st.x) * st.y; xh.w = (xv.w - st.x) * st.y;
+    if (relu) {
+        if (xh.x * ga.x + be.x <= 0.f) gq.x = 0.f;
+        if (xh.y * ga.y + be.y <= 0.f) gq.y = 0.f;
+        if (xh.z * ga.z + be.z <= 0.f) gq.z = 0.f;
+        if (xh.w * ga.w + be.w <= 0.f) gq.w = 0.f;
+    }
+}
+
+// partial sums of q = g*gamma and q*xhat per sample
+__global__ void __launch_bounds__(T) bwd_stats_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float2* __restrict__ stats, Geo g, int n,
+                                                      int chunk, int relu, float2* __restrict__ partial) {
+    __shared__ float red[32];
+    const int s = blockIdx.x, S = gridDim.x;
+    const long b = blockIdx.y;
+    const int e0 = s * chunk, e1 = min(n, e0 + chunk);
+    const float2 st = stats[b];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < E4; ++i) {
+        const int e = e0 + (i * T + threadIdx.x) * 4;
+        if (e < e1) {
+            const int pix = g.cshift >= 0 ? (e >> g.cshift) : (e / g.C);
+            const int ch = e - pix * g.C;
+            const float4 ga = ld4(gamma + e);
+            const float4 be = relu ? ld4(beta + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            float4 gq, xh;
+            load_g_xh(x, g1, g2, b * g.HW + pix, ch, ga, be, st, relu, gq, xh);
+            const float4 q = make_float4(gq.x * ga.x, gq.y * ga.y, gq.z * ga.z, gq.w * ga.w);
+            s1 += hsum(q);
+            s2 += (q.x * xh.x + q.y * xh.y) + (q.z * xh.z + q.w * xh.w);
+        }
+    }
+    s1 = block_sum(s1, red);
+    s2 = block_sum(s2, red);
+    if (threadIdx.x == 0) partial[b * S + s] = make_float2(s1, s2);
+}
+
+// thread per 4 elements, loop over this CTA's batch chunk: dx, and dgamma / dbeta += (one 128-bit reduction each)
+__global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float2* __restrict__ stats,
+                                                       const float2* __restrict__ partial, int S, int B, int bchunk, Geo g, int n,
+                                                       int relu, View dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    extern __shared__ float4 tot[];              // [bchunk] : (mean, rstd, mean q, mean q*xhat)
+    const int b0 = blockIdx.y * bchunk, nb = min(bchunk, B - b0);
+    for (int i = threadIdx.x; i < nb; i += TB) {
+        float a = 0.f, c = 0.f;
+        for (int s = 0; s < S; ++s) { const float2 p = partial[(long)(b0 + i) * S + s]; a += p.x; c += p.y; }
+        const float2 st = stats[b0 + i];
+        tot[i] = make_float4(st.x, st.y, a / (float)n, c / (float)n);
+    }
+    __syncthreads();
+    const int e = (blockIdx.x * TB + threadIdx.x) * 4;
+    if (e >= n) return;
+    const int pix = g.cshift >= 0 ? (e >> g.cshift) : (e / g.C);
+    const int ch = e - pix * g.C;
+    const float4 ga = ld4(gamma + e);
+    const float4 be = relu ? ld4(beta + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+#pragma unroll 4
+    for (int i = 0; i < nb; ++i) {
+        const long row = (long)(b0 + i) * g.HW + pix;
+        const float4 t = tot[i];
+        float4 gq, xh;
+        load_g_xh(x, g1, g2, row, ch, ga, be, make_float2(t.x, t.y), relu, gq, xh);
+        dg.x += gq.x * xh.x; dg.y += gq.y * xh.y; dg.z += gq.z * xh.z; dg.w += gq.w * xh.w;
+        db.x += gq.x; db.y += gq.y; db.z += gq.z; db.w += gq.w;
+        float4 d;
+        d.x = (gq.x * ga.x - t.z - xh.x * t.w) * t.y;
+        d.y = (gq.y * ga.y - t.z - xh.y * t.w) * t.y;
+        d.z = (gq.z * ga.z - t.z - xh.z * t.w) * t.y;
+        d.w = (gq.w * ga.w - t.z - xh.w * t.w) * t.y;
+        *reinterpret_cast<float4*>(dx.p + row * dx.cs + dx.co + ch) = d;
+    }
+    atomicAdd(reinterpret_cast<float4*>(dgamma + e), dg);
+    atomicAdd(reinterpret_cast<float4*>(dbeta + e), db);
+}
+
+static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool view_ok(const float* p, int cs, int co) { return !p || (a16(p) && cs % 4 == 0 && co % 4 == 0); }
+static bool disabled() {
+    const char* v = getenv("PIVP_LN_SCALAR");                                               // debugging switch: force the scalar kernels
+    return v && atoi(v) != 0;
+}
+static Geo make_geo(int HW, int C) {
+    Geo g{HW, C, -1};
+    if ((C & (C - 1)) == 0) { int s = 0; while ((1 << s) < C) ++s; g.cshift = s; }
+    return g;
+}
+
+}  // namespace lnv
+
+// Both return 1 when the vectorised path ran, 0 when the caller must use the scalar kernels, < 0 on a launch error.
+int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
+               float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co, int relu,
+               float* stats, void* workspace, int S, int chunk, cudaStream_t st) {
+    using namespace lnv;
+    const int n = HW * C;
+    if (disabled() || C % 4 || chunk % 4 || chunk > T * E4 * 4 || !view_ok(x, x_cs, x_co) || !view_ok(y, y_cs, y_co) || !view_ok(y2, y2_cs, y2_co) ||
+        !a16(gamma) || !a16(beta) || (y_bf16 && ((reinterpret_cast<uintptr_t>(y_bf16) & 7) || yb_cs % 4 || yb_co % 4)))
+        return 0;
+    const Geo g = make_geo(HW, C);
+    stats_kernel<<<dim3(S, B), T, 0, st>>>(CView{x, x_cs, x_co}, g, n, chunk, (float2*)workspace);
+    if (int e = check_launch("layernorm_fwd(stats)")) return e;
+    int gx = (n / 4 + T - 1) / T;
+    if (gx > 64) gx = 64;
+    apply_kernel<<<dim3(gx, B), T, 0, st>>>(CView{x, x_cs, x_co}, gamma, beta, g, n, (const float2*)workspace, S, chunk, eps,
+                                           View{y, y_cs, y_co}, View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16, yb_cs, yb_co, relu,
+                                           (float2*)stats);
+    if (int e = check_launch("layernorm_fwd(apply)")) return e;
+    return 1;
+}
+
+int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+               const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu, float* dx, int dx_cs,
+               int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st) {
+    using namespace lnv;
+    const int n = HW * C;
+    if (disabled() || C % 4 || chunk % 4 || chunk > T * E4 * 4 || !view_ok(x, x_cs, x_co) || !view_ok(g1, g1_cs, g1_co) || !view_ok(g2, g2_cs, g2_co) ||
+        !view_ok(dx, dx_cs, dx_co) || !a16(gamma) || !a16(beta) || !a16(dgamma) || !a16(dbeta))
+        return 0;
+    const Geo g = make_geo(HW, C);
+    bwd_stats_kernel<<<dim3(S, B), T, 0, st>>>(CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta,
+                                              (const float2*)stats, g, n, chunk, relu, (float2*)workspace);
+    if (int e = check_launch("layernorm_bwd(stats)")) return e;
+    const int gx = (n / 4 + TB - 1) / TB;
+    int nby = (592 + gx - 1) / gx;                            // aim for ~4 CTAs per SM
+    if (nby > B) nby = B;
+    if (nby < 1) nby = 1;
+    const int bchunk = (B + nby - 1) / nby;
+    nby = (B + bchunk - 1) / bchunk;
+    bwd_apply_kernel<<<dim3(gx, nby), TB, (size_t)bchunk * sizeof(float4), st>>>(
+        CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
+        (const float2*)workspace, S, B, bchunk, g, n, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta);
+    if (int e = check_launch("layernorm_bwd(apply)")) return e;
+    return 1;
+}
+
+}  // namespace pivp

@@ -559,5 +559,7 @@ class Engine(object):
                 self._conv_dgrad(de0, B, H // 2, W // 2, p["enc0/W"], None, 5, 2, 2, View(ws["d_img_nhwc"], 3, 0, 3), H, W)
                 L.call("pivp_nhwc_to_nchw", _ptr(ws["d_img_nhwc"]), 3, 0, _ptr(d_prev), B, 3, HW[1], 1, s)
                 L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)
+            if getattr(self, "debug_stop_t", None) == t:
+                return                             # scripts/dbg_bwd_stage.py: leave this step's backward temporaries in place
         if self.tc is not None:
             self.tc.wgrad_all()                # ConvLSTM weight/bias gradients: one tcgen05 GEMM per layer over all time steps
