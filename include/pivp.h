@@ -129,6 +129,10 @@ int pivp_stp_fused_bwd(const float* g_out, const float* prev, const float* enc7_
 /* ---- tcgen05 / TMEM / TMA path for the seven ConvLSTM 5x5 convolutions (bf16 operands, fp32 accumulate) ---------- */
 /* fp32 master W[n][tap][c] -> bf16 forward operand Wf[n][tap][Kpad] and tap-flipped dgrad operand Wd[c][tap'][n] */
 int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream);
+/* Debugging aid (scripts/dbg_halo_timeline.py): device buffer of [CTAs][8] 64-bit slots the halo-patch convolution kernel fills
+ * with clock64() stamps (0 launch, 1 set-up done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready, 5 epilogue done);
+ * null switches it off.  Process-wide, not thread-safe. */
+int pivp_tc_set_debug_buffer(void* device_buffer);
 /* D[m,n] = sum_{tap,c} In[pixel(m)+tap-2, c] * Wt[n][tap][c]  (In bf16 NHWC with row stride in_cs; Wt bf16 [N][25][Kc]).
  * mode 0: out[m*out_cs+out_co+n] = D (+bias)                      -- Convolution2D input-gradient (D.5) with Wd
  * mode 1: bias + gates + cell + h fused (train_model.py:262-272)  -- BN must be 128, N = 4C in the gate-interleaved order;

@@ -19,37 +19,13 @@
 //  * Two CTAs are resident per SM (<= 110 KB smem, <= 256 TMEM columns each), so one CTA's epilogue overlaps the other's
 //    main loop without an in-kernel tile scheduler.
 #include "tc_common.cuh"
+#include "tc_epilogue.cuh"
 
 namespace pivp {
 
 constexpr int TC_BM = 128;          // pixels per CTA (TMEM lanes)
 constexpr int TC_BK = 64;           // bf16 elements per k-block row = 128 B = one swizzle span
 constexpr int TC_THREADS = 192;
-
-__device__ __forceinline__ float tanh_fast(float x) {
-    float y;
-    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
-    return y;
-}
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
-
-struct TcEpilogue {
-    int mode;                    // 0: plain fp32 store (+bias), 1: ConvLSTM gates
-    const float* bias;           // [N] (may be null in mode 0)
-    float* out; int out_cs, out_co;              // mode 0: D -> out[row(m)*out_cs + out_co + n]  (may be null)
-    __nv_bfloat16* out_bf16; int ob_cs, ob_co;   // mode 0: optional bf16 copy (next GEMM's operand), same row mapping
-    int relu;                                    // mode 0: ReLU after bias
-    int accumulate;                              // mode 0: out += D (fp32 view only)
-    float* gates;                                // mode 1: activated gates [M][N] (saved for backward)
-    const float* c_prev; float* c_out;           // [M][C]  (c_prev may be null)
-    float* h_out; int h_cs, h_co;                // fp32 h view (next step's xh h-slot)
-    __nv_bfloat16* h_bf16; int hb_cs, hb_co;     // bf16 shadow (GEMM operand of the next step)
-    __nv_bfloat16* h_t; long h_t_ld;             // optional channel-major bf16 copy  h_t[(hT_co + ch) * h_t_ld + m]  (wgrad operand)
-    int hT_co;
-    int C;                                       // LSTM channels (N = 4C)
-    float forget_bias;
-    int accurate;                                // 1: expf/tanhf, 0: tanh.approx
-};
 
 constexpr int TC_MAXTAPS = 25;
 struct TcGeom {
@@ -147,100 +123,12 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         mbar_wait(smem_u32(accum_full), 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
-        if (ep.mode == 0) {
-            // output row of this A-grid pixel (identity for stride-1 convs, phase scatter for transposed convs)
-            const int hw = g.H * g.W;
-            const int bi = (int)(m / hw), rem = (int)(m - (long)bi * hw);
-            const int iy = rem / g.W, ix = rem - iy * g.W;
-            const long orow = ((long)bi * g.OH + iy * g.os + g.oa) * g.OW + ix * g.os + g.ob;
-            for (int c0 = 0; c0 < g.BN; c0 += 8) {
-                float v[8];
-                tc_ld8(trow + (uint32_t)c0, v);
-                tc_ld_wait();
-                if (ep.bias) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] += bias_s[c0 + i];
-                }
-                if (ep.relu) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
-                }
-                if (ep.out) {
-                    float* dst = ep.out + orow * ep.out_cs + ep.out_co + n0 + c0;
-                    if (ep.accumulate) {
-                        const float4 o0 = *reinterpret_cast<const float4*>(dst), o1 = *reinterpret_cast<const float4*>(dst + 4);
-                        v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;
-                    }
-                    *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
-                    *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
-                }
-                if (ep.out_bf16) {
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                    *reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ob_cs + ep.ob_co + n0 + c0) = pk;
-                }
-            }
-        } else {
-            // tile = 32 channels x 4 gates: columns [0,32) j, [32,64) i, [64,96) f, [96,128) o
-            const int ch0 = n_tile * 32;
-            for (int c0 = 0; c0 < 32; c0 += 8) {
-                float gj[8], gi[8], gf[8], go[8];
-                tc_ld8(trow + (uint32_t)(c0), gj);
-                tc_ld8(trow + (uint32_t)(32 + c0), gi);
-                tc_ld8(trow + (uint32_t)(64 + c0), gf);
-                tc_ld8(trow + (uint32_t)(96 + c0), go);
-                tc_ld_wait();
-                float cp[8], cn[8], hn[8];
-                if (ep.c_prev) {
-                    const float4 a = *reinterpret_cast<const float4*>(ep.c_prev + m * ep.C + ch0 + c0);
-                    const float4 b = *reinterpret_cast<const float4*>(ep.c_prev + m * ep.C + ch0 + c0 + 4);
-                    cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
-                } else {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) cp[i] = 0.f;
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float j = gj[i] + bias_s[c0 + i], ii = gi[i] + bias_s[32 + c0 + i];
-                    float f = gf[i] + bias_s[64 + c0 + i] + ep.forget_bias, o = go[i] + bias_s[96 + c0 + i];
-                    if (ep.accurate) { j = tanhf(j); ii = sigmoid_acc(ii); f = sigmoid_acc(f); o = sigmoid_acc(o); }
-                    else { j = tanh_fast(j); ii = sigmoid_fast(ii); f = sigmoid_fast(f); o = sigmoid_fast(o); }
-                    cn[i] = cp[i] * f + ii * j;
-                    hn[i] = (ep.accurate ? tanhf(cn[i]) : tanh_fast(cn[i])) * o;
-                    gj[i] = j; gi[i] = ii; gf[i] = f; go[i] = o;
-                }
-                float* gp = ep.gates + m * (4 * ep.C) + n0 + c0;
-                *reinterpret_cast<float4*>(gp) = make_float4(gj[0], gj[1], gj[2], gj[3]);
-                *reinterpret_cast<float4*>(gp + 4) = make_float4(gj[4], gj[5], gj[6], gj[7]);
-                *reinterpret_cast<float4*>(gp + 32) = make_float4(gi[0], gi[1], gi[2], gi[3]);
-                *reinterpret_cast<float4*>(gp + 36) = make_float4(gi[4], gi[5], gi[6], gi[7]);
-                *reinterpret_cast<float4*>(gp + 64) = make_float4(gf[0], gf[1], gf[2], gf[3]);
-                *reinterpret_cast<float4*>(gp + 68) = make_float4(gf[4], gf[5], gf[6], gf[7]);
-                *reinterpret_cast<float4*>(gp + 96) = make_float4(go[0], go[1], go[2], go[3]);
-                *reinterpret_cast<float4*>(gp + 100) = make_float4(go[4], go[5], go[6], go[7]);
-                float* cdst = ep.c_out + m * ep.C + ch0 + c0;
-                *reinterpret_cast<float4*>(cdst) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                *reinterpret_cast<float4*>(cdst + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
-                float* hdst = ep.h_out + m * ep.h_cs + ep.h_co + ch0 + c0;
-                *reinterpret_cast<float4*>(hdst) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                *reinterpret_cast<float4*>(hdst + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
-                if (ep.h_bf16) {
-                    __nv_bfloat162 p0 = __floats2bfloat162_rn(hn[0], hn[1]), p1 = __floats2bfloat162_rn(hn[2], hn[3]);
-                    __nv_bfloat162 p2 = __floats2bfloat162_rn(hn[4], hn[5]), p3 = __floats2bfloat162_rn(hn[6], hn[7]);
-                    uint4 pk;
-                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
-                    *reinterpret_cast<uint4*>(ep.h_bf16 + m * ep.hb_cs + ep.hb_co + ch0 + c0) = pk;
-                }
-                if (ep.h_t) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) ep.h_t[(long)(ep.hT_co + ch0 + c0 + i) * ep.h_t_ld + m] = __float2bfloat16(hn[i]);
-                }
-            }
-        }
+        // output row of this A-grid pixel (identity for stride-1 convs, phase scatter for transposed convs)
+        const int hw = g.H * g.W;
+        const int bi = (int)(m / hw), rem = (int)(m - (long)bi * hw);
+        const int iy = rem / g.W, ix = rem - iy * g.W;
+        const long orow = ((long)bi * g.OH + iy * g.os + g.oa) * g.OW + ix * g.os + g.ob;
+        tc_epilogue_row(ep, trow, m, orow, n0, g.BN, n_tile, bias_s);
         tc_fence_before();
     }
     __syncthreads();
@@ -351,11 +239,20 @@ static int launch_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W,
     return check_launch(who);
 }
 
+// halo-patch variant (conv_tc_halo.cu): A operand staged once per 64-channel block instead of once per tap
+bool tc_halo_supported(int B, int H, int W, int Kc, int BN);
+void tc_halo_set_debug(long long* p);
+int launch_conv5x5_halo(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, const void* wt_bf16, int N, int BN, TcEpilogue ep,
+                        void* stream, const char* who);
+
 }  // namespace pivp
 
 using namespace pivp;
 
 extern "C" {
+
+/* Debugging aid: device buffer of [CTAs][8] long long that the halo kernel fills with clock64() stamps (null = off). */
+int pivp_tc_set_debug_buffer(void* p) { tc_halo_set_debug((long long*)p); return PIVP_OK; }
 
 int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream) {
     PIVP_REQUIRE(W && N > 0 && Cx > 0 && Kpad >= Cx && (w_fwd_bf16 || w_dgrad_bf16), "tc_prep_weights: bad argument");
@@ -394,6 +291,7 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
     ep.c_out = c_out; ep.h_out = h_out; ep.h_cs = h_cs; ep.h_co = h_co; ep.h_bf16 = (__nv_bfloat16*)h_bf16; ep.hb_cs = hb_cs; ep.hb_co = hb_co;
     ep.h_t = (__nv_bfloat16*)h_t; ep.h_t_ld = h_t_ld; ep.hT_co = hT_co;
     ep.C = C; ep.forget_bias = forget_bias; ep.accurate = accurate;
+    if (tc_halo_supported(B, H, W, Kc, BN)) return launch_conv5x5_halo(in_bf16, in_cs, B, H, W, Kc, wt_bf16, N, BN, ep, stream, "tc_conv5x5");
     return launch_conv_taps(in_bf16, in_cs, B, H, W, Kc, 25, dy, dx, co, wt_bf16, N, BN, ep, H, W, 1, 0, 0, stream, "tc_conv5x5");
 }
 

@@ -1,0 +1,349 @@
+// tcgen05 implicit-GEMM 5x5 "same" convolution with the A operand staged ONCE per 64-channel block as a halo patch in shared memory.
+//
+// Same GEMM and epilogues as conv_tc.cu (ConvLSTM forward with the fused gate epilogue, train_model.py:262-272; Convolution2D input
+// gradient), different operand movement.  conv_tc.cu fetches the 128-pixel A tile again for each of the 25 taps
+// (25 x 16 KB per 64 channels, all of it L2 -> SMEM traffic, which is what bounds that kernel).  Here a CTA owns an 8 x 16 pixel tile
+// and loads the (16+4) x (8+4 -> 16) pixel neighbourhood once (one 4-D TMA box {64 ch, 16, 20, 1} = 40 KB, zero-filled outside the
+// image = the convolution's padding).  With 128-byte rows (64 bf16 channels of one pixel) and the 128-byte swizzle, the A operand of
+// tap (dy, dx) is the SAME shared memory seen through a UMMA descriptor whose start address is moved by ((dy+2)*16 + (dx+2)) rows:
+// an 8-pixel tile row is exactly one 8-row swizzle atom, consecutive tile rows are one patch row (SBO = 16 * 128 B) apart, and the
+// swizzle is a function of the shared-memory address bits, so a row-shifted view stays consistent with what TMA wrote.
+// A traffic drops 25 x 16 KB -> 40 KB per (tile, 64 channels); the weight tiles stream through the ring as before.
+#include "tc_common.cuh"
+#include "tc_epilogue.cuh"
+#include <stdlib.h>
+
+namespace pivp {
+namespace halo {
+
+constexpr int TW = 8, TH = 16;                    // output pixels per CTA: 8 wide x 16 tall = 128 TMEM lanes
+constexpr int PW = 16, PH = TH + 4;               // patch: 16 x 20 pixels (x0-2 .. x0+13, y0-2 .. y0+17)
+constexpr int PATCH_BYTES = PW * PH * 128;        // 40960
+constexpr int GP = 132, CP = 36;                  // padded row pitches (floats) of the epilogue staging: gates 128 + 4, c / h 32 + 4
+constexpr int STG_FLOATS = 128 * (GP + 2 * CP);   // per pixel tile: 104448 bytes
+
+struct Geom {
+    int H, W, Kc, N, BN, stages, tmem_cols;
+    long long* dbg;                               // optional per-CTA clock64 stamps [grid][8] (pivp_tc_set_debug_buffer), else null
+};
+#define HALO_STAMP(i) do { if (g.dbg && lane == 0) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+
+// K-major SW128 descriptor with an explicit stride between 8-row groups.  The swizzle XOR is taken from the shared-memory ADDRESS
+// bits [7,10) (measured on B200: a start address moved by whole 128-byte rows needs no base-offset field; setting it breaks the result).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(sbo_bytes >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+__device__ __forceinline__ bool elect_one() {
+    uint32_t p;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}" : "=r"(p));
+    return p != 0;
+}
+// tcgen05.mma with the two 64-bit shared-memory descriptors given as (lo, hi) halves: lo carries the address, hi is loop-invariant
+__device__ __forceinline__ void tc_mma_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t a_hi, uint32_t b_hi, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n.reg .pred p;\n.reg .b64 da, db;\nsetp.ne.b32 p, %6, 0;\nmov.b64 da, {%1, %3};\nmov.b64 db, {%2, %4};\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n}"
+        ::"r"(tmem_d), "r"(a_lo), "r"(b_lo), "r"(a_hi), "r"(b_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// MS = pixel tiles (of 128) per CTA: each weight stage feeds 4*MS MMAs, i.e. MS*BN/4... cycles of tensor work per 128*BN bytes fetched.
+// One CTA per SM: all shared memory that the MS patches leave goes to the weight ring, deep enough to cover the L2 round trip.
+template <int MS>
+__global__ void __launch_bounds__(64 + 128 * MS, 1)
+conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Geom g, TcEpilogue ep) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* patch = smem;
+    uint8_t* bring = smem + MS * PATCH_BYTES;
+    const uint32_t b_bytes = (uint32_t)g.BN * 128;
+    uint64_t* bars = (uint64_t*)(bring + (size_t)g.stages * b_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + g.stages;
+    uint64_t* patch_full = bars + 2 * g.stages;
+    uint64_t* patch_empty = patch_full + 1;
+    uint64_t* accum_full = patch_full + 2;
+    uint32_t* tmem_slot = (uint32_t*)(patch_full + 3);
+    float* bias_s = (float*)(tmem_slot + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tile = blockIdx.y;
+    const int n0 = n_tile * g.BN;
+    const int ncb = g.Kc / 64;
+    const int tiles_x = g.W / TW, tiles_y = g.H / TH;
+    if (warp == 0) HALO_STAMP(0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
+        mbar_init(smem_u32(patch_full), 1);
+        mbar_init(smem_u32(patch_empty), 1);
+        mbar_init(smem_u32(accum_full), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_b) : "memory");
+    }
+    if (warp == 1) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    if (warp >= 2 && ep.bias) {
+        for (int i = threadIdx.x - 64; i < g.BN; i += 128 * MS) bias_s[i] = ep.bias[n0 + i];
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (warp == 1) HALO_STAMP(1);
+
+    // Producer and MMA issuer run warp-uniform loops (every operand derives from kernel parameters and loop counters, the TMEM
+    // base is broadcast with a shuffle) and one elected lane issues: otherwise the compiler cannot keep descriptors in uniform
+    // registers and wraps every tcgen05.mma in a per-lane waterfall loop -- ~20 issue slots per MMA, which is what bounded the
+    // per-tap kernel at ~25 % tensor-pipe utilisation (profiles/r01_ncu_halo_issue_bound.md).
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), ring0 = smem_u32(bring);
+        uint32_t st = 0, ph = 1;                                  // waits on `empty` start with parity 1 (fresh barrier)
+        for (int cb = 0; cb < ncb; ++cb) {
+            mbar_wait(smem_u32(patch_empty), (uint32_t)(cb & 1) ^ 1u);
+            if (elect_one()) {
+                mbar_expect_tx(smem_u32(patch_full), MS * PATCH_BYTES);
+#pragma unroll
+                for (int i = 0; i < MS; ++i) {
+                    const int mt = blockIdx.x * MS + i;
+                    const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
+                    tma_load_4d(smem_u32(patch + i * PATCH_BYTES), &map_a, smem_u32(patch_full), cb * 64, tx * TW - 2, ty * TH - 2, tb);
+                }
+            }
+            __syncwarp();
+            for (int tap = 0; tap < 25; ++tap) {
+                mbar_wait(empty0 + 8 * st, ph);
+                if (elect_one()) {
+                    mbar_expect_tx(full0 + 8 * st, b_bytes);
+                    tma_load_2d(ring0 + st * b_bytes, &map_b, full0 + 8 * st, tap * g.Kc + cb * 64, n0);
+                }
+                __syncwarp();
+                if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        // descriptor halves: lo = (addr >> 4) | LBO(1) << 16; hi = SBO >> 4 | version 1 (bit 46) | SWIZZLE_128B (bits 61-63)
+        const uint32_t hi_b = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t hi_a = ((uint32_t)(PW * 128) >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t ring_lo = ((smem_u32(bring) & 0x3FFFFu) >> 4) | 0x10000u, b_step = b_bytes >> 4;
+        const uint32_t patch_lo = ((smem_u32(patch) & 0x3FFFFu) >> 4) | 0x10000u;
+        const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+        uint32_t st = 0, ph = 0, b_lo = ring_lo;
+        for (int cb = 0; cb < ncb; ++cb) {
+            mbar_wait(smem_u32(patch_full), (uint32_t)(cb & 1));
+            if (cb == 0) HALO_STAMP(2);
+            for (int ky = 0; ky < 5; ++ky) {
+#pragma unroll
+                for (int kx = 0; kx < 5; ++kx) {
+                    mbar_wait(full0 + 8 * st, ph);
+                    tc_fence_after();
+                    if (elect_one()) {
+                        const uint32_t a_lo = patch_lo + (uint32_t)(ky * PW + kx) * 8u;      // one pixel row = 128 B = 8 descriptor units
+#pragma unroll
+                        for (int i = 0; i < MS; ++i)
+#pragma unroll
+                            for (int k = 0; k < 4; ++k)
+                                tc_mma_lohi(tmem_u + (uint32_t)(i * g.BN), a_lo + (uint32_t)(i * (PATCH_BYTES >> 4) + 2 * k), b_lo + 2 * k, hi_a, hi_b,
+                                            idesc, (k == 0) ? ((cb | ky | kx) ? 1u : 0u) : 1u);
+                        tc_commit(empty0 + 8 * st);
+                        if (ky == 4 && kx == 4) {
+                            tc_commit(smem_u32(patch_empty));
+                            if (cb == ncb - 1) tc_commit(smem_u32(accum_full));
+                        }
+                    }
+                    __syncwarp();
+                    b_lo += b_step;
+                    if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; b_lo = ring_lo; }
+                }
+            }
+        }
+        HALO_STAMP(3);
+    } else {
+        // ===================== epilogue: warps 2..5 -> tile 0, warps 6..9 -> tile 1 =====================
+        const int sub = (warp - 2) >> 2, q = warp & 3;      // q = TMEM lane quarter this warp may read
+        const int row = q * 32 + lane;
+        const int mt = blockIdx.x * MS + sub;
+        const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
+        const long m00 = ((long)tb * g.H + ty * TH) * g.W + tx * TW;                           // NHWC pixel index of accumulator row 0
+        const long m = m00 + (long)(row >> 3) * g.W + (row & 7);                               // ... and of this thread's row
+        const uint32_t trow = tmem_base + (uint32_t)(sub * g.BN) + ((uint32_t)(q * 32) << 16);
+        if (ep.mode == 1) {
+            // ---- ConvLSTM gate epilogue, staged: every thread owns one pixel row of the accumulator (that is how tcgen05.ld hands
+            // it out), but the outputs are pixel-major, so per-thread stores would scatter 16-byte pieces over 32 cache lines per
+            // instruction (measured: 25.8k of the CTA's 42k cycles).  The row results go to shared memory instead -- the operand
+            // ring is dead once accum_full fires -- and are written out with fully coalesced 128-bit stores.
+            const int ch0 = n_tile * 32;
+            float cp[32];
+            if (ep.c_prev) {                                 // issued before the accumulator wait: the main loop hides the latency
+                const float4* src = reinterpret_cast<const float4*>(ep.c_prev + m * ep.C + ch0);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float4 v = __ldg(src + i); cp[4 * i] = v.x; cp[4 * i + 1] = v.y; cp[4 * i + 2] = v.z; cp[4 * i + 3] = v.w; }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) cp[i] = 0.f;
+            }
+            mbar_wait(smem_u32(accum_full), 0);
+            tc_fence_after();
+            if (warp == 2) HALO_STAMP(4);
+            float* G = reinterpret_cast<float*>(smem) + (size_t)sub * STG_FLOATS;     // [128][GP] gates | [128][CP] c | [128][CP] h
+            float* Cc = G + 128 * GP;
+            float* Hh = Cc + 128 * CP;
+#pragma unroll
+            for (int c0 = 0; c0 < 32; c0 += 8) {
+                float gj[8], gi[8], gf[8], go[8], cn[8], hn[8];
+                tc_ld8(trow + (uint32_t)(c0), gj);
+                tc_ld8(trow + (uint32_t)(32 + c0), gi);
+                tc_ld8(trow + (uint32_t)(64 + c0), gf);
+                tc_ld8(trow + (uint32_t)(96 + c0), go);
+                tc_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float j = gj[i] + bias_s[c0 + i], ii = gi[i] + bias_s[32 + c0 + i];
+                    float f = gf[i] + bias_s[64 + c0 + i] + ep.forget_bias, o = go[i] + bias_s[96 + c0 + i];
+                    if (ep.accurate) { j = tanhf(j); ii = sigmoid_acc(ii); f = sigmoid_acc(f); o = sigmoid_acc(o); }
+                    else { j = tanh_fast(j); ii = sigmoid_fast(ii); f = sigmoid_fast(f); o = sigmoid_fast(o); }
+                    cn[i] = cp[c0 + i] * f + ii * j;
+                    hn[i] = (ep.accurate ? tanhf(cn[i]) : tanh_fast(cn[i])) * o;
+                    gj[i] = j; gi[i] = ii; gf[i] = f; go[i] = o;
+                }
+                float* gr = G + row * GP + c0;
+                *reinterpret_cast<float4*>(gr) = make_float4(gj[0], gj[1], gj[2], gj[3]);
+                *reinterpret_cast<float4*>(gr + 4) = make_float4(gj[4], gj[5], gj[6], gj[7]);
+                *reinterpret_cast<float4*>(gr + 32) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+                *reinterpret_cast<float4*>(gr + 36) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+                *reinterpret_cast<float4*>(gr + 64) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+                *reinterpret_cast<float4*>(gr + 68) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+                *reinterpret_cast<float4*>(gr + 96) = make_float4(go[0], go[1], go[2], go[3]);
+                *reinterpret_cast<float4*>(gr + 100) = make_float4(go[4], go[5], go[6], go[7]);
+                *reinterpret_cast<float4*>(Cc + row * CP + c0) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+                *reinterpret_cast<float4*>(Cc + row * CP + c0 + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+                *reinterpret_cast<float4*>(Hh + row * CP + c0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
+                *reinterpret_cast<float4*>(Hh + row * CP + c0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
+            }
+            asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");          // the four warps of this pixel tile
+            const int lw = (warp - 2) & 3;
+            // gates: one 512-byte row per warp instruction
+            for (int r = lw; r < 128; r += 4) {
+                const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
+                const float4 v = *reinterpret_cast<const float4*>(G + r * GP + 4 * lane);
+                *reinterpret_cast<float4*>(ep.gates + mr * (4 * ep.C) + n0 + 4 * lane) = v;
+            }
+            // c, h (fp32) and the bf16 shadow of h: 8 lanes per 128-byte row, four rows per warp instruction
+            const int sub_r = lane >> 3, l8 = lane & 7;
+            for (int r0 = lw * 4; r0 < 128; r0 += 16) {
+                const int r = r0 + sub_r;
+                const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
+                const float4 cv = *reinterpret_cast<const float4*>(Cc + r * CP + 4 * l8);
+                const float4 hv = *reinterpret_cast<const float4*>(Hh + r * CP + 4 * l8);
+                *reinterpret_cast<float4*>(ep.c_out + mr * ep.C + ch0 + 4 * l8) = cv;
+                *reinterpret_cast<float4*>(ep.h_out + mr * ep.h_cs + ep.h_co + ch0 + 4 * l8) = hv;
+                if (ep.h_bf16) {
+                    __nv_bfloat162 p0 = __floats2bfloat162_rn(hv.x, hv.y), p1 = __floats2bfloat162_rn(hv.z, hv.w);
+                    uint2 pk;
+                    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                    *reinterpret_cast<uint2*>(ep.h_bf16 + mr * ep.hb_cs + ep.hb_co + ch0 + 4 * l8) = pk;
+                }
+                if (ep.h_t) {
+                    const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) ep.h_t[(long)(ep.hT_co + ch0 + 4 * l8 + i) * ep.h_t_ld + mr] = __float2bfloat16(hh[i]);
+                }
+            }
+        } else {
+            mbar_wait(smem_u32(accum_full), 0);
+            tc_fence_after();
+            if (warp == 2) HALO_STAMP(4);
+            tc_epilogue_row(ep, trow, m, m, n0, g.BN, n_tile, bias_s);
+        }
+        tc_fence_before();
+        if (warp == 2) HALO_STAMP(5);
+    }
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+    }
+}
+
+template <int MS>
+static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g, const TcEpilogue& ep, int tiles, void* stream, const char* who) {
+    const int b_bytes = g.BN * 128;
+    int stages = (225 * 1024 - MS * PATCH_BYTES) / b_bytes;     // one CTA per SM, the ring takes what the patches leave
+    if (stages > 12) stages = 12;
+    g.stages = stages;
+    const int cols = MS * g.BN;
+    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    const size_t smem = 1024 + (size_t)MS * PATCH_BYTES + (size_t)stages * b_bytes + (2 * stages + 3) * 8 + 16 + (size_t)g.BN * 4;
+    PIVP_REQUIRE(ep.mode != 1 || (size_t)MS * PATCH_BYTES + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4,
+                 "%s(halo): operand ring too small to stage the gate epilogue", who);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(conv5x5_halo_tc_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        if (e != cudaSuccess) { set_error("%s(halo): cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
+        attr_set = true;
+    }
+    dim3 grid((unsigned)(tiles / MS), (unsigned)(g.N / g.BN));
+    conv5x5_halo_tc_kernel<MS><<<grid, 64 + 128 * MS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
+    return check_launch(who);
+}
+
+}  // namespace halo
+
+static long long* g_halo_dbg = nullptr;          // set through pivp_tc_set_debug_buffer (scripts/dbg_halo_timeline.py)
+void tc_halo_set_debug(long long* p) { g_halo_dbg = p; }
+
+// PIVP_TC_HALO: 0 = use the per-tap kernel of conv_tc.cu, 1 = default, 3 = always one tile per CTA, 4 = always two (tuning switches)
+int tc_halo_mode() {
+    const char* v = getenv("PIVP_TC_HALO");
+    return v ? atoi(v) : 1;
+}
+
+bool tc_halo_supported(int B, int H, int W, int Kc, int BN) {
+    return tc_halo_mode() != 0 && W % halo::TW == 0 && H % halo::TH == 0 && Kc % 64 == 0 && BN % 16 == 0 && BN >= 16 && BN <= 256 && B > 0;
+}
+
+int launch_conv5x5_halo(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, const void* wt_bf16, int N, int BN, TcEpilogue ep,
+                        void* stream, const char* who) {
+    using namespace halo;
+    PIVP_REQUIRE(in_bf16 && wt_bf16 && in_cs % 8 == 0 && N % BN == 0, "%s(halo): bad operand", who);
+    Geom g;
+    g.H = H; g.W = W; g.Kc = Kc; g.N = N; g.BN = BN;
+    g.dbg = g_halo_dbg;
+    CUtensorMap map_a, map_b;
+    {
+        cuuint64_t dims[4] = {(cuuint64_t)in_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+        cuuint64_t str[3] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, (cuuint64_t)H * W * in_cs * 2};
+        cuuint32_t box[4] = {64u, (cuuint32_t)PW, (cuuint32_t)PH, 1u};
+        CUresult r = encode_tmap(&map_a, in_bf16, 4, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("%s(halo): cuTensorMapEncodeTiled(A) failed (%d)", who, (int)r); return PIVP_ECUDA; }
+    }
+    {
+        cuuint64_t dims[2] = {(cuuint64_t)25 * Kc, (cuuint64_t)N};
+        cuuint64_t str[1] = {(cuuint64_t)25 * Kc * 2};
+        cuuint32_t box[2] = {64u, (cuuint32_t)BN};
+        CUresult r = encode_tmap(&map_b, wt_bf16, 2, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("%s(halo): cuTensorMapEncodeTiled(B) failed (%d)", who, (int)r); return PIVP_ECUDA; }
+    }
+    const int tiles = B * (H / TH) * (W / TW);
+    // two pixel tiles per CTA halve the weight traffic per FLOP; only worth it while the grid still covers most of the SMs
+    const int force = tc_halo_mode();
+    const bool two = (force == 3) ? false : (tiles % 2 == 0 && 2 * BN <= 512 && ((tiles / 2) * (N / BN) >= 96 || force == 4));
+    return two ? launch_ms<2>(map_a, map_b, g, ep, tiles, stream, who) : launch_ms<1>(map_a, map_b, g, ep, tiles, stream, who);
+}
+
+}  // namespace pivp
