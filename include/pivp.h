@@ -107,6 +107,15 @@ int pivp_sched_select(const float* gt, const float* gen, const int* take, float*
 int pivp_adam_step(float* p, const float* g, float* m, float* v, long n, int* step, float alpha, float beta1, float beta2, float eps,
                    float gscale, void* stream);
 
+/* ---- the two 1x1 "head" deconvolutions on enc6 (train_model.py:288/364/429 + 527, applied at :315/:388/:454 and :719) fused:
+ * x = NHWC rows of 64 channels, W = [NH][64] (enc7 rows, then mask rows), outputs / output gradients as NCHW planes
+ * out_a (B,Na,H,W) | out_b (B,NH-Na,H,W).  NH in {14, 27}; anything else returns PIVP_EUNSUPPORTED (use pivp_conv2d_*).
+ * backward: dx overwritten, dW [NH][64] and db [NH] accumulated into. */
+int pivp_heads_fwd(const float* x, int x_cs, int x_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
+                   int B, int HW, void* stream);
+int pivp_heads_bwd(const float* x, int x_cs, int x_co, const float* W, const float* dy_a, int Na, const float* dy_b, int NH,
+                   float* dx, int dx_cs, int dx_co, float* dW, float* db, int B, int HW, void* stream);
+
 /* ---- fused transform + mask softmax + composite (train_model.py:315-349 / 388-415 / 454-471 + 719-728) - */
 int pivp_cdna_fused_fwd(const float* prev, const float* enc7_pre, const float* mask_pre, const float* kern_raw, float* out,
                         int B, int H, int W, int num_masks, void* stream);

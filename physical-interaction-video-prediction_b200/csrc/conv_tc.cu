@@ -77,43 +77,52 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // Warp-uniform producer / issuer loops with one elected lane (see conv_tc_halo.cu: a `lane == 0` branch makes ptxas wrap every
+    // tcgen05.mma in a per-lane waterfall loop, ~20 issue slots per MMA).
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            // first pixel of this M tile: tiles walk x fastest, then y, then batch
-            const int tiles_x = g.W / g.TW, tiles_y = g.H / g.TH;
-            const int tx = m_tile % tiles_x, ty = (m_tile / tiles_x) % tiles_y, tb = m_tile / (tiles_x * tiles_y);
-            const int x0 = tx * g.TW, y0 = ty * g.TH, b0 = tb * g.TB;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % g.stages;
-                const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-                mbar_wait(smem_u32(empty + s), ph ^ 1u);
-                const int tap = kb / kblocks_per_tap, cb = kb - tap * kblocks_per_tap;
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
-                mbar_expect_tx(smem_u32(full + s), stage_bytes);
-                tma_load_4d(sa, &map_a, smem_u32(full + s), g.coff[tap] + cb * TC_BK, x0 + g.dx[tap], y0 + g.dy[tap], b0);
-                tma_load_2d(sb, &map_b, smem_u32(full + s), tap * g.Kc + cb * TC_BK, n0);
+        // first pixel of this M tile: tiles walk x fastest, then y, then batch
+        const int tiles_x = g.W / g.TW, tiles_y = g.H / g.TH;
+        const int tx = m_tile % tiles_x, ty = (m_tile / tiles_x) % tiles_y, tb = m_tile / (tiles_x * tiles_y);
+        const int x0 = tx * g.TW, y0 = ty * g.TH, b0 = tb * g.TB;
+        const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), ring0 = smem_u32(smem);
+        uint32_t st = 0, ph = 1;
+        for (int tap = 0; tap < g.ntaps; ++tap) {
+            const int cx = x0 + g.dx[tap], cy = y0 + g.dy[tap], cc = g.coff[tap];
+            for (int cb = 0; cb < kblocks_per_tap; ++cb) {
+                mbar_wait(empty0 + 8 * st, ph);
+                if (elect_one()) {
+                    const uint32_t sa = ring0 + st * stage_bytes;
+                    mbar_expect_tx(full0 + 8 * st, stage_bytes);
+                    tma_load_4d(sa, &map_a, full0 + 8 * st, cc + cb * TC_BK, cx, cy, b0);
+                    tma_load_2d(sa + a_bytes, &map_b, full0 + 8 * st, tap * g.Kc + cb * TC_BK, n0);
+                }
+                __syncwarp();
+                if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         // instruction descriptor: D=f32, A=B=bf16, both K-major, N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);           // SBO | version 1 | SWIZZLE_128B
+        const uint32_t ring_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | 0x10000u, step_lo = stage_bytes >> 4, a_lo_sz = a_bytes >> 4;
+        const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+        uint32_t st = 0, ph = 0, lo = ring_lo;
         for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % g.stages;
-            const uint32_t ph = (uint32_t)(kb / g.stages) & 1u;
-            mbar_wait(smem_u32(full + s), ph);
+            mbar_wait(full0 + 8 * st, ph);
             tc_fence_after();
-            if (lane == 0) {
-                const uint32_t sa = smem_u32(smem + (size_t)s * stage_bytes), sb = sa + a_bytes;
-                const uint64_t ad = make_kmajor_sw128_desc(sa), bd = make_kmajor_sw128_desc(sb);
+            if (elect_one()) {
 #pragma unroll
                 for (int k = 0; k < TC_BK / 16; ++k)      // advance 16 bf16 = 32 B = 2 (>>4 units) inside the swizzle span
-                    tc_mma_bf16(tmem_base, ad + (uint64_t)(2 * k), bd + (uint64_t)(2 * k), idesc, (kb | k) ? 1u : 0u);
-                tc_commit(smem_u32(empty + s));           // frees the smem slot when these MMAs retire
+                    tc_mma_lohi(tmem_u, lo + 2 * k, lo + a_lo_sz + 2 * k, hi, hi, idesc, (k == 0) ? (kb ? 1u : 0u) : 1u);
+                tc_commit(empty0 + 8 * st);               // frees the smem slot when these MMAs retire
                 if (kb == num_kb - 1) tc_commit(smem_u32(accum_full));
             }
             __syncwarp();
+            lo += step_lo;
+            if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; lo = ring_lo; }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================

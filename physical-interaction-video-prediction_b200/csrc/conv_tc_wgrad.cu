@@ -85,63 +85,71 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // warp-uniform producer / issuer loops, one elected lane (see conv_tc_halo.cu)
     if (warp == 0) {
-        if (lane == 0) {
-            const int hw = g.H * g.W;
-            uint32_t ai = 0, bi = 0;
-            for (int kb = kb0; kb < kb1; ++kb) {
-                const uint32_t sa = ai % WG_ASTAGES;
-                mbar_wait(smem_u32(a_empty + sa), ((ai / WG_ASTAGES) & 1u) ^ 1u);
-                mbar_expect_tx(smem_u32(a_full + sa), a_bytes);
-                const uint32_t adst = smem_u32(smem_a + sa * a_bytes);
-                tma_load_2d(adst, &map_a, smem_u32(a_full + sa), n0, kb * 64);
-                tma_load_2d(adst + chunk_bytes, &map_a, smem_u32(a_full + sa), n0 + 64, kb * 64);
-                ++ai;
-                const long p = (long)kb * 64;
-                const int bimg = (int)(p / hw), rem = (int)(p - (long)bimg * hw);
-                const int y0 = rem / g.W, x0 = rem - y0 * g.W;
-                for (int tl = 0; tl < ntaps; ++tl) {
-                    const int tap = tap0 + tl;
-                    const uint32_t sb = bi % (uint32_t)g.b_stages;
-                    mbar_wait(smem_u32(b_empty + sb), ((bi / (uint32_t)g.b_stages) & 1u) ^ 1u);
-                    mbar_expect_tx(smem_u32(b_full + sb), b_bytes);
-                    const uint32_t bdst = smem_u32(smem_b + (size_t)sb * b_bytes);
+        const int hw = g.H * g.W;
+        const uint32_t afull0 = smem_u32(a_full), aempty0 = smem_u32(a_empty), bfull0 = smem_u32(b_full), bempty0 = smem_u32(b_empty);
+        uint32_t sa = 0, pa = 1, sb = 0, pb = 1;
+        for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(aempty0 + 8 * sa, pa);
+            if (elect_one()) {
+                mbar_expect_tx(afull0 + 8 * sa, a_bytes);
+                const uint32_t adst = smem_u32(smem_a) + sa * a_bytes;
+                tma_load_2d(adst, &map_a, afull0 + 8 * sa, n0, kb * 64);
+                tma_load_2d(adst + chunk_bytes, &map_a, afull0 + 8 * sa, n0 + 64, kb * 64);
+            }
+            __syncwarp();
+            if (++sa == WG_ASTAGES) { sa = 0; pa ^= 1u; }
+            const long p = (long)kb * 64;
+            const int bimg = (int)(p / hw), rem = (int)(p - (long)bimg * hw);
+            const int y0 = rem / g.W, x0 = rem - y0 * g.W;
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const int tap = tap0 + tl;
+                mbar_wait(bempty0 + 8 * sb, pb);
+                if (elect_one()) {
+                    mbar_expect_tx(bfull0 + 8 * sb, b_bytes);
+                    const uint32_t bdst = smem_u32(smem_b) + sb * b_bytes;
                     for (int ch = 0; ch < g.chunks; ++ch)
-                        tma_load_4d(bdst + ch * chunk_bytes, &map_b, smem_u32(b_full + sb), g.coff[tap] + ch * 64, x0 + g.dx[tap], y0 + g.dy[tap], bimg);
-                    ++bi;
+                        tma_load_4d(bdst + ch * chunk_bytes, &map_b, bfull0 + 8 * sb, g.coff[tap] + ch * 64, x0 + g.dx[tap], y0 + g.dy[tap], bimg);
                 }
+                __syncwarp();
+                if (++sb == (uint32_t)g.b_stages) { sb = 0; pb ^= 1u; }
             }
         }
     } else if (warp == 1) {
         // D=f32, A=B=bf16, BOTH MN-major (bits 15, 16), N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(g.Cx >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
-        uint32_t ai = 0, bi = 0;
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
+        // MN-major SW128 descriptor halves: lo = addr >> 4 | (LBO = 8192 B between 64-element MN chunks) >> 4 << 16; hi = SBO 1024 | v1 | SW128
+        const uint32_t hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+        const uint32_t lbo = ((chunk_bytes >> 4) & 0x3FFFu) << 16;
+        const uint32_t a_lo0 = ((smem_u32(smem_a) & 0x3FFFFu) >> 4) | lbo, b_lo0 = ((smem_u32(smem_b) & 0x3FFFFu) >> 4) | lbo;
+        const uint32_t a_step = a_bytes >> 4, b_step = b_bytes >> 4;
+        const uint32_t afull0 = smem_u32(a_full), aempty0 = smem_u32(a_empty), bfull0 = smem_u32(b_full), bempty0 = smem_u32(b_empty);
+        uint32_t sa = 0, pa = 0, sb = 0, pb = 0, a_lo = a_lo0, b_lo = b_lo0;
         for (int kb = kb0; kb < kb1; ++kb) {
-            const uint32_t sa = ai % WG_ASTAGES;
-            mbar_wait(smem_u32(a_full + sa), (ai / WG_ASTAGES) & 1u);
-            const uint32_t abase = smem_u32(smem_a + sa * a_bytes);
+            mbar_wait(afull0 + 8 * sa, pa);
+            const uint32_t acc0 = kb > kb0 ? 1u : 0u;
             for (int tl = 0; tl < ntaps; ++tl) {
-                const uint32_t sb = bi % (uint32_t)g.b_stages;
-                mbar_wait(smem_u32(b_full + sb), (bi / (uint32_t)g.b_stages) & 1u);
+                mbar_wait(bfull0 + 8 * sb, pb);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t bbase = smem_u32(smem_b + (size_t)sb * b_bytes);
+                if (elect_one()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k)        // 16 pixels (K) = 16 rows x 128 B = 2048 B per MMA
-                        tc_mma_bf16(tmem_base + (uint32_t)(tl * g.Cx), make_mnmajor_sw128_desc(abase + k * 2048, chunk_bytes),
-                                    make_mnmajor_sw128_desc(bbase + k * 2048, chunk_bytes), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-                    tc_commit(smem_u32(b_empty + sb));
+                        tc_mma_lohi(tmem_u + (uint32_t)(tl * g.Cx), a_lo + 128 * k, b_lo + 128 * k, hi, hi, idesc, (k == 0) ? acc0 : 1u);
+                    tc_commit(bempty0 + 8 * sb);
+                    if (tl == ntaps - 1) {
+                        tc_commit(aempty0 + 8 * sa);
+                        if (kb == kb1 - 1) tc_commit(smem_u32(accum_full));
+                    }
                 }
                 __syncwarp();
-                ++bi;
+                b_lo += b_step;
+                if (++sb == (uint32_t)g.b_stages) { sb = 0; pb ^= 1u; b_lo = b_lo0; }
             }
-            if (lane == 0) {
-                tc_commit(smem_u32(a_empty + sa));
-                if (kb == kb1 - 1) tc_commit(smem_u32(accum_full));
-            }
-            __syncwarp();
-            ++ai;
+            a_lo += a_step;
+            if (++sa == WG_ASTAGES) { sa = 0; pa ^= 1u; a_lo = a_lo0; }
         }
     } else {
         const int q = warp & 3;

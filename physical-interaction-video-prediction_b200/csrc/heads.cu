@@ -1,0 +1,229 @@
+// The two 1x1 "head" deconvolutions on enc6 (train_model.py:288/364/429 enc7 and :527 masks, applied at :315/:388/:454 and :719)
+// as ONE bandwidth-bound kernel each way.  enc6 is the widest activation of the model (B*H*W x 64 fp32 = 33.5 MB at b32); the generic
+// path read it three times per time step (forward, weight gradient, input gradient) through implicit-GEMM tiles sized for real
+// convolutions and moved the 14 output planes through two extra NHWC<->NCHW transposes.
+//
+//   forward : [enc7_pre | mask_pre] (NCHW planes) = e6 (NHWC rows) . W^T + b          reads 256 B, writes 4*NH B per pixel
+//   backward: d_e6 = dY . W ; dW += dY^T . e6 ; db += sum dY                          reads 256 + 4*NH B, writes 256 B per pixel
+//
+// CTA tile = 128 pixels staged in shared memory with coalesced 128-bit accesses (row pitch 68 floats: conflict-free for one
+// row per thread).  Arithmetic is packed fp32 (FFMA2).  NH (heads: 3+11 for CDNA/STP with 10 masks, 25+2 for DNA) is a template
+// parameter so every accumulator stays in a register.
+#include "common.cuh"
+
+namespace pivp {
+namespace hd {
+
+constexpr int TP = 128;              // pixels per tile = threads per CTA
+constexpr int C = 64;                // enc6 channels
+constexpr int XP = 68;               // smem row pitch of the pixel tile (floats)
+
+__device__ __forceinline__ unsigned long long pk2(float2 a) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a.x), "f"(a.y));
+    return r;
+}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a)), "l"(pk2(b)), "l"(pk2(c)));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(r));
+    return d;
+}
+
+// coalesced copy of a 128-pixel x 64-channel tile between global rows (stride cs, offset co) and shared memory
+__device__ __forceinline__ void load_tile(const float* __restrict__ x, int cs, int co, long m0, long M, float* xs) {
+    for (int i = threadIdx.x; i < TP * (C / 4); i += TP) {
+        const int r = i >> 4, c4 = i & 15;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m0 + r < M) v = __ldg(reinterpret_cast<const float4*>(x + (m0 + r) * cs + co) + c4);
+        *reinterpret_cast<float4*>(xs + r * XP + 4 * c4) = v;
+    }
+}
+
+template <int NH>
+__global__ void __launch_bounds__(TP) heads_fwd_kernel(const float* __restrict__ x, int cs, int co, const float* __restrict__ Wt,
+                                                       const float* __restrict__ bias, float* __restrict__ out_a, int Na,
+                                                       float* __restrict__ out_b, long M, int HW) {
+    constexpr int NP = (NH + 3) / 4 * 4;                         // padded to float4
+    __shared__ __align__(16) float xs[TP * XP];
+    __shared__ __align__(16) float wt[C * NP];                   // W transposed: wt[c][n]
+    for (int i = threadIdx.x; i < C * NP; i += TP) {
+        const int c = i / NP, n = i - c * NP;
+        wt[i] = n < NH ? __ldg(Wt + n * C + c) : 0.f;
+    }
+    const long m0 = (long)blockIdx.x * TP;
+    load_tile(x, cs, co, m0, M, xs);
+    __syncthreads();
+    float2 acc[NP / 2];
+#pragma unroll
+    for (int j = 0; j < NP / 2; ++j) acc[j] = make_float2(2 * j < NH ? __ldg(bias + 2 * j) : 0.f, 2 * j + 1 < NH ? __ldg(bias + 2 * j + 1) : 0.f);
+    const float* xr = xs + threadIdx.x * XP;
+#pragma unroll 4
+    for (int c4 = 0; c4 < C / 4; ++c4) {
+        const float4 xv = *reinterpret_cast<const float4*>(xr + 4 * c4);
+        const float xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float4* wr = reinterpret_cast<const float4*>(wt + (4 * c4 + k) * NP);
+#pragma unroll
+            for (int j = 0; j < NP / 4; ++j) {
+                const float4 w4 = wr[j];
+                acc[2 * j] = ffma2(make_float2(xa[k], xa[k]), make_float2(w4.x, w4.y), acc[2 * j]);
+                acc[2 * j + 1] = ffma2(make_float2(xa[k], xa[k]), make_float2(w4.z, w4.w), acc[2 * j + 1]);
+            }
+        }
+    }
+    const long m = m0 + threadIdx.x;
+    if (m >= M) return;
+    const long b = m / HW, p = m - b * HW;
+    const int Nb = NH - Na;
+#pragma unroll
+    for (int n = 0; n < NH; ++n) {
+        const float v = (n & 1) ? acc[n >> 1].y : acc[n >> 1].x;
+        if (n < Na) out_a[(b * Na + n) * HW + p] = v;
+        else out_b[(b * Nb + (n - Na)) * HW + p] = v;
+    }
+}
+
+// Persistent: CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; dW / db partials live in registers across tiles.
+template <int NH>
+__global__ void __launch_bounds__(TP) heads_bwd_kernel(const float* __restrict__ x, int cs, int co, const float* __restrict__ Wt,
+                                                       const float* __restrict__ dy_a, int Na, const float* __restrict__ dy_b,
+                                                       float* __restrict__ dx, int dcs, int dco, float* __restrict__ dW,
+                                                       float* __restrict__ db, long M, int HW, int ntiles) {
+    constexpr int NP = (NH + 3) / 4 * 4, NH2 = (NH + 1) / 2;     // NH2 heads per thread half
+    extern __shared__ __align__(16) float hsm[];
+    float* xs = hsm;                                             // [TP][XP] pixel tile
+    float* ds = xs + TP * XP;                                    // [TP][NP] dY tile [pixel][n]
+    float* ws = ds + TP * NP;                                    // [NH][C]  W
+    for (int i = threadIdx.x; i < NH * C; i += TP) ws[i] = __ldg(Wt + i);
+    // weight-gradient ownership: 4 channels x NH2 heads (n = half, half + 2, ...) x one quarter of the tile's pixels
+    const int cg = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1, pq = threadIdx.x >> 5;
+    float4 aw[NH2];
+    float ab[NH2];
+#pragma unroll
+    for (int j = 0; j < NH2; ++j) { aw[j] = make_float4(0.f, 0.f, 0.f, 0.f); ab[j] = 0.f; }
+    const int Nb = NH - Na;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long m0 = (long)tile * TP;
+        __syncthreads();                                          // previous tile's readers are done
+        load_tile(x, cs, co, m0, M, xs);
+        {
+            const long m = m0 + threadIdx.x;
+            const long b = m / HW, p = m - b * HW;
+#pragma unroll
+            for (int n = 0; n < NP; ++n) {
+                float v = 0.f;
+                if (m < M && n < NH) v = n < Na ? __ldg(dy_a + (b * Na + n) * HW + p) : __ldg(dy_b + (b * Nb + (n - Na)) * HW + p);
+                ds[threadIdx.x * NP + n] = v;
+            }
+        }
+        __syncthreads();
+        // ---- dW[n][c] += sum_p dY[p][n] x[p][c]   (this thread: 32 pixels, 4 channels, NH2 heads)
+#pragma unroll 4
+        for (int i = 0; i < TP / 4; ++i) {
+            const int p = pq * (TP / 4) + i;
+            const float4 xv = *reinterpret_cast<const float4*>(xs + p * XP + 4 * cg);
+#pragma unroll
+            for (int j = 0; j < NH2; ++j) {
+                const int n = half + 2 * j;
+                const float d = n < NH ? ds[p * NP + n] : 0.f;
+                aw[j].x = fmaf(d, xv.x, aw[j].x); aw[j].y = fmaf(d, xv.y, aw[j].y);
+                aw[j].z = fmaf(d, xv.z, aw[j].z); aw[j].w = fmaf(d, xv.w, aw[j].w);
+                if (cg == 0) ab[j] += d;
+            }
+        }
+        // ---- d_x[c] = sum_n dY[n] W[n][c] for this thread's pixel
+        float2 acc[C / 2];
+#pragma unroll
+        for (int j = 0; j < C / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NH; ++n) {
+            const float d = ds[threadIdx.x * NP + n];
+            const float4* wr = reinterpret_cast<const float4*>(ws + n * C);
+#pragma unroll
+            for (int j = 0; j < C / 4; ++j) {
+                const float4 w4 = wr[j];
+                acc[2 * j] = ffma2(make_float2(d, d), make_float2(w4.x, w4.y), acc[2 * j]);
+                acc[2 * j + 1] = ffma2(make_float2(d, d), make_float2(w4.z, w4.w), acc[2 * j + 1]);
+            }
+        }
+        __syncthreads();                                          // everyone has finished reading the x tile
+        float* xr = xs + threadIdx.x * XP;
+#pragma unroll
+        for (int j = 0; j < C / 4; ++j) *reinterpret_cast<float4*>(xr + 4 * j) = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
+        __syncthreads();
+        for (int i = threadIdx.x; i < TP * (C / 4); i += TP) {
+            const int r = i >> 4, c4 = i & 15;
+            if (m0 + r < M) *(reinterpret_cast<float4*>(dx + (m0 + r) * dcs + dco) + c4) = *reinterpret_cast<const float4*>(xs + r * XP + 4 * c4);
+        }
+    }
+    // ---- reduce the four pixel-quarter partials of dW / db inside the CTA, then one atomic per element
+    __syncthreads();
+    float* red = xs;                                              // [4][NH2*2][64 + 1]
+    constexpr int RP = C + 1;
+#pragma unroll
+    for (int j = 0; j < NH2; ++j) {
+        float* r = red + ((pq * NH2 * 2) + (half + 2 * j)) * RP + 4 * cg;
+        r[0] = aw[j].x; r[1] = aw[j].y; r[2] = aw[j].z; r[3] = aw[j].w;
+        if (cg == 0) red[((pq * NH2 * 2) + (half + 2 * j)) * RP + C] = ab[j];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < NH * RP; i += TP) {
+        const int n = i / RP, c = i - n * RP;
+        const float v = red[(0 * NH2 * 2 + n) * RP + c] + red[(1 * NH2 * 2 + n) * RP + c] + red[(2 * NH2 * 2 + n) * RP + c] +
+                        red[(3 * NH2 * 2 + n) * RP + c];
+        if (c < C) atomicAdd(dW + n * C + c, v);
+        else atomicAdd(db + n, v);
+    }
+}
+
+static_assert(4 * ((27 + 1) / 2) * 2 * (C + 1) <= TP * XP, "weight-gradient reduction scratch must fit in the pixel tile");
+
+static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace hd
+}  // namespace pivp
+
+using namespace pivp;
+
+extern "C" {
+
+/* x: NHWC rows (stride x_cs, offset x_co, 64 channels); W: [NH][64] (enc7 rows then mask rows, the internal "head" layout);
+ * out_a (B,Na,H,W) and out_b (B,NH-Na,H,W) NCHW planes.  NH in {14, 27}; other head counts -> PIVP_EUNSUPPORTED (use the conv path). */
+int pivp_heads_fwd(const float* x, int x_cs, int x_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
+                   int B, int HW, void* stream) {
+    PIVP_REQUIRE(x && W && bias && out_a && out_b && B > 0 && HW > 0 && Na > 0 && Na < NH, "heads_fwd: bad argument");
+    PIVP_REQUIRE(hd::a16(x) && x_cs % 4 == 0 && x_co % 4 == 0, "heads_fwd: rows must be 16-byte aligned");
+    const long M = (long)B * HW;
+    const unsigned grid = (unsigned)((M + hd::TP - 1) / hd::TP);
+    if (NH == 14) hd::heads_fwd_kernel<14><<<grid, hd::TP, 0, (cudaStream_t)stream>>>(x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
+    else if (NH == 27) hd::heads_fwd_kernel<27><<<grid, hd::TP, 0, (cudaStream_t)stream>>>(x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
+    else { set_error("heads_fwd: %d heads not instantiated (14 or 27)", NH); return PIVP_EUNSUPPORTED; }
+    return check_launch("heads_fwd");
+}
+
+/* dx is OVERWRITTEN; dW [NH][64] and db [NH] are ACCUMULATED into (atomics). */
+int pivp_heads_bwd(const float* x, int x_cs, int x_co, const float* W, const float* dy_a, int Na, const float* dy_b, int NH,
+                   float* dx, int dx_cs, int dx_co, float* dW, float* db, int B, int HW, void* stream) {
+    PIVP_REQUIRE(x && W && dy_a && dy_b && dx && dW && db && B > 0 && HW > 0 && Na > 0 && Na < NH, "heads_bwd: bad argument");
+    PIVP_REQUIRE(hd::a16(x) && hd::a16(dx) && x_cs % 4 == 0 && x_co % 4 == 0 && dx_cs % 4 == 0 && dx_co % 4 == 0, "heads_bwd: rows must be 16-byte aligned");
+    const long M = (long)B * HW;
+    const int ntiles = (int)((M + hd::TP - 1) / hd::TP);
+    int grid = 148 * 4;
+    if (grid > ntiles) grid = ntiles;
+    const size_t smem = sizeof(float) * ((size_t)hd::TP * hd::XP + (size_t)hd::TP * ((NH + 3) / 4 * 4) + (size_t)NH * hd::C);
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(hd::heads_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(hd::heads_bwd_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        attr_set = true;
+    }
+    if (NH == 14) hd::heads_bwd_kernel<14><<<grid, hd::TP, smem, (cudaStream_t)stream>>>(x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
+    else if (NH == 27) hd::heads_bwd_kernel<27><<<grid, hd::TP, smem, (cudaStream_t)stream>>>(x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
+    else { set_error("heads_bwd: %d heads not instantiated (14 or 27)", NH); return PIVP_EUNSUPPORTED; }
+    return check_launch("heads_bwd");
+}
+
+}  // extern "C"

@@ -368,10 +368,14 @@ class Engine(object):
             self._ln_fwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), B, HW[1], View(ws["e6"][t], 64, 0, 64), None, 1,
                          ws["ln_stats"]["norm_enc6"][t])
             # ---- heads (enc7 + masks 1x1), NCHW planes out
-            self._conv_fwd(View(ws["e6"][t], 64, 0, 64), B, H, W, p["model/enc7/W"], p["model/enc7/b"], self.Nh, 1, 1, 0,
-                           View(ws["head"][t], self.Nh, 0, self.Nh))
-            L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, 0, _ptr(ws["enc7_pre"][t]), B, self.Ne, HW[1], 0, s)
-            L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, self.Ne, _ptr(ws["mask_pre"][t]), B, self.M1, HW[1], 0, s)
+            if self.Nh in (14, 27):       # fused heads: e6 read once, planes written directly (heads.cu)
+                L.call("pivp_heads_fwd", _ptr(ws["e6"][t]), 64, 0, _ptr(p["model/enc7/W"]), _ptr(p["model/enc7/b"]),
+                       _ptr(ws["enc7_pre"][t]), self.Ne, _ptr(ws["mask_pre"][t]), self.Nh, B, HW[1], s)
+            else:
+                self._conv_fwd(View(ws["e6"][t], 64, 0, 64), B, H, W, p["model/enc7/W"], p["model/enc7/b"], self.Nh, 1, 1, 0,
+                               View(ws["head"][t], self.Nh, 0, self.Nh))
+                L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, 0, _ptr(ws["enc7_pre"][t]), B, self.Ne, HW[1], 0, s)
+                L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, self.Ne, _ptr(ws["mask_pre"][t]), B, self.M1, HW[1], 0, s)
             # ---- transform + masks + composite
             K5 = 128 * HW[8]
             if self.model_type == "CDNA":
@@ -461,11 +465,16 @@ class Engine(object):
                        _ptr(ws["d_hid5"]), K5, 0, _ptr(g["model/stp_input/W"]), _ptr(g["model/stp_input/b"]), B, K5, 100, s)
                 hid5_has_grad = True
             # ---- heads backward: planes -> NHWC, then 1x1 conv dgrad / wgrad
-            L.call("pivp_nchw_to_nhwc", _ptr(ws["d_enc7_pre"]), _ptr(ws["d_head"]), self.Nh, 0, B, self.Ne, HW[1], s)
-            L.call("pivp_nchw_to_nhwc", _ptr(ws["d_mask_pre"]), _ptr(ws["d_head"]), self.Nh, self.Ne, B, self.M1, HW[1], s)
-            dhead = View(ws["d_head"], self.Nh, 0, self.Nh)
-            self._conv_wgrad(View(ws["e6"][t], 64, 0, 64), B, H, W, dhead, H, W, 1, 1, 0, g["model/enc7/W"], g["model/enc7/b"])
-            self._conv_dgrad(dhead, B, H, W, p["model/enc7/W"], None, 1, 1, 0, View(ws["d_e6"], 64, 0, 64), H, W)
+            if self.Nh in (14, 27):
+                L.call("pivp_heads_bwd", _ptr(ws["e6"][t]), 64, 0, _ptr(p["model/enc7/W"]), _ptr(ws["d_enc7_pre"]), self.Ne,
+                       _ptr(ws["d_mask_pre"]), self.Nh, _ptr(ws["d_e6"]), 64, 0, _ptr(g["model/enc7/W"]), _ptr(g["model/enc7/b"]),
+                       B, HW[1], s)
+            else:
+                L.call("pivp_nchw_to_nhwc", _ptr(ws["d_enc7_pre"]), _ptr(ws["d_head"]), self.Nh, 0, B, self.Ne, HW[1], s)
+                L.call("pivp_nchw_to_nhwc", _ptr(ws["d_mask_pre"]), _ptr(ws["d_head"]), self.Nh, self.Ne, B, self.M1, HW[1], s)
+                dhead = View(ws["d_head"], self.Nh, 0, self.Nh)
+                self._conv_wgrad(View(ws["e6"][t], 64, 0, 64), B, H, W, dhead, H, W, 1, 1, 0, g["model/enc7/W"], g["model/enc7/b"])
+                self._conv_dgrad(dhead, B, H, W, p["model/enc7/W"], None, 1, 1, 0, View(ws["d_e6"], 64, 0, 64), H, W)
             # ---- norm_enc6 (+relu) and enc6 deconv
             self._ln_bwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), View(ws["d_e6"], 64, 0, 64), None, B, HW[1], 1,
                          ws["ln_stats"]["norm_enc6"][t], View(ws["d_e6pre"], 64, 0, 64))
