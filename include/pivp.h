@@ -166,6 +166,13 @@ int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int K
                       const void* wt_bf16, int N, int BN, const float* bias, int relu, int accumulate,
                       float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
                       int OH, int OW, int os, int oa, int ob, void* stream);
+/* Up to four tap lists in ONE launch (grid z = phase): the four output phases (oa[p], ob[p]) of a stride-2 Deconvolution2D
+ * (train_model.py:505-507) or of the input gradient of a stride-2 Convolution2D.  ntaps[p] <= 4; dy / dx / coff hold 4 slots per phase;
+ * wt_bf16[p] = bf16 weights [N][ntaps[p]*Kc] of phase p (host array of device pointers). */
+int pivp_tc_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int nph, const int* ntaps, const int* dy,
+                            const int* dx, const int* coff, const void* const* wt_bf16, int N, int BN, const float* bias, int relu,
+                            int accumulate, float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
+                            int OH, int OW, int os, const int* oa, const int* ob, void* stream);
 /* fp32 NHWC view -> bf16 copy; s2d=1 writes the space-to-depth layout the stride-2 layers contract over
  * (row = (b, y/2, x/2), channel = d_co + ((y&1)*2 + (x&1))*cblk + ch) */
 int pivp_cast_bf16(const float* src, int s_cs, int s_co, void* dst_bf16, int d_cs, int d_co, long M, int C, int H, int W, int s2d, int cblk,

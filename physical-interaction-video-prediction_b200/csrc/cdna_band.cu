@@ -582,28 +582,21 @@ __global__ void __launch_bounds__(W*(R / P), 2)
 }
 
 // d_kraw from the per-band partials: dkt = (dK - sum_t K_t dK_t) / s ; d_r = dkt * [r - eps > 0]   (D.1)
-__global__ void cdna_band_kern_bwd_kernel(const float* __restrict__ kraw, const float* __restrict__ dKp, float* __restrict__ d_kraw,
-                                          int B, int nbands) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over B*M kernels
+// One warp per (sample, kernel): lane = tap, so the band partials are read coalesced and the two 25-term sums are warp shuffles.
+__global__ void __launch_bounds__(128) cdna_band_kern_bwd_kernel(const float* __restrict__ kraw, const float* __restrict__ dKp,
+                                                                 float* __restrict__ d_kraw, int B, int nbands) {
+    const int i = blockIdx.x * 4 + (threadIdx.x >> 5), t = threadIdx.x & 31;       // i over B*M kernels
     if (i >= B * M) return;
     const int b = i / M, m = i - b * M;
-    float kt[25], dk[25], s = 0.f, dot = 0.f;
-#pragma unroll
-    for (int t = 0; t < 25; ++t) {
-        kt[t] = fmaxf(kraw[i * 25 + t] - RELU_SHIFT, 0.f) + RELU_SHIFT;
-        s += kt[t];
-        dk[t] = 0.f;
-    }
-    if (m < M - 1)
-        for (int band = 0; band < nbands; ++band) {
-            const float* src = dKp + ((size_t)(b * nbands + band)) * 225 + m * 25;
-#pragma unroll
-            for (int t = 0; t < 25; ++t) dk[t] += src[t];
-        }
-#pragma unroll
-    for (int t = 0; t < 25; ++t) dot = fmaf(kt[t] / s, dk[t], dot);
-#pragma unroll
-    for (int t = 0; t < 25; ++t) d_kraw[i * 25 + t] = (kraw[i * 25 + t] - RELU_SHIFT > 0.f) ? (dk[t] - dot) / s : 0.f;
+    const bool live = t < 25;
+    const float r = live ? kraw[i * 25 + t] : 0.f;
+    const float kt = live ? fmaxf(r - RELU_SHIFT, 0.f) + RELU_SHIFT : 0.f;
+    const float s = warp_sum(kt);
+    float dk = 0.f;
+    if (live && m < M - 1)
+        for (int band = 0; band < nbands; ++band) dk += dKp[((size_t)(b * nbands + band)) * 225 + m * 25 + t];
+    const float dot = warp_sum(kt / s * dk);
+    if (live) d_kraw[i * 25 + t] = (r - RELU_SHIFT > 0.f) ? (dk - dot) / s : 0.f;
 }
 
 template <typename K>
@@ -672,7 +665,7 @@ int cdna_band_bwd(const float* gout, const float* prev, const float* e_pre, cons
     if (int e = (P == 2 ? cb::launch_bwd<2>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)
                         : cb::launch_bwd<4>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)))
         return e;
-    cb::cdna_band_kern_bwd_kernel<<<(B * cb::M + 127) / 128, 128, 0, st>>>(kraw, dKp, d_kraw, B, H / cb::R);
+    cb::cdna_band_kern_bwd_kernel<<<(B * cb::M + 3) / 4, 128, 0, st>>>(kraw, dKp, d_kraw, B, H / cb::R);
     return check_launch("cdna_fused_bwd(kern)");
 }
 

@@ -41,8 +41,17 @@ struct TcGeom {
     int OH, OW, os, oa, ob;
 };
 
+// Up to four independent tap lists ("phases": the output phases of a stride-2 transposed convolution) share one launch:
+// blockIdx.z picks the weight tensor map and the geometry; the A tensor, tile counts and epilogue are common.
+constexpr int TC_MAXPH = 4;
+struct TcMapsB { CUtensorMap m[TC_MAXPH]; };
+struct TcGeomPack { TcGeom g[TC_MAXPH]; };
+
 __global__ void __launch_bounds__(TC_THREADS, 2)
-conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, TcGeom g, TcEpilogue ep) {
+conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ TcMapsB maps_b, const __grid_constant__ TcGeomPack gp,
+                    TcEpilogue ep) {
+    const TcGeom& g = gp.g[blockIdx.z];
+    const CUtensorMap& map_b = maps_b.m[blockIdx.z];
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][A 16 KB | B BN*128] then barriers
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -194,11 +203,16 @@ __global__ void gather_bf16_kernel(const float* __restrict__ src, const int* __r
     }
 }
 
-static int launch_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int ntaps, const int* dy, const int* dx, const int* coff,
-                            const void* wt_bf16, int N, int BN, TcEpilogue ep, int OH, int OW, int os, int oa, int ob, void* stream,
-                            const char* who) {
-    PIVP_REQUIRE(in_bf16 && wt_bf16, "%s: null operand", who);
-    PIVP_REQUIRE(ntaps >= 1 && ntaps <= TC_MAXTAPS, "%s: 1..25 taps", who);
+struct TapPhase {
+    int ntaps;
+    const int *dy, *dx, *coff;
+    const void* wt_bf16;
+    int oa, ob;
+};
+
+static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int nph, const TapPhase* ph, int N, int BN,
+                                  TcEpilogue ep, int OH, int OW, int os, void* stream, const char* who) {
+    PIVP_REQUIRE(in_bf16 && nph >= 1 && nph <= TC_MAXPH, "%s: null operand or bad phase count", who);
     PIVP_REQUIRE(Kc > 0 && Kc % TC_BK == 0 && in_cs % 8 == 0, "%s: Kc must be a multiple of 64 and rows 16-byte aligned", who);
     PIVP_REQUIRE(BN >= 16 && BN <= 256 && BN % 16 == 0 && N % BN == 0, "%s: BN must be a multiple of 16 <= 256 dividing N", who);
     int TW, TH, TB;
@@ -206,15 +220,15 @@ static int launch_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W,
         set_error("%s: cannot tile B=%d H=%d W=%d into 128-pixel boxes", who, B, H, W);
         return PIVP_EUNSUPPORTED;
     }
-    TcGeom g;
-    g.H = H; g.W = W; g.TW = TW; g.TH = TH; g.TB = TB; g.Kc = Kc; g.N = N; g.BN = BN; g.ntaps = ntaps;
-    for (int t = 0; t < ntaps; ++t) {
-        PIVP_REQUIRE(dy[t] >= -64 && dy[t] <= 64 && dx[t] >= -64 && dx[t] <= 64 && coff[t] >= 0 && coff[t] + Kc <= in_cs && coff[t] % 8 == 0,
-                     "%s: tap %d out of range", who, t);
-        g.dy[t] = (signed char)dy[t]; g.dx[t] = (signed char)dx[t]; g.coff[t] = (short)coff[t];
-    }
-    g.OH = OH; g.OW = OW; g.os = os; g.oa = oa; g.ob = ob;
-    CUtensorMap map_a, map_b;
+    const int stage_bytes = TC_BM * 128 + BN * 128;
+    int stages = (100 * 1024) / stage_bytes;
+    if (stages > 6) stages = 6;
+    if (stages < 2) stages = 2;
+    TcGeomPack gp;                                 // by-value kernel parameters
+    TcMapsB mb;
+    memset(&gp, 0, sizeof(gp));
+    memset(&mb, 0, sizeof(mb));
+    CUtensorMap map_a;
     {
         cuuint64_t dims[4] = {(cuuint64_t)in_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, (cuuint64_t)H * W * in_cs * 2};
@@ -222,19 +236,26 @@ static int launch_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W,
         CUresult r = encode_tmap(&map_a, in_bf16, 4, dims, str, box);
         if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(A) failed (%d)", who, (int)r); return PIVP_ECUDA; }
     }
-    {
-        cuuint64_t dims[2] = {(cuuint64_t)ntaps * Kc, (cuuint64_t)N};
-        cuuint64_t str[1] = {(cuuint64_t)ntaps * Kc * 2};
+    for (int p = 0; p < nph; ++p) {
+        const TapPhase& q = ph[p];
+        PIVP_REQUIRE(q.wt_bf16 && q.ntaps >= 1 && q.ntaps <= TC_MAXTAPS, "%s: phase %d: null weights or tap count outside 1..25", who, p);
+        TcGeom& g = gp.g[p];
+        g.H = H; g.W = W; g.TW = TW; g.TH = TH; g.TB = TB; g.Kc = Kc; g.N = N; g.BN = BN; g.ntaps = q.ntaps;
+        for (int t = 0; t < q.ntaps; ++t) {
+            PIVP_REQUIRE(q.dy[t] >= -64 && q.dy[t] <= 64 && q.dx[t] >= -64 && q.dx[t] <= 64 && q.coff[t] >= 0 && q.coff[t] + Kc <= in_cs &&
+                             q.coff[t] % 8 == 0,
+                         "%s: phase %d tap %d out of range", who, p, t);
+            g.dy[t] = (signed char)q.dy[t]; g.dx[t] = (signed char)q.dx[t]; g.coff[t] = (short)q.coff[t];
+        }
+        g.OH = OH; g.OW = OW; g.os = os; g.oa = q.oa; g.ob = q.ob;
+        g.stages = stages;
+        g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+        cuuint64_t dims[2] = {(cuuint64_t)q.ntaps * Kc, (cuuint64_t)N};
+        cuuint64_t str[1] = {(cuuint64_t)q.ntaps * Kc * 2};
         cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
-        CUresult r = encode_tmap(&map_b, wt_bf16, 2, dims, str, box);
-        if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B) failed (%d)", who, (int)r); return PIVP_ECUDA; }
+        CUresult r = encode_tmap(&mb.m[p], q.wt_bf16, 2, dims, str, box);
+        if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B%d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
     }
-    const int stage_bytes = TC_BM * 128 + BN * 128;
-    int stages = (100 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
-    if (stages < 2) stages = 2;
-    g.stages = stages;
-    g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
     const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)BN * 4;
     static bool attr_set = false;
     if (!attr_set) {
@@ -243,9 +264,17 @@ static int launch_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W,
         attr_set = true;
     }
     const long M = (long)B * H * W;
-    dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN));
-    conv_taps_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
+    dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN), (unsigned)nph);
+    conv_taps_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, mb, gp, ep);
     return check_launch(who);
+}
+
+static int launch_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int ntaps, const int* dy, const int* dx, const int* coff,
+                            const void* wt_bf16, int N, int BN, TcEpilogue ep, int OH, int OW, int os, int oa, int ob, void* stream,
+                            const char* who) {
+    PIVP_REQUIRE(in_bf16 && wt_bf16, "%s: null operand", who);
+    TapPhase ph{ntaps, dy, dx, coff, wt_bf16, oa, ob};
+    return launch_conv_taps_multi(in_bf16, in_cs, B, H, W, Kc, 1, &ph, N, BN, ep, OH, OW, os, stream, who);
 }
 
 // halo-patch variant (conv_tc_halo.cu): A operand staged once per 64-channel block instead of once per tap
@@ -321,6 +350,31 @@ int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int K
     ep.mode = 0; ep.bias = bias; ep.relu = relu; ep.accumulate = accumulate; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co;
     ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ob_cs = ob_cs; ep.ob_co = ob_co;
     return launch_conv_taps(in_bf16, in_cs, B, H, W, Kc, ntaps, dy, dx, coff, wt_bf16, N, BN, ep, OH, OW, os, oa, ob, stream, "tc_conv_taps");
+}
+
+/* Up to four tap lists in ONE launch (blockIdx.z = phase): the output phases (oa[p], ob[p]) of a stride-2 Deconvolution2D, or of the
+ * input gradient of a stride-2 Convolution2D.  ntaps[p] <= 4 taps per phase; dy / dx / coff hold 4 slots per phase; wt[p] = bf16
+ * weights [N][ntaps[p] * Kc] of phase p.  Everything else as pivp_tc_conv_taps. */
+int pivp_tc_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int nph, const int* ntaps, const int* dy,
+                            const int* dx, const int* coff, const void* const* wt_bf16, int N, int BN, const float* bias, int relu,
+                            int accumulate, float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
+                            int OH, int OW, int os, const int* oa, const int* ob, void* stream) {
+    PIVP_REQUIRE(ntaps && dy && dx && coff && wt_bf16 && oa && ob && nph >= 1 && nph <= TC_MAXPH, "tc_conv_taps_multi: null list or bad phase count");
+    PIVP_REQUIRE(out || out_bf16, "tc_conv_taps_multi: no output");
+    PIVP_REQUIRE((!out || (out_cs % 4 == 0 && out_co % 4 == 0)) && (!out_bf16 || (ob_cs % 8 == 0 && ob_co % 8 == 0)),
+                 "tc_conv_taps_multi: output views must be 16-byte aligned");
+    TapPhase ph[TC_MAXPH];
+    for (int p = 0; p < nph; ++p) {
+        PIVP_REQUIRE(ntaps[p] >= 1 && ntaps[p] <= 4, "tc_conv_taps_multi: 1..4 taps per phase");
+        PIVP_REQUIRE(os >= 1 && oa[p] >= 0 && ob[p] >= 0 && OH >= (H - 1) * os + oa[p] + 1 && OW >= (W - 1) * os + ob[p] + 1,
+                     "tc_conv_taps_multi: bad output mapping");
+        ph[p] = TapPhase{ntaps[p], dy + 4 * p, dx + 4 * p, coff + 4 * p, wt_bf16[p], oa[p], ob[p]};
+    }
+    TcEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.mode = 0; ep.bias = bias; ep.relu = relu; ep.accumulate = accumulate; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co;
+    ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ob_cs = ob_cs; ep.ob_co = ob_co;
+    return launch_conv_taps_multi(in_bf16, in_cs, B, H, W, Kc, nph, ph, N, BN, ep, OH, OW, os, stream, "tc_conv_taps_multi");
 }
 
 }  // extern "C"

@@ -128,9 +128,14 @@ class TensorCorePlan(object):
                                    co=arr([0] * len(taps)), idx=torch.from_numpy(idx.reshape(-1)).to(dev),
                                    wt=torch.empty(cout, len(taps) * kc, dtype=torch.bfloat16, device=dev)))
         bn = cout if cout <= 128 else 128
-        if (self.ws["Mr"][lv] // 128) * (cout // bn) < 64 and cout % 64 == 0:
+        if 4 * (self.ws["Mr"][lv] // 128) * (cout // bn) < 120 and cout % 64 == 0:      # the four phases share one launch
             bn = 64
-        return dict(cin=cin, cout=cout, kc=kc, lv=lv, phases=phases, bn=bn)
+        # flattened per-phase lists for pivp_tc_conv_taps_multi (4 slots per phase)
+        flat = lambda key: (ctypes.c_int * 16)(*[(list(ph[key]) + [0] * 4)[:4][i] for ph in phases for i in range(4)])
+        multi = dict(ntaps=(ctypes.c_int * 4)(*[ph["n"] for ph in phases]), dy=flat("dy"), dx=flat("dx"), co=flat("co"),
+                     wt=(ctypes.c_void_p * 4)(*[ph["wt"].data_ptr() for ph in phases]),
+                     oa=(ctypes.c_int * 4)(*[ph["a"] for ph in phases]), ob=(ctypes.c_int * 4)(*[ph["b"] for ph in phases]))
+        return dict(cin=cin, cout=cout, kc=kc, lv=lv, phases=phases, bn=bn, multi=multi)
 
     def refresh_weights(self):
         e = self.eng
@@ -173,10 +178,10 @@ class TensorCorePlan(object):
         optional bf16 copy (the next ConvLSTM's x slot): four tcgen05 launches, one per output phase."""
         e, d = self.eng, self.dec[name]
         h, w = e.H // d["lv"], e.W // d["lv"]
-        for ph in d["phases"]:
-            e.L.call("pivp_tc_conv_taps", _ptr(x_bf16), d["kc"], self.ws["B"], h, w, d["kc"], ph["n"], ph["dy"], ph["dx"], ph["co"],
-                     _ptr(ph["wt"]), d["cout"], d["bn"], _ptr(e.p[name + "/b"]) if bias else 0, relu, 0,
-                     _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, 2 * h, 2 * w, 2, ph["a"], ph["b"], e._s())
+        m = d["multi"]                       # the four output phases in one launch (grid z = phase)
+        e.L.call("pivp_tc_conv_taps_multi", _ptr(x_bf16), d["kc"], self.ws["B"], h, w, d["kc"], 4, m["ntaps"], m["dy"], m["dx"], m["co"],
+                 m["wt"], d["cout"], d["bn"], _ptr(e.p[name + "/b"]) if bias else 0, relu, 0,
+                 _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, 2 * h, 2 * w, 2, m["oa"], m["ob"], e._s())
 
     def xview(self, li, t):
         """bf16 x-slot of layer li at time t (what the producer of the layer input also writes)."""
