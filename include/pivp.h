@@ -95,6 +95,10 @@ int pivp_state_bwd(const float* dn_a, const float* dn_b, const float* sa, const 
 
 /* ---- L.Linear (train_model.py:289,321-322,430-431,457-466) -------------------------------------------- */
 int pivp_linear_fwd(const float* x, int xs, const float* W, const float* bias, float* y, int B, int K, int N, int relu, void* stream);
+/* split-K variant for wide inputs (the 8192 -> 250 kernel Linear, train_model.py:321-322): same result, caller-provided scratch */
+size_t pivp_linear_fwd_workspace_bytes(int B, int K, int N);
+int pivp_linear_fwd_splitk(const float* x, int xs, const float* W, const float* bias, float* y, int B, int K, int N, int relu,
+                           void* workspace, size_t ws_bytes, void* stream);
 int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, float* dx, int dxs, int accumulate_dx,
                     float* dW, float* db, int B, int K, int N, void* stream);
 

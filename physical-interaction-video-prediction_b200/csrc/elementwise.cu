@@ -372,6 +372,158 @@ __global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* 
     }
 }
 
+// ---- wide Linear (K a multiple of 4, batch <= 32, 16-byte aligned rows): the weight matrix is streamed exactly once per kernel.
+// All three keep 32 batch rows x one float4 of K per thread in registers.
+constexpr int LW_T = 128, LW_B = 32;
+
+// y partial: one WARP per (4 outputs n, K slice): lane l owns the float4 columns k = k0 + 4*(l + 32*i) and keeps 4 x 32 batch
+// accumulators; the 32 lane partials of each (n, b) are combined by a warp reduce-scatter (lane b ends with batch row b).
+// part[ks][b][n]; a second tiny kernel adds the slices, the bias and the ReLU.
+__device__ __forceinline__ float warp_reduce_scatter32(const float (&v)[LW_B], int lane) {
+    float a16[16], a8[8], a4[4], a2[2];
+    {
+        const bool hi = lane & 16;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) a16[k] = (hi ? v[k + 16] : v[k]) + __shfl_xor_sync(0xffffffffu, hi ? v[k] : v[k + 16], 16);
+    }
+    {
+        const bool hi = lane & 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) a8[k] = (hi ? a16[k + 8] : a16[k]) + __shfl_xor_sync(0xffffffffu, hi ? a16[k] : a16[k + 8], 8);
+    }
+    {
+        const bool hi = lane & 4;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) a4[k] = (hi ? a8[k + 4] : a8[k]) + __shfl_xor_sync(0xffffffffu, hi ? a8[k] : a8[k + 4], 4);
+    }
+    {
+        const bool hi = lane & 2;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) a2[k] = (hi ? a4[k + 2] : a4[k]) + __shfl_xor_sync(0xffffffffu, hi ? a4[k] : a4[k + 2], 2);
+    }
+    const bool hi = lane & 1;
+    return (hi ? a2[1] : a2[0]) + __shfl_xor_sync(0xffffffffu, hi ? a2[0] : a2[1], 1);      // lane l holds element l
+}
+
+__global__ void __launch_bounds__(128) linear_fwd_wide_kernel(const float* __restrict__ x, int xs, const float* __restrict__ W,
+                                                              float* __restrict__ part, int B, int K, int N, int kchunk, int KS) {
+    const int lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);           // warp id over (n group, K slice), K slice fastest
+    const int ng = wid / KS, ks = wid - ng * KS;
+    const int n0 = ng * 4;
+    if (n0 >= N) return;
+    const int k0 = ks * kchunk, k1 = min(K, k0 + kchunk);
+    float acc[4][LW_B];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int b = 0; b < LW_B; ++b) acc[i][b] = 0.f;
+    for (int k = k0 + 4 * lane; k < k1; k += 128) {
+        float4 w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) w[i] = (n0 + i < N) ? __ldg(reinterpret_cast<const float4*>(W + (long)(n0 + i) * K + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b = 0; b < LW_B; ++b) {
+            const float4 xv = b < B ? __ldg(reinterpret_cast<const float4*>(x + (long)b * xs + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                acc[i][b] = fmaf(w[i].x, xv.x, acc[i][b]); acc[i][b] = fmaf(w[i].y, xv.y, acc[i][b]);
+                acc[i][b] = fmaf(w[i].z, xv.z, acc[i][b]); acc[i][b] = fmaf(w[i].w, xv.w, acc[i][b]);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float v = warp_reduce_scatter32(acc[i], lane);
+        if (lane < B && n0 + i < N) part[((long)ks * B + lane) * N + n0 + i] = v;
+    }
+}
+__global__ void linear_fwd_finish_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ y, int BN_, int N,
+                                         int KS, int relu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= BN_) return;
+    float v = bias ? bias[i % N] : 0.f;
+    for (int s = 0; s < KS; ++s) v += part[(long)s * BN_ + i];
+    y[i] = relu ? fmaxf(v, 0.f) : v;
+}
+
+// dx[b][k4] += sum_{n in chunk} dy[b][n] W[n][k4]   grid (K/4/LW_T, n chunks); 128-bit reductions into a zeroed / accumulated dx
+__global__ void __launch_bounds__(LW_T) linear_bwd_dx_wide_kernel(const float* __restrict__ dy, const float* __restrict__ W,
+                                                                  float* __restrict__ dx, int dxs, int B, int K, int N, int nchunk) {
+    extern __shared__ __align__(16) float dys[];                 // [nchunk][LW_B]
+    const int na = blockIdx.y * nchunk, nb = min(N, na + nchunk);
+    for (int i = threadIdx.x; i < (nb - na) * LW_B; i += LW_T) {
+        const int n = i / LW_B, b = i - n * LW_B;
+        dys[i] = b < B ? __ldg(dy + (long)b * N + na + n) : 0.f;
+    }
+    __syncthreads();
+    const int k = 4 * (blockIdx.x * LW_T + threadIdx.x);
+    if (k >= K) return;
+    float4 acc[LW_B];
+#pragma unroll
+    for (int b = 0; b < LW_B; ++b) acc[b] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+    for (int n = na; n < nb; ++n) {
+        const float4 w = __ldg(reinterpret_cast<const float4*>(W + (long)n * K + k));
+        const float4* dr = reinterpret_cast<const float4*>(dys + (n - na) * LW_B);
+#pragma unroll
+        for (int b4 = 0; b4 < LW_B / 4; ++b4) {
+            const float4 d = dr[b4];
+            const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float4& a = acc[4 * b4 + j];
+                a.x = fmaf(dd[j], w.x, a.x); a.y = fmaf(dd[j], w.y, a.y); a.z = fmaf(dd[j], w.z, a.z); a.w = fmaf(dd[j], w.w, a.w);
+            }
+        }
+    }
+#pragma unroll
+    for (int b = 0; b < LW_B; ++b)
+        if (b < B) atomicAdd(reinterpret_cast<float4*>(dx + (long)b * dxs + k), acc[b]);
+}
+
+// dW[n][k4] += sum_b dy[b][n] x[b][k4]; db[n] += sum_b dy[b][n]     grid (K/4/LW_T, n chunks)
+__global__ void __launch_bounds__(LW_T) linear_bwd_dw_wide_kernel(const float* __restrict__ dy, const float* __restrict__ x, int xs,
+                                                                  float* __restrict__ dW, float* __restrict__ db, int B, int K, int N,
+                                                                  int nchunk) {
+    extern __shared__ __align__(16) float dys[];                 // [nchunk][LW_B]
+    const int na = blockIdx.y * nchunk, nb = min(N, na + nchunk);
+    for (int i = threadIdx.x; i < (nb - na) * LW_B; i += LW_T) {
+        const int n = i / LW_B, b = i - n * LW_B;
+        dys[i] = b < B ? __ldg(dy + (long)b * N + na + n) : 0.f;
+    }
+    __syncthreads();
+    if (db && blockIdx.x == 0)
+        for (int n = na + threadIdx.x; n < nb; n += LW_T) {
+            float s = 0.f;
+            for (int b = 0; b < LW_B; ++b) s += dys[(n - na) * LW_B + b];
+            db[n] += s;
+        }
+    const int k = 4 * (blockIdx.x * LW_T + threadIdx.x);
+    if (k >= K) return;
+    float4 xv[LW_B];
+#pragma unroll
+    for (int b = 0; b < LW_B; ++b) xv[b] = b < B ? __ldg(reinterpret_cast<const float4*>(x + (long)b * xs + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int n = na; n < nb; ++n) {
+        const float4* dr = reinterpret_cast<const float4*>(dys + (n - na) * LW_B);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int b4 = 0; b4 < LW_B / 4; ++b4) {
+            const float4 d = dr[b4];
+            const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 v = xv[4 * b4 + j];
+                a.x = fmaf(dd[j], v.x, a.x); a.y = fmaf(dd[j], v.y, a.y); a.z = fmaf(dd[j], v.z, a.z); a.w = fmaf(dd[j], v.w, a.w);
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(dW + (long)n * K + k);
+        float4 o = *dst;
+        o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
+        *dst = o;
+    }
+}
+
 // relu'(y) applied in place to a dense gradient (y is the saved post-ReLU output)
 __global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict__ g, long n) {
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -577,9 +729,54 @@ int pivp_linear_fwd(const float* x, int xs, const float* W, const float* bias, f
     return check_launch("linear_fwd");
 }
 
+static int linear_ks(int K) { int ks = K / 512; return ks > 16 ? 16 : (ks < 1 ? 1 : ks); }
+
+size_t pivp_linear_fwd_workspace_bytes(int B, int K, int N) { return sizeof(float) * (size_t)linear_ks(K) * B * N; }
+
+/* Same result as pivp_linear_fwd; split-K over the caller's workspace so the weight matrix is streamed once by >= 2 CTAs per SM.
+ * Falls back to the plain kernel when the wide path does not apply (batch > 32, K < 1024 or not a multiple of 4, unaligned rows). */
+int pivp_linear_fwd_splitk(const float* x, int xs, const float* W, const float* bias, float* y, int B, int K, int N, int relu,
+                           void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(x && W && y && B > 0 && K > 0 && N > 0 && xs >= K, "linear_fwd_splitk: bad argument");
+    if (!(B <= LW_B && K >= 1024 && K % 4 == 0 && xs % 4 == 0 && !(((uintptr_t)x | (uintptr_t)W) & 15) && workspace))
+        return pivp_linear_fwd(x, xs, W, bias, y, B, K, N, relu, stream);
+    PIVP_REQUIRE(ws_bytes >= pivp_linear_fwd_workspace_bytes(B, K, N), "linear_fwd_splitk: workspace too small");
+    const int KS = linear_ks(K);
+    const int kchunk = ((K / KS) + 3) / 4 * 4;
+    float* part = (float*)workspace;
+    const int warps = ((N + 3) / 4) * KS;
+    linear_fwd_wide_kernel<<<(warps + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, xs, W, part, B, K, N, kchunk, KS);
+    if (int e = check_launch("linear_fwd(wide)")) return e;
+    linear_fwd_finish_kernel<<<(B * N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part, bias, y, B * N, N, KS, relu);
+    return check_launch("linear_fwd(finish)");
+}
+
 int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, float* dx, int dxs, int accumulate_dx,
                     float* dW, float* db, int B, int K, int N, void* stream) {
     PIVP_REQUIRE(dy && x && W && dW && B > 0 && K > 0 && N > 0, "linear_bwd: bad argument");
+    if (B <= LW_B && K >= 1024 && K % 4 == 0 && xs % 4 == 0 && !(((uintptr_t)x | (uintptr_t)W | (uintptr_t)dW) & 15) &&
+        (!dx || (dxs % 4 == 0 && !((uintptr_t)dx & 15)))) {
+        cudaStream_t st = (cudaStream_t)stream;
+        const int kblocks = (K / 4 + LW_T - 1) / LW_T;
+        if (dx) {
+            if (!accumulate_dx) {
+                if (dxs == K) cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)B * K, st);
+                else cudaMemset2DAsync(dx, sizeof(float) * dxs, 0, sizeof(float) * K, B, st);
+            }
+            int nsplit = (296 + kblocks - 1) / kblocks;
+            if (nsplit > N) nsplit = N;
+            const int nchunk = (N + nsplit - 1) / nsplit;
+            linear_bwd_dx_wide_kernel<<<dim3(kblocks, (N + nchunk - 1) / nchunk), LW_T, sizeof(float) * nchunk * LW_B, st>>>(dy, W, dx, dxs, B, K, N,
+                                                                                                                          nchunk);
+            if (int e = check_launch("linear_bwd(dx wide)")) return e;
+        }
+        int nsplit = (444 + kblocks - 1) / kblocks;
+        if (nsplit > N) nsplit = N;
+        const int nchunk = (N + nsplit - 1) / nsplit;
+        linear_bwd_dw_wide_kernel<<<dim3(kblocks, (N + nchunk - 1) / nchunk), LW_T, sizeof(float) * nchunk * LW_B, st>>>(dy, x, xs, dW, db, B, K, N,
+                                                                                                                      nchunk);
+        return check_launch("linear_bwd(dw wide)");
+    }
     if (dx) {
         linear_bwd_dx_kernel<<<dim3((K + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(dy, W, dx, dxs, B, K, N, accumulate_dx);
         if (int e = check_launch("linear_bwd(dx)")) return e;

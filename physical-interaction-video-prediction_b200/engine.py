@@ -182,6 +182,8 @@ class Engine(object):
             ws["d_stp_s"] = A(B, 100)
             nb = self.L.query("pivp_stp_fused_bwd_workspace_bytes", B, H, W, self.M)
         ws["fused_ws"] = torch.empty(nb, dtype=torch.uint8, device=self.dev)
+        ws["lin_ws"] = torch.empty(max(16, self.L.query("pivp_linear_fwd_workspace_bytes", B, 128 * HW[8], max(25 * self.M, 100))),
+                                   dtype=torch.uint8, device=self.dev)
         nb = self.L.query("pivp_layernorm_workspace_bytes", B, 64 * H * W)
         ws["ln_ws"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)
         self.ws = ws
@@ -379,15 +381,15 @@ class Engine(object):
             # ---- transform + masks + composite
             K5 = 128 * HW[8]
             if self.model_type == "CDNA":
-                L.call("pivp_linear_fwd", _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]), _ptr(p["model/cdna_kerns/b"]),
-                       _ptr(ws["kern_raw"][t]), B, K5, 25 * self.M, 0, s)
+                L.call("pivp_linear_fwd_splitk", _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]), _ptr(p["model/cdna_kerns/b"]),
+                       _ptr(ws["kern_raw"][t]), B, K5, 25 * self.M, 0, _ptr(ws["lin_ws"]), ws["lin_ws"].numel(), s)
                 L.call("pivp_cdna_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["kern_raw"][t]),
                        _ptr(ws["gen"][t]), B, H, W, self.M, s)
             elif self.model_type == "DNA":
                 L.call("pivp_dna_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["gen"][t]), B, H, W, s)
             else:
-                L.call("pivp_linear_fwd", _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]), _ptr(p["model/stp_input/b"]),
-                       _ptr(ws["stp_s"][t]), B, K5, 100, 1, s)
+                L.call("pivp_linear_fwd_splitk", _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]), _ptr(p["model/stp_input/b"]),
+                       _ptr(ws["stp_s"][t]), B, K5, 100, 1, _ptr(ws["lin_ws"]), ws["lin_ws"].numel(), s)
                 L.call("pivp_linear_fwd", _ptr(ws["stp_s"][t]), 100, _ptr(p["model/identity_params/W"]),
                        _ptr(p["model/identity_params/b"]), _ptr(ws["theta_raw"][t]), B, 100, 6, 0, s)
                 L.call("pivp_stp_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["theta_raw"][t]),

@@ -263,6 +263,36 @@ def test_adam_matches_chainer_rule(pk):
     assert rel(p, params["w"]) < 1e-6
 
 
+@pytest.mark.parametrize("B,K,N,relu", [(32, 8192, 250, 0), (7, 2048, 100, 1), (3, 1024, 6, 0)])
+def test_linear_wide_paths_match_oracle(pk, B, K, N, relu):
+    """The split-K forward and the wide backward kernels (weight matrix streamed once) against the oracle's Linear."""
+    rs = np.random.RandomState(12)
+    L = pk.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    x, W, b = rs.standard_normal((B, K)).astype(np.float32), (rs.standard_normal((N, K)) / np.sqrt(K)).astype(np.float32), rs.standard_normal(N).astype(np.float32)
+    vx, vw, vb = G.Var(x.astype(np.float64)), G.Var(W.astype(np.float64)), G.Var(b.astype(np.float64))
+    y = G.linear(vx, vw, vb)
+    if relu:
+        y = G.relu(y)
+    gy = rs.standard_normal((B, N)).astype(np.float32)
+    G.backward(y, seed=gy.astype(np.float64))
+    xg, Wg, bg = cu(x), cu(W), cu(b)
+    yg = torch.empty(B, N, device="cuda")
+    nb = L.query("pivp_linear_fwd_workspace_bytes", B, K, N)
+    ws = torch.empty(nb, dtype=torch.uint8, device="cuda")
+    L.call("pivp_linear_fwd_splitk", xg.data_ptr(), K, Wg.data_ptr(), bg.data_ptr(), yg.data_ptr(), B, K, N, relu, ws.data_ptr(), nb, s)
+    assert rel(yg, y.data) < FWD_TOL
+    gyg = cu(gy * (y.data > 0) if relu else gy)
+    dx = torch.full((B, K), 7.0, device="cuda")                         # overwritten (accumulate_dx = 0)
+    dW0, db0 = rs.standard_normal((N, K)).astype(np.float32), rs.standard_normal(N).astype(np.float32)
+    dW, db = cu(dW0), cu(db0)                                           # accumulated into
+    L.call("pivp_linear_bwd", gyg.data_ptr(), xg.data_ptr(), K, Wg.data_ptr(), dx.data_ptr(), K, 0, dW.data_ptr(), db.data_ptr(), B, K, N, s)
+    assert rel(dx, vx.grad) < GRAD_TOL and rel(dW, dW0 + vw.grad) < GRAD_TOL and rel(db, db0 + vb.grad) < GRAD_TOL
+    dx2 = dx.clone()
+    L.call("pivp_linear_bwd", gyg.data_ptr(), xg.data_ptr(), K, Wg.data_ptr(), dx2.data_ptr(), K, 1, dW.data_ptr(), db.data_ptr(), B, K, N, s)
+    assert rel(dx2, 2 * vx.grad) < GRAD_TOL
+
+
 def test_linear_mse_state(pk):
     rs = np.random.RandomState(11)
     L = pk.lib()
