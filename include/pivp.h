@@ -64,6 +64,10 @@ int pivp_lstm_gates_fwd(float* gates, const float* c_prev, float* c_out, float* 
 int pivp_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, const float* dh_a,
                         const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* dg_bf16,
                         long M, int C, void* stream);
+/* bf16 gate storage (tensor-core mode; pivp_tc_conv5x5 flags bit 1): same math, gates read and d(pre-activations) written as bf16 */
+int pivp_lstm_gates_bwd_bf16(const void* gates_bf16, const float* c_prev, const float* c_cur, const float* dh_a,
+                             const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* dg_bf16,
+                             long M, int C, void* stream);
 
 /* ---- LayerNormalizationConv2D (train_model.py:186-208; A.4, D.4) -------------------------------------- */
 size_t pivp_layernorm_workspace_bytes(int B, int n);
@@ -150,6 +154,7 @@ int pivp_tc_set_debug_buffer(void* device_buffer);
  * mode 0: out[m*out_cs+out_co+n] = D (+bias)                      -- Convolution2D input-gradient (D.5) with Wd
  * mode 1: bias + gates + cell + h fused (train_model.py:262-272)  -- BN must be 128, N = 4C in the gate-interleaved order;
  *         writes activated gates (M,4C), c_out, h (fp32 view + optional bf16 view + optional channel-major bf16 copy).
+ *         flags: bit 0 = accurate tanhf/expf instead of tanh.approx; bit 1 = `gates` points to bf16 storage (M,4C) (pivp_lstm_gates_bwd_bf16).
  * Returns PIVP_EUNSUPPORTED when B*H*W cannot be cut into 128-pixel TMA boxes. */
 int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     const void* wt_bf16, int N, int BN,
@@ -158,7 +163,7 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     float* gates, const float* c_prev, float* c_out,
                     float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
                     void* h_t, long h_t_ld, int hT_co,
-                    int C, float forget_bias, int accurate, void* stream);
+                    int C, float forget_bias, int flags, void* stream);
 
 /* dst[i] = bf16(src[idx[i]]) (idx < 0 -> 0): builds permuted / zero-padded bf16 weight operands from the fp32 master parameters */
 int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, void* stream);

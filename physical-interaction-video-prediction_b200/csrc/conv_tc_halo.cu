@@ -43,7 +43,7 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 // MS = pixel tiles (of 128) per CTA: each weight stage feeds 4*MS MMAs, i.e. MS*BN/4... cycles of tensor work per 128*BN bytes fetched.
 // One CTA per SM: all shared memory that the MS patches leave goes to the weight ring, deep enough to cover the L2 round trip.
 template <int MS>
-__global__ void __launch_bounds__(64 + 128 * MS, 1)
+__global__ void __launch_bounds__(64 + 256 * MS, 1)
 conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Geom g, TcEpilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -80,7 +80,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     if (warp >= 2 && ep.bias) {
-        for (int i = threadIdx.x - 64; i < g.BN; i += 128 * MS) bias_s[i] = ep.bias[n0 + i];
+        for (int i = threadIdx.x - 64; i < g.BN; i += 256 * MS) bias_s[i] = ep.bias[n0 + i];
     }
     tc_fence_before();
     __syncthreads();
@@ -159,8 +159,8 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         }
         HALO_STAMP(3);
     } else {
-        // ===================== epilogue: warps 2..5 -> tile 0, warps 6..9 -> tile 1 =====================
-        const int sub = (warp - 2) >> 2, q = warp & 3;      // q = TMEM lane quarter this warp may read
+        // ===================== epilogue: 8 warps per pixel tile (lane quarter q x column half) =====================
+        const int ew = warp - 2, sub = ew >> 3, half = (ew >> 2) & 1, q = warp & 3;       // q = TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         const int mt = blockIdx.x * MS + sub;
         const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
@@ -171,16 +171,17 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             // ---- ConvLSTM gate epilogue, staged: every thread owns one pixel row of the accumulator (that is how tcgen05.ld hands
             // it out), but the outputs are pixel-major, so per-thread stores would scatter 16-byte pieces over 32 cache lines per
             // instruction (measured: 25.8k of the CTA's 42k cycles).  The row results go to shared memory instead -- the operand
-            // ring is dead once accum_full fires -- and are written out with fully coalesced 128-bit stores.
+            // ring is dead once accum_full fires -- and are written out with fully coalesced 128-bit stores.  Two warps share a
+            // lane quarter (16 of the 32 channels each) so that the TMEM-load / MUFU latency chains overlap.
             const int ch0 = n_tile * 32;
-            float cp[32];
+            float cp[16];
             if (ep.c_prev) {                                 // issued before the accumulator wait: the main loop hides the latency
-                const float4* src = reinterpret_cast<const float4*>(ep.c_prev + m * ep.C + ch0);
+                const float4* src = reinterpret_cast<const float4*>(ep.c_prev + m * ep.C + ch0 + half * 16);
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { const float4 v = __ldg(src + i); cp[4 * i] = v.x; cp[4 * i + 1] = v.y; cp[4 * i + 2] = v.z; cp[4 * i + 3] = v.w; }
+                for (int i = 0; i < 4; ++i) { const float4 v = __ldg(src + i); cp[4 * i] = v.x; cp[4 * i + 1] = v.y; cp[4 * i + 2] = v.z; cp[4 * i + 3] = v.w; }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) cp[i] = 0.f;
+                for (int i = 0; i < 16; ++i) cp[i] = 0.f;
             }
             mbar_wait(smem_u32(accum_full), 0);
             tc_fence_after();
@@ -189,7 +190,8 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             float* Cc = G + 128 * GP;
             float* Hh = Cc + 128 * CP;
 #pragma unroll
-            for (int c0 = 0; c0 < 32; c0 += 8) {
+            for (int cc = 0; cc < 16; cc += 8) {
+                const int c0 = half * 16 + cc;
                 float gj[8], gi[8], gf[8], go[8], cn[8], hn[8];
                 tc_ld8(trow + (uint32_t)(c0), gj);
                 tc_ld8(trow + (uint32_t)(32 + c0), gi);
@@ -202,7 +204,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     float f = gf[i] + bias_s[64 + c0 + i] + ep.forget_bias, o = go[i] + bias_s[96 + c0 + i];
                     if (ep.accurate) { j = tanhf(j); ii = sigmoid_acc(ii); f = sigmoid_acc(f); o = sigmoid_acc(o); }
                     else { j = tanh_fast(j); ii = sigmoid_fast(ii); f = sigmoid_fast(f); o = sigmoid_fast(o); }
-                    cn[i] = cp[c0 + i] * f + ii * j;
+                    cn[i] = cp[cc + i] * f + ii * j;
                     hn[i] = (ep.accurate ? tanhf(cn[i]) : tanh_fast(cn[i])) * o;
                     gj[i] = j; gi[i] = ii; gf[i] = f; go[i] = o;
                 }
@@ -220,17 +222,30 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 *reinterpret_cast<float4*>(Hh + row * CP + c0) = make_float4(hn[0], hn[1], hn[2], hn[3]);
                 *reinterpret_cast<float4*>(Hh + row * CP + c0 + 4) = make_float4(hn[4], hn[5], hn[6], hn[7]);
             }
-            asm volatile("bar.sync %0, 128;" ::"r"(1 + sub) : "memory");          // the four warps of this pixel tile
-            const int lw = (warp - 2) & 3;
-            // gates: one 512-byte row per warp instruction
-            for (int r = lw; r < 128; r += 4) {
-                const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
-                const float4 v = *reinterpret_cast<const float4*>(G + r * GP + 4 * lane);
-                *reinterpret_cast<float4*>(ep.gates + mr * (4 * ep.C) + n0 + 4 * lane) = v;
+            asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");          // the eight warps of this pixel tile
+            const int lw = ew & 7;
+            if (ep.gates_bf16) {
+                // bf16 gate storage: 256-byte rows, 16 lanes x 16 B per row, two rows per warp instruction
+                __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(ep.gates);
+                const int sr = lane >> 4, l16 = lane & 15;
+                for (int r0 = lw * 2; r0 < 128; r0 += 16) {
+                    const int r = r0 + sr;
+                    const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
+                    const float4 a = *reinterpret_cast<const float4*>(G + r * GP + 8 * l16), b4 = *reinterpret_cast<const float4*>(G + r * GP + 8 * l16 + 4);
+                    const float v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
+                    *reinterpret_cast<uint4*>(gb + mr * (4 * ep.C) + n0 + 8 * l16) = pack8_bf16(v);
+                }
+            } else {
+                // fp32 gates: one 512-byte row per warp instruction
+                for (int r = lw; r < 128; r += 8) {
+                    const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
+                    const float4 v = *reinterpret_cast<const float4*>(G + r * GP + 4 * lane);
+                    *reinterpret_cast<float4*>(ep.gates + mr * (4 * ep.C) + n0 + 4 * lane) = v;
+                }
             }
             // c, h (fp32) and the bf16 shadow of h: 8 lanes per 128-byte row, four rows per warp instruction
             const int sub_r = lane >> 3, l8 = lane & 7;
-            for (int r0 = lw * 4; r0 < 128; r0 += 16) {
+            for (int r0 = lw * 4; r0 < 128; r0 += 32) {
                 const int r = r0 + sub_r;
                 const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
                 const float4 cv = *reinterpret_cast<const float4*>(Cc + r * CP + 4 * l8);
@@ -253,7 +268,10 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             mbar_wait(smem_u32(accum_full), 0);
             tc_fence_after();
             if (warp == 2) HALO_STAMP(4);
-            tc_epilogue_row(ep, trow, m, m, n0, g.BN, n_tile, bias_s);
+            // plain epilogue: the two warps of a lane quarter split the columns
+            const int hc = (g.BN / 2 + 7) / 8 * 8;
+            const int cbeg = half ? hc : 0, cend = half ? g.BN : hc;
+            if (cend > cbeg) tc_epilogue_row(ep, trow + (uint32_t)cbeg, m, m, n0 + cbeg, cend - cbeg, n_tile, bias_s + cbeg);
         }
         tc_fence_before();
         if (warp == 2) HALO_STAMP(5);
@@ -283,7 +301,7 @@ static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g,
         attr_set = true;
     }
     dim3 grid((unsigned)(tiles / MS), (unsigned)(g.N / g.BN));
-    conv5x5_halo_tc_kernel<MS><<<grid, 64 + 128 * MS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
+    conv5x5_halo_tc_kernel<MS><<<grid, 64 + 256 * MS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
     return check_launch(who);
 }
 

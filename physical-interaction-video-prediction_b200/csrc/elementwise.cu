@@ -60,6 +60,83 @@ __global__ void lstm_gates_bwd_kernel(float* __restrict__ gates, const float* __
     }
 }
 
+// bf16 gate storage (tensor-core mode): activated gates bf16 in, gate pre-activation gradients bf16 out (the tcgen05 input-gradient and
+// weight-gradient GEMMs only ever read the bf16 copy).  One thread = 8 channels of one pixel: four 16-byte gate loads / stores.
+__device__ __forceinline__ void unpack8(const uint4& u, float (&v)[8]) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(p[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&v)[8]) {
+    uint4 u;
+    __nv_bfloat162* p = reinterpret_cast<__nv_bfloat162*>(&u);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+    return u;
+}
+__global__ void __launch_bounds__(256) lstm_gates_bwd_bf16_kernel(const __nv_bfloat16* __restrict__ gates, const float* __restrict__ c_prev,
+                                                                  const float* __restrict__ c_cur, const float* __restrict__ dh_a, CView dh_b,
+                                                                  float* __restrict__ dc, int dc_valid, __nv_bfloat16* __restrict__ dg,
+                                                                  long M, int C) {
+    const int c8 = C >> 3;
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * c8) return;
+    const long m = idx / c8;
+    const int ch = (int)(idx - m * c8) * 8;
+    const long e = m * C + ch;
+    const __nv_bfloat16* g = gates + m * 4 * C + gate_col(ch, 0);
+    float j[8], i[8], f[8], o[8];
+    unpack8(*reinterpret_cast<const uint4*>(g), j);
+    unpack8(*reinterpret_cast<const uint4*>(g + 32), i);
+    unpack8(*reinterpret_cast<const uint4*>(g + 64), f);
+    unpack8(*reinterpret_cast<const uint4*>(g + 96), o);
+    float dh[8], cc[8], cp[8], dcn[8];
+    auto ld8 = [](const float* p, float (&v)[8]) {
+        const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    };
+    if (dh_a) ld8(dh_a + e, dh);
+    else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dh[k] = 0.f;
+    }
+    if (dh_b.p) {
+        float t[8];
+        ld8(dh_b.p + m * dh_b.cs + dh_b.co + ch, t);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dh[k] += t[k];
+    }
+    ld8(c_cur + e, cc);
+    if (c_prev) ld8(c_prev + e, cp);
+    else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) cp[k] = 0.f;
+    }
+    if (dc_valid) ld8(dc + e, dcn);
+    else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dcn[k] = 0.f;
+    }
+    float dj[8], di[8], df[8], dout[8], dcp[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const float tc = tanhf(cc[k]);
+        dout[k] = dh[k] * tc * o[k] * (1.f - o[k]);
+        const float dcv = dh[k] * o[k] * (1.f - tc * tc) + dcn[k];
+        df[k] = dcv * cp[k] * f[k] * (1.f - f[k]);
+        di[k] = dcv * j[k] * i[k] * (1.f - i[k]);
+        dj[k] = dcv * i[k] * (1.f - j[k] * j[k]);
+        dcp[k] = dcv * f[k];
+    }
+    *reinterpret_cast<float4*>(dc + e) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+    *reinterpret_cast<float4*>(dc + e + 4) = make_float4(dcp[4], dcp[5], dcp[6], dcp[7]);
+    __nv_bfloat16* d = dg + m * 4 * C + gate_col(ch, 0);
+    *reinterpret_cast<uint4*>(d) = pack8(dj);
+    *reinterpret_cast<uint4*>(d + 32) = pack8(di);
+    *reinterpret_cast<uint4*>(d + 64) = pack8(df);
+    *reinterpret_cast<uint4*>(d + 96) = pack8(dout);
+}
+
 // ----------------------------------------------------------------------------- LayerNorm over (H*W*C) per sample
 constexpr int LN_T = 256, LN_E = 16;        // a stats CTA keeps LN_T*LN_E elements in registers
 
@@ -611,6 +688,18 @@ int pivp_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, c
     lstm_gates_bwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_cur, dh_a, CView{dh_b, dhb_cs, dhb_co},
                                                                               dc, dc_valid, (__nv_bfloat16*)dg_bf16, M, C);
     return check_launch("lstm_gates_bwd");
+}
+
+/* Tensor-core mode: activated gates stored bf16 (pivp_tc_conv5x5 flags bit 1); writes d(pre-activations) bf16 to dg_bf16 (may alias
+ * gates_bf16) and dc in place.  Same math as pivp_lstm_gates_bwd. */
+int pivp_lstm_gates_bwd_bf16(const void* gates_bf16, const float* c_prev, const float* c_cur, const float* dh_a,
+                             const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* dg_bf16,
+                             long M, int C, void* stream) {
+    PIVP_REQUIRE(gates_bf16 && dg_bf16 && c_cur && dc && (dh_a || dh_b) && M > 0 && C % 32 == 0, "lstm_gates_bwd_bf16: bad argument");
+    PIVP_REQUIRE(!dh_b || (dhb_cs % 4 == 0 && dhb_co % 4 == 0), "lstm_gates_bwd_bf16: dh view must be 16-byte aligned");
+    lstm_gates_bwd_bf16_kernel<<<nblk(M * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)gates_bf16, c_prev, c_cur, dh_a, CView{dh_b, dhb_cs, dhb_co}, dc, dc_valid, (__nv_bfloat16*)dg_bf16, M, C);
+    return check_launch("lstm_gates_bwd_bf16");
 }
 
 static int ln_split(int n, int* chunk) {

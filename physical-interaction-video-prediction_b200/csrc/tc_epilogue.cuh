@@ -20,7 +20,8 @@ struct TcEpilogue {
     __nv_bfloat16* out_bf16; int ob_cs, ob_co;   // mode 0: optional bf16 copy (next GEMM's operand), same row mapping
     int relu;                                    // mode 0: ReLU after bias
     int accumulate;                              // mode 0: out += D (fp32 view only)
-    float* gates;                                // mode 1: activated gates [M][N] (saved for backward)
+    float* gates;                                // mode 1: activated gates [M][N] (saved for backward); bf16 storage when gates_bf16
+    int gates_bf16;
     const float* c_prev; float* c_out;           // [M][C]  (c_prev may be null)
     float* h_out; int h_cs, h_co;                // fp32 h view (next step's xh h-slot)
     __nv_bfloat16* h_bf16; int hb_cs, hb_co;     // bf16 shadow (GEMM operand of the next step)
@@ -30,6 +31,15 @@ struct TcEpilogue {
     float forget_bias;
     int accurate;                                // 1: expf/tanhf, 0: tanh.approx
 };
+
+__device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(v[4], v[5]), p3 = __floats2bfloat162_rn(v[6], v[7]);
+    uint4 pk;
+    pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+    pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+    return pk;
+}
 
 // trow: TMEM address of this thread's lane at the tile's first column; n0 = first output channel of the tile; bias_s: BN floats in smem
 __device__ __forceinline__ void tc_epilogue_row(const TcEpilogue& ep, uint32_t trow, long m, long orow, int n0, int BN, int n_tile,
@@ -94,15 +104,23 @@ __device__ __forceinline__ void tc_epilogue_row(const TcEpilogue& ep, uint32_t t
                 hn[i] = (ep.accurate ? tanhf(cn[i]) : tanh_fast(cn[i])) * o;
                 gj[i] = j; gi[i] = ii; gf[i] = f; go[i] = o;
             }
-            float* gp = ep.gates + m * (4 * ep.C) + n0 + c0;
-            *reinterpret_cast<float4*>(gp) = make_float4(gj[0], gj[1], gj[2], gj[3]);
-            *reinterpret_cast<float4*>(gp + 4) = make_float4(gj[4], gj[5], gj[6], gj[7]);
-            *reinterpret_cast<float4*>(gp + 32) = make_float4(gi[0], gi[1], gi[2], gi[3]);
-            *reinterpret_cast<float4*>(gp + 36) = make_float4(gi[4], gi[5], gi[6], gi[7]);
-            *reinterpret_cast<float4*>(gp + 64) = make_float4(gf[0], gf[1], gf[2], gf[3]);
-            *reinterpret_cast<float4*>(gp + 68) = make_float4(gf[4], gf[5], gf[6], gf[7]);
-            *reinterpret_cast<float4*>(gp + 96) = make_float4(go[0], go[1], go[2], go[3]);
-            *reinterpret_cast<float4*>(gp + 100) = make_float4(go[4], go[5], go[6], go[7]);
+            if (ep.gates_bf16) {
+                __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(ep.gates) + m * (4 * ep.C) + n0 + c0;
+                *reinterpret_cast<uint4*>(gb) = pack8_bf16(gj);
+                *reinterpret_cast<uint4*>(gb + 32) = pack8_bf16(gi);
+                *reinterpret_cast<uint4*>(gb + 64) = pack8_bf16(gf);
+                *reinterpret_cast<uint4*>(gb + 96) = pack8_bf16(go);
+            } else {
+                float* gp = ep.gates + m * (4 * ep.C) + n0 + c0;
+                *reinterpret_cast<float4*>(gp) = make_float4(gj[0], gj[1], gj[2], gj[3]);
+                *reinterpret_cast<float4*>(gp + 4) = make_float4(gj[4], gj[5], gj[6], gj[7]);
+                *reinterpret_cast<float4*>(gp + 32) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+                *reinterpret_cast<float4*>(gp + 36) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+                *reinterpret_cast<float4*>(gp + 64) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+                *reinterpret_cast<float4*>(gp + 68) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+                *reinterpret_cast<float4*>(gp + 96) = make_float4(go[0], go[1], go[2], go[3]);
+                *reinterpret_cast<float4*>(gp + 100) = make_float4(go[4], go[5], go[6], go[7]);
+            }
             float* cdst = ep.c_out + m * ep.C + ch0 + c0;
             *reinterpret_cast<float4*>(cdst) = make_float4(cn[0], cn[1], cn[2], cn[3]);
             *reinterpret_cast<float4*>(cdst + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);

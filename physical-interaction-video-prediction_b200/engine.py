@@ -119,7 +119,8 @@ class Engine(object):
         ws["xh"], ws["G"], ws["c"] = [], [], []
         for cin, c, lv in zip(LSTM_IN, LSTM_SIZES, LSTM_LEVEL):
             ws["xh"].append([A(Mr[lv], cin + c, zero=(t == 0)) for t in range(T)])     # xh[.][0] h-slot = zeros
-            ws["G"].append([A(Mr[lv], 4 * c) for _ in range(S)])
+            # activated gates saved for BPTT: fp32 here; in bf16 mode they live (as bf16) in TensorCorePlan.dg_bf16 instead
+            ws["G"].append([A(Mr[lv], 4 * c) if self.compute == "f32" else None for _ in range(S)])
             ws["c"].append([A(Mr[lv], c) for _ in range(S)])
         ws["hid2"] = [A(Mr[2], 32) for _ in range(S)]
         ws["hid4"] = [A(Mr[4], 64) for _ in range(S)]
@@ -250,10 +251,15 @@ class Engine(object):
         h, w = self.H // lv, self.W // lv
         name = "lstm%d/conv" % (li + 1)
         Gt, dxh = ws["G"][li][t], ws["dxh"][li]
-        dg_bf16 = None if self.tc is None else self.tc.dg_bf16[li][t]
-        self.L.call("pivp_lstm_gates_bwd", _ptr(Gt), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
-                    _ptr(ws["dln"][li]), 0 if last else _ptr(dxh), cin + C, cin, _ptr(ws["dc"][li]), 0 if last else 1,
-                    _ptr(dg_bf16), ws["Mr"][lv], C, self._s())
+        if self.tc is not None:       # bf16 mode: gates were stored bf16 in dg_bf16[li][t]; dG overwrites them in place
+            dgb = self.tc.dg_bf16[li][t]
+            self.L.call("pivp_lstm_gates_bwd_bf16", _ptr(dgb), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
+                        _ptr(ws["dln"][li]), 0 if last else _ptr(dxh), cin + C, cin, _ptr(ws["dc"][li]), 0 if last else 1,
+                        _ptr(dgb), ws["Mr"][lv], C, self._s())
+        else:
+            self.L.call("pivp_lstm_gates_bwd", _ptr(Gt), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
+                        _ptr(ws["dln"][li]), 0 if last else _ptr(dxh), cin + C, cin, _ptr(ws["dc"][li]), 0 if last else 1,
+                        0, ws["Mr"][lv], C, self._s())
         dG = View(Gt, 4 * C, 0, 4 * C)
         xh = View(ws["xh"][li][t], cin + C, 0, cin + C)
         if self.tc is not None:

@@ -36,7 +36,7 @@ class TensorCorePlan(object):
                                 "(needs a multiple of 64); use an even batch / 64x64 or larger images, or compute='f32'"
                                 % (li + 1, M, h * w))
             xa = torch.zeros(T, M, self.Kpad[li], dtype=torch.bfloat16, device=dev)      # zeros: h_{-1}, pad channels
-            da = torch.empty(S, M, 4 * c, dtype=torch.bfloat16, device=dev)
+            da = torch.empty(S, M, 4 * c, dtype=torch.bfloat16, device=dev)      # forward: activated gates; backward: overwritten by dG
             self.xh_all.append(xa)
             self.dg_all.append(da)
             self.xh_bf16.append([xa[t] for t in range(T)])
@@ -195,10 +195,10 @@ class TensorCorePlan(object):
         e.L.call("pivp_tc_conv5x5", _ptr(self.xh_bf16[li][t]), self.Kpad[li], ws["B"], h, w, self.Kpad[li],
                  _ptr(self.Wf[li]), 4 * C, 128, 1, _ptr(e.p["lstm%d/conv/b" % (li + 1)]),
                  0, 0, 0,
-                 _ptr(ws["G"][li][t]), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
+                 _ptr(self.dg_bf16[li][t]), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
                  _ptr(ws["xh"][li][t + 1]), cin + C, cin, _ptr(self.xh_bf16[li][t + 1]), self.Kpad[li], cin,
                  0, 0, 0,
-                 C, 1.0, self.accurate, e._s())
+                 C, 1.0, self.accurate | 2, e._s())       # flags bit 1: the activated gates are stored bf16, in dg_bf16[li][t]
 
     def lstm_dgrad(self, li, t):
         """dxh = conv(dG_t, tap-flipped W): gradient w.r.t. the concatenated input [x | h_{t-1}] (D.5)."""
