@@ -214,6 +214,12 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
     }
 }
 
+// halo-patch variant for the 5x5 stride-1 case (conv_tc_wgrad_halo.cu)
+bool wgrad_halo_supported(int H, int W, int Cx, int N4);
+size_t wgrad_halo_ws_bytes(int SB, int H, int W, int Cx, int N4);
+int launch_wgrad5x5_halo(const void* dg_bf16, int dg_cs, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* part,
+                         size_t ws_bytes, void* stream, const char* who);
+
 }  // namespace pivp
 
 using namespace pivp;
@@ -254,7 +260,14 @@ static size_t wgrad_ws_bytes(int SB, int H, int W, int Cx, int N4, int ntaps) {
     return (size_t)splits * Mrows * ntaps * Cx * sizeof(float);
 }
 
-size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4) { return wgrad_ws_bytes(SB, H, W, Cx, N4, 25); }
+size_t pivp_tc_wgrad_workspace_bytes(int SB, int H, int W, int Cx, int N4) {
+    size_t a = wgrad_ws_bytes(SB, H, W, Cx, N4, 25);
+    if (wgrad_halo_supported(H, W, Cx, N4)) {
+        const size_t b = wgrad_halo_ws_bytes(SB, H, W, Cx, N4);
+        if (b > a) a = b;
+    }
+    return a;
+}
 size_t pivp_tc_wgrad_taps_workspace_bytes(int SB, int H, int W, int Cx, int N4, int ntaps) { return wgrad_ws_bytes(SB, H, W, Cx, N4, ntaps); }
 
 static int launch_wgrad(const void* dg_bf16, int dg_cs, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, int ntaps,
@@ -320,6 +333,14 @@ static int launch_wgrad(const void* dg_bf16, int dg_cs, const void* xh_bf16, int
 int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* dW,
                      void* workspace, size_t ws_bytes, void* stream) {
     PIVP_REQUIRE(N4 % 128 == 0 && xh_cs >= (Cx + 63) / 64 * 64, "tc_wgrad5x5: 4C must be a multiple of 128 and XH rows hold ceil(Cx/64)*64 channels");
+    if (wgrad_halo_supported(H, W, Cx, N4)) {
+        PIVP_REQUIRE(dg_bf16 && xh_bf16 && dW && workspace, "tc_wgrad5x5: null pointer");
+        const int splits = launch_wgrad5x5_halo(dg_bf16, N4, xh_bf16, xh_cs, SB, H, W, Cx, N4, (float*)workspace, ws_bytes, stream, "tc_wgrad5x5");
+        if (splits < 0) return splits;
+        const long n = (long)N4 * 25 * Cx, stride = (long)((N4 + 127) / 128 * 128) * 25 * Cx;
+        splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dW, n, stride, splits);
+        return check_launch("tc_wgrad5x5(reduce)");
+    }
     int dy[25], dx[25], co[25];
     for (int t = 0; t < 25; ++t) { dy[t] = t / 5 - 2; dx[t] = t % 5 - 2; co[t] = 0; }
     return launch_wgrad(dg_bf16, N4, xh_bf16, xh_cs, SB, H, W, Cx, N4, 25, dy, dx, co, dW, workspace, ws_bytes, stream, "tc_wgrad5x5");
