@@ -219,21 +219,21 @@ def main():
     h2d = sum(a.numel() * 4 for a in host) + (T - 1) * B * 4
     d2h = 2 * (T - 1) * 4
 
-    # ---------------- roofline: instrument ONE eager step with CUDA events around the dominant kernel's launches
-    roof, cdna_op = None, None
+    # ---------------- roofline: the dominant kernel = the tcgen05 ConvLSTM implicit GEMM (forward with the fused gate epilogue and
+    # input gradient; 126 launches per step).  One eager step records every launch with its real arguments; the recorded launches
+    # are then replayed back to back as ONE CUDA graph on the same buffers and timed with CUDA events on the launching stream --
+    # an eager event pair around a 20 us kernel mostly measures the host's launch cadence, not the kernel.
+    roof, roof_wgrad, cdna_op = None, None, None
     if True:                                  # every rank runs the instrumented step (it contains the all-reduce); rank 0 reports
         L = pk.lib()
         orig = L.call
         recs = []
 
-        def timed_call(name, *a):
-            if name in ("pivp_tc_conv5x5", "pivp_cdna_fused_fwd", "pivp_cdna_fused_bwd"):
-                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                s.record(); orig(name, *a); e.record()
-                recs.append((name, a, s, e))
-            else:
-                orig(name, *a)
-        L.call = timed_call
+        def recording_call(name, *a):
+            if name in ("pivp_tc_conv5x5", "pivp_tc_wgrad5x5"):
+                recs.append((name, a))
+            orig(name, *a)
+        L.call = recording_call
         eager = pk.TrainStep(model, opt, B, T, graph=False)
         eager.images, eager.actions, eager.states = step.images, step.actions, step.states
         eager(it); it += 1
@@ -242,35 +242,98 @@ def main():
         pk_, src = peaks()
         fl = lstm_flops(B)
         tcp = model.engine.tc
-        by_ptr = {}
+
+        def replay_time(calls, reps=5):
+            """Average device time per launch (s) of `calls` replayed back to back as one CUDA graph; best of `reps` replays."""
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                cur = torch.cuda.current_stream().cuda_stream
+                for name, a in calls:
+                    orig(name, *(a[:-1] + (cur,)))
+            g.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e9
+            for _ in range(reps):
+                e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) * 1e-3)
+            return best / len(calls)
+
         if tcp is not None:
+            by_ptr = {}
             for li, f in enumerate(fl):
                 by_ptr[tcp.Wf[li].data_ptr()] = f          # forward launch of layer li
                 by_ptr[tcp.Wd[li].data_ptr()] = f          # input-gradient launch: same 2*M*N*K
-        tc_t, tc_f, n_tc = 0.0, 0.0, 0
-        fw_t = fw_n = bw_t = bw_n = 0
-        for name, a, s, e in recs:
-            dt = s.elapsed_time(e) * 1e-3
-            if name == "pivp_tc_conv5x5":
-                tc_f += by_ptr[a[6]]; tc_t += dt; n_tc += 1
-            elif name == "pivp_cdna_fused_fwd":
-                fw_t += dt; fw_n += 1
-            else:
-                bw_t += dt; bw_n += 1
-        if n_tc:
-            ach = tc_f / tc_t / 1e12
-            roof = {"bound": "tensor", "kernel": "conv5x5_tc_kernel (tcgen05 ConvLSTM implicit GEMM, fwd+dgrad launches)",
-                    "achieved": ach, "peak": pk_["bf16_tflops_sustained"], "unit": "TFLOP/s", "frac": ach / pk_["bf16_tflops_sustained"],
-                    "traffic": None, "peak_source": src + " (sustained: kernel timed inside a long step)", "launches": n_tc,
-                    "avg_launch_us": tc_t / n_tc * 1e6}
-        if fw_n:
-            fb, bb = 328680.0 * B, 608208.0 * B
-            cdna_op = {"bound": "hbm", "unit": "GB/s", "peak": pk_["hbm_gbs"],
-                       "fwd": {"achieved": fb / (fw_t / fw_n) / 1e9, "avg_launch_us": fw_t / fw_n * 1e6, "bytes": fb},
-                       "bwd": {"achieved": bb / (bw_t / bw_n) / 1e9, "avg_launch_us": bw_t / bw_n * 1e6, "bytes": bb,
-                               "note": "3 kernels + memset per call; v1 writes and re-reads the mu*dmu planes"}}
-            cdna_op["fwd"]["frac"] = cdna_op["fwd"]["achieved"] / pk_["hbm_gbs"]
-            cdna_op["bwd"]["frac"] = cdna_op["bwd"]["achieved"] / pk_["hbm_gbs"]
+            conv_calls = [(n, a) for n, a in recs if n == "pivp_tc_conv5x5"]
+            if conv_calls:
+                per = replay_time(conv_calls)
+                flops = sum(by_ptr[a[6]] for _, a in conv_calls) / len(conv_calls)
+                ach = flops / per / 1e12
+                roof = {"bound": "tensor",
+                        "kernel": "conv5x5_halo_tc_kernel (tcgen05 ConvLSTM implicit GEMM with halo-patch A operand; forward + fused gates, "
+                                  "and input gradient) -- lstm5's 8x8 maps use conv_taps_tc_kernel",
+                        "achieved": ach, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk_["bf16_tflops"],
+                        "frac_of_sustained": ach / pk_["bf16_tflops_sustained"], "traffic": None,
+                        "peak_source": src + " (burst figure: the step's %d launches are replayed back to back as one CUDA graph, "
+                                             "about 3 ms, outside the long step)" % len(conv_calls),
+                        "launches": len(conv_calls), "avg_launch_us": per * 1e6,
+                        "flops_per_launch": flops, "how": "algorithmic 2*M*N*K (un-padded channels) / CUDA-event time of the graph replay"}
+            wg_calls = [(n, a) for n, a in recs if n == "pivp_tc_wgrad5x5"]
+            if wg_calls:
+                per = replay_time(wg_calls)
+                flops = sum(fl) * (T - 1) / len(wg_calls)
+                ach = flops / per / 1e12
+                roof_wgrad = {"bound": "tensor", "kernel": "wgrad5x5_halo_kernel + splitk_reduce (weight gradient over all T-1 steps, one launch "
+                              "per layer)", "achieved": ach, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk_["bf16_tflops"],
+                              "launches": len(wg_calls), "avg_launch_us": per * 1e6}
+        # ---- fused CDNA transform + mask softmax + composite: graph of 20 launches walking input sets that exceed L2 ("cold")
+        if model.engine.model_type == "CDNA":
+            def cdna_time(Bc, nsets, iters=20):
+                HWc = H * W
+                sets = []
+                for _ in range(nsets):
+                    t = dict(prev=torch.rand(Bc, 3, H, W, device=dev), e=torch.randn(Bc, 3, H, W, device=dev),
+                             a=2 * torch.randn(Bc, MASKS + 1, H, W, device=dev), k=torch.randn(Bc, 25 * MASKS, device=dev),
+                             g=torch.randn(Bc, 3, H, W, device=dev))
+                    t.update(out=torch.empty_like(t["prev"]), de=torch.empty_like(t["e"]), da=torch.empty_like(t["a"]), dk=torch.empty_like(t["k"]))
+                    sets.append(t)
+                nb = L.query("pivp_cdna_fused_bwd_workspace_bytes", Bc, H, W, MASKS)
+                wsb = torch.empty(nb, dtype=torch.uint8, device=dev)
+
+                def fwd(t, st):
+                    orig("pivp_cdna_fused_fwd", t["prev"].data_ptr(), t["e"].data_ptr(), t["a"].data_ptr(), t["k"].data_ptr(), t["out"].data_ptr(),
+                         Bc, H, W, MASKS, st)
+
+                def bwd(t, st):
+                    orig("pivp_cdna_fused_bwd", t["g"].data_ptr(), t["prev"].data_ptr(), t["e"].data_ptr(), t["a"].data_ptr(), t["k"].data_ptr(),
+                         t["de"].data_ptr(), t["da"].data_ptr(), t["dk"].data_ptr(), 0, 0, Bc, H, W, MASKS, wsb.data_ptr(), nb, st)
+                res = {}
+                for nm, fn in (("fwd", fwd), ("bwd", bwd)):
+                    for i in range(nsets):
+                        fn(sets[i], torch.cuda.current_stream().cuda_stream)
+                    torch.cuda.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        for i in range(iters):
+                            fn(sets[i % nsets], torch.cuda.current_stream().cuda_stream)
+                    g.replay(); torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    best = 1e9
+                    for _ in range(5):
+                        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+                        best = min(best, e0.elapsed_time(e1) * 1e-3 / iters)
+                    res[nm] = best
+                return res
+            cdna_op = {"bound": "hbm", "unit": "GB/s", "peak": pk_["hbm_gbs"], "peak_source": src,
+                       "bytes_per_sample": {"fwd": 328680, "bwd": 559056},
+                       "note": "algorithmic bytes (SURVEY 8d): fwd reads prev, enc7_pre, mask_pre, kern_raw and writes gen; bwd reads g, prev, "
+                               "enc7_pre, mask_pre, kern_raw and writes d_enc7_pre, d_mask_pre, d_kern_raw (no d_prev: the previous frame is "
+                               "detached in scheduled-sampling training).  Cold = a CUDA graph of 20 launches walking input sets that "
+                               "together exceed the 126 MB L2."}
+            for Bc in sorted({B, 256}):
+                per = Bc * 37 * H * W * 4
+                tm = cdna_time(Bc, max(2, int(600e6 // per) + 1))
+                cdna_op["b%d" % Bc] = {d: {"avg_launch_us": tm[d] * 1e6, "achieved": cdna_op["bytes_per_sample"][d] * Bc / tm[d] / 1e9,
+                                           "frac": cdna_op["bytes_per_sample"][d] * Bc / tm[d] / 1e9 / pk_["hbm_gbs"]} for d in ("fwd", "bwd")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
@@ -280,11 +343,13 @@ def main():
                                        "one step = forward + BPTT + grad all-reduce + Adam" % (B, ITER0),
                            "global_batch": B * world, "seq_len": T, "parallelism": "dp%d" % world,
                            "l2": "per-step working set ~%.1f GB of activations >> 126 MB L2 (no flush needed)" % (2.2 * B / 32),
-                           "cuda_graph": bool(step.use_graph), "lstm_gemm": "tcgen05 bf16 fwd(+fused gates)/dgrad/wgrad, deconv fwd on tcgen05; remaining convs SIMT fp32" if args.compute == "bf16" else "SIMT fp32"},
+                           "cuda_graph": bool(step.use_graph), "lstm_gemm": "tcgen05 bf16: ConvLSTM fwd (+fused gates) / dgrad / wgrad with halo-patch operands, deconvolutions fwd+bwd; enc0-3 convs SIMT fp32" if args.compute == "bf16" else "SIMT fp32"},
                 "clocks": clocks, "gpu_launches": int(launches), "loss": loss_now,
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}}
         if roof:
             line["roofline"] = roof
+        if roof_wgrad:
+            line["roofline_wgrad"] = roof_wgrad
         if cdna_op:
             line["cdna_op"] = cdna_op
         if world == 1 and not args.no_cpu_baseline:
