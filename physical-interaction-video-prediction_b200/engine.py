@@ -114,7 +114,9 @@ class Engine(object):
         ws["HW"], ws["Mr"] = HW, Mr
         A = self._alloc
         S = T - 1
-        ws["img_nhwc"] = [A(Mr[1], 3) for _ in range(S)]
+        # inputs of the four encoder convolutions, stacked over time: their weight gradients are ONE launch each over all T-1 steps
+        stack = lambda rows, ch: (lambda t_: [t_[i] for i in range(S)])(A(S, rows, ch))
+        ws["img_nhwc"] = stack(Mr[1], 3)
         ws["enc0_pre"] = [A(Mr[2], 32) for _ in range(S)]
         ws["xh"], ws["G"], ws["c"] = [], [], []
         for cin, c, lv in zip(LSTM_IN, LSTM_SIZES, LSTM_LEVEL):
@@ -122,9 +124,9 @@ class Engine(object):
             # activated gates saved for BPTT: fp32 here; in bf16 mode they live (as bf16) in TensorCorePlan.dg_bf16 instead
             ws["G"].append([A(Mr[lv], 4 * c) if self.compute == "f32" else None for _ in range(S)])
             ws["c"].append([A(Mr[lv], c) for _ in range(S)])
-        ws["hid2"] = [A(Mr[2], 32) for _ in range(S)]
-        ws["hid4"] = [A(Mr[4], 64) for _ in range(S)]
-        ws["in3"] = [A(Mr[8], 64 + self.sa) for _ in range(S)]
+        ws["hid2"] = stack(Mr[2], 32)
+        ws["hid4"] = stack(Mr[4], 64)
+        ws["in3"] = stack(Mr[8], 64 + self.sa)
         ws["hid5"] = [A(Mr[8], 128) for _ in range(S)]
         ws["cat5"] = [A(Mr[4], 96) for _ in range(S)]
         ws["cat6"] = [A(Mr[2], 64) for _ in range(S)]
@@ -166,13 +168,13 @@ class Engine(object):
         ws["d_cat5"] = A(Mr[4], 96)
         ws["d_e5pre"] = A(Mr[2], 96)
         ws["d_e4pre"] = A(Mr[4], 128)
-        ws["d_e3pre"] = A(Mr[8], 64)
+        ws["d_e3pre"] = stack(Mr[8], 64)               # d(pre-activation) of enc0..enc3 kept per time step for the deferred weight gradients
         ws["d_in3"] = A(Mr[8], 64 + self.sa)
-        ws["d_e2pre"] = A(Mr[8], 64)
+        ws["d_e2pre"] = stack(Mr[8], 64)
         ws["d_hid4"] = A(Mr[4], 64)
-        ws["d_e1pre"] = A(Mr[4], 32)
+        ws["d_e1pre"] = stack(Mr[4], 32)
         ws["d_hid2"] = A(Mr[2], 32)
-        ws["d_enc0pre"] = A(Mr[2], 32)
+        ws["d_enc0pre"] = stack(Mr[2], 32)
         if self.model_type == "CDNA":
             ws["d_kern_raw"] = A(B, 25 * self.M)
             nb = self.L.query("pivp_cdna_fused_bwd_workspace_bytes", B, H, W, self.M)
@@ -525,10 +527,9 @@ class Engine(object):
                          ws["ln_stats"]["hidden5"][t], View(ws["dln"][4], 128, 0, 128))
             self._lstm_bwd(4, t, B, last)
             # ---- enc3 (1x1 on concat(enc2 out, smear))
-            self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"], 64, 0, 64), Mr[8])
-            de3 = View(ws["d_e3pre"], 64, 0, 64)
+            self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"][t], 64, 0, 64), Mr[8])
+            de3 = View(ws["d_e3pre"][t], 64, 0, 64)
             cin3 = 64 + self.sa
-            self._conv_wgrad(View(ws["in3"][t], cin3, 0, cin3), B, H // 8, W // 8, de3, H // 8, W // 8, 1, 1, 0, g["enc3/W"], g["enc3/b"])
             self._conv_dgrad(de3, B, H // 8, W // 8, p["enc3/W"], None, 1, 1, 0, View(ws["d_in3"], cin3, 0, cin3), H // 8, W // 8)
             # ---- state predictor + smear backward; produces d cur[t] for step t-1
             d_cur_out = ws["d_cur"][t & 1]
@@ -537,11 +538,10 @@ class Engine(object):
                    _ptr(g["current_state/W"]), _ptr(g["current_state/b"]), s)
             d_cur_in = d_cur_out
             # ---- enc2
-            self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, View(ws["d_e2pre"], 64, 0, 64), Mr[8])
-            de2 = View(ws["d_e2pre"], 64, 0, 64)
-            self._conv_wgrad(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, de2, H // 8, W // 8, 3, 2, 1, g["enc2/W"], g["enc2/b"])
+            self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, View(ws["d_e2pre"][t], 64, 0, 64), Mr[8])
+            de2 = View(ws["d_e2pre"][t], 64, 0, 64)
             if self.tc is not None:
-                self.tc.conv_s2_dgrad("enc2", ws["d_e2pre"], self.tc.de2_b, Mr[8], 64, ws["d_hid4"], 64)
+                self.tc.conv_s2_dgrad("enc2", ws["d_e2pre"][t], self.tc.de2_b, Mr[8], 64, ws["d_hid4"], 64)
             else:
                 self._conv_dgrad(de2, B, H // 8, W // 8, p["enc2/W"], None, 3, 2, 1, View(ws["d_hid4"], 64, 0, 64), H // 4, W // 4)
             # ---- lstm4, lstm3
@@ -553,11 +553,10 @@ class Engine(object):
             self._lstm_bwd(2, t, B, last)
             # ---- enc1: encs[1] feeds lstm3 (x slot) and the enc5 skip slot
             self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32),
-                           View(ws["d_e1pre"], 32, 0, 32), Mr[4])
-            de1 = View(ws["d_e1pre"], 32, 0, 32)
-            self._conv_wgrad(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, de1, H // 4, W // 4, 3, 2, 1, g["enc1/W"], g["enc1/b"])
+                           View(ws["d_e1pre"][t], 32, 0, 32), Mr[4])
+            de1 = View(ws["d_e1pre"][t], 32, 0, 32)
             if self.tc is not None:
-                self.tc.conv_s2_dgrad("enc1", ws["d_e1pre"], self.tc.de1_b, Mr[4], 32, ws["d_hid2"], 32)
+                self.tc.conv_s2_dgrad("enc1", ws["d_e1pre"][t], self.tc.de1_b, Mr[4], 32, ws["d_hid2"], 32)
             else:
                 self._conv_dgrad(de1, B, H // 4, W // 4, p["enc1/W"], None, 3, 2, 1, View(ws["d_hid2"], 32, 0, 32), H // 2, W // 2)
             # ---- lstm2, lstm1
@@ -569,14 +568,27 @@ class Engine(object):
             self._lstm_bwd(0, t, B, last)
             # ---- norm_enc0 (+relu): encs[0] feeds lstm1 (x slot) and the enc6 skip slot; enc0
             self._ln_bwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), View(ws["dxh"][0], 64, 0, 32), View(ws["d_cat6"], 64, 32, 32),
-                         B, HW[2], 1, ws["ln_stats"]["norm_enc0"][t], View(ws["d_enc0pre"], 32, 0, 32))
-            de0 = View(ws["d_enc0pre"], 32, 0, 32)
-            self._conv_wgrad(View(ws["img_nhwc"][t], 3, 0, 3), B, H, W, de0, H // 2, W // 2, 5, 2, 2, g["enc0/W"], g["enc0/b"])
+                         B, HW[2], 1, ws["ln_stats"]["norm_enc0"][t], View(ws["d_enc0pre"][t], 32, 0, 32))
+            de0 = View(ws["d_enc0pre"][t], 32, 0, 32)
             if need_dprev:
                 self._conv_dgrad(de0, B, H // 2, W // 2, p["enc0/W"], None, 5, 2, 2, View(ws["d_img_nhwc"], 3, 0, 3), H, W)
                 L.call("pivp_nhwc_to_nchw", _ptr(ws["d_img_nhwc"]), 3, 0, _ptr(d_prev), B, 3, HW[1], 1, s)
                 L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)
             if getattr(self, "debug_stop_t", None) == t:
                 return                             # scripts/dbg_bwd_stage.py: leave this step's backward temporaries in place
+        # ---- deferred weight gradients of enc0..enc3: the per-step tensors are stacked over time, so each is ONE launch with
+        # S*B "images" (9x longer reduction per launch instead of 9 launches that cannot fill the GPU)
+        if getattr(self, "debug_stop_t", None) is None:
+            S = T - 1
+            first = lambda lst: lst[0]
+            cin3 = 64 + self.sa
+            self._conv_wgrad(View(first(ws["img_nhwc"]), 3, 0, 3), S * B, H, W, View(first(ws["d_enc0pre"]), 32, 0, 32), H // 2, W // 2, 5, 2, 2,
+                             g["enc0/W"], g["enc0/b"])
+            self._conv_wgrad(View(first(ws["hid2"]), 32, 0, 32), S * B, H // 2, W // 2, View(first(ws["d_e1pre"]), 32, 0, 32), H // 4, W // 4,
+                             3, 2, 1, g["enc1/W"], g["enc1/b"])
+            self._conv_wgrad(View(first(ws["hid4"]), 64, 0, 64), S * B, H // 4, W // 4, View(first(ws["d_e2pre"]), 64, 0, 64), H // 8, W // 8,
+                             3, 2, 1, g["enc2/W"], g["enc2/b"])
+            self._conv_wgrad(View(first(ws["in3"]), cin3, 0, cin3), S * B, H // 8, W // 8, View(first(ws["d_e3pre"]), 64, 0, 64), H // 8, W // 8,
+                             1, 1, 0, g["enc3/W"], g["enc3/b"])
         if self.tc is not None:
             self.tc.wgrad_all()                # ConvLSTM weight/bias gradients: one tcgen05 GEMM per layer over all time steps
