@@ -292,6 +292,56 @@ __global__ void copy_view_kernel(CView src, View dst, __nv_bfloat16* __restrict_
     if (dst_bf16) dst_bf16[m * db_cs + db_co + ch] = __float2bfloat16(v);
 }
 
+// 128-bit variants of the three view kernels above: one thread = 4 consecutive channels (C, strides and offsets multiples of 4)
+__device__ __forceinline__ uint2 pack4_bf16(float4 v) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&lo);
+    u.y = *reinterpret_cast<unsigned*>(&hi);
+    return u;
+}
+__global__ void relu_bwd_v4_kernel(CView out, CView ga, CView gb, View dst, long M, int C4) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C4) return;
+    const long m = idx / C4;
+    const int ch = (int)(idx - m * C4) * 4;
+    float4 g = __ldg(reinterpret_cast<const float4*>(ga.p + m * ga.cs + ga.co + ch));
+    if (gb.p) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(gb.p + m * gb.cs + gb.co + ch));
+        g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+    }
+    const float4 o = __ldg(reinterpret_cast<const float4*>(out.p + m * out.cs + out.co + ch));
+    *reinterpret_cast<float4*>(dst.p + m * dst.cs + dst.co + ch) =
+        make_float4(o.x > 0.f ? g.x : 0.f, o.y > 0.f ? g.y : 0.f, o.z > 0.f ? g.z : 0.f, o.w > 0.f ? g.w : 0.f);
+}
+__global__ void copy_view_v4_kernel(CView src, View dst, __nv_bfloat16* __restrict__ dst_bf16, int db_cs, int db_co, long M, int C4) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C4) return;
+    const long m = idx / C4;
+    const int ch = (int)(idx - m * C4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src.p + m * src.cs + src.co + ch));
+    if (dst.p) *reinterpret_cast<float4*>(dst.p + m * dst.cs + dst.co + ch) = v;
+    if (dst_bf16) *reinterpret_cast<uint2*>(dst_bf16 + m * db_cs + db_co + ch) = pack4_bf16(v);
+}
+__global__ void cast_bf16_v4_kernel(CView src, __nv_bfloat16* __restrict__ dst, int d_cs, int d_co, long M, int C4, int H, int W, int s2d, int cblk) {
+    const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= M * C4) return;
+    const long m = idx / C4;
+    const int ch = (int)(idx - m * C4) * 4;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(src.p + m * src.cs + src.co + ch));
+    long row = m;
+    int cc = d_co + ch;
+    if (s2d) {
+        const long hw = (long)H * W;
+        const long b = m / hw;
+        const int r = (int)(m - b * hw), y = r / W, x = r - y * W;
+        row = (b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+        cc += ((y & 1) * 2 + (x & 1)) * cblk;
+    }
+    *reinterpret_cast<uint2*>(dst + row * d_cs + cc) = pack4_bf16(v);
+}
+static inline bool v4ok(const void* p, int cs, int co) { return !p || (!((uintptr_t)p & 15) && cs % 4 == 0 && co % 4 == 0); }
+
 // planar (B,C,HW) <-> NHWC view rows (b*HW + pix)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, View dst, int B, int C, int HW) {
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*HW pixels
@@ -759,6 +809,11 @@ int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int 
 int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,
                   float* dst, int d_cs, int d_co, long M, int C, void* stream) {
     PIVP_REQUIRE(out && ga && dst && M > 0 && C > 0, "relu_bwd: bad argument");
+    if (C % 4 == 0 && v4ok(out, o_cs, o_co) && v4ok(ga, ga_cs, ga_co) && v4ok(gb, gb_cs, gb_co) && v4ok(dst, d_cs, d_co)) {
+        relu_bwd_v4_kernel<<<nblk(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co},
+                                                                                    CView{gb, gb_cs, gb_co}, View{dst, d_cs, d_co}, M, C / 4);
+        return check_launch("relu_bwd");
+    }
     relu_bwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
                                                                         View{dst, d_cs, d_co}, M, C);
     return check_launch("relu_bwd");
@@ -767,6 +822,11 @@ int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_
 int pivp_copy_view(const float* src, int s_cs, int s_co, float* dst, int d_cs, int d_co, void* dst_bf16, int db_cs, int db_co,
                    long M, int C, void* stream) {
     PIVP_REQUIRE(src && (dst || dst_bf16) && M > 0 && C > 0, "copy_view: bad argument");
+    if (C % 4 == 0 && v4ok(src, s_cs, s_co) && v4ok(dst, d_cs, d_co) && (!dst_bf16 || (!((uintptr_t)dst_bf16 & 7) && db_cs % 4 == 0 && db_co % 4 == 0))) {
+        copy_view_v4_kernel<<<nblk(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, View{dst, d_cs, d_co},
+                                                                                     (__nv_bfloat16*)dst_bf16, db_cs, db_co, M, C / 4);
+        return check_launch("copy_view");
+    }
     copy_view_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, View{dst, d_cs, d_co},
                                                                          (__nv_bfloat16*)dst_bf16, db_cs, db_co, M, C);
     return check_launch("copy_view");
@@ -788,6 +848,11 @@ int pivp_cast_bf16(const float* src, int s_cs, int s_co, void* dst_bf16, int d_c
                    void* stream) {
     PIVP_REQUIRE(src && dst_bf16 && M > 0 && C > 0, "cast_bf16: bad argument");
     PIVP_REQUIRE(!s2d || (H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && M % ((long)H * W) == 0 && cblk >= C), "cast_bf16: bad space-to-depth geometry");
+    if (C % 4 == 0 && v4ok(src, s_cs, s_co) && !((uintptr_t)dst_bf16 & 7) && d_cs % 4 == 0 && d_co % 4 == 0 && cblk % 4 == 0) {
+        cast_bf16_v4_kernel<<<nblk(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, (__nv_bfloat16*)dst_bf16, d_cs, d_co, M,
+                                                                                     C / 4, H, W, s2d, cblk);
+        return check_launch("cast_bf16");
+    }
     cast_bf16_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, (__nv_bfloat16*)dst_bf16, d_cs, d_co, M, C, H, W, s2d, cblk);
     return check_launch("cast_bf16");
 }
