@@ -83,6 +83,12 @@ int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int 
 /* ---- small view ops (F.relu backward :698, F.concat copies, layout packing) --------------------------- */
 int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,
                   float* dst, int d_cs, int d_co, long M, int C, void* stream);
+/* Fused gradient hand-over: g = ga (+ gb) [* (out > 0)] -> optional fp32 view, optional bf16 view (plain or space-to-depth with channel
+ * block cblk on the H x W grid, as pivp_cast_bf16), optional bias gradient db[C] += column sums of g.  One launch instead of
+ * relu_bwd + colsum + cast_bf16 between the ReLU / LayerNorm backward and the tensor-core transposed-convolution backward. */
+int pivp_grad_handover(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,
+                       float* dst, int d_cs, int d_co, void* dst_bf16, int b_cs, int b_co, int H, int W, int s2d, int cblk,
+                       float* db, long M, int C, void* stream);
 int pivp_copy_view(const float* src, int s_cs, int s_co, float* dst, int d_cs, int d_co, void* dst_bf16, int db_cs, int db_co,
                    long M, int C, void* stream);
 int pivp_nchw_to_nhwc(const float* src, float* dst, int d_cs, int d_co, int B, int C, int HW, void* stream);

@@ -383,8 +383,8 @@ constexpr int GB_FLOATS = ((M1 * NG + 1) / 2 + 1) & ~1;                   // ReL
 constexpr size_t bwd_smem_floats() { return (size_t)st_floats<true>() + M1 * CL + M * KNB + GB_FLOATS + 4; }
 
 // dKp: per-band partial kernel gradients [B][H/8][9][25] (kernels 0..8; kernel 9 has no gradient, B.3).
-template <int P>
-__global__ void __launch_bounds__(W*(R / P), 2)
+template <int P, int MINB>
+__global__ void __launch_bounds__(W*(R / P), MINB)
     cdna_band_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ prev, const float* __restrict__ e_pre,
                          const float* __restrict__ a_pre, const float* __restrict__ kraw, float* __restrict__ d_e,
                          float* __restrict__ d_a, float* __restrict__ dKp, int H) {
@@ -633,12 +633,12 @@ static int launch_fwd(const float* prev, const float* e_pre, const float* a_pre,
     cdna_band_fwd_kernel<P><<<grid, W*(R / P), smem, st>>>(prev, e_pre, a_pre, kraw, out, H, nitems);
     return check_launch("cdna_fused_fwd(band)");
 }
-template <int P>
+template <int P, int MINB>
 static int launch_bwd(const float* gout, const float* prev, const float* e_pre, const float* a_pre, const float* kraw, float* d_e,
                       float* d_a, float* dKp, int B, int H, cudaStream_t st) {
     const size_t smem = sizeof(float) * bwd_smem_floats();
-    if (int e = allow_smem(cdna_band_bwd_kernel<P>, smem)) return e;
-    cdna_band_bwd_kernel<P><<<dim3(H / R, B), W*(R / P), smem, st>>>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, H);
+    if (int e = allow_smem(cdna_band_bwd_kernel<P, MINB>, smem)) return e;
+    cdna_band_bwd_kernel<P, MINB><<<dim3(H / R, B), W*(R / P), smem, st>>>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, H);
     return check_launch("cdna_fused_bwd(band)");
 }
 
@@ -661,9 +661,10 @@ size_t cdna_band_bwd_workspace_floats(int B, int H) { return (size_t)B * (H / cb
 
 int cdna_band_bwd(const float* gout, const float* prev, const float* e_pre, const float* a_pre, const float* kraw, float* d_e,
                   float* d_a, float* d_kraw, float* dKp, int B, int H, cudaStream_t st) {
-    static const int P = getenv("PIVP_CDNA_PB") ? atoi(getenv("PIVP_CDNA_PB")) : 4;
-    if (int e = (P == 2 ? cb::launch_bwd<2>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)
-                        : cb::launch_bwd<4>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)))
+    static const int P = getenv("PIVP_CDNA_PB") ? atoi(getenv("PIVP_CDNA_PB")) : 43;    // 43 = 4 pixels per thread, 3 CTAs per SM
+    if (int e = (P == 2 ? cb::launch_bwd<2, 2>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)
+                 : P == 43 ? cb::launch_bwd<4, 3>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)
+                           : cb::launch_bwd<4, 2>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)))
         return e;
     cb::cdna_band_kern_bwd_kernel<<<(B * cb::M + 3) / 4, 128, 0, st>>>(kraw, dKp, d_kraw, B, H / cb::R);
     return check_launch("cdna_fused_bwd(kern)");

@@ -340,6 +340,55 @@ __global__ void cast_bf16_v4_kernel(CView src, __nv_bfloat16* __restrict__ dst, 
     }
     *reinterpret_cast<uint2*>(dst + row * d_cs + cc) = pack4_bf16(v);
 }
+// Fused "gradient hand-over" between a ReLU / LayerNorm backward and a tensor-core transposed-convolution backward:
+//   g = ga (+ gb), masked by [out > 0] when `out` is given;  optional fp32 copy;  optional bf16 copy (plain or space-to-depth, the
+//   GEMM operand);  optional bias gradient db[c] += sum over rows of g.   One thread owns 4 channels and walks rows (grid-stride), so
+//   the column sums cost one 128-bit reduction per block and channel quad instead of a separate colsum kernel.
+__global__ void __launch_bounds__(256) grad_handover_kernel(CView out, CView ga, CView gb, View dst, __nv_bfloat16* __restrict__ dst_bf16,
+                                                            int b_cs, int b_co, int H, int W, int s2d, int cblk, float* __restrict__ db,
+                                                            long M, int C4, int RPB) {
+    __shared__ float4 red[256];
+    const int c4 = threadIdx.x % C4, ty = threadIdx.x / C4;
+    const int ch = c4 * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ty < RPB)
+        for (long m = (long)blockIdx.x * RPB + ty; m < M; m += (long)gridDim.x * RPB) {
+            float4 g = __ldg(reinterpret_cast<const float4*>(ga.p + m * ga.cs + ga.co + ch));
+            if (gb.p) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(gb.p + m * gb.cs + gb.co + ch));
+                g.x += t.x; g.y += t.y; g.z += t.z; g.w += t.w;
+            }
+            if (out.p) {
+                const float4 o = __ldg(reinterpret_cast<const float4*>(out.p + m * out.cs + out.co + ch));
+                g = make_float4(o.x > 0.f ? g.x : 0.f, o.y > 0.f ? g.y : 0.f, o.z > 0.f ? g.z : 0.f, o.w > 0.f ? g.w : 0.f);
+            }
+            if (dst.p) *reinterpret_cast<float4*>(dst.p + m * dst.cs + dst.co + ch) = g;
+            if (dst_bf16) {
+                long row = m;
+                int cc = b_co + ch;
+                if (s2d) {
+                    const long hw = (long)H * W;
+                    const long b = m / hw;
+                    const int r = (int)(m - b * hw), y = r / W, x = r - y * W;
+                    row = (b * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+                    cc += ((y & 1) * 2 + (x & 1)) * cblk;
+                }
+                *reinterpret_cast<uint2*>(dst_bf16 + row * b_cs + cc) = pack4_bf16(g);
+            }
+            acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+        }
+    if (!db) return;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    if (ty == 0) {
+        for (int r = 1; r < RPB; ++r) {
+            const float4 t = red[r * C4 + c4];
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        }
+        atomicAdd(reinterpret_cast<float4*>(db + ch), acc);
+    }
+}
+
 static inline bool v4ok(const void* p, int cs, int co) { return !p || (!((uintptr_t)p & 15) && cs % 4 == 0 && co % 4 == 0); }
 
 // planar (B,C,HW) <-> NHWC view rows (b*HW + pix)
@@ -817,6 +866,27 @@ int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_
     relu_bwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
                                                                         View{dst, d_cs, d_co}, M, C);
     return check_launch("relu_bwd");
+}
+
+/* g = ga (+ gb) [* (out > 0)] -> optional fp32 view `dst`, optional bf16 view (plain, or space-to-depth on the H x W grid with channel
+ * block cblk, as pivp_cast_bf16), optional bias gradient db[C] += column sums.  Replaces relu_bwd + colsum + cast_bf16 by one launch. */
+int pivp_grad_handover(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,
+                       float* dst, int d_cs, int d_co, void* dst_bf16, int b_cs, int b_co, int H, int W, int s2d, int cblk,
+                       float* db, long M, int C, void* stream) {
+    PIVP_REQUIRE(ga && (dst || dst_bf16 || db) && M > 0 && C > 0 && C % 4 == 0 && C <= 1024, "grad_handover: bad argument (C must be a multiple of 4)");
+    PIVP_REQUIRE(v4ok(out, o_cs, o_co) && v4ok(ga, ga_cs, ga_co) && v4ok(gb, gb_cs, gb_co) && v4ok(dst, d_cs, d_co) && v4ok(db, 4, 0),
+                 "grad_handover: views must be 16-byte aligned");
+    PIVP_REQUIRE(!dst_bf16 || (!((uintptr_t)dst_bf16 & 7) && b_cs % 4 == 0 && b_co % 4 == 0 && cblk % 4 == 0), "grad_handover: bf16 view must be 8-byte aligned");
+    PIVP_REQUIRE(!s2d || (H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && M % ((long)H * W) == 0 && cblk >= C), "grad_handover: bad space-to-depth geometry");
+    const int C4 = C / 4;
+    int RPB = 256 / C4;
+    if (RPB < 1) RPB = 1;
+    long blocks = (M + RPB - 1) / RPB;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    grad_handover_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
+                                                                           View{dst, d_cs, d_co}, (__nv_bfloat16*)dst_bf16, b_cs, b_co, H, W, s2d,
+                                                                           cblk, db, M, C4, RPB);
+    return check_launch("grad_handover");
 }
 
 int pivp_copy_view(const float* src, int s_cs, int s_co, float* dst, int d_cs, int d_co, void* dst_bf16, int db_cs, int db_co,

@@ -489,10 +489,10 @@ class Engine(object):
             self._ln_bwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), View(ws["d_e6"], 64, 0, 64), None, B, HW[1], 1,
                          ws["ln_stats"]["norm_enc6"][t], View(ws["d_e6pre"], 64, 0, 64))
             de6 = View(ws["d_e6pre"], 64, 0, 64)
-            L.call("pivp_colsum", de6.ptr, 64, 0, Mr[1], 64, _ptr(g["enc6/b"]), s)
-            if self.tc is not None:
-                self.tc.deconv_bwd_data("enc6", t, ws["d_e6pre"], ws["d_cat6"], 0)       # weight gradient deferred (wgrad_all)
+            if self.tc is not None:           # bias gradient + bf16 space-to-depth operand in one hand-over launch; weight gradient deferred
+                self.tc.deconv_bwd_fused("enc6", t, None, de6, None, g["enc6/b"], ws["d_cat6"], 0)
             else:
+                L.call("pivp_colsum", de6.ptr, 64, 0, Mr[1], 64, _ptr(g["enc6/b"]), s)
                 self._conv_wgrad(de6, B, H, W, View(ws["cat6"][t], 64, 0, 64), H // 2, W // 2, 3, 2, 1, g["enc6/W"], None)
                 self._conv_fwd(de6, B, H, W, p["enc6/W"], None, 64, 3, 2, 1, View(ws["d_cat6"], 64, 0, 64))
             # ---- lstm7
@@ -500,12 +500,13 @@ class Engine(object):
                          ws["ln_stats"]["hidden7"][t], View(ws["dln"][6], 32, 0, 32))
             self._lstm_bwd(6, t, B, last)
             # ---- enc5 deconv (input concat(hidden6, encs[1]))
-            self._relu_bwd(View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, View(ws["d_e5pre"], 96, 0, 96), Mr[2])
             de5 = View(ws["d_e5pre"], 96, 0, 96)
-            L.call("pivp_colsum", de5.ptr, 96, 0, Mr[2], 96, _ptr(g["enc5/b"]), s)
             if self.tc is not None:
-                self.tc.deconv_bwd_data("enc5", t, ws["d_e5pre"], ws["d_cat5"], 0)
+                self.tc.deconv_bwd_fused("enc5", t, View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, g["enc5/b"],
+                                         ws["d_cat5"], 0)
             else:
+                self._relu_bwd(View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, de5, Mr[2])
+                L.call("pivp_colsum", de5.ptr, 96, 0, Mr[2], 96, _ptr(g["enc5/b"]), s)
                 self._conv_wgrad(de5, B, H // 2, W // 2, View(ws["cat5"][t], 96, 0, 96), H // 4, W // 4, 3, 2, 1, g["enc5/W"], None)
                 self._conv_fwd(de5, B, H // 2, W // 2, p["enc5/W"], None, 96, 3, 2, 1, View(ws["d_cat5"], 96, 0, 96))
             # ---- lstm6
@@ -513,12 +514,13 @@ class Engine(object):
                          ws["ln_stats"]["hidden6"][t], View(ws["dln"][5], 64, 0, 64))
             self._lstm_bwd(5, t, B, last)
             # ---- enc4 deconv (input hidden5); d_hid5 may already hold the kernel-Linear contribution
-            self._relu_bwd(View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, View(ws["d_e4pre"], 128, 0, 128), Mr[4])
             de4 = View(ws["d_e4pre"], 128, 0, 128)
-            L.call("pivp_colsum", de4.ptr, 128, 0, Mr[4], 128, _ptr(g["enc4/b"]), s)
             if self.tc is not None:
-                self.tc.deconv_bwd_data("enc4", t, ws["d_e4pre"], ws["d_hid5"], 1 if hid5_has_grad else 0)
+                self.tc.deconv_bwd_fused("enc4", t, View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, g["enc4/b"],
+                                         ws["d_hid5"], 1 if hid5_has_grad else 0)
             else:
+                self._relu_bwd(View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, de4, Mr[4])
+                L.call("pivp_colsum", de4.ptr, 128, 0, Mr[4], 128, _ptr(g["enc4/b"]), s)
                 self._conv_wgrad(de4, B, H // 4, W // 4, View(ws["hid5"][t], 128, 0, 128), H // 8, W // 8, 3, 2, 1, g["enc4/W"], None)
                 self._conv_fwd(de4, B, H // 4, W // 4, p["enc4/W"], None, 128, 3, 2, 1, View(ws["d_hid5"], 128, 0, 128),
                                acc=1 if hid5_has_grad else 0)
@@ -538,11 +540,15 @@ class Engine(object):
                    _ptr(g["current_state/W"]), _ptr(g["current_state/b"]), s)
             d_cur_in = d_cur_out
             # ---- enc2
-            self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, View(ws["d_e2pre"][t], 64, 0, 64), Mr[8])
             de2 = View(ws["d_e2pre"][t], 64, 0, 64)
-            if self.tc is not None:
+            if self.tc is not None and cin3 % 4 == 0:
+                self.tc.conv_s2_dgrad_fused("enc2", View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, de2, self.tc.de2_b,
+                                            Mr[8], 64, ws["d_hid4"], 64)
+            elif self.tc is not None:
+                self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, de2, Mr[8])
                 self.tc.conv_s2_dgrad("enc2", ws["d_e2pre"][t], self.tc.de2_b, Mr[8], 64, ws["d_hid4"], 64)
             else:
+                self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, de2, Mr[8])
                 self._conv_dgrad(de2, B, H // 8, W // 8, p["enc2/W"], None, 3, 2, 1, View(ws["d_hid4"], 64, 0, 64), H // 4, W // 4)
             # ---- lstm4, lstm3
             self._ln_bwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), View(ws["d_hid4"], 64, 0, 64), None, B, HW[4], 0,
@@ -552,12 +558,12 @@ class Engine(object):
                          ws["ln_stats"]["hidden3"][t], View(ws["dln"][2], 64, 0, 64))
             self._lstm_bwd(2, t, B, last)
             # ---- enc1: encs[1] feeds lstm3 (x slot) and the enc5 skip slot
-            self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32),
-                           View(ws["d_e1pre"][t], 32, 0, 32), Mr[4])
             de1 = View(ws["d_e1pre"][t], 32, 0, 32)
             if self.tc is not None:
-                self.tc.conv_s2_dgrad("enc1", ws["d_e1pre"][t], self.tc.de1_b, Mr[4], 32, ws["d_hid2"], 32)
+                self.tc.conv_s2_dgrad_fused("enc1", View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32),
+                                            de1, self.tc.de1_b, Mr[4], 32, ws["d_hid2"], 32)
             else:
+                self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32), de1, Mr[4])
                 self._conv_dgrad(de1, B, H // 4, W // 4, p["enc1/W"], None, 3, 2, 1, View(ws["d_hid2"], 32, 0, 32), H // 2, W // 2)
             # ---- lstm2, lstm1
             self._ln_bwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), View(ws["d_hid2"], 32, 0, 32), None, B, HW[2], 0,

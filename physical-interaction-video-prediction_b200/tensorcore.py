@@ -158,6 +158,28 @@ class TensorCorePlan(object):
         e.L.call("pivp_tc_conv_taps", _ptr(d["dys"][t]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
                  d["cin"], d["bn"], 0, 0, accumulate, _ptr(out), d["cin"], 0, 0, 0, 0, h, w, 1, 0, 0, e._s())
 
+    def deconv_bwd_fused(self, name, t, out, ga, gb, db, d_in, accumulate):
+        """Backward of a stride-2 deconvolution fed by a ReLU (``out`` = its output view, or None for a plain gradient):
+        ONE hand-over launch masks the gradient, accumulates the bias gradient and writes the space-to-depth bf16 operand
+        (kept for the deferred weight gradient), then the 9-tap tcgen05 GEMM produces d_in."""
+        e, d = self.eng, self.dbw[name]
+        h, w = e.H // d["lv"], e.W // d["lv"]
+        B = self.ws["B"]
+        z = lambda v: (0, 0, 0) if v is None else (v.ptr, v.cs, v.co)
+        e.L.call("pivp_grad_handover", *z(out), *z(ga), *z(gb), 0, 0, 0, _ptr(d["dys"][t]), 4 * d["cb"], 0, 2 * h, 2 * w, 1, d["cb"],
+                 _ptr(db), B * 4 * h * w, d["cout"], e._s())
+        e.L.call("pivp_tc_conv_taps", _ptr(d["dys"][t]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
+                 d["cin"], d["bn"], 0, 0, accumulate, _ptr(d_in), d["cin"], 0, 0, 0, 0, h, w, 1, 0, 0, e._s())
+
+    def conv_s2_dgrad_fused(self, name, out, ga, gb, d_pre, dy_b, M, C, d_in, d_in_cs):
+        """ReLU backward of a stride-2 convolution's output + its input gradient: the hand-over writes d(pre-activation) fp32 (kept for
+        the deferred weight gradient) and the bf16 GEMM operand in one launch; then the four output phases in one tcgen05 launch."""
+        e = self.eng
+        z = lambda v: (0, 0, 0) if v is None else (v.ptr, v.cs, v.co)
+        e.L.call("pivp_grad_handover", *z(out), *z(ga), *z(gb), d_pre.ptr, d_pre.cs, d_pre.co, _ptr(dy_b), dy_b.shape[1], 0, 0, 0, 0, 0,
+                 0, M, C, e._s())
+        self.deconv_fwd(name, dy_b, d_in, d_in_cs, None, 0, 0, bias=False)
+
     def deconv_wgrad_all(self):
         """Deferred weight gradients of enc4/5/6 over all time steps (one MN-major GEMM each)."""
         e, S, B = self.eng, self.S, self.ws["B"]
