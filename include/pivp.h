@@ -71,7 +71,9 @@ int pivp_lstm_gates_bwd_bf16(const void* gates_bf16, const float* c_prev, const 
 
 /* ---- LayerNormalizationConv2D (train_model.py:186-208; A.4, D.4) -------------------------------------- */
 size_t pivp_layernorm_workspace_bytes(int B, int n);
-/* per-sample LN over HW*C with per-element gamma/beta (HWC order); stats (B,2) = mean, rstd saved for bwd */
+/* per-sample LN over HW*C with per-element gamma/beta (HWC order); stats (B,2) = mean, rstd saved for bwd.
+ * relu: bit 0 = ReLU after the affine; bit 1 = the (mean, M2) chunk partials are already in `workspace` (written by the epilogue of
+ * pivp_tc_conv5x5 ..., ln_partial) -- the statistics pass is skipped. */
 int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
                        float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
                        int relu, float* stats, void* workspace, size_t ws_bytes, void* stream);
@@ -160,6 +162,9 @@ int pivp_tc_set_debug_buffer(void* device_buffer);
  * mode 0: out[m*out_cs+out_co+n] = D (+bias)                      -- Convolution2D input-gradient (D.5) with Wd
  * mode 1: bias + gates + cell + h fused (train_model.py:262-272)  -- BN must be 128, N = 4C in the gate-interleaved order;
  *         writes activated gates (M,4C), c_out, h (fp32 view + optional bf16 view + optional channel-major bf16 copy).
+ *         ln_partial (optional, mode 1 on maps with H % 16 == 0, W % 8 == 0): the epilogue also writes the LayerNorm statistics of h as
+ *         per-tile (mean, M2) pairs in the workspace layout of pivp_layernorm_fwd, which can then be called with relu | 2 (skip its
+ *         own statistics pass).
  *         flags: bit 0 = accurate tanhf/expf instead of tanh.approx; bit 1 = `gates` points to bf16 storage (M,4C) (pivp_lstm_gates_bwd_bf16).
  * Returns PIVP_EUNSUPPORTED when B*H*W cannot be cut into 128-pixel TMA boxes. */
 int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
@@ -169,7 +174,7 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     float* gates, const float* c_prev, float* c_out,
                     float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
                     void* h_t, long h_t_ld, int hT_co,
-                    int C, float forget_bias, int flags, void* stream);
+                    int C, float forget_bias, int flags, float* ln_partial, void* stream);
 
 /* dst[i] = bf16(src[idx[i]]) (idx < 0 -> 0): builds permuted / zero-padded bf16 weight operands from the fp32 master parameters */
 int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, void* stream);

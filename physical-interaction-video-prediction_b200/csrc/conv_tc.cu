@@ -313,7 +313,7 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     float* gates, const float* c_prev, float* c_out,
                     float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
                     void* h_t, long h_t_ld, int hT_co,
-                    int C, float forget_bias, int flags, void* stream) {
+                    int C, float forget_bias, int flags, float* ln_partial, void* stream) {
     PIVP_REQUIRE(in_cs >= Kc, "tc_conv5x5: row stride smaller than Kc");
     if (mode == 1) {
         PIVP_REQUIRE(BN == 128 && N == 4 * C && C % 32 == 0 && gates && c_out && h_out && bias, "tc_conv5x5: gate epilogue needs BN=128, N=4C, bias");
@@ -329,6 +329,12 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
     ep.c_out = c_out; ep.h_out = h_out; ep.h_cs = h_cs; ep.h_co = h_co; ep.h_bf16 = (__nv_bfloat16*)h_bf16; ep.hb_cs = hb_cs; ep.hb_co = hb_co;
     ep.h_t = (__nv_bfloat16*)h_t; ep.h_t_ld = h_t_ld; ep.hT_co = hT_co;
     ep.C = C; ep.forget_bias = forget_bias; ep.accurate = flags & 1; ep.gates_bf16 = (flags >> 1) & 1;
+    if (ln_partial) {
+        PIVP_REQUIRE(mode == 1 && tc_halo_supported(B, H, W, Kc, BN) && (H * W) % 128 == 0,
+                     "tc_conv5x5: LayerNorm partials are produced by the halo-patch kernel only (H % 16 == 0, W % 8 == 0)");
+        ep.ln_partial = reinterpret_cast<float2*>(ln_partial);
+        ep.ln_S = (H * W / 128) * (C / 32);
+    }
     if (tc_halo_supported(B, H, W, Kc, BN)) return launch_conv5x5_halo(in_bf16, in_cs, B, H, W, Kc, wt_bf16, N, BN, ep, stream, "tc_conv5x5");
     return launch_conv_taps(in_bf16, in_cs, B, H, W, Kc, 25, dy, dx, co, wt_bf16, N, BN, ep, H, W, 1, 0, 0, stream, "tc_conv5x5");
 }

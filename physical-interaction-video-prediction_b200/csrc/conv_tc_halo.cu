@@ -224,6 +224,41 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             }
             asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");          // the eight warps of this pixel tile
             const int lw = ew & 7;
+            if (ep.ln_partial) {
+                // LayerNorm statistics of the h tile (128 pixels x 32 channels = one 4096-value chunk of the sample), two-pass in
+                // shared memory, in the (mean, M2) form the LayerNorm apply kernel merges (train_model.py:203-208; layernorm_vec.cu)
+                float* red = reinterpret_cast<float*>(smem) + (size_t)MS * STG_FLOATS + sub * 16;       // 8 warp sums + mean
+                const int t256 = lw * 32 + lane;                                     // 0..255: row t256 >> 1, 16-channel half t256 & 1
+                const float* hr = Hh + (t256 >> 1) * CP + (t256 & 1) * 16;
+                float hv[16], sum = 0.f;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float4 v = *reinterpret_cast<const float4*>(hr + 4 * i);
+                    hv[4 * i] = v.x; hv[4 * i + 1] = v.y; hv[4 * i + 2] = v.z; hv[4 * i + 3] = v.w;
+                    sum += (v.x + v.y) + (v.z + v.w);
+                }
+                sum = warp_sum(sum);
+                if (lane == 0) red[lw] = sum;
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");
+                float tot = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) tot += red[i];
+                const float mean = tot * (1.f / 4096.f);
+                float m2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) { const float d = hv[i] - mean; m2 = fmaf(d, d, m2); }
+                m2 = warp_sum(m2);
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");          // everyone has read the sums
+                if (lane == 0) red[lw] = m2;
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");
+                if (lw == 0 && lane == 0) {
+                    float t2 = 0.f;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) t2 += red[i];
+                    const int tiles_per_img = tiles_x * tiles_y;
+                    ep.ln_partial[(long)tb * ep.ln_S + (mt - tb * tiles_per_img) * (ep.C >> 5) + n_tile] = make_float2(mean, t2);
+                }
+            }
             if (ep.gates_bf16) {
                 // bf16 gate storage: 256-byte rows, 16 lanes x 16 B per row, two rows per warp instruction
                 __nv_bfloat16* gb = reinterpret_cast<__nv_bfloat16*>(ep.gates);
@@ -292,7 +327,7 @@ static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g,
     const int cols = MS * g.BN;
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
     const size_t smem = 1024 + (size_t)MS * PATCH_BYTES + (size_t)stages * b_bytes + (2 * stages + 3) * 8 + 16 + (size_t)g.BN * 4;
-    PIVP_REQUIRE(ep.mode != 1 || (size_t)MS * PATCH_BYTES + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4,
+    PIVP_REQUIRE(ep.mode != 1 || (size_t)MS * PATCH_BYTES + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4 + 256,
                  "%s(halo): operand ring too small to stage the gate epilogue", who);
     static bool attr_set = false;
     if (!attr_set) {

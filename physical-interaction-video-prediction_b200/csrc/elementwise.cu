@@ -822,9 +822,11 @@ int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, c
     int chunk;
     const int S = ln_split(n, &chunk);
     PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_fwd: workspace too small");
+    PIVP_REQUIRE(!(relu & 2) || (n % 4096 == 0 && chunk == 4096), "layernorm_fwd: precomputed partials need n to be a multiple of 4096");
     if (int r = ln_vec_fwd(x, x_cs, x_co, gamma, beta, B, HW, C, eps, y, y_cs, y_co, y2, y2_cs, y2_co, y_bf16, yb_cs, yb_co, relu, stats,
                            workspace, S, chunk, (cudaStream_t)stream))
         return r < 0 ? r : PIVP_OK;
+    PIVP_REQUIRE(!(relu & 2), "layernorm_fwd: precomputed partials are only supported by the vectorised path");
     ln_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, n, C, chunk, (float2*)workspace);
     if (int e = check_launch("layernorm_fwd(stats)")) return e;
     int gx = (n + LN_T * 4 - 1) / (LN_T * 4);

@@ -215,8 +215,12 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
         !a16(gamma) || !a16(beta) || (y_bf16 && ((reinterpret_cast<uintptr_t>(y_bf16) & 7) || yb_cs % 4 || yb_co % 4)))
         return 0;
     const Geo g = make_geo(HW, C);
-    stats_kernel<<<dim3(S, B), T, 0, st>>>(CView{x, x_cs, x_co}, g, n, chunk, (float2*)workspace);
-    if (int e = check_launch("layernorm_fwd(stats)")) return e;
+    const int have_stats = relu & 2;                           // the producer's epilogue already wrote the (mean, M2) partials
+    relu &= 1;
+    if (!have_stats) {
+        stats_kernel<<<dim3(S, B), T, 0, st>>>(CView{x, x_cs, x_co}, g, n, chunk, (float2*)workspace);
+        if (int e = check_launch("layernorm_fwd(stats)")) return e;
+    }
     int gx = (n / 4 + T - 1) / T;
     if (gx > 64) gx = 64;
     apply_kernel<<<dim3(gx, B), T, 0, st>>>(CView{x, x_cs, x_co}, gamma, beta, g, n, (const float2*)workspace, S, chunk, eps,

@@ -22,6 +22,8 @@ struct TcEpilogue {
     int accumulate;                              // mode 0: out += D (fp32 view only)
     float* gates;                                // mode 1: activated gates [M][N] (saved for backward); bf16 storage when gates_bf16
     int gates_bf16;
+    float2* ln_partial;                          // mode 1, halo kernel only: per-tile (mean, M2) of h for the LayerNorm that follows
+    int ln_S;                                    //   partial[b * ln_S + tile_in_sample * (C / 32) + n_tile], 4096 values each
     const float* c_prev; float* c_out;           // [M][C]  (c_prev may be null)
     float* h_out; int h_cs, h_co;                // fp32 h view (next step's xh h-slot)
     __nv_bfloat16* h_bf16; int hb_cs, hb_co;     // bf16 shadow (GEMM operand of the next step)

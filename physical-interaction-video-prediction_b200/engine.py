@@ -212,8 +212,9 @@ class Engine(object):
         self.L.call("pivp_conv2d_wgrad", x.ptr, x.cs, x.co, B, H, W, x.C, dy.ptr, dy.cs, dy.co, Ho, Wo, dy.C,
                     k, k, stride, pad, _ptr(dw), _ptr(db), self._s())
 
-    def _ln_fwd(self, name, x, B, HW, y, y2, relu, stats, y_bf16=None):
+    def _ln_fwd(self, name, x, B, HW, y, y2, relu, stats, y_bf16=None, have_stats=False):
         ws = self.ws
+        relu = relu | (2 if have_stats else 0)          # bit 1: the producing tcgen05 epilogue already wrote the (mean, M2) partials
         self.L.call("pivp_layernorm_fwd", x.ptr, x.cs, x.co, _ptr(self.p[name + "/norm/gamma"]), _ptr(self.p[name + "/norm/beta"]),
                     B, HW, x.C, 1e-6, y.ptr, y.cs, y.co, 0 if y2 is None else y2.ptr, 0 if y2 is None else y2.cs,
                     0 if y2 is None else y2.co, 0 if y_bf16 is None else y_bf16.ptr, 0 if y_bf16 is None else y_bf16.cs,
@@ -321,10 +322,10 @@ class Engine(object):
             # ---- group 1
             self._lstm_fwd(0, t, B)
             self._ln_fwd("hidden1", View(ws["xh"][0][t + 1], 64, 32, 32), B, HW[2], View(ws["xh"][1][t], 64, 0, 32), None, 0,
-                         ws["ln_stats"]["hidden1"][t], None if self.tc is None else self.tc.xview(1, t))
+                         ws["ln_stats"]["hidden1"][t], None if self.tc is None else self.tc.xview(1, t), have_stats=self.tc is not None and self.tc.ln_fused[0])
             self._lstm_fwd(1, t, B)
             self._ln_fwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), B, HW[2], View(ws["hid2"][t], 32, 0, 32), None, 0,
-                         ws["ln_stats"]["hidden2"][t])
+                         ws["ln_stats"]["hidden2"][t], have_stats=self.tc is not None and self.tc.ln_fused[1])
             self._conv_fwd(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, p["enc1/W"], p["enc1/b"], 32, 3, 2, 1,
                            View(ws["xh"][2][t], 96, 0, 32), relu=1)
             L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64,
@@ -334,10 +335,10 @@ class Engine(object):
             # ---- group 2
             self._lstm_fwd(2, t, B)
             self._ln_fwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), B, HW[4], View(ws["xh"][3][t], 128, 0, 64), None, 0,
-                         ws["ln_stats"]["hidden3"][t], None if self.tc is None else self.tc.xview(3, t))
+                         ws["ln_stats"]["hidden3"][t], None if self.tc is None else self.tc.xview(3, t), have_stats=self.tc is not None and self.tc.ln_fused[2])
             self._lstm_fwd(3, t, B)
             self._ln_fwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), B, HW[4], View(ws["hid4"][t], 64, 0, 64), None, 0,
-                         ws["ln_stats"]["hidden4"][t])
+                         ws["ln_stats"]["hidden4"][t], have_stats=self.tc is not None and self.tc.ln_fused[3])
             self._conv_fwd(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, p["enc2/W"], p["enc2/b"], 64, 3, 2, 1,
                            View(ws["in3"][t], 64 + self.sa, 0, 64), relu=1)
             # ---- group 3: smear + enc3; state predictor (train_model.py:676,730)
@@ -351,7 +352,7 @@ class Engine(object):
             # ---- group 4
             self._lstm_fwd(4, t, B)
             self._ln_fwd("hidden5", View(ws["xh"][4][t + 1], 192, 64, 128), B, HW[8], View(ws["hid5"][t], 128, 0, 128), None, 0,
-                         ws["ln_stats"]["hidden5"][t], None if self.tc is None else View(self.tc.hid5_b[t], 128, 0, 128))
+                         ws["ln_stats"]["hidden5"][t], None if self.tc is None else View(self.tc.hid5_b[t], 128, 0, 128), have_stats=self.tc is not None and self.tc.ln_fused[4])
             if self.tc is not None:
                 self.tc.deconv_fwd("enc4", self.tc.hid5_b[t], ws["xh"][5][t], 192, self.tc.xh_bf16[5][t], self.tc.Kpad[5], 1)
             else:
@@ -360,7 +361,7 @@ class Engine(object):
             # ---- group 5
             self._lstm_fwd(5, t, B)
             self._ln_fwd("hidden6", View(ws["xh"][5][t + 1], 192, 128, 64), B, HW[4], View(ws["cat5"][t], 96, 0, 64), None, 0,
-                         ws["ln_stats"]["hidden6"][t], None if self.tc is None else View(self.tc.cat5_b[t], 128, 0, 64))
+                         ws["ln_stats"]["hidden6"][t], None if self.tc is None else View(self.tc.cat5_b[t], 128, 0, 64), have_stats=self.tc is not None and self.tc.ln_fused[5])
             if self.tc is not None:
                 self.tc.deconv_fwd("enc5", self.tc.cat5_b[t], ws["xh"][6][t], 128, self.tc.xh_bf16[6][t], self.tc.Kpad[6], 1)
             else:
@@ -369,7 +370,7 @@ class Engine(object):
             # ---- group 6
             self._lstm_fwd(6, t, B)
             self._ln_fwd("hidden7", View(ws["xh"][6][t + 1], 128, 96, 32), B, HW[2], View(ws["cat6"][t], 64, 0, 32), None, 0,
-                         ws["ln_stats"]["hidden7"][t], None if self.tc is None else View(self.tc.cat6_b[t], 64, 0, 32))
+                         ws["ln_stats"]["hidden7"][t], None if self.tc is None else View(self.tc.cat6_b[t], 64, 0, 32), have_stats=self.tc is not None and self.tc.ln_fused[6])
             if self.tc is not None:
                 self.tc.deconv_fwd("enc6", self.tc.cat6_b[t], ws["e6pre"][t], 64, None, 0, 0)
             else:

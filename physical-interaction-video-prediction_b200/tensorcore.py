@@ -46,6 +46,9 @@ class TensorCorePlan(object):
             wsb = max(wsb, eng.L.query("pivp_tc_wgrad_workspace_bytes", S * B, h, w, cin + c, 4 * c))
         self.wgrad_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         self.accurate = 0
+        # layers whose maps the halo-patch kernel tiles (H % 16 == 0, W % 8 == 0): its epilogue also produces the LayerNorm statistics
+        self.ln_fused = [(eng.H // lv) % 16 == 0 and (eng.W // lv) % 8 == 0 and ((eng.H // lv) * (eng.W // lv) * c) % 4096 == 0
+                         for c, lv in zip(LSTM_SIZES, LSTM_LEVEL)]
         # ---- stride-2 Deconvolution2D layers enc4/enc5/enc6 (train_model.py:505-507) as 4 output phases each
         M8, M4, M2 = ws["Mr"][8], ws["Mr"][4], ws["Mr"][2]
         self.hid5_b = [torch.zeros(M8, 128, dtype=torch.bfloat16, device=dev) for _ in range(S)]
@@ -220,7 +223,8 @@ class TensorCorePlan(object):
                  _ptr(self.dg_bf16[li][t]), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
                  _ptr(ws["xh"][li][t + 1]), cin + C, cin, _ptr(self.xh_bf16[li][t + 1]), self.Kpad[li], cin,
                  0, 0, 0,
-                 C, 1.0, self.accurate | 2, e._s())       # flags bit 1: the activated gates are stored bf16, in dg_bf16[li][t]
+                 C, 1.0, self.accurate | 2, _ptr(ws["ln_ws"]) if self.ln_fused[li] else 0, e._s())
+        # flags bit 1: the activated gates are stored bf16, in dg_bf16[li][t]; ln_ws: LayerNorm statistics of h from the epilogue
 
     def lstm_dgrad(self, li, t):
         """dxh = conv(dG_t, tap-flipped W): gradient w.r.t. the concatenated input [x | h_{t-1}] (D.5)."""
@@ -239,7 +243,7 @@ class TensorCorePlan(object):
                  _ptr(self.Wd[li]), cx, bn, 0, 0,
                  _ptr(ws["dxh"][li]), cx, 0,
                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
-                 C, 0.0, 0, e._s())
+                 C, 0.0, 0, 0, e._s())
 
     def wgrad_all(self):
         """After BPTT: weight and bias gradients of all seven ConvLSTM convolutions, each as ONE GEMM over all time steps."""

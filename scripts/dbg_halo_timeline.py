@@ -18,10 +18,10 @@ def run(B, H, W, Kc, C, mode, N=None, BN=128):
     def call():
         if mode == 1:
             L.call("pivp_tc_conv5x5", x.data_ptr(), Kc, B, H, W, Kc, w.data_ptr(), N, 128, 1, bias.data_ptr(), 0, 0, 0,
-                   gates.data_ptr(), cp.data_ptr(), co.data_ptr(), h.data_ptr(), Kc, Kc - C, hb.data_ptr(), Kc, Kc - C, 0, 0, 0, C, 1.0, 0, st)
+                   gates.data_ptr(), cp.data_ptr(), co.data_ptr(), h.data_ptr(), Kc, Kc - C, hb.data_ptr(), Kc, Kc - C, 0, 0, 0, C, 1.0, 0, 0, st)
         else:
             L.call("pivp_tc_conv5x5", x.data_ptr(), Kc, B, H, W, Kc, w.data_ptr(), N, BN, 0, 0, out.data_ptr(), N, 0,
-                   0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, C, 0.0, 0, st)
+                   0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, C, 0.0, 0, 0, st)
     for _ in range(3): call()
     torch.cuda.synchronize()
     L.call("pivp_tc_set_debug_buffer", dbg.data_ptr())
