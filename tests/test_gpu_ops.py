@@ -263,6 +263,68 @@ def test_adam_matches_chainer_rule(pk):
     assert rel(p, params["w"]) < 1e-6
 
 
+@pytest.mark.parametrize("B,H,W,Ne,M1", [(2, 16, 24, 3, 11), (3, 8, 8, 25, 2), (1, 64, 64, 3, 11)])
+def test_heads_fused_fwd_bwd(pk, B, H, W, Ne, M1):
+    """The two 1x1 head deconvolutions (enc7 + masks) fused: NCHW planes out / in, against the oracle's Deconvolution2D."""
+    rs = np.random.RandomState(21)
+    L = pk.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    NH, HW, M = Ne + M1, H * W, B * H * W
+    x = rs.standard_normal((B, 64, H, W)).astype(np.float32)
+    Wa, Wb = (rs.standard_normal((64, Ne, 1, 1)) / 8).astype(np.float32), (rs.standard_normal((64, M1, 1, 1)) / 8).astype(np.float32)
+    ba, bb = rs.standard_normal(Ne).astype(np.float32), rs.standard_normal(M1).astype(np.float32)
+    vx = G.Var(x.astype(np.float64))
+    va, vb, vba, vbb = (G.Var(v.astype(np.float64)) for v in (Wa, Wb, ba, bb))
+    ya = G.deconvolution_2d(vx, va, vba, 1, 0, (H, W))
+    yb = G.deconvolution_2d(vx, vb, vbb, 1, 0, (H, W))
+    ga, gb = rs.standard_normal(ya.data.shape).astype(np.float32), rs.standard_normal(yb.data.shape).astype(np.float32)
+    G.backward(G.sum_(ya * G.Var(ga.astype(np.float64)), (0, 1, 2, 3)) + G.sum_(yb * G.Var(gb.astype(np.float64)), (0, 1, 2, 3)))
+    # internal layouts: x NHWC rows inside a wider buffer (stride 72, offset 4), W [NH][64], b [NH]
+    xb = torch.zeros(M, 72, device="cuda")
+    xb[:, 4:68] = cu(x.transpose(0, 2, 3, 1).reshape(M, 64))
+    Wi = cu(np.concatenate([Wa[:, :, 0, 0].T, Wb[:, :, 0, 0].T], 0))
+    bi = cu(np.concatenate([ba, bb]))
+    oa, ob = torch.empty(B, Ne, H, W, device="cuda"), torch.empty(B, M1, H, W, device="cuda")
+    L.call("pivp_heads_fwd", xb.data_ptr(), 72, 4, Wi.data_ptr(), bi.data_ptr(), oa.data_ptr(), Ne, ob.data_ptr(), NH, B, HW, s)
+    assert rel(oa, ya.data) < FWD_TOL and rel(ob, yb.data) < FWD_TOL
+    dx = torch.full((M, 72), 3.0, device="cuda")
+    dW, db = torch.full((NH, 64), 0.5, device="cuda"), torch.full((NH,), 0.25, device="cuda")      # accumulated into
+    gad, gbd = cu(ga), cu(gb)                                   # keep the device buffers alive across the call
+    L.call("pivp_heads_bwd", xb.data_ptr(), 72, 4, Wi.data_ptr(), gad.data_ptr(), Ne, gbd.data_ptr(), NH, dx.data_ptr(), 72, 4,
+           dW.data_ptr(), db.data_ptr(), B, HW, s)
+    assert rel(dx[:, 4:68].reshape(B, H, W, 64).permute(0, 3, 1, 2), vx.grad) < GRAD_TOL
+    assert torch.all(dx[:, :4] == 3.0) and torch.all(dx[:, 68:] == 3.0)                             # outside the view untouched
+    dW_ref = np.concatenate([va.grad[:, :, 0, 0].T, vb.grad[:, :, 0, 0].T], 0)
+    assert rel(dW - 0.5, dW_ref) < GRAD_TOL and rel(db - 0.25, np.concatenate([vba.grad, vbb.grad])) < GRAD_TOL
+
+
+@pytest.mark.parametrize("M,C,H,W,s2d,mask,two", [(2 * 16 * 16, 96, 16, 16, 1, 1, 0), (3 * 8 * 8, 64, 8, 8, 1, 0, 0), (500, 32, 0, 0, 0, 1, 1)])
+def test_grad_handover_matches_separate_kernels(pk, M, C, H, W, s2d, mask, two):
+    """relu_bwd + colsum + cast_bf16 in one launch: bit-identical fp32 / bf16 outputs, column sums to fp32 rounding."""
+    L = pk.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    gen = torch.Generator(device="cuda"); gen.manual_seed(5)
+    out = torch.randn(M, C + 8, device="cuda", generator=gen)
+    ga, gb = torch.randn(M, C + 4, device="cuda", generator=gen), torch.randn(M, C, device="cuda", generator=gen)
+    cb = (C + 63) // 64 * 64
+    rows = M // 4 if s2d else M
+    bcs = 4 * cb if s2d else cb
+    d1, d2 = torch.zeros(M, C, device="cuda"), torch.zeros(M, C, device="cuda")
+    b1, b2 = torch.zeros(rows, bcs, dtype=torch.bfloat16, device="cuda"), torch.zeros(rows, bcs, dtype=torch.bfloat16, device="cuda")
+    db1, db2 = torch.full((C,), 0.5, device="cuda"), torch.full((C,), 0.5, device="cuda")
+    L.call("pivp_grad_handover", out.data_ptr() if mask else 0, C + 8, 4, ga.data_ptr(), C + 4, 0, gb.data_ptr() if two else 0, C, 0,
+           d1.data_ptr(), C, 0, b1.data_ptr(), bcs, 0, H, W, s2d, cb, db1.data_ptr(), M, C, s)
+    if mask:
+        L.call("pivp_relu_bwd", out.data_ptr(), C + 8, 4, ga.data_ptr(), C + 4, 0, gb.data_ptr() if two else 0, C, 0, d2.data_ptr(), C, 0, M, C, s)
+    else:
+        d2.copy_(ga[:, :C] + (gb if two else 0))
+    L.call("pivp_colsum", d2.data_ptr(), C, 0, M, C, db2.data_ptr(), s)
+    L.call("pivp_cast_bf16", d2.data_ptr(), C, 0, b2.data_ptr(), bcs, 0, M, C, H, W, s2d, cb, s)
+    torch.cuda.synchronize()
+    assert torch.equal(d1, d2) and torch.equal(b1, b2)
+    assert rel(db1, db2.double().cpu().numpy()) < 1e-5
+
+
 @pytest.mark.parametrize("B,K,N,relu", [(32, 8192, 250, 0), (7, 2048, 100, 1), (3, 1024, 6, 0)])
 def test_linear_wide_paths_match_oracle(pk, B, K, N, relu):
     """The split-K forward and the wide backward kernels (weight matrix streamed once) against the oracle's Linear."""

@@ -102,6 +102,22 @@ def test_tc_convlstm_fused_matches_simt_and_gate_kernel(pk, B, H, W, cin, C, t0)
         assert rel(gates, G_ref) < tol and rel(c_out, c_ref) < tol and rel(h_out, h_ref) < tol
         assert float(h_out[:, :cin].abs().max()) == 0.0                       # only the h slot is written
         assert rel(h_b[:, cin:cx], h_out[:, cin:cx]) < 1e-2                   # bf16 shadow of h
+    if H % 16 == 0 and W % 8 == 0:
+        # bf16 gate storage (flags bit 1) and the LayerNorm statistics of h from the same epilogue (ln_partial)
+        gates_b = torch.empty(M, 4 * C, dtype=torch.bfloat16, device="cuda")
+        n = H * W * C
+        S = n // 4096
+        part = torch.zeros(B, S, 2, device="cuda")
+        L.call("pivp_tc_conv5x5", xh_b.data_ptr(), Kp, B, H, W, Kp, Wf.data_ptr(), 4 * C, 128, 1, bias.data_ptr(),
+               0, 0, 0, gates_b.data_ptr(), 0 if c_prev is None else c_prev.data_ptr(), c_out.data_ptr(),
+               h_out.data_ptr(), cx, cin, h_b.data_ptr(), Kp, cin, 0, 0, 0, C, 1.0, 2, part.data_ptr(), stream())
+        torch.cuda.synchronize()
+        assert rel(gates_b, gates) < 1e-2                                     # same activations, bf16 rounding only
+        hs = h_out[:, cin:cx].reshape(B, -1).double()
+        mean = (part[:, :, 0].double() * 4096).sum(1) / n                     # Chan merge of the per-tile (mean, M2) pairs
+        m2 = (part[:, :, 1].double() + 4096 * (part[:, :, 0].double() - mean[:, None]) ** 2).sum(1)
+        assert float((mean - hs.mean(1)).abs().max()) < 1e-6
+        assert float((m2 / n - hs.var(1, unbiased=False)).abs().max() / hs.var(1, unbiased=False).max()) < 1e-5
 
 
 def test_tc_unsupported_shapes_are_reported(pk):
@@ -170,6 +186,61 @@ def test_model_bf16_within_tolerance_of_oracle(pk, mt, nm, k):
         if e > (0.5 if mt == "STP" else 0.25) or cos < (0.9 if mt == "STP" else 0.97):
             bad[key] = (e, cos)
     assert not bad, bad
+
+
+@pytest.mark.parametrize("M,C,cin,first", [(2 * 32 * 32, 32, 32, False), (2 * 16 * 16, 64, 64, True)])
+def test_lstm_gates_bwd_bf16_matches_fp32_kernel(pk, M, C, cin, first):
+    """bf16 gate storage: same math as pivp_lstm_gates_bwd on the bf16-rounded activations; dG is written bf16 in place."""
+    L = pk.lib()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(9)
+    act = torch.rand(M, 4 * C, device="cuda", generator=gen) * 1.6 - 0.8
+    gates_b = act.bfloat16()
+    gates_f = gates_b.float().contiguous()
+    c_prev = None if first else torch.randn(M, C, device="cuda", generator=gen)
+    c_cur = torch.randn(M, C, device="cuda", generator=gen)
+    dh_a = torch.randn(M, C, device="cuda", generator=gen)
+    dxh = torch.randn(M, cin + C, device="cuda", generator=gen)
+    dc1 = torch.randn(M, C, device="cuda", generator=gen)
+    dc2 = dc1.clone()
+    L.call("pivp_lstm_gates_bwd", gates_f.data_ptr(), 0 if first else c_prev.data_ptr(), c_cur.data_ptr(), dh_a.data_ptr(), dxh.data_ptr(),
+           cin + C, cin, dc1.data_ptr(), 1, 0, M, C, stream())
+    L.call("pivp_lstm_gates_bwd_bf16", gates_b.data_ptr(), 0 if first else c_prev.data_ptr(), c_cur.data_ptr(), dh_a.data_ptr(), dxh.data_ptr(),
+           cin + C, cin, dc2.data_ptr(), 1, gates_b.data_ptr(), M, C, stream())
+    torch.cuda.synchronize()
+    assert rel(dc2, dc1) < 1e-5
+    # dG: bf16 rounding of the same fp32 values (FMA contraction may move a value across a rounding boundary: one bf16 ulp = 2^-8)
+    assert rel(gates_b, gates_f) < 2 ** -8
+
+
+def test_tc_conv_taps_multi_equals_single_phase_launches(pk):
+    """The four output phases of a stride-2 deconvolution in one launch (grid z = phase) == four single-phase launches, bit for bit."""
+    import ctypes
+    L = pk.lib()
+    rs = np.random.RandomState(4)
+    B, h, w, cin, cout = 2, 16, 16, 96, 96
+    kc = 128
+    M = B * h * w
+    x = torch.zeros(M, kc, device="cuda"); x[:, :cin] = torch.from_numpy(rs.standard_normal((M, cin)).astype(np.float32)).cuda()
+    xb = x.bfloat16()
+    bias = torch.from_numpy(rs.standard_normal(cout).astype(np.float32)).cuda()
+    sel = {0: [(0, 1)], 1: [(1, 0), (0, 2)]}
+    phases = []
+    for a in (0, 1):
+        for b in (0, 1):
+            taps = [(dy, dx) for (dy, _) in sel[a] for (dx, _) in sel[b]]
+            wt = torch.from_numpy((rs.standard_normal((cout, len(taps) * kc)) / 10).astype(np.float32)).cuda().bfloat16()
+            phases.append((a, b, taps, wt))
+    o1, o2 = torch.zeros(4 * M, cout, device="cuda"), torch.zeros(4 * M, cout, device="cuda")
+    for a, b, taps, wt in phases:
+        arr = lambda v: (ctypes.c_int * len(v))(*v)
+        L.call("pivp_tc_conv_taps", xb.data_ptr(), kc, B, h, w, kc, len(taps), arr([t[0] for t in taps]), arr([t[1] for t in taps]),
+               arr([0] * len(taps)), wt.data_ptr(), cout, 96, bias.data_ptr(), 1, 0, o1.data_ptr(), cout, 0, 0, 0, 0, 2 * h, 2 * w, 2, a, b, stream())
+    flat = lambda k: (ctypes.c_int * 16)(*[(list(p[2][i] if k >= 0 else (0, 0)) + [0])[max(k, 0)] if i < len(p[2]) else 0 for p in phases for i in range(4)])
+    L.call("pivp_tc_conv_taps_multi", xb.data_ptr(), kc, B, h, w, kc, 4, (ctypes.c_int * 4)(*[len(p[2]) for p in phases]), flat(0), flat(1),
+           (ctypes.c_int * 16)(*([0] * 16)), (ctypes.c_void_p * 4)(*[p[3].data_ptr() for p in phases]), cout, 96, bias.data_ptr(), 1, 0,
+           o2.data_ptr(), cout, 0, 0, 0, 0, 2 * h, 2 * w, 2, (ctypes.c_int * 4)(*[p[0] for p in phases]), (ctypes.c_int * 4)(*[p[1] for p in phases]), stream())
+    torch.cuda.synchronize()
+    assert float(o1.abs().max()) > 0 and torch.equal(o1, o2)
 
 
 @pytest.mark.parametrize("SB,H,W,Cx,N4", [
