@@ -64,6 +64,7 @@ class Engine(object):
         self.M1 = self.M + 1
         self.Nh = self.Ne + self.M1
         self.sa = 10 if self.use_state else 0
+        self.cs3 = (64 + self.sa + 3) // 4 * 4          # row stride of the enc3 input [enc2 out | smear]: 74 channels in 76-float rows (16-B aligned)
         self.specs, self.nparam = layout.param_specs(model_type, self.M, self.use_state, self.H, self.W)
         self.spec = {s.name: s for s in self.specs}
         self.flat_p = torch.zeros(self.nparam, dtype=torch.float32, device=self.dev)
@@ -126,7 +127,7 @@ class Engine(object):
             ws["c"].append([A(Mr[lv], c) for _ in range(S)])
         ws["hid2"] = stack(Mr[2], 32)
         ws["hid4"] = stack(Mr[4], 64)
-        ws["in3"] = stack(Mr[8], 64 + self.sa)
+        ws["in3"] = stack(Mr[8], self.cs3)
         ws["hid5"] = [A(Mr[8], 128) for _ in range(S)]
         ws["cat5"] = [A(Mr[4], 96) for _ in range(S)]
         ws["cat6"] = [A(Mr[2], 64) for _ in range(S)]
@@ -169,7 +170,7 @@ class Engine(object):
         ws["d_e5pre"] = A(Mr[2], 96)
         ws["d_e4pre"] = A(Mr[4], 128)
         ws["d_e3pre"] = stack(Mr[8], 64)               # d(pre-activation) of enc0..enc3 kept per time step for the deferred weight gradients
-        ws["d_in3"] = A(Mr[8], 64 + self.sa)
+        ws["d_in3"] = A(Mr[8], self.cs3)
         ws["d_e2pre"] = stack(Mr[8], 64)
         ws["d_hid4"] = A(Mr[4], 64)
         ws["d_e1pre"] = stack(Mr[4], 32)
@@ -326,12 +327,13 @@ class Engine(object):
             self._lstm_fwd(1, t, B)
             self._ln_fwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), B, HW[2], View(ws["hid2"][t], 32, 0, 32), None, 0,
                          ws["ln_stats"]["hidden2"][t], have_stats=self.tc is not None and self.tc.ln_fused[1])
-            self._conv_fwd(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, p["enc1/W"], p["enc1/b"], 32, 3, 2, 1,
-                           View(ws["xh"][2][t], 96, 0, 32), relu=1)
-            L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64,
-                   0 if self.tc is None else self.tc.xview(2, t).ptr, 0 if self.tc is None else self.tc.Kpad[2], 0, Mr[4], 32, s)
-            if self.tc is not None:
-                L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, 0, 0, 0, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, s)
+            if self.tc is not None:       # stride-2 conv as a 9-tap tcgen05 GEMM on the space-to-depth bf16 input; bf16 x slot from the epilogue
+                self.tc.conv_s2_fwd("enc1", ws["hid2"][t], 32, ws["xh"][2][t], 96, self.tc.xview(2, t).t, self.tc.Kpad[2])
+                L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, s)
+            else:
+                self._conv_fwd(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, p["enc1/W"], p["enc1/b"], 32, 3, 2, 1,
+                               View(ws["xh"][2][t], 96, 0, 32), relu=1)
+                L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, 0, 0, 0, Mr[4], 32, s)
             # ---- group 2
             self._lstm_fwd(2, t, B)
             self._ln_fwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), B, HW[4], View(ws["xh"][3][t], 128, 0, 64), None, 0,
@@ -339,13 +341,16 @@ class Engine(object):
             self._lstm_fwd(3, t, B)
             self._ln_fwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), B, HW[4], View(ws["hid4"][t], 64, 0, 64), None, 0,
                          ws["ln_stats"]["hidden4"][t], have_stats=self.tc is not None and self.tc.ln_fused[3])
-            self._conv_fwd(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, p["enc2/W"], p["enc2/b"], 64, 3, 2, 1,
-                           View(ws["in3"][t], 64 + self.sa, 0, 64), relu=1)
+            if self.tc is not None:
+                self.tc.conv_s2_fwd("enc2", ws["hid4"][t], 64, ws["in3"][t], self.cs3, None, 0)
+            else:
+                self._conv_fwd(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, p["enc2/W"], p["enc2/b"], 64, 3, 2, 1,
+                               View(ws["in3"][t], self.cs3, 0, 64), relu=1)
             # ---- group 3: smear + enc3; state predictor (train_model.py:676,730)
             L.call("pivp_state_fwd", _ptr(actions[t]), _ptr(ws["cur"][t]), _ptr(p["current_state/W"]), _ptr(p["current_state/b"]),
-                   _ptr(ws["sa"][t]), _ptr(ws["cur"][t + 1]), _ptr(ws["in3"][t]) if self.use_state else 0, 64 + self.sa, 64,
+                   _ptr(ws["sa"][t]), _ptr(ws["cur"][t + 1]), _ptr(ws["in3"][t]) if self.use_state else 0, self.cs3, 64,
                    HW[8], B, s)
-            self._conv_fwd(View(ws["in3"][t], 64 + self.sa, 0, 64 + self.sa), B, H // 8, W // 8, p["enc3/W"], p["enc3/b"], 64, 1, 1, 0,
+            self._conv_fwd(View(ws["in3"][t], self.cs3, 0, 64 + self.sa), B, H // 8, W // 8, p["enc3/W"], p["enc3/b"], 64, 1, 1, 0,
                            View(ws["xh"][4][t], 192, 0, 64), relu=1)
             if self.tc is not None:
                 L.call("pivp_copy_view", _ptr(ws["xh"][4][t]), 192, 0, 0, 0, 0, self.tc.xview(4, t).ptr, self.tc.Kpad[4], 0, Mr[8], 64, s)
@@ -532,24 +537,21 @@ class Engine(object):
             # ---- enc3 (1x1 on concat(enc2 out, smear))
             self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"][t], 64, 0, 64), Mr[8])
             de3 = View(ws["d_e3pre"][t], 64, 0, 64)
-            cin3 = 64 + self.sa
-            self._conv_dgrad(de3, B, H // 8, W // 8, p["enc3/W"], None, 1, 1, 0, View(ws["d_in3"], cin3, 0, cin3), H // 8, W // 8)
+            cin3, cs3 = 64 + self.sa, self.cs3
+            self._conv_dgrad(de3, B, H // 8, W // 8, p["enc3/W"], None, 1, 1, 0, View(ws["d_in3"], cs3, 0, cin3), H // 8, W // 8)
             # ---- state predictor + smear backward; produces d cur[t] for step t-1
             d_cur_out = ws["d_cur"][t & 1]
             L.call("pivp_state_bwd", _ptr(ws["d_gs"][t]), _ptr(d_cur_in), _ptr(ws["sa"][t]), _ptr(p["current_state/W"]),
-                   _ptr(ws["d_in3"]) if self.use_state else 0, cin3, 64, HW[8], B, _ptr(d_cur_out),
+                   _ptr(ws["d_in3"]) if self.use_state else 0, cs3, 64, HW[8], B, _ptr(d_cur_out),
                    _ptr(g["current_state/W"]), _ptr(g["current_state/b"]), s)
             d_cur_in = d_cur_out
             # ---- enc2
             de2 = View(ws["d_e2pre"][t], 64, 0, 64)
-            if self.tc is not None and cin3 % 4 == 0:
-                self.tc.conv_s2_dgrad_fused("enc2", View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, de2, self.tc.de2_b,
+            if self.tc is not None:
+                self.tc.conv_s2_dgrad_fused("enc2", View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, de2, self.tc.de2_b,
                                             Mr[8], 64, ws["d_hid4"], 64)
-            elif self.tc is not None:
-                self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, de2, Mr[8])
-                self.tc.conv_s2_dgrad("enc2", ws["d_e2pre"][t], self.tc.de2_b, Mr[8], 64, ws["d_hid4"], 64)
             else:
-                self._relu_bwd(View(ws["in3"][t], cin3, 0, 64), View(ws["d_in3"], cin3, 0, 64), None, de2, Mr[8])
+                self._relu_bwd(View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, de2, Mr[8])
                 self._conv_dgrad(de2, B, H // 8, W // 8, p["enc2/W"], None, 3, 2, 1, View(ws["d_hid4"], 64, 0, 64), H // 4, W // 4)
             # ---- lstm4, lstm3
             self._ln_bwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), View(ws["d_hid4"], 64, 0, 64), None, B, HW[4], 0,
@@ -595,7 +597,7 @@ class Engine(object):
                              3, 2, 1, g["enc1/W"], g["enc1/b"])
             self._conv_wgrad(View(first(ws["hid4"]), 64, 0, 64), S * B, H // 4, W // 4, View(first(ws["d_e2pre"]), 64, 0, 64), H // 8, W // 8,
                              3, 2, 1, g["enc2/W"], g["enc2/b"])
-            self._conv_wgrad(View(first(ws["in3"]), cin3, 0, cin3), S * B, H // 8, W // 8, View(first(ws["d_e3pre"]), 64, 0, 64), H // 8, W // 8,
+            self._conv_wgrad(View(first(ws["in3"]), self.cs3, 0, cin3), S * B, H // 8, W // 8, View(first(ws["d_e3pre"]), 64, 0, 64), H // 8, W // 8,
                              1, 1, 0, g["enc3/W"], g["enc3/b"])
         if self.tc is not None:
             self.tc.wgrad_all()                # ConvLSTM weight/bias gradients: one tcgen05 GEMM per layer over all time steps

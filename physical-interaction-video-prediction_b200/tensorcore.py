@@ -61,6 +61,8 @@ class TensorCorePlan(object):
         # (conv weight [N][ky][kx][C] has the deconv form with in := N, out := C)
         self.dec["enc1"] = self._plan_deconv("enc1", 32, 32, 4)
         self.dec["enc2"] = self._plan_deconv("enc2", 64, 64, 8)
+        # forward of the stride-2 convolutions enc1 / enc2: 9-tap stride-1 GEMM on the space-to-depth bf16 input (half grid, 4 phases x cb ch)
+        self.s2f = {"enc1": self._plan_conv_s2_fwd("enc1", 32, 32, 2), "enc2": self._plan_conv_s2_fwd("enc2", 64, 64, 4)}
         self.de1_b = torch.zeros(M4, 64, dtype=torch.bfloat16, device=dev)      # bf16 d(enc1 pre-activation), 32 used
         self.de2_b = torch.zeros(M8, 64, dtype=torch.bfloat16, device=dev)
         # ---- deconvolution backward: dY in space-to-depth bf16 (all time steps kept for the deferred weight gradient)
@@ -78,6 +80,40 @@ class TensorCorePlan(object):
             setattr(self, nm + "_all", allt)
             setattr(self, nm, [allt[t] for t in range(S)])
         self.refresh_weights()
+
+    def _plan_conv_s2_fwd(self, name, cin, cout, lv_in):
+        """out[oy,ox][n] = sum_{ky,kx,c} W[n][ky][kx][c] in[2oy+ky-1, 2ox+kx-1][c]: on the space-to-depth input (pixel (y', x') of the half
+        grid holds the 2x2 phases (py,px) in channel blocks of cb) tap k reads half-grid offset {0:-1, 1:0, 2:0}[k] and phase {0:1, 1:0, 2:1}[k]."""
+        e = self.eng
+        dev = e.dev
+        cb = (cin + 63) // 64 * 64
+        lv = 2 * lv_in
+        M = self.ws["Mr"][lv]
+        tapdef = {0: (-1, 1), 1: (0, 0), 2: (0, 1)}
+        taps = []
+        for ky in range(3):
+            for kx in range(3):
+                (dy, py), (dx, px) = tapdef[ky], tapdef[kx]
+                taps.append((dy, dx, (py * 2 + px) * cb))
+        base = e.spec[name + "/W"].offset                      # internal conv layout [N][ky][kx][C]
+        idx = np.full((cout, 9, cb), -1, np.int32)
+        c = np.arange(cin)
+        for n in range(cout):
+            for tp in range(9):
+                idx[n, tp, :cin] = base + (n * 9 + tp) * cin + c
+        arr = lambda v: (ctypes.c_int * 9)(*v)
+        return dict(cin=cin, cout=cout, cb=cb, lv=lv, dy=arr([q[0] for q in taps]), dx=arr([q[1] for q in taps]), co=arr([q[2] for q in taps]),
+                    idx=torch.from_numpy(idx.reshape(-1)).to(dev), wt=torch.empty(cout, 9 * cb, dtype=torch.bfloat16, device=dev),
+                    xs=torch.zeros(M, 4 * cb, dtype=torch.bfloat16, device=dev))
+
+    def conv_s2_fwd(self, name, x_f32, x_cs, out, out_cs, out_bf16, ob_cs):
+        """Stride-2 Convolution2D + bias + ReLU (train_model.py:501-502): cast the fp32 input to space-to-depth bf16, one tcgen05 launch."""
+        e, d = self.eng, self.s2f[name]
+        h, w = e.H // d["lv"], e.W // d["lv"]
+        B = self.ws["B"]
+        e.L.call("pivp_cast_bf16", _ptr(x_f32), x_cs, 0, _ptr(d["xs"]), 4 * d["cb"], 0, B * 4 * h * w, d["cin"], 2 * h, 2 * w, 1, d["cb"], e._s())
+        e.L.call("pivp_tc_conv_taps", _ptr(d["xs"]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
+                 d["cout"], d["cout"], _ptr(e.p[name + "/b"]), 1, 0, _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, h, w, 1, 0, 0, e._s())
 
     def _plan_deconv_bwd(self, name, cin, cout, lv):
         """Backward of a stride-2 deconvolution on the tensor cores.  dY (big grid) is cast to space-to-depth bf16
@@ -148,7 +184,7 @@ class TensorCorePlan(object):
         for d in getattr(self, "dec", {}).values():
             for ph in d["phases"]:
                 e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(ph["idx"]), ph["idx"].numel(), _ptr(ph["wt"]), e._s())
-        for d in getattr(self, "dbw", {}).values():
+        for d in list(getattr(self, "dbw", {}).values()) + list(getattr(self, "s2f", {}).values()):
             e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(d["idx"]), d["idx"].numel(), _ptr(d["wt"]), e._s())
 
     def deconv_bwd_data(self, name, t, dy_f32, out, accumulate):
