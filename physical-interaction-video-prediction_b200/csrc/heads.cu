@@ -87,23 +87,24 @@ __global__ void __launch_bounds__(TP) heads_fwd_kernel(const float* __restrict__
 }
 
 // Persistent: CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ...; dW / db partials live in registers across tiles.
+// Weight-gradient ownership per thread: 4 channels x NB contiguous heads (n = half * NB + j) x one quarter of the tile's pixels.
 template <int NH>
-__global__ void __launch_bounds__(TP) heads_bwd_kernel(const float* __restrict__ x, int cs, int co, const float* __restrict__ Wt,
-                                                       const float* __restrict__ dy_a, int Na, const float* __restrict__ dy_b,
-                                                       float* __restrict__ dx, int dcs, int dco, float* __restrict__ dW,
-                                                       float* __restrict__ db, long M, int HW, int ntiles) {
-    constexpr int NP = (NH + 3) / 4 * 4, NH2 = (NH + 1) / 2;     // NH2 heads per thread half
+__global__ void __launch_bounds__(TP, 4) heads_bwd_kernel(const float* __restrict__ x, int cs, int co, const float* __restrict__ Wt,
+                                                          const float* __restrict__ dy_a, int Na, const float* __restrict__ dy_b,
+                                                          float* __restrict__ dx, int dcs, int dco, float* __restrict__ dW,
+                                                          float* __restrict__ db, long M, int HW, int ntiles) {
+    constexpr int NB = ((NH + 1) / 2 + 3) / 4 * 4;               // heads per thread half, padded to float4 (8 for 14, 16 for 27)
+    constexpr int NP = 2 * NB;                                   // dY tile pitch: [pixel][NP], heads >= NH are zero
     extern __shared__ __align__(16) float hsm[];
     float* xs = hsm;                                             // [TP][XP] pixel tile
-    float* ds = xs + TP * XP;                                    // [TP][NP] dY tile [pixel][n]
+    float* ds = xs + TP * XP;                                    // [TP][NP] dY tile
     float* ws = ds + TP * NP;                                    // [NH][C]  W
     for (int i = threadIdx.x; i < NH * C; i += TP) ws[i] = __ldg(Wt + i);
-    // weight-gradient ownership: 4 channels x NH2 heads (n = half, half + 2, ...) x one quarter of the tile's pixels
     const int cg = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1, pq = threadIdx.x >> 5;
-    float4 aw[NH2];
-    float ab[NH2];
+    float2 aw[NB][2];
+    float ab[NB];
 #pragma unroll
-    for (int j = 0; j < NH2; ++j) { aw[j] = make_float4(0.f, 0.f, 0.f, 0.f); ab[j] = 0.f; }
+    for (int j = 0; j < NB; ++j) { aw[j][0] = aw[j][1] = make_float2(0.f, 0.f); ab[j] = 0.f; }
     const int Nb = NH - Na;
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long m0 = (long)tile * TP;
@@ -112,41 +113,58 @@ __global__ void __launch_bounds__(TP) heads_bwd_kernel(const float* __restrict__
         {
             const long m = m0 + threadIdx.x;
             const long b = m / HW, p = m - b * HW;
+            float v[NP];
 #pragma unroll
             for (int n = 0; n < NP; ++n) {
-                float v = 0.f;
-                if (m < M && n < NH) v = n < Na ? __ldg(dy_a + (b * Na + n) * HW + p) : __ldg(dy_b + (b * Nb + (n - Na)) * HW + p);
-                ds[threadIdx.x * NP + n] = v;
+                v[n] = 0.f;
+                if (m < M && n < NH) v[n] = n < Na ? __ldg(dy_a + (b * Na + n) * HW + p) : __ldg(dy_b + (b * Nb + (n - Na)) * HW + p);
             }
+#pragma unroll
+            for (int n4 = 0; n4 < NP / 4; ++n4)
+                *reinterpret_cast<float4*>(ds + threadIdx.x * NP + 4 * n4) = make_float4(v[4 * n4], v[4 * n4 + 1], v[4 * n4 + 2], v[4 * n4 + 3]);
         }
         __syncthreads();
-        // ---- dW[n][c] += sum_p dY[p][n] x[p][c]   (this thread: 32 pixels, 4 channels, NH2 heads)
-#pragma unroll 4
+        // ---- dW[n][c] += sum_p dY[p][n] x[p][c]   (this thread: 32 pixels, 4 channels, NB heads) -- packed FFMA2, broadcast dY
+#pragma unroll 2
         for (int i = 0; i < TP / 4; ++i) {
             const int p = pq * (TP / 4) + i;
             const float4 xv = *reinterpret_cast<const float4*>(xs + p * XP + 4 * cg);
+            const float2 x01 = make_float2(xv.x, xv.y), x23 = make_float2(xv.z, xv.w);
+            const float4* dr = reinterpret_cast<const float4*>(ds + p * NP + half * NB);
 #pragma unroll
-            for (int j = 0; j < NH2; ++j) {
-                const int n = half + 2 * j;
-                const float d = n < NH ? ds[p * NP + n] : 0.f;
-                aw[j].x = fmaf(d, xv.x, aw[j].x); aw[j].y = fmaf(d, xv.y, aw[j].y);
-                aw[j].z = fmaf(d, xv.z, aw[j].z); aw[j].w = fmaf(d, xv.w, aw[j].w);
-                if (cg == 0) ab[j] += d;
+            for (int j4 = 0; j4 < NB / 4; ++j4) {
+                const float4 d4 = dr[j4];
+                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int j = 4 * j4 + k;
+                    aw[j][0] = ffma2(make_float2(dd[k], dd[k]), x01, aw[j][0]);
+                    aw[j][1] = ffma2(make_float2(dd[k], dd[k]), x23, aw[j][1]);
+                    if (cg == 0) ab[j] += dd[k];
+                }
             }
         }
         // ---- d_x[c] = sum_n dY[n] W[n][c] for this thread's pixel
         float2 acc[C / 2];
 #pragma unroll
         for (int j = 0; j < C / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+        {
+            float dmy[NP];
 #pragma unroll
-        for (int n = 0; n < NH; ++n) {
-            const float d = ds[threadIdx.x * NP + n];
-            const float4* wr = reinterpret_cast<const float4*>(ws + n * C);
+            for (int n4 = 0; n4 < NP / 4; ++n4) {
+                const float4 d4 = *reinterpret_cast<const float4*>(ds + threadIdx.x * NP + 4 * n4);
+                dmy[4 * n4] = d4.x; dmy[4 * n4 + 1] = d4.y; dmy[4 * n4 + 2] = d4.z; dmy[4 * n4 + 3] = d4.w;
+            }
 #pragma unroll
-            for (int j = 0; j < C / 4; ++j) {
-                const float4 w4 = wr[j];
-                acc[2 * j] = ffma2(make_float2(d, d), make_float2(w4.x, w4.y), acc[2 * j]);
-                acc[2 * j + 1] = ffma2(make_float2(d, d), make_float2(w4.z, w4.w), acc[2 * j + 1]);
+            for (int n = 0; n < NH; ++n) {
+                const float d = dmy[n];
+                const float4* wr = reinterpret_cast<const float4*>(ws + n * C);
+#pragma unroll
+                for (int j = 0; j < C / 4; ++j) {
+                    const float4 w4 = wr[j];
+                    acc[2 * j] = ffma2(make_float2(d, d), make_float2(w4.x, w4.y), acc[2 * j]);
+                    acc[2 * j + 1] = ffma2(make_float2(d, d), make_float2(w4.z, w4.w), acc[2 * j + 1]);
+                }
             }
         }
         __syncthreads();                                          // everyone has finished reading the x tile
@@ -161,25 +179,24 @@ __global__ void __launch_bounds__(TP) heads_bwd_kernel(const float* __restrict__
     }
     // ---- reduce the four pixel-quarter partials of dW / db inside the CTA, then one atomic per element
     __syncthreads();
-    float* red = xs;                                              // [4][NH2*2][64 + 1]
+    float* red = xs;                                              // [4][NP][C + 1]
     constexpr int RP = C + 1;
 #pragma unroll
-    for (int j = 0; j < NH2; ++j) {
-        float* r = red + ((pq * NH2 * 2) + (half + 2 * j)) * RP + 4 * cg;
-        r[0] = aw[j].x; r[1] = aw[j].y; r[2] = aw[j].z; r[3] = aw[j].w;
-        if (cg == 0) red[((pq * NH2 * 2) + (half + 2 * j)) * RP + C] = ab[j];
+    for (int j = 0; j < NB; ++j) {
+        float* r = red + ((pq * NP) + (half * NB + j)) * RP + 4 * cg;
+        r[0] = aw[j][0].x; r[1] = aw[j][0].y; r[2] = aw[j][1].x; r[3] = aw[j][1].y;
+        if (cg == 0) red[((pq * NP) + (half * NB + j)) * RP + C] = ab[j];
     }
     __syncthreads();
     for (int i = threadIdx.x; i < NH * RP; i += TP) {
         const int n = i / RP, c = i - n * RP;
-        const float v = red[(0 * NH2 * 2 + n) * RP + c] + red[(1 * NH2 * 2 + n) * RP + c] + red[(2 * NH2 * 2 + n) * RP + c] +
-                        red[(3 * NH2 * 2 + n) * RP + c];
+        const float v = red[(0 * NP + n) * RP + c] + red[(1 * NP + n) * RP + c] + red[(2 * NP + n) * RP + c] + red[(3 * NP + n) * RP + c];
         if (c < C) atomicAdd(dW + n * C + c, v);
         else atomicAdd(db + n, v);
     }
 }
 
-static_assert(4 * ((27 + 1) / 2) * 2 * (C + 1) <= TP * XP, "weight-gradient reduction scratch must fit in the pixel tile");
+static_assert(4 * 32 * (C + 1) <= TP * XP, "weight-gradient reduction scratch must fit in the pixel tile");
 
 static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -213,7 +230,8 @@ int pivp_heads_bwd(const float* x, int x_cs, int x_co, const float* W, const flo
     const int ntiles = (int)((M + hd::TP - 1) / hd::TP);
     int grid = 148 * 4;
     if (grid > ntiles) grid = ntiles;
-    const size_t smem = sizeof(float) * ((size_t)hd::TP * hd::XP + (size_t)hd::TP * ((NH + 3) / 4 * 4) + (size_t)NH * hd::C);
+    const int NB = ((NH + 1) / 2 + 3) / 4 * 4;
+    const size_t smem = sizeof(float) * ((size_t)hd::TP * hd::XP + (size_t)hd::TP * 2 * NB + (size_t)NH * hd::C);
     static bool attr_set = false;
     if (!attr_set) {
         cudaFuncSetAttribute(hd::heads_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
