@@ -270,7 +270,10 @@ class TensorCorePlan(object):
         cx = cin + C
         bn = cx                                # one N tile if that already fills the GPU, else the largest split reaching ~1 wave
         mt = ws["Mr"][lv] // 128
+        halo = h % 16 == 0 and w % 8 == 0      # halo-patch kernel: narrow N tiles starve it (4 KB weight stages, 16-cycle MMAs): never split N
         for cand in (cx, cx // 2, cx // 3, cx // 6):      # multiples of 32 only: N=48 tiles measured 2.4x slower than N=96
+            if halo:
+                break
             if cand >= 32 and cand % 32 == 0 and cx % cand == 0:
                 bn = cand
                 if mt * (cx // cand) >= 120:
