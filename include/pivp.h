@@ -81,6 +81,13 @@ int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, c
 int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                        const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
                        float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream);
+/* LayerNorm backward of a ConvLSTM output h_t fused with that layer's gate backward (tensor-core mode, bf16 gate storage): instead of
+ * writing d h_t, each thread adds the recurrent d h_t (dh_b view, may be NULL) and produces the gate pre-activation gradients, written
+ * bf16 over gates_bf16 (pivp_tc_conv5x5 flags bit 1); dc updated in place.  Replaces pivp_layernorm_bwd + pivp_lstm_gates_bwd_bf16. */
+int pivp_layernorm_bwd_lstm(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+                            const float* gamma, const float* beta, const float* stats, int B, int HW, int C,
+                            float* dgamma, float* dbeta, void* gates_bf16, const float* c_prev, const float* c_cur,
+                            const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* workspace, size_t ws_bytes, void* stream);
 
 /* ---- small view ops (F.relu backward :698, F.concat copies, layout packing) --------------------------- */
 int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,

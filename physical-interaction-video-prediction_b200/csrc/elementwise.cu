@@ -764,7 +764,8 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
                float* stats, void* workspace, int S, int chunk, cudaStream_t st);
 int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu, float* dx, int dx_cs,
-               int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st);
+               int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st, void* gates_bf16,
+               const float* c_prev, const float* c_cur, const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid);
 
 }  // namespace pivp
 
@@ -846,7 +847,7 @@ int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int 
     PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_bwd: workspace too small");
     PIVP_REQUIRE(B <= 4096, "layernorm_bwd: batch too large for the shared-memory totals");
     if (int r = ln_vec_bwd(x, x_cs, x_co, g1, g1_cs, g1_co, g2, g2_cs, g2_co, gamma, beta, stats, B, HW, C, relu, dx, dx_cs, dx_co, dgamma,
-                           dbeta, workspace, S, chunk, (cudaStream_t)stream))
+                           dbeta, workspace, S, chunk, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, 0))
         return r < 0 ? r : PIVP_OK;
     ln_bwd_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co},
                                                                         gamma, beta, (const float2*)stats, n, C, chunk, relu, (float2*)workspace);
@@ -855,6 +856,27 @@ int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int 
         CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
         (const float2*)workspace, S, B, n, C, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta);
     return check_launch("layernorm_bwd(apply)");
+}
+
+/* LayerNorm backward of a ConvLSTM output h_t fused with the gate backward of that layer (tensor-core mode, bf16 gate storage):
+ * instead of writing dx = d h_t, each thread adds the recurrent d h_t (dh_b view, may be NULL) and turns it into the gate
+ * pre-activation gradients, written bf16 over `gates_bf16`; dc is updated in place.  x is the LayerNorm input = h_t (HW*C per sample). */
+int pivp_layernorm_bwd_lstm(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+                            const float* gamma, const float* beta, const float* stats, int B, int HW, int C,
+                            float* dgamma, float* dbeta, void* gates_bf16, const float* c_prev, const float* c_cur,
+                            const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(x && g1 && gamma && beta && stats && dgamma && dbeta && workspace && gates_bf16 && c_cur && dc, "layernorm_bwd_lstm: null pointer");
+    PIVP_REQUIRE(C % 32 == 0 && !((uintptr_t)gates_bf16 & 7) && !(((uintptr_t)c_cur | (uintptr_t)c_prev | (uintptr_t)dc) & 15) &&
+                     (!dh_b || (!((uintptr_t)dh_b & 15) && dhb_cs % 4 == 0 && dhb_co % 4 == 0)),
+                 "layernorm_bwd_lstm: C must be a multiple of 32 and the state tensors 16-byte aligned");
+    const int n = HW * C;
+    int chunk;
+    const int S = ln_split(n, &chunk);
+    PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_bwd_lstm: workspace too small");
+    const int r = ln_vec_bwd(x, x_cs, x_co, g1, g1_cs, g1_co, g2, g2_cs, g2_co, gamma, beta, stats, B, HW, C, 0, (float*)c_cur /*unused*/, C, 0,
+                             dgamma, dbeta, workspace, S, chunk, (cudaStream_t)stream, gates_bf16, c_prev, c_cur, dh_b, dhb_cs, dhb_co, dc, dc_valid);
+    if (r == 0) { set_error("layernorm_bwd_lstm: views must be 16-byte aligned with channel counts that are multiples of 4"); return PIVP_EUNSUPPORTED; }
+    return r < 0 ? r : PIVP_OK;
 }
 
 int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_cs, int ga_co, const float* gb, int gb_cs, int gb_co,

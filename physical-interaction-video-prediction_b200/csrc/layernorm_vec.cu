@@ -151,11 +151,68 @@ __global__ void __launch_bounds__(T) bwd_stats_kernel(CView x, CView g1, CView g
     if (threadIdx.x == 0) partial[b * S + s] = make_float2(s1, s2);
 }
 
+// ConvLSTM gate backward fused behind the LayerNorm backward of the layer's output h (train_model.py:269-272 reversed; D.5): the
+// LayerNorm's dx IS d h_t, so the same thread goes on to the gate pre-activation gradients of its 4 channels instead of writing dx.
+struct GateFuse {
+    __nv_bfloat16* gates;          // activated gates bf16 [M][4C] in the [32-ch block][j,i,f,o][ch] order; overwritten by dG (null = no fusion)
+    const float* c_prev;           // [M][C] or null (t = 0)
+    const float* c_cur;            // [M][C]
+    const float* dh_b; int dhb_cs, dhb_co;   // recurrent d h_t from step t+1 (view) or null
+    float* dc;                     // [M][C] in: d c_t from step t+1 (when dc_valid), out: d c_{t-1}
+    int dc_valid;
+};
+__device__ __forceinline__ void unpack4(uint2 u, float (&v)[4]) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
+    const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
+    v[0] = a.x; v[1] = a.y; v[2] = b.x; v[3] = b.y;
+}
+__device__ __forceinline__ uint2 pack4(const float (&v)[4]) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+    uint2 u;
+    u.x = *reinterpret_cast<unsigned*>(&lo);
+    u.y = *reinterpret_cast<unsigned*>(&hi);
+    return u;
+}
+__device__ __forceinline__ void gate_backward4(const GateFuse& gf, long m, int ch, int C, float4 dh4) {
+    const long e = m * C + ch;
+    float dh[4] = {dh4.x, dh4.y, dh4.z, dh4.w};
+    if (gf.dh_b) {
+        const float4 t = ld4(gf.dh_b + m * gf.dhb_cs + gf.dhb_co + ch);
+        dh[0] += t.x; dh[1] += t.y; dh[2] += t.z; dh[3] += t.w;
+    }
+    __nv_bfloat16* g = gf.gates + m * 4 * C + (ch >> 5) * 128 + (ch & 31);
+    float j[4], i[4], f[4], o[4];
+    unpack4(*reinterpret_cast<const uint2*>(g), j);
+    unpack4(*reinterpret_cast<const uint2*>(g + 32), i);
+    unpack4(*reinterpret_cast<const uint2*>(g + 64), f);
+    unpack4(*reinterpret_cast<const uint2*>(g + 96), o);
+    const float4 cc4 = ld4(gf.c_cur + e);
+    const float4 cp4 = gf.c_prev ? ld4(gf.c_prev + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 dn4 = gf.dc_valid ? *reinterpret_cast<const float4*>(gf.dc + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+    const float cc[4] = {cc4.x, cc4.y, cc4.z, cc4.w}, cp[4] = {cp4.x, cp4.y, cp4.z, cp4.w}, dn[4] = {dn4.x, dn4.y, dn4.z, dn4.w};
+    float dj[4], di[4], df[4], dout[4], dcp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float tc = tanhf(cc[k]);
+        dout[k] = dh[k] * tc * o[k] * (1.f - o[k]);
+        const float dcv = dh[k] * o[k] * (1.f - tc * tc) + dn[k];
+        df[k] = dcv * cp[k] * f[k] * (1.f - f[k]);
+        di[k] = dcv * j[k] * i[k] * (1.f - i[k]);
+        dj[k] = dcv * i[k] * (1.f - j[k] * j[k]);
+        dcp[k] = dcv * f[k];
+    }
+    *reinterpret_cast<float4*>(gf.dc + e) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+    *reinterpret_cast<uint2*>(g) = pack4(dj);
+    *reinterpret_cast<uint2*>(g + 32) = pack4(di);
+    *reinterpret_cast<uint2*>(g + 64) = pack4(df);
+    *reinterpret_cast<uint2*>(g + 96) = pack4(dout);
+}
+
 // thread per 4 elements, loop over this CTA's batch chunk: dx, and dgamma / dbeta += (one 128-bit reduction each)
 __global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float2* __restrict__ stats,
                                                        const float2* __restrict__ partial, int S, int B, int bchunk, Geo g, int n,
-                                                       int relu, View dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                       int relu, View dx, float* __restrict__ dgamma, float* __restrict__ dbeta, GateFuse gf) {
     extern __shared__ float4 tot[];              // [bchunk] : (mean, rstd, mean q, mean q*xhat)
     const int b0 = blockIdx.y * bchunk, nb = min(bchunk, B - b0);
     for (int i = threadIdx.x; i < nb; i += TB) {
@@ -185,7 +242,8 @@ __global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView 
         d.y = (gq.y * ga.y - t.z - xh.y * t.w) * t.y;
         d.z = (gq.z * ga.z - t.z - xh.z * t.w) * t.y;
         d.w = (gq.w * ga.w - t.z - xh.w * t.w) * t.y;
-        *reinterpret_cast<float4*>(dx.p + row * dx.cs + dx.co + ch) = d;
+        if (gf.gates) gate_backward4(gf, row, ch, g.C, d);
+        else *reinterpret_cast<float4*>(dx.p + row * dx.cs + dx.co + ch) = d;
     }
     atomicAdd(reinterpret_cast<float4*>(dgamma + e), dg);
     atomicAdd(reinterpret_cast<float4*>(dbeta + e), db);
@@ -232,8 +290,10 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
 
 int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu, float* dx, int dx_cs,
-               int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st) {
+               int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st, void* gates_bf16,
+               const float* c_prev, const float* c_cur, const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid) {
     using namespace lnv;
+    GateFuse gf{(__nv_bfloat16*)gates_bf16, c_prev, c_cur, dh_b, dhb_cs, dhb_co, dc, dc_valid};
     const int n = HW * C;
     if (disabled() || C % 4 || chunk % 4 || chunk > T * E4 * 4 || !view_ok(x, x_cs, x_co) || !view_ok(g1, g1_cs, g1_co) || !view_ok(g2, g2_cs, g2_co) ||
         !view_ok(dx, dx_cs, dx_co) || !a16(gamma) || !a16(beta) || !a16(dgamma) || !a16(dbeta))
@@ -250,7 +310,7 @@ int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, i
     nby = (B + bchunk - 1) / bchunk;
     bwd_apply_kernel<<<dim3(gx, nby), TB, (size_t)bchunk * sizeof(float4), st>>>(
         CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
-        (const float2*)workspace, S, B, bchunk, g, n, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta);
+        (const float2*)workspace, S, B, bchunk, g, n, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta, gf);
     if (int e = check_launch("layernorm_bwd(apply)")) return e;
     return 1;
 }

@@ -229,6 +229,24 @@ class Engine(object):
                     _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(ws["ln_ws"]),
                     ws["ln_ws"].numel(), self._s())
 
+    def _ln_lstm_bwd(self, name, li, t, x, g1, g2, B, HW, last):
+        """LayerNorm backward of ConvLSTM layer li's output at step t, then the layer's gate / input-gradient backward.
+        Tensor-core mode: ONE kernel does the LayerNorm dx and the gate backward (d h_t never reaches memory), then the tcgen05 dgrad."""
+        ws = self.ws
+        cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
+        if self.tc is None:
+            self._ln_bwd(name, x, g1, g2, B, HW, 0, ws["ln_stats"][name][t], View(ws["dln"][li], C, 0, C))
+            self._lstm_bwd(li, t, B, last)
+            return
+        dgb = self.tc.dg_bf16[li][t]
+        self.L.call("pivp_layernorm_bwd_lstm", x.ptr, x.cs, x.co, g1.ptr, g1.cs, g1.co, 0 if g2 is None else g2.ptr,
+                    0 if g2 is None else g2.cs, 0 if g2 is None else g2.co, _ptr(self.p[name + "/norm/gamma"]),
+                    _ptr(self.p[name + "/norm/beta"]), _ptr(ws["ln_stats"][name][t]), B, HW, C,
+                    _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(dgb),
+                    _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]), 0 if last else _ptr(ws["dxh"][li]), cin + C, cin,
+                    _ptr(ws["dc"][li]), 0 if last else 1, _ptr(ws["ln_ws"]), ws["ln_ws"].numel(), self._s())
+        self.tc.lstm_dgrad(li, t)
+
     def _relu_bwd(self, out, ga, gb, dst, M):
         self.L.call("pivp_relu_bwd", out.ptr, out.cs, out.co, ga.ptr, ga.cs, ga.co, 0 if gb is None else gb.ptr,
                     0 if gb is None else gb.cs, 0 if gb is None else gb.co, dst.ptr, dst.cs, dst.co, M, dst.C, self._s())
@@ -502,9 +520,7 @@ class Engine(object):
                 self._conv_wgrad(de6, B, H, W, View(ws["cat6"][t], 64, 0, 64), H // 2, W // 2, 3, 2, 1, g["enc6/W"], None)
                 self._conv_fwd(de6, B, H, W, p["enc6/W"], None, 64, 3, 2, 1, View(ws["d_cat6"], 64, 0, 64))
             # ---- lstm7
-            self._ln_bwd("hidden7", View(ws["xh"][6][t + 1], 128, 96, 32), View(ws["d_cat6"], 64, 0, 32), None, B, HW[2], 0,
-                         ws["ln_stats"]["hidden7"][t], View(ws["dln"][6], 32, 0, 32))
-            self._lstm_bwd(6, t, B, last)
+            self._ln_lstm_bwd("hidden7", 6, t, View(ws["xh"][6][t + 1], 128, 96, 32), View(ws["d_cat6"], 64, 0, 32), None, B, HW[2], last)
             # ---- enc5 deconv (input concat(hidden6, encs[1]))
             de5 = View(ws["d_e5pre"], 96, 0, 96)
             if self.tc is not None:
@@ -516,9 +532,7 @@ class Engine(object):
                 self._conv_wgrad(de5, B, H // 2, W // 2, View(ws["cat5"][t], 96, 0, 96), H // 4, W // 4, 3, 2, 1, g["enc5/W"], None)
                 self._conv_fwd(de5, B, H // 2, W // 2, p["enc5/W"], None, 96, 3, 2, 1, View(ws["d_cat5"], 96, 0, 96))
             # ---- lstm6
-            self._ln_bwd("hidden6", View(ws["xh"][5][t + 1], 192, 128, 64), View(ws["d_cat5"], 96, 0, 64), None, B, HW[4], 0,
-                         ws["ln_stats"]["hidden6"][t], View(ws["dln"][5], 64, 0, 64))
-            self._lstm_bwd(5, t, B, last)
+            self._ln_lstm_bwd("hidden6", 5, t, View(ws["xh"][5][t + 1], 192, 128, 64), View(ws["d_cat5"], 96, 0, 64), None, B, HW[4], last)
             # ---- enc4 deconv (input hidden5); d_hid5 may already hold the kernel-Linear contribution
             de4 = View(ws["d_e4pre"], 128, 0, 128)
             if self.tc is not None:
@@ -531,9 +545,7 @@ class Engine(object):
                 self._conv_fwd(de4, B, H // 4, W // 4, p["enc4/W"], None, 128, 3, 2, 1, View(ws["d_hid5"], 128, 0, 128),
                                acc=1 if hid5_has_grad else 0)
             # ---- lstm5
-            self._ln_bwd("hidden5", View(ws["xh"][4][t + 1], 192, 64, 128), View(ws["d_hid5"], 128, 0, 128), None, B, HW[8], 0,
-                         ws["ln_stats"]["hidden5"][t], View(ws["dln"][4], 128, 0, 128))
-            self._lstm_bwd(4, t, B, last)
+            self._ln_lstm_bwd("hidden5", 4, t, View(ws["xh"][4][t + 1], 192, 64, 128), View(ws["d_hid5"], 128, 0, 128), None, B, HW[8], last)
             # ---- enc3 (1x1 on concat(enc2 out, smear))
             self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"][t], 64, 0, 64), Mr[8])
             de3 = View(ws["d_e3pre"][t], 64, 0, 64)
@@ -554,12 +566,8 @@ class Engine(object):
                 self._relu_bwd(View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, de2, Mr[8])
                 self._conv_dgrad(de2, B, H // 8, W // 8, p["enc2/W"], None, 3, 2, 1, View(ws["d_hid4"], 64, 0, 64), H // 4, W // 4)
             # ---- lstm4, lstm3
-            self._ln_bwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), View(ws["d_hid4"], 64, 0, 64), None, B, HW[4], 0,
-                         ws["ln_stats"]["hidden4"][t], View(ws["dln"][3], 64, 0, 64))
-            self._lstm_bwd(3, t, B, last)
-            self._ln_bwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), View(ws["dxh"][3], 128, 0, 64), None, B, HW[4], 0,
-                         ws["ln_stats"]["hidden3"][t], View(ws["dln"][2], 64, 0, 64))
-            self._lstm_bwd(2, t, B, last)
+            self._ln_lstm_bwd("hidden4", 3, t, View(ws["xh"][3][t + 1], 128, 64, 64), View(ws["d_hid4"], 64, 0, 64), None, B, HW[4], last)
+            self._ln_lstm_bwd("hidden3", 2, t, View(ws["xh"][2][t + 1], 96, 32, 64), View(ws["dxh"][3], 128, 0, 64), None, B, HW[4], last)
             # ---- enc1: encs[1] feeds lstm3 (x slot) and the enc5 skip slot
             de1 = View(ws["d_e1pre"][t], 32, 0, 32)
             if self.tc is not None:
@@ -569,12 +577,8 @@ class Engine(object):
                 self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32), de1, Mr[4])
                 self._conv_dgrad(de1, B, H // 4, W // 4, p["enc1/W"], None, 3, 2, 1, View(ws["d_hid2"], 32, 0, 32), H // 2, W // 2)
             # ---- lstm2, lstm1
-            self._ln_bwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), View(ws["d_hid2"], 32, 0, 32), None, B, HW[2], 0,
-                         ws["ln_stats"]["hidden2"][t], View(ws["dln"][1], 32, 0, 32))
-            self._lstm_bwd(1, t, B, last)
-            self._ln_bwd("hidden1", View(ws["xh"][0][t + 1], 64, 32, 32), View(ws["dxh"][1], 64, 0, 32), None, B, HW[2], 0,
-                         ws["ln_stats"]["hidden1"][t], View(ws["dln"][0], 32, 0, 32))
-            self._lstm_bwd(0, t, B, last)
+            self._ln_lstm_bwd("hidden2", 1, t, View(ws["xh"][1][t + 1], 64, 32, 32), View(ws["d_hid2"], 32, 0, 32), None, B, HW[2], last)
+            self._ln_lstm_bwd("hidden1", 0, t, View(ws["xh"][0][t + 1], 64, 32, 32), View(ws["dxh"][1], 64, 0, 32), None, B, HW[2], last)
             # ---- norm_enc0 (+relu): encs[0] feeds lstm1 (x slot) and the enc6 skip slot; enc0
             self._ln_bwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), View(ws["dxh"][0], 64, 0, 32), View(ws["d_cat6"], 64, 32, 32),
                          B, HW[2], 1, ws["ln_stats"]["norm_enc0"][t], View(ws["d_enc0pre"][t], 32, 0, 32))

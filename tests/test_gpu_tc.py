@@ -212,6 +212,45 @@ def test_lstm_gates_bwd_bf16_matches_fp32_kernel(pk, M, C, cin, first):
     assert rel(gates_b, gates_f) < 2 ** -8
 
 
+@pytest.mark.parametrize("B,HW,C,cin,last", [(3, 256, 64, 32, False), (2, 1024, 32, 32, True)])
+def test_layernorm_bwd_lstm_equals_separate_kernels(pk, B, HW, C, cin, last):
+    """LayerNorm backward fused with the ConvLSTM gate backward == pivp_layernorm_bwd followed by pivp_lstm_gates_bwd_bf16."""
+    L = pk.lib()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(13)
+    M, n = B * HW, HW * C
+    R = lambda *sh: torch.randn(*sh, device="cuda", generator=gen)
+    xh = R(M, cin + C)                                    # LayerNorm input = h slot of the xh buffer
+    g1 = R(M, C + 8)
+    gamma, beta = 1 + 0.2 * R(n), 0.2 * R(n)
+    stats = torch.zeros(B, 2, device="cuda")
+    y = torch.empty(M, C, device="cuda")
+    nb = L.query("pivp_layernorm_workspace_bytes", B, n)
+    ws = torch.empty(max(nb, 16), dtype=torch.uint8, device="cuda")
+    L.call("pivp_layernorm_fwd", xh.data_ptr(), cin + C, cin, gamma.data_ptr(), beta.data_ptr(), B, HW, C, 1e-6, y.data_ptr(), C, 0,
+           0, 0, 0, 0, 0, 0, 0, stats.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+    gates = (torch.rand(M, 4 * C, device="cuda", generator=gen) * 1.6 - 0.8).bfloat16()
+    c_prev, c_cur, dxh = R(M, C), R(M, C), R(M, cin + C)
+    dc0 = R(M, C)
+    outs = []
+    for fused in (False, True):
+        gt, dc = gates.clone(), dc0.clone()
+        dga, dbe = torch.zeros(n, device="cuda"), torch.zeros(n, device="cuda")
+        if fused:
+            L.call("pivp_layernorm_bwd_lstm", xh.data_ptr(), cin + C, cin, g1.data_ptr(), C + 8, 4, 0, 0, 0, gamma.data_ptr(), beta.data_ptr(),
+                   stats.data_ptr(), B, HW, C, dga.data_ptr(), dbe.data_ptr(), gt.data_ptr(), c_prev.data_ptr(), c_cur.data_ptr(),
+                   0 if last else dxh.data_ptr(), cin + C, cin, dc.data_ptr(), 0 if last else 1, ws.data_ptr(), ws.numel(), stream())
+        else:
+            dln = torch.empty(M, C, device="cuda")
+            L.call("pivp_layernorm_bwd", xh.data_ptr(), cin + C, cin, g1.data_ptr(), C + 8, 4, 0, 0, 0, gamma.data_ptr(), beta.data_ptr(),
+                   stats.data_ptr(), B, HW, C, 0, dln.data_ptr(), C, 0, dga.data_ptr(), dbe.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+            L.call("pivp_lstm_gates_bwd_bf16", gt.data_ptr(), c_prev.data_ptr(), c_cur.data_ptr(), dln.data_ptr(),
+                   0 if last else dxh.data_ptr(), cin + C, cin, dc.data_ptr(), 0 if last else 1, gt.data_ptr(), M, C, stream())
+        torch.cuda.synchronize()
+        outs.append((gt.float(), dc, dga, dbe))
+    for a, b in zip(*outs):
+        assert rel(b, a) < 2 ** -8 if a is outs[0][0] else rel(b, a) < 1e-5
+
+
 def test_tc_conv_taps_multi_equals_single_phase_launches(pk):
     """The four output phases of a stride-2 deconvolution in one launch (grid z = phase) == four single-phase launches, bit for bit."""
     import ctypes
