@@ -322,7 +322,7 @@ template <int MS>
 static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g, const TcEpilogue& ep, int tiles, void* stream, const char* who) {
     const int b_bytes = g.BN * 128;
     int stages = (225 * 1024 - MS * PATCH_BYTES) / b_bytes;     // one CTA per SM, the ring takes what the patches leave
-    if (stages > 12) stages = 12;
+    if (stages > 20) stages = 20;
     g.stages = stages;
     const int cols = MS * g.BN;
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;

@@ -46,6 +46,8 @@ class TensorCorePlan(object):
             wsb = max(wsb, eng.L.query("pivp_tc_wgrad_workspace_bytes", S * B, h, w, cin + c, 4 * c))
         self.wgrad_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         self.accurate = 0
+        import os
+        self.split_n = int(os.environ.get("PIVP_TC_SPLIT_N", "1"))       # tuning switch for the input-gradient N split
         # layers whose maps the halo-patch kernel tiles (H % 16 == 0, W % 8 == 0): its epilogue also produces the LayerNorm statistics
         self.ln_fused = [(eng.H // lv) % 16 == 0 and (eng.W // lv) % 8 == 0 and ((eng.H // lv) * (eng.W // lv) * c) % 4096 == 0
                          for c, lv in zip(LSTM_SIZES, LSTM_LEVEL)]
@@ -270,7 +272,9 @@ class TensorCorePlan(object):
         cx = cin + C
         bn = cx                                # one N tile if that already fills the GPU, else the largest split reaching ~1 wave
         mt = ws["Mr"][lv] // 128
-        halo = h % 16 == 0 and w % 8 == 0      # halo-patch kernel: narrow N tiles starve it (4 KB weight stages, 16-cycle MMAs): never split N
+        halo = h % 16 == 0 and w % 8 == 0      # halo-patch kernel: one CTA per SM, so 64 pixel tiles leave half the GPU idle:
+        if halo and mt < 100 and (cx // 2) % 16 == 0 and self.split_n:      # two N tiles of cx/2 (narrower tiles starve the weight ring)
+            bn = cx // 2
         for cand in (cx, cx // 2, cx // 3, cx // 6):      # multiples of 32 only: N=48 tiles measured 2.4x slower than N=96
             if halo:
                 break
