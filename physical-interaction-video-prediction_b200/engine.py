@@ -346,7 +346,7 @@ class Engine(object):
             self._ln_fwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), B, HW[2], View(ws["hid2"][t], 32, 0, 32), None, 0,
                          ws["ln_stats"]["hidden2"][t], have_stats=self.tc is not None and self.tc.ln_fused[1])
             if self.tc is not None:       # stride-2 conv as a 9-tap tcgen05 GEMM on the space-to-depth bf16 input; bf16 x slot from the epilogue
-                self.tc.conv_s2_fwd("enc1", ws["hid2"][t], 32, ws["xh"][2][t], 96, self.tc.xview(2, t).t, self.tc.Kpad[2])
+                self.tc.conv_s2_fwd("enc1", t, ws["hid2"][t], 32, ws["xh"][2][t], 96, self.tc.xview(2, t).t, self.tc.Kpad[2])
                 L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, s)
             else:
                 self._conv_fwd(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, p["enc1/W"], p["enc1/b"], 32, 3, 2, 1,
@@ -360,7 +360,7 @@ class Engine(object):
             self._ln_fwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), B, HW[4], View(ws["hid4"][t], 64, 0, 64), None, 0,
                          ws["ln_stats"]["hidden4"][t], have_stats=self.tc is not None and self.tc.ln_fused[3])
             if self.tc is not None:
-                self.tc.conv_s2_fwd("enc2", ws["hid4"][t], 64, ws["in3"][t], self.cs3, None, 0)
+                self.tc.conv_s2_fwd("enc2", t, ws["hid4"][t], 64, ws["in3"][t], self.cs3, None, 0)
             else:
                 self._conv_fwd(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, p["enc2/W"], p["enc2/b"], 64, 3, 2, 1,
                                View(ws["in3"][t], self.cs3, 0, 64), relu=1)
@@ -560,7 +560,7 @@ class Engine(object):
             # ---- enc2
             de2 = View(ws["d_e2pre"][t], 64, 0, 64)
             if self.tc is not None:
-                self.tc.conv_s2_dgrad_fused("enc2", View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, de2, self.tc.de2_b,
+                self.tc.conv_s2_dgrad_fused("enc2", t, View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, g["enc2/b"],
                                             Mr[8], 64, ws["d_hid4"], 64)
             else:
                 self._relu_bwd(View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, de2, Mr[8])
@@ -571,8 +571,8 @@ class Engine(object):
             # ---- enc1: encs[1] feeds lstm3 (x slot) and the enc5 skip slot
             de1 = View(ws["d_e1pre"][t], 32, 0, 32)
             if self.tc is not None:
-                self.tc.conv_s2_dgrad_fused("enc1", View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32),
-                                            de1, self.tc.de1_b, Mr[4], 32, ws["d_hid2"], 32)
+                self.tc.conv_s2_dgrad_fused("enc1", t, View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32),
+                                            g["enc1/b"], Mr[4], 32, ws["d_hid2"], 32)
             else:
                 self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32), de1, Mr[4])
                 self._conv_dgrad(de1, B, H // 4, W // 4, p["enc1/W"], None, 3, 2, 1, View(ws["d_hid2"], 32, 0, 32), H // 2, W // 2)
@@ -597,10 +597,11 @@ class Engine(object):
             cin3 = 64 + self.sa
             self._conv_wgrad(View(first(ws["img_nhwc"]), 3, 0, 3), S * B, H, W, View(first(ws["d_enc0pre"]), 32, 0, 32), H // 2, W // 2, 5, 2, 2,
                              g["enc0/W"], g["enc0/b"])
-            self._conv_wgrad(View(first(ws["hid2"]), 32, 0, 32), S * B, H // 2, W // 2, View(first(ws["d_e1pre"]), 32, 0, 32), H // 4, W // 4,
-                             3, 2, 1, g["enc1/W"], g["enc1/b"])
-            self._conv_wgrad(View(first(ws["hid4"]), 64, 0, 64), S * B, H // 4, W // 4, View(first(ws["d_e2pre"]), 64, 0, 64), H // 8, W // 8,
-                             3, 2, 1, g["enc2/W"], g["enc2/b"])
+            if self.tc is None:                # bf16 mode: tcgen05 weight-gradient GEMMs in tc.wgrad_all(), bias gradients from the hand-over
+                self._conv_wgrad(View(first(ws["hid2"]), 32, 0, 32), S * B, H // 2, W // 2, View(first(ws["d_e1pre"]), 32, 0, 32), H // 4, W // 4,
+                                 3, 2, 1, g["enc1/W"], g["enc1/b"])
+                self._conv_wgrad(View(first(ws["hid4"]), 64, 0, 64), S * B, H // 4, W // 4, View(first(ws["d_e2pre"]), 64, 0, 64), H // 8, W // 8,
+                                 3, 2, 1, g["enc2/W"], g["enc2/b"])
             self._conv_wgrad(View(first(ws["in3"]), self.cs3, 0, cin3), S * B, H // 8, W // 8, View(first(ws["d_e3pre"]), 64, 0, 64), H // 8, W // 8,
                              1, 1, 0, g["enc3/W"], g["enc3/b"])
         if self.tc is not None:

@@ -65,14 +65,16 @@ class TensorCorePlan(object):
         self.dec["enc2"] = self._plan_deconv("enc2", 64, 64, 8)
         # forward of the stride-2 convolutions enc1 / enc2: 9-tap stride-1 GEMM on the space-to-depth bf16 input (half grid, 4 phases x cb ch)
         self.s2f = {"enc1": self._plan_conv_s2_fwd("enc1", 32, 32, 2), "enc2": self._plan_conv_s2_fwd("enc2", 64, 64, 4)}
-        self.de1_b = torch.zeros(M4, 64, dtype=torch.bfloat16, device=dev)      # bf16 d(enc1 pre-activation), 32 used
-        self.de2_b = torch.zeros(M8, 64, dtype=torch.bfloat16, device=dev)
+        # bf16 d(pre-activation) of enc1 (32 of 64 used) / enc2, all time steps kept: operand of the input gradient AND of the deferred weight gradient
+        self.de_b = {"enc1": torch.zeros(S, M4, 64, dtype=torch.bfloat16, device=dev), "enc2": torch.zeros(S, M8, 64, dtype=torch.bfloat16, device=dev)}
         # ---- deconvolution backward: dY in space-to-depth bf16 (all time steps kept for the deferred weight gradient)
         self.dbw = {}
         wsb2 = 16
         for name, cin, cout, lv, xs in (("enc4", 128, 128, 8, self.hid5_b), ("enc5", 96, 96, 4, self.cat5_b), ("enc6", 64, 64, 2, self.cat6_b)):
             self.dbw[name] = self._plan_deconv_bwd(name, cin, cout, lv)
             wsb2 = max(wsb2, eng.L.query("pivp_tc_wgrad_taps_workspace_bytes", S * B, eng.H // lv, eng.W // lv, cout, cin, 9))
+        for name, d in self.s2f.items():
+            wsb2 = max(wsb2, eng.L.query("pivp_tc_wgrad_taps_workspace_bytes", S * B, eng.H // d["lv"], eng.W // d["lv"], d["cin"], d["cout"], 9))
         if wsb2 > self.wgrad_ws.numel():
             self.wgrad_ws = torch.empty(wsb2, dtype=torch.uint8, device=dev)
         # the deferred weight gradient needs the deconv inputs of all time steps stacked: re-home them in one tensor each
@@ -106,15 +108,16 @@ class TensorCorePlan(object):
         arr = lambda v: (ctypes.c_int * 9)(*v)
         return dict(cin=cin, cout=cout, cb=cb, lv=lv, dy=arr([q[0] for q in taps]), dx=arr([q[1] for q in taps]), co=arr([q[2] for q in taps]),
                     idx=torch.from_numpy(idx.reshape(-1)).to(dev), wt=torch.empty(cout, 9 * cb, dtype=torch.bfloat16, device=dev),
-                    xs=torch.zeros(M, 4 * cb, dtype=torch.bfloat16, device=dev))
+                    xs=torch.zeros(self.S, M, 4 * cb, dtype=torch.bfloat16, device=dev))      # kept per time step for the weight gradient
 
-    def conv_s2_fwd(self, name, x_f32, x_cs, out, out_cs, out_bf16, ob_cs):
+    def conv_s2_fwd(self, name, t, x_f32, x_cs, out, out_cs, out_bf16, ob_cs):
         """Stride-2 Convolution2D + bias + ReLU (train_model.py:501-502): cast the fp32 input to space-to-depth bf16, one tcgen05 launch."""
         e, d = self.eng, self.s2f[name]
         h, w = e.H // d["lv"], e.W // d["lv"]
         B = self.ws["B"]
-        e.L.call("pivp_cast_bf16", _ptr(x_f32), x_cs, 0, _ptr(d["xs"]), 4 * d["cb"], 0, B * 4 * h * w, d["cin"], 2 * h, 2 * w, 1, d["cb"], e._s())
-        e.L.call("pivp_tc_conv_taps", _ptr(d["xs"]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
+        xs = d["xs"][t]
+        e.L.call("pivp_cast_bf16", _ptr(x_f32), x_cs, 0, _ptr(xs), 4 * d["cb"], 0, B * 4 * h * w, d["cin"], 2 * h, 2 * w, 1, d["cb"], e._s())
+        e.L.call("pivp_tc_conv_taps", _ptr(xs), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
                  d["cout"], d["cout"], _ptr(e.p[name + "/b"]), 1, 0, _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, h, w, 1, 0, 0, e._s())
 
     def _plan_deconv_bwd(self, name, cin, cout, lv):
@@ -212,14 +215,27 @@ class TensorCorePlan(object):
         e.L.call("pivp_tc_conv_taps", _ptr(d["dys"][t]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
                  d["cin"], d["bn"], 0, 0, accumulate, _ptr(d_in), d["cin"], 0, 0, 0, 0, h, w, 1, 0, 0, e._s())
 
-    def conv_s2_dgrad_fused(self, name, out, ga, gb, d_pre, dy_b, M, C, d_in, d_in_cs):
-        """ReLU backward of a stride-2 convolution's output + its input gradient: the hand-over writes d(pre-activation) fp32 (kept for
-        the deferred weight gradient) and the bf16 GEMM operand in one launch; then the four output phases in one tcgen05 launch."""
+    def conv_s2_dgrad_fused(self, name, t, out, ga, gb, db, M, C, d_in, d_in_cs):
+        """ReLU backward of a stride-2 convolution's output + its input gradient: the hand-over masks the gradient, accumulates the bias
+        gradient and writes the bf16 GEMM operand (kept for the deferred weight gradient) in one launch; then the four output phases
+        of the transposed convolution in one tcgen05 launch."""
         e = self.eng
         z = lambda v: (0, 0, 0) if v is None else (v.ptr, v.cs, v.co)
-        e.L.call("pivp_grad_handover", *z(out), *z(ga), *z(gb), d_pre.ptr, d_pre.cs, d_pre.co, _ptr(dy_b), dy_b.shape[1], 0, 0, 0, 0, 0,
-                 0, M, C, e._s())
+        dy_b = self.de_b[name][t]
+        e.L.call("pivp_grad_handover", *z(out), *z(ga), *z(gb), 0, 0, 0, _ptr(dy_b), dy_b.shape[1], 0, 0, 0, 0, 0,
+                 _ptr(db), M, C, e._s())
         self.deconv_fwd(name, dy_b, d_in, d_in_cs, None, 0, 0, bias=False)
+
+    def conv_s2_wgrad_all(self):
+        """Deferred weight gradients of the stride-2 convolutions enc1 / enc2 over all time steps: dW[n][ky][kx][c] contracts the bf16
+        d(pre-activation) with the tap-shifted space-to-depth input the forward already wrote (train_model.py:501-502 backward)."""
+        e, S, B = self.eng, self.S, self.ws["B"]
+        for name in ("enc1", "enc2"):
+            d = self.s2f[name]
+            h, w = e.H // d["lv"], e.W // d["lv"]
+            a = self.de_b[name]
+            e.L.call("pivp_tc_wgrad_taps", _ptr(a), a.shape[2], _ptr(d["xs"]), 4 * d["cb"], S * B, h, w, d["cin"], d["cout"], 9,
+                     d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
 
     def deconv_wgrad_all(self):
         """Deferred weight gradients of enc4/5/6 over all time steps (one MN-major GEMM each)."""
@@ -229,12 +245,6 @@ class TensorCorePlan(object):
             h, w = e.H // d["lv"], e.W // d["lv"]
             e.L.call("pivp_tc_wgrad_taps", _ptr(xall), xall.shape[2], _ptr(d["dys"]), 4 * d["cb"], S * B, h, w, d["cout"], d["cin"], 9,
                      d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
-
-    def conv_s2_dgrad(self, name, dy_f32, dy_b, M, C, out, out_cs):
-        """Input gradient of the stride-2 convolutions enc1 / enc2: cast d(pre-activation) to bf16, four phase launches."""
-        e = self.eng
-        e.L.call("pivp_cast_bf16", _ptr(dy_f32), C, 0, _ptr(dy_b), dy_b.shape[1], 0, M, C, 0, 0, 0, 0, e._s())
-        self.deconv_fwd(name, dy_b, out, out_cs, None, 0, 0, bias=False)
 
     def deconv_fwd(self, name, x_bf16, out, out_cs, out_bf16, ob_cs, relu, bias=True):
         """Deconvolution2D forward (+bias, optional ReLU) -> fp32 view `out` (row stride out_cs, channel offset 0) and an
@@ -301,3 +311,4 @@ class TensorCorePlan(object):
             e.L.call("pivp_tc_wgrad5x5", _ptr(self.dg_all[li]), _ptr(self.xh_all[li]), self.Kpad[li], S * B, h, w, cx, 4 * C,
                      _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
         self.deconv_wgrad_all()
+        self.conv_s2_wgrad_all()
