@@ -266,6 +266,15 @@ static int check_geom(const ConvGeom& g) {
     return PIVP_OK;
 }
 
+namespace img {   // conv_image.cu: direct kernels for the 3-channel image convolution enc0
+bool supported(int H, int W, int Cin, int Ho, int Wo, int Nout, int KH, int KW, int stride, int pad);
+int launch_fwd(const float* x, int x_cs, int x_co, int B, int H, int W, const float* w, const float* bias, float* y, int y_cs, int y_co,
+               int Ho, int Wo, int relu, void* stream);
+int launch_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, const float* dy, int dy_cs, int dy_co, int Ho, int Wo, float* dw,
+                 void* stream);
+}  // namespace img
+static inline bool vec4_view(const void* p, int cs, int co) { return !((uintptr_t)p & 15) && cs % 4 == 0 && co % 4 == 0; }
+
 }  // namespace pivp
 
 using namespace pivp;
@@ -279,6 +288,8 @@ int pivp_conv2d_fwd(const float* x, int x_cs, int x_co, int B, int H, int W, int
     ConvGeom g{B, H, W, C, Ho, Wo, N, KH, KW, stride, pad};
     if (int e = check_geom(g)) return e;
     PIVP_REQUIRE(x_cs >= x_co + C && y_cs >= y_co + N, "conv2d_fwd: channel slice exceeds row stride");
+    if (!accumulate && vec4_view(y, y_cs, y_co) && img::supported(H, W, C, Ho, Wo, N, KH, KW, stride, pad))
+        return img::launch_fwd(x, x_cs, x_co, B, H, W, w, bias, y, y_cs, y_co, Ho, Wo, relu, stream);
     const long M = (long)B * Ho * Wo;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
     conv_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, w, bias, View{y, y_cs, y_co}, relu, accumulate);
@@ -312,9 +323,13 @@ int pivp_conv2d_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, i
     if (split < 1) split = 1;
     int pchunk = ((P + split - 1) / split + BK - 1) / BK * BK;
     split = (P + pchunk - 1) / pchunk;
-    dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((J + BN - 1) / BN), (unsigned)split);
-    conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, pchunk);
-    if (int e = check_launch("conv2d_wgrad")) return e;
+    if (vec4_view(dy, dy_cs, dy_co) && img::supported(H, W, C, Ho, Wo, N, KH, KW, stride, pad)) {
+        if (int e = img::launch_wgrad(x, x_cs, x_co, B, H, W, dy, dy_cs, dy_co, Ho, Wo, dw, stream)) return e;
+    } else {
+        dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((J + BN - 1) / BN), (unsigned)split);
+        conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, pchunk);
+        if (int e = check_launch("conv2d_wgrad")) return e;
+    }
     if (dbias) {
         int s2 = (P + 255) / 256;
         int pc = (P + s2 - 1) / s2;

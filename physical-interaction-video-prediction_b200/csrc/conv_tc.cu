@@ -221,8 +221,12 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
         return PIVP_EUNSUPPORTED;
     }
     const int stage_bytes = TC_BM * 128 + BN * 128;
-    int stages = (100 * 1024) / stage_bytes;
-    if (stages > 6) stages = 6;
+    // ring depth: at most one CTA per SM fits anyway when the grid is <= 148 CTAs, so a small launch takes the whole shared memory
+    // (the 8x8-map layers were bound by 3 stages x ~1.5 us TMA round trip, not by the MMAs); larger grids leave room for two CTAs per SM
+    const long ctas = ((long)B * H * W / TC_BM) * (N / BN) * nph;
+    const int env_ring = getenv("PIVP_TC_TAPS_RING_KB") ? atoi(getenv("PIVP_TC_TAPS_RING_KB")) : 0;
+    int stages = ((env_ring > 0 ? env_ring : ctas <= 148 ? 190 : 100) * 1024) / stage_bytes;
+    if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     TcGeomPack gp;                                 // by-value kernel parameters
     TcMapsB mb;

@@ -9,6 +9,10 @@
 // an 8-pixel tile row is exactly one 8-row swizzle atom, consecutive tile rows are one patch row (SBO = 16 * 128 B) apart, and the
 // swizzle is a function of the shared-memory address bits, so a row-shifted view stays consistent with what TMA wrote.
 // A traffic drops 25 x 16 KB -> 40 KB per (tile, 64 channels); the weight tiles stream through the ring as before.
+//
+// 8 x 8 maps (ConvLSTM layer 5) use the "pair" geometry: a tile is two whole images, and the patch interleaves their rows --
+// tensor-map dimensions ordered (channel, x, image, y), box {64, 16, 2, 12} = 48 KB -- so that the 16 eight-pixel groups (y, image)
+// are again one uniform 2048 B apart and tap (dy, dx) is a start address moved by (2*(dy+2)*16 + (dx+2)) rows.
 #include "tc_common.cuh"
 #include "tc_epilogue.cuh"
 #include <stdlib.h>
@@ -19,11 +23,14 @@ namespace halo {
 constexpr int TW = 8, TH = 16;                    // output pixels per CTA: 8 wide x 16 tall = 128 TMEM lanes
 constexpr int PW = 16, PH = TH + 4;               // patch: 16 x 20 pixels (x0-2 .. x0+13, y0-2 .. y0+17)
 constexpr int PATCH_BYTES = PW * PH * 128;        // 40960
+constexpr int PAIR_PATCH_BYTES = PW * 2 * 12 * 128;   // 49152: two 8x8 images, rows interleaved
 constexpr int GP = 132, CP = 36;                  // padded row pitches (floats) of the epilogue staging: gates 128 + 4, c / h 32 + 4
 constexpr int STG_FLOATS = 128 * (GP + 2 * CP);   // per pixel tile: 104448 bytes
 
 struct Geom {
     int H, W, Kc, N, BN, stages, tmem_cols;
+    int pair;                                     // 8 x 8 maps: one tile = two images (see the header)
+    int patch_bytes;
     long long* dbg;                               // optional per-CTA clock64 stamps [grid][8] (pivp_tc_set_debug_buffer), else null
 };
 #define HALO_STAMP(i) do { if (g.dbg && lane == 0) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
@@ -48,7 +55,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* patch = smem;
-    uint8_t* bring = smem + MS * PATCH_BYTES;
+    uint8_t* bring = smem + MS * g.patch_bytes;
     const uint32_t b_bytes = (uint32_t)g.BN * 128;
     uint64_t* bars = (uint64_t*)(bring + (size_t)g.stages * b_bytes);
     uint64_t* full = bars;
@@ -99,12 +106,16 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         for (int cb = 0; cb < ncb; ++cb) {
             mbar_wait(smem_u32(patch_empty), (uint32_t)(cb & 1) ^ 1u);
             if (elect_one()) {
-                mbar_expect_tx(smem_u32(patch_full), MS * PATCH_BYTES);
+                mbar_expect_tx(smem_u32(patch_full), MS * g.patch_bytes);
 #pragma unroll
                 for (int i = 0; i < MS; ++i) {
                     const int mt = blockIdx.x * MS + i;
-                    const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
-                    tma_load_4d(smem_u32(patch + i * PATCH_BYTES), &map_a, smem_u32(patch_full), cb * 64, tx * TW - 2, ty * TH - 2, tb);
+                    if (g.pair) {
+                        tma_load_4d(smem_u32(patch + i * g.patch_bytes), &map_a, smem_u32(patch_full), cb * 64, -2, 2 * mt, -2);
+                    } else {
+                        const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
+                        tma_load_4d(smem_u32(patch + i * g.patch_bytes), &map_a, smem_u32(patch_full), cb * 64, tx * TW - 2, ty * TH - 2, tb);
+                    }
                 }
             }
             __syncwarp();
@@ -128,6 +139,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const uint32_t ring_lo = ((smem_u32(bring) & 0x3FFFFu) >> 4) | 0x10000u, b_step = b_bytes >> 4;
         const uint32_t patch_lo = ((smem_u32(patch) & 0x3FFFFu) >> 4) | 0x10000u;
         const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
+        const uint32_t ky_rows = g.pair ? 2u * PW : (uint32_t)PW, patch_step = (uint32_t)g.patch_bytes >> 4;
         uint32_t st = 0, ph = 0, b_lo = ring_lo;
         for (int cb = 0; cb < ncb; ++cb) {
             mbar_wait(smem_u32(patch_full), (uint32_t)(cb & 1));
@@ -138,12 +150,12 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     mbar_wait(full0 + 8 * st, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_lo = patch_lo + (uint32_t)(ky * PW + kx) * 8u;      // one pixel row = 128 B = 8 descriptor units
+                        const uint32_t a_lo = patch_lo + ((uint32_t)ky * ky_rows + (uint32_t)kx) * 8u;      // one pixel row = 128 B = 8 descriptor units
 #pragma unroll
                         for (int i = 0; i < MS; ++i)
 #pragma unroll
                             for (int k = 0; k < 4; ++k)
-                                tc_mma_lohi(tmem_u + (uint32_t)(i * g.BN), a_lo + (uint32_t)(i * (PATCH_BYTES >> 4) + 2 * k), b_lo + 2 * k, hi_a, hi_b,
+                                tc_mma_lohi(tmem_u + (uint32_t)(i * g.BN), a_lo + (uint32_t)i * patch_step + 2u * k, b_lo + 2 * k, hi_a, hi_b,
                                             idesc, (k == 0) ? ((cb | ky | kx) ? 1u : 0u) : 1u);
                         tc_commit(empty0 + 8 * st);
                         if (ky == 4 && kx == 4) {
@@ -164,8 +176,12 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const int row = q * 32 + lane;
         const int mt = blockIdx.x * MS + sub;
         const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
-        const long m00 = ((long)tb * g.H + ty * TH) * g.W + tx * TW;                           // NHWC pixel index of accumulator row 0
-        const long m = m00 + (long)(row >> 3) * g.W + (row & 7);                               // ... and of this thread's row
+        // NHWC pixel index of accumulator row r: tile rows are 8-pixel groups; pair geometry: group = (y, image) of two 8x8 images
+        const long m00 = g.pair ? (long)mt * 128 : ((long)tb * g.H + ty * TH) * g.W + tx * TW;
+        auto pixel_of = [&](int r) -> long {
+            return g.pair ? m00 + ((r >> 3) & 1) * 64 + (r >> 4) * 8 + (r & 7) : m00 + (long)(r >> 3) * g.W + (r & 7);
+        };
+        const long m = pixel_of(row);
         const uint32_t trow = tmem_base + (uint32_t)(sub * g.BN) + ((uint32_t)(q * 32) << 16);
         if (ep.mode == 1) {
             // ---- ConvLSTM gate epilogue, staged: every thread owns one pixel row of the accumulator (that is how tcgen05.ld hands
@@ -265,7 +281,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 const int sr = lane >> 4, l16 = lane & 15;
                 for (int r0 = lw * 2; r0 < 128; r0 += 16) {
                     const int r = r0 + sr;
-                    const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
+                    const long mr = pixel_of(r);
                     const float4 a = *reinterpret_cast<const float4*>(G + r * GP + 8 * l16), b4 = *reinterpret_cast<const float4*>(G + r * GP + 8 * l16 + 4);
                     const float v[8] = {a.x, a.y, a.z, a.w, b4.x, b4.y, b4.z, b4.w};
                     *reinterpret_cast<uint4*>(gb + mr * (4 * ep.C) + n0 + 8 * l16) = pack8_bf16(v);
@@ -273,7 +289,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             } else {
                 // fp32 gates: one 512-byte row per warp instruction
                 for (int r = lw; r < 128; r += 8) {
-                    const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
+                    const long mr = pixel_of(r);
                     const float4 v = *reinterpret_cast<const float4*>(G + r * GP + 4 * lane);
                     *reinterpret_cast<float4*>(ep.gates + mr * (4 * ep.C) + n0 + 4 * lane) = v;
                 }
@@ -282,7 +298,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             const int sub_r = lane >> 3, l8 = lane & 7;
             for (int r0 = lw * 4; r0 < 128; r0 += 32) {
                 const int r = r0 + sub_r;
-                const long mr = m00 + (long)(r >> 3) * g.W + (r & 7);
+                const long mr = pixel_of(r);
                 const float4 cv = *reinterpret_cast<const float4*>(Cc + r * CP + 4 * l8);
                 const float4 hv = *reinterpret_cast<const float4*>(Hh + r * CP + 4 * l8);
                 *reinterpret_cast<float4*>(ep.c_out + mr * ep.C + ch0 + 4 * l8) = cv;
@@ -321,13 +337,13 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 template <int MS>
 static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g, const TcEpilogue& ep, int tiles, void* stream, const char* who) {
     const int b_bytes = g.BN * 128;
-    int stages = (225 * 1024 - MS * PATCH_BYTES) / b_bytes;     // one CTA per SM, the ring takes what the patches leave
-    if (stages > 20) stages = 20;
+    int stages = (225 * 1024 - MS * g.patch_bytes) / b_bytes;     // one CTA per SM, the ring takes what the patches leave
+    if (stages > 24) stages = 24;
     g.stages = stages;
     const int cols = MS * g.BN;
     g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    const size_t smem = 1024 + (size_t)MS * PATCH_BYTES + (size_t)stages * b_bytes + (2 * stages + 3) * 8 + 16 + (size_t)g.BN * 4;
-    PIVP_REQUIRE(ep.mode != 1 || (size_t)MS * PATCH_BYTES + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4 + 256,
+    const size_t smem = 1024 + (size_t)MS * g.patch_bytes + (size_t)stages * b_bytes + (2 * stages + 3) * 8 + 16 + (size_t)g.BN * 4;
+    PIVP_REQUIRE(ep.mode != 1 || (size_t)MS * g.patch_bytes + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4 + 256,
                  "%s(halo): operand ring too small to stage the gate epilogue", who);
     static bool attr_set = false;
     if (!attr_set) {
@@ -352,7 +368,9 @@ int tc_halo_mode() {
 }
 
 bool tc_halo_supported(int B, int H, int W, int Kc, int BN) {
-    return tc_halo_mode() != 0 && W % halo::TW == 0 && H % halo::TH == 0 && Kc % 64 == 0 && BN % 16 == 0 && BN >= 16 && BN <= 256 && B > 0;
+    const bool tiled = W % halo::TW == 0 && H % halo::TH == 0;
+    const bool pair = W == 8 && H == 8 && B % 2 == 0 && tc_halo_mode() != 5;      // 5 = pair geometry off (tuning switch)
+    return tc_halo_mode() != 0 && (tiled || pair) && Kc % 64 == 0 && BN % 16 == 0 && BN >= 16 && BN <= 256 && B > 0;
 }
 
 int launch_conv5x5_halo(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, const void* wt_bf16, int N, int BN, TcEpilogue ep,
@@ -362,11 +380,19 @@ int launch_conv5x5_halo(const void* in_bf16, int in_cs, int B, int H, int W, int
     Geom g;
     g.H = H; g.W = W; g.Kc = Kc; g.N = N; g.BN = BN;
     g.dbg = g_halo_dbg;
+    g.pair = (H == 8 && W == 8) ? 1 : 0;
+    g.patch_bytes = g.pair ? PAIR_PATCH_BYTES : PATCH_BYTES;
+    PIVP_REQUIRE(!g.pair || !ep.ln_partial, "%s(halo): no LayerNorm partials in the 8x8 pair geometry (a tile spans two samples)", who);
     CUtensorMap map_a, map_b;
     {
         cuuint64_t dims[4] = {(cuuint64_t)in_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
         cuuint64_t str[3] = {(cuuint64_t)in_cs * 2, (cuuint64_t)W * in_cs * 2, (cuuint64_t)H * W * in_cs * 2};
         cuuint32_t box[4] = {64u, (cuuint32_t)PW, (cuuint32_t)PH, 1u};
+        if (g.pair) {                      // (channel, x, image, y): the two images' rows interleave in the patch
+            dims[2] = (cuuint64_t)B; dims[3] = (cuuint64_t)H;
+            str[1] = (cuuint64_t)H * W * in_cs * 2; str[2] = (cuuint64_t)W * in_cs * 2;
+            box[2] = 2u; box[3] = 12u;
+        }
         CUresult r = encode_tmap(&map_a, in_bf16, 4, dims, str, box);
         if (r != CUDA_SUCCESS) { set_error("%s(halo): cuTensorMapEncodeTiled(A) failed (%d)", who, (int)r); return PIVP_ECUDA; }
     }
@@ -377,7 +403,7 @@ int launch_conv5x5_halo(const void* in_bf16, int in_cs, int B, int H, int W, int
         CUresult r = encode_tmap(&map_b, wt_bf16, 2, dims, str, box);
         if (r != CUDA_SUCCESS) { set_error("%s(halo): cuTensorMapEncodeTiled(B) failed (%d)", who, (int)r); return PIVP_ECUDA; }
     }
-    const int tiles = B * (H / TH) * (W / TW);
+    const int tiles = g.pair ? B / 2 : B * (H / TH) * (W / TW);
     // two pixel tiles per CTA halve the weight traffic per FLOP; only worth it while the grid still covers most of the SMs
     const int force = tc_halo_mode();
     const bool two = (force == 3) ? false : (tiles % 2 == 0 && 2 * BN <= 512 && ((tiles / 2) * (N / BN) >= 96 || force == 4));

@@ -48,6 +48,7 @@ class TensorCorePlan(object):
         self.accurate = 0
         import os
         self.split_n = int(os.environ.get("PIVP_TC_SPLIT_N", "1"))       # tuning switch for the input-gradient N split
+        self.pair_bn = int(os.environ.get("PIVP_TC_PAIR_BN", "32"))      # N tile of the 8x8-map input gradient (0: per-tap kernel's choice)
         # layers whose maps the halo-patch kernel tiles (H % 16 == 0, W % 8 == 0): its epilogue also produces the LayerNorm statistics
         self.ln_fused = [(eng.H // lv) % 16 == 0 and (eng.W // lv) % 8 == 0 and ((eng.H // lv) * (eng.W // lv) * c) % 4096 == 0
                          for c, lv in zip(LSTM_SIZES, LSTM_LEVEL)]
@@ -285,6 +286,9 @@ class TensorCorePlan(object):
         halo = h % 16 == 0 and w % 8 == 0      # halo-patch kernel: one CTA per SM, so 64 pixel tiles leave half the GPU idle:
         if halo and mt < 100 and (cx // 2) % 16 == 0 and self.split_n:      # two N tiles of cx/2 (narrower tiles starve the weight ring)
             bn = cx // 2
+        if h == 8 and w == 8 and ws["B"] % 2 == 0 and self.pair_bn:        # 8x8 maps: halo kernel in its two-image geometry, 16 pixel tiles only
+            halo = True
+            bn = self.pair_bn if cx % self.pair_bn == 0 else cx
         for cand in (cx, cx // 2, cx // 3, cx // 6):      # multiples of 32 only: N=48 tiles measured 2.4x slower than N=96
             if halo:
                 break

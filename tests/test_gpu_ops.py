@@ -35,7 +35,9 @@ def pk():
 
 # ---------------------------------------------------------------------------------------------- convolutions
 @pytest.mark.parametrize("B,C,H,W,O,k,s,p", [
-    (2, 3, 16, 24, 32, 5, 2, 2),      # enc0
+    (2, 3, 16, 24, 32, 5, 2, 2),      # enc0 (generic implicit-GEMM kernels: output not tileable by 8 x 16)
+    (2, 3, 32, 64, 32, 5, 2, 2),      # enc0 on the direct image kernels (conv_image.cu)
+    (3, 3, 64, 64, 32, 5, 2, 2),
     (2, 32, 16, 16, 32, 3, 2, 1),     # enc1
     (3, 74, 8, 8, 64, 1, 1, 0),       # enc3 (74 input channels: not a multiple of 4)
     (2, 64, 16, 16, 128, 5, 1, 2),    # a ConvLSTM gate conv
