@@ -224,6 +224,16 @@ def main():
     # are then replayed back to back as ONE CUDA graph on the same buffers and timed with CUDA events on the launching stream --
     # an eager event pair around a 20 us kernel mostly measures the host's launch cadence, not the kernel.
     roof, roof_wgrad, cdna_op = None, None, None
+
+    def traffic_from_profile():
+        """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture of one step
+        (profiles/r01_ncu_full_halo_traffic.json, written by scripts/ncu_traffic_summary.py); None when the summary is absent."""
+        f = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_halo_traffic.json")
+        try:
+            with open(f) as fh:
+                return json.load(fh)["dram_bytes_per_launch"]
+        except (OSError, KeyError, ValueError):
+            return None
     if True:                                  # every rank runs the instrumented step (it contains the all-reduce); rank 0 reports
         L = pk.lib()
         orig = L.call
@@ -270,9 +280,9 @@ def main():
                 ach = flops / per / 1e12
                 roof = {"bound": "tensor",
                         "kernel": "conv5x5_halo_tc_kernel (tcgen05 ConvLSTM implicit GEMM with halo-patch A operand; forward + fused gates, "
-                                  "and input gradient) -- lstm5's 8x8 maps use conv_taps_tc_kernel",
+                                  "and input gradient; the 8x8 maps of layer 5 in the two-image pair geometry)",
                         "achieved": ach, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk_["bf16_tflops"],
-                        "frac_of_sustained": ach / pk_["bf16_tflops_sustained"], "traffic": None,
+                        "frac_of_sustained": ach / pk_["bf16_tflops_sustained"], "traffic": traffic_from_profile(),
                         "peak_source": src + " (burst figure: the step's %d launches are replayed back to back as one CUDA graph, "
                                              "about 3 ms, outside the long step)" % len(conv_calls),
                         "launches": len(conv_calls), "avg_launch_us": per * 1e6,
@@ -343,7 +353,7 @@ def main():
                                        "one step = forward + BPTT + grad all-reduce + Adam" % (B, ITER0),
                            "global_batch": B * world, "seq_len": T, "parallelism": "dp%d" % world,
                            "l2": "per-step working set ~%.1f GB of activations >> 126 MB L2 (no flush needed)" % (2.2 * B / 32),
-                           "cuda_graph": bool(step.use_graph), "lstm_gemm": "tcgen05 bf16: ConvLSTM fwd (+fused gates) / dgrad / wgrad with halo-patch operands, deconvolutions fwd+bwd; enc0-3 convs SIMT fp32" if args.compute == "bf16" else "SIMT fp32"},
+                           "cuda_graph": bool(step.use_graph), "lstm_gemm": "tcgen05 bf16: ConvLSTM fwd (+fused gates) / dgrad / wgrad with halo-patch operands, stride-2 convolutions / deconvolutions fwd+bwd+wgrad; enc0 (3 channels) and enc3 (1x1) SIMT fp32" if args.compute == "bf16" else "SIMT fp32"},
                 "clocks": clocks, "gpu_launches": int(launches), "loss": loss_now,
                 "e2e": {"value": e2e_val, "unit": "frames/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)}}
         if roof:

@@ -31,6 +31,7 @@ struct Geom {
     int H, W, Kc, N, BN, stages, tmem_cols;
     int pair;                                     // 8 x 8 maps: one tile = two images (see the header)
     int patch_bytes;
+    int npatch;                                   // patch buffers (1..3): the next 64-channel block's patch loads under this block's MMAs
     long long* dbg;                               // optional per-CTA clock64 stamps [grid][8] (pivp_tc_set_debug_buffer), else null
 };
 #define HALO_STAMP(i) do { if (g.dbg && lane == 0) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
@@ -49,21 +50,24 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes
 
 // MS = pixel tiles (of 128) per CTA: each weight stage feeds 4*MS MMAs, i.e. MS*BN/4... cycles of tensor work per 128*BN bytes fetched.
 // One CTA per SM: all shared memory that the MS patches leave goes to the weight ring, deep enough to cover the L2 round trip.
-template <int MS>
+// NP = patch buffers (compile-time: the buffer index and barrier parity of a block must stay on the uniform datapath, a run-time
+// modulus pushes the whole issue loop back onto vector registers + per-MMA R2UR / divergence checks).
+template <int MS, int NP>
 __global__ void __launch_bounds__(64 + 256 * MS, 1)
 conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Geom g, TcEpilogue ep) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* patch = smem;
-    uint8_t* bring = smem + MS * g.patch_bytes;
+    const uint32_t pbuf_bytes = (uint32_t)(MS * g.patch_bytes);     // one patch buffer = the MS tiles' patches of one 64-channel block
+    uint8_t* bring = smem + NP * pbuf_bytes;
     const uint32_t b_bytes = (uint32_t)g.BN * 128;
     uint64_t* bars = (uint64_t*)(bring + (size_t)g.stages * b_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + g.stages;
-    uint64_t* patch_full = bars + 2 * g.stages;
-    uint64_t* patch_empty = patch_full + 1;
-    uint64_t* accum_full = patch_full + 2;
-    uint32_t* tmem_slot = (uint32_t*)(patch_full + 3);
+    uint64_t* patch_full = bars + 2 * g.stages;                     // [3]
+    uint64_t* patch_empty = patch_full + 3;                         // [3]
+    uint64_t* accum_full = patch_full + 6;
+    uint32_t* tmem_slot = (uint32_t*)(patch_full + 7);
     float* bias_s = (float*)(tmem_slot + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -75,8 +79,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-        mbar_init(smem_u32(patch_full), 1);
-        mbar_init(smem_u32(patch_empty), 1);
+        for (int s = 0; s < 3; ++s) { mbar_init(smem_u32(patch_full + s), 1); mbar_init(smem_u32(patch_empty + s), 1); }
         mbar_init(smem_u32(accum_full), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
@@ -103,23 +106,39 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         // ===================== TMA producer =====================
         const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), ring0 = smem_u32(bring);
         uint32_t st = 0, ph = 1;                                  // waits on `empty` start with parity 1 (fresh barrier)
-        for (int cb = 0; cb < ncb; ++cb) {
-            mbar_wait(smem_u32(patch_empty), (uint32_t)(cb & 1) ^ 1u);
+        const uint32_t pfull0 = smem_u32(patch_full), pempty0 = smem_u32(patch_empty);
+        constexpr int np = NP;
+        int next = 0;                                             // next 64-channel block whose patch has not been requested yet
+        // patch n goes to buffer n % np once the MMAs of block n - np have drained it (use count u = n / np -> parity (u & 1) ^ 1)
+        auto issue_patch = [&](int n) {
+            const uint32_t slot = (uint32_t)(n % np);
             if (elect_one()) {
-                mbar_expect_tx(smem_u32(patch_full), MS * g.patch_bytes);
+                mbar_expect_tx(pfull0 + 8 * slot, pbuf_bytes);
 #pragma unroll
                 for (int i = 0; i < MS; ++i) {
                     const int mt = blockIdx.x * MS + i;
+                    const uint32_t dst = smem_u32(patch) + slot * pbuf_bytes + (uint32_t)(i * g.patch_bytes);
                     if (g.pair) {
-                        tma_load_4d(smem_u32(patch + i * g.patch_bytes), &map_a, smem_u32(patch_full), cb * 64, -2, 2 * mt, -2);
+                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, n * 64, -2, 2 * mt, -2);
                     } else {
                         const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
-                        tma_load_4d(smem_u32(patch + i * g.patch_bytes), &map_a, smem_u32(patch_full), cb * 64, tx * TW - 2, ty * TH - 2, tb);
+                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, n * 64, tx * TW - 2, ty * TH - 2, tb);
                     }
                 }
             }
             __syncwarp();
+        };
+        for (int cb = 0; cb < ncb; ++cb) {
+            if (next == cb) {                                     // this block's patch must be on its way before its weights fill the ring
+                mbar_wait(pempty0 + 8 * (uint32_t)(next % np), (uint32_t)((next / np) & 1) ^ 1u);
+                issue_patch(next++);
+            }
             for (int tap = 0; tap < 25; ++tap) {
+                // prefetch later patches as soon as their buffer is free (non-blocking test), after this block's first weight tiles
+                if (NP > 1 && tap >= 2 && next < ncb && next < cb + np) {
+                    const int freed = (int)mbar_test(pempty0 + 8 * (uint32_t)(next % np), (uint32_t)((next / np) & 1) ^ 1u);
+                    if (__all_sync(0xffffffffu, freed)) issue_patch(next++);      // a vote keeps the branch (and with it the whole kernel) warp-uniform for ptxas
+                }
                 mbar_wait(empty0 + 8 * st, ph);
                 if (elect_one()) {
                     mbar_expect_tx(full0 + 8 * st, b_bytes);
@@ -140,9 +159,13 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         const uint32_t patch_lo = ((smem_u32(patch) & 0x3FFFFu) >> 4) | 0x10000u;
         const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
         const uint32_t ky_rows = g.pair ? 2u * PW : (uint32_t)PW, patch_step = (uint32_t)g.patch_bytes >> 4;
+        const uint32_t pfull0 = smem_u32(patch_full), pempty0 = smem_u32(patch_empty);
         uint32_t st = 0, ph = 0, b_lo = ring_lo;
         for (int cb = 0; cb < ncb; ++cb) {
-            mbar_wait(smem_u32(patch_full), (uint32_t)(cb & 1));
+            const uint32_t slot = (uint32_t)(cb % NP), use_par = (uint32_t)((cb / NP) & 1);      // patch buffer of this block, parity of its use count
+            const uint32_t pf_bar = pfull0 + 8 * slot, pe_bar = pempty0 + 8 * slot;
+            const uint32_t pb_lo = patch_lo + slot * (pbuf_bytes >> 4);
+            mbar_wait(pf_bar, use_par);
             if (cb == 0) HALO_STAMP(2);
             for (int ky = 0; ky < 5; ++ky) {
 #pragma unroll
@@ -150,7 +173,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     mbar_wait(full0 + 8 * st, ph);
                     tc_fence_after();
                     if (elect_one()) {
-                        const uint32_t a_lo = patch_lo + ((uint32_t)ky * ky_rows + (uint32_t)kx) * 8u;      // one pixel row = 128 B = 8 descriptor units
+                        const uint32_t a_lo = pb_lo + ((uint32_t)ky * ky_rows + (uint32_t)kx) * 8u;      // one pixel row = 128 B = 8 descriptor units
 #pragma unroll
                         for (int i = 0; i < MS; ++i)
 #pragma unroll
@@ -159,7 +182,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                                             idesc, (k == 0) ? ((cb | ky | kx) ? 1u : 0u) : 1u);
                         tc_commit(empty0 + 8 * st);
                         if (ky == 4 && kx == 4) {
-                            tc_commit(smem_u32(patch_empty));
+                            tc_commit(pe_bar);
                             if (cb == ncb - 1) tc_commit(smem_u32(accum_full));
                         }
                     }
@@ -334,26 +357,45 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     }
 }
 
-template <int MS>
-static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g, const TcEpilogue& ep, int tiles, void* stream, const char* who) {
-    const int b_bytes = g.BN * 128;
-    int stages = (225 * 1024 - MS * g.patch_bytes) / b_bytes;     // one CTA per SM, the ring takes what the patches leave
-    if (stages > 24) stages = 24;
-    g.stages = stages;
-    const int cols = MS * g.BN;
-    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
-    const size_t smem = 1024 + (size_t)MS * g.patch_bytes + (size_t)stages * b_bytes + (2 * stages + 3) * 8 + 16 + (size_t)g.BN * 4;
-    PIVP_REQUIRE(ep.mode != 1 || (size_t)MS * g.patch_bytes + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4 + 256,
-                 "%s(halo): operand ring too small to stage the gate epilogue", who);
+template <int MS, int NP>
+static int launch_ms_np(const CUtensorMap& map_a, const CUtensorMap& map_b, const Geom& g, const TcEpilogue& ep, int tiles, size_t smem, void* stream,
+                        const char* who) {
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(conv5x5_halo_tc_kernel<MS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaError_t e = cudaFuncSetAttribute(conv5x5_halo_tc_kernel<MS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("%s(halo): cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
         attr_set = true;
     }
     dim3 grid((unsigned)(tiles / MS), (unsigned)(g.N / g.BN));
-    conv5x5_halo_tc_kernel<MS><<<grid, 64 + 256 * MS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
+    conv5x5_halo_tc_kernel<MS, NP><<<grid, 64 + 256 * MS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
     return check_launch(who);
+}
+
+template <int MS>
+static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g, const TcEpilogue& ep, int tiles, void* stream, const char* who) {
+    const int b_bytes = g.BN * 128;
+    // one CTA per SM.  Patch buffers: up to 3 (never more than the 64-channel blocks), as long as the weight ring keeps >= 8 stages and
+    // the staged gate epilogue still fits; the ring takes what the patches leave.
+    const int ncb = g.Kc / 64;
+    const char* env_np = getenv("PIVP_TC_HALO_NP");
+    int np = env_np ? atoi(env_np) : 3;
+    if (MS > 1) np = 1;                                  // two-tile CTAs: 80 KB per buffer, the ring needs the rest
+    if (np > 3) np = 3;
+    if (np > ncb) np = ncb;
+    if (np < 1) np = 1;
+    while (np > 1 && (225 * 1024 - np * MS * g.patch_bytes) / b_bytes < 8) --np;
+    g.npatch = np;
+    int stages = (225 * 1024 - np * MS * g.patch_bytes) / b_bytes;
+    if (stages > 24) stages = 24;
+    g.stages = stages;
+    const int cols = MS * g.BN;
+    g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : cols <= 256 ? 256 : 512;
+    const size_t smem = 1024 + (size_t)np * MS * g.patch_bytes + (size_t)stages * b_bytes + (2 * stages + 7) * 8 + 16 + (size_t)g.BN * 4;
+    PIVP_REQUIRE(ep.mode != 1 || (size_t)np * MS * g.patch_bytes + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4 + 256,
+                 "%s(halo): operand ring too small to stage the gate epilogue", who);
+    if (MS == 1 && np == 3) return launch_ms_np<1, 3>(map_a, map_b, g, ep, tiles, smem, stream, who);
+    if (MS == 1 && np == 2) return launch_ms_np<1, 2>(map_a, map_b, g, ep, tiles, smem, stream, who);
+    return launch_ms_np<MS, 1>(map_a, map_b, g, ep, tiles, smem, stream, who);
 }
 
 }  // namespace halo

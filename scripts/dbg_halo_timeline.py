@@ -40,3 +40,6 @@ run(32, 32, 32, 128, 32, 1)
 run(32, 16, 16, 128, 64, 1)
 run(32, 32, 32, 128, 32, 0, N=64, BN=64)
 run(32, 16, 16, 256, 64, 0, N=192, BN=192)
+run(32, 16, 16, 256, 64, 0, N=192, BN=96)      # lstm6 input gradient as the engine launches it (two N tiles)
+run(32, 8, 8, 192, 128, 1)                     # lstm5 forward: two-image pair geometry
+run(32, 8, 8, 512, 128, 0, N=192, BN=32)       # lstm5 input gradient
