@@ -32,12 +32,24 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
 }
 
 // coalesced copy of a 128-pixel x 64-channel tile between global rows (stride cs, offset co) and shared memory
+template <int BATCH>
 __device__ __forceinline__ void load_tile(const float* __restrict__ x, int cs, int co, long m0, long M, float* xs) {
-    for (int i = threadIdx.x; i < TP * (C / 4); i += TP) {
-        const int r = i >> 4, c4 = i & 15;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m0 + r < M) v = __ldg(reinterpret_cast<const float4*>(x + (m0 + r) * cs + co) + c4);
-        *reinterpret_cast<float4*>(xs + r * XP + 4 * c4) = v;
+    // BATCH loads of a thread are issued before their shared-memory stores (16 / BATCH memory round trips per tile, not sixteen)
+    constexpr int NL = TP * (C / 4) / TP;
+#pragma unroll
+    for (int k0 = 0; k0 < NL; k0 += BATCH) {
+        float4 v[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = threadIdx.x + (k0 + k) * TP, r = i >> 4, c4 = i & 15;
+            v[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < M) v[k] = __ldg(reinterpret_cast<const float4*>(x + (m0 + r) * cs + co) + c4);
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = threadIdx.x + (k0 + k) * TP, r = i >> 4, c4 = i & 15;
+            *reinterpret_cast<float4*>(xs + r * XP + 4 * c4) = v[k];
+        }
     }
 }
 
@@ -48,16 +60,26 @@ __global__ void __launch_bounds__(TP) heads_fwd_kernel(const float* __restrict__
     constexpr int NP = (NH + 3) / 4 * 4;                         // padded to float4
     __shared__ __align__(16) float xs[TP * XP];
     __shared__ __align__(16) float wt[C * NP];                   // W transposed: wt[c][n]
-    for (int i = threadIdx.x; i < C * NP; i += TP) {
-        const int c = i / NP, n = i - c * NP;
-        wt[i] = n < NH ? __ldg(Wt + n * C + c) : 0.f;
+    {   // W rows are contiguous ([n][64]): 128-bit loads, all in flight together with the pixel tile and the bias
+        constexpr int NW = (NP * (C / 4) + TP - 1) / TP;
+        float4 wv[NW];
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int i = threadIdx.x + k * TP, n = i >> 4;
+            wv[k] = (i < NP * (C / 4) && n < NH) ? __ldg(reinterpret_cast<const float4*>(Wt) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int k = 0; k < NW; ++k) {
+            const int i = threadIdx.x + k * TP, n = i >> 4, c = 4 * (i & 15);
+            if (i < NP * (C / 4)) { wt[c * NP + n] = wv[k].x; wt[(c + 1) * NP + n] = wv[k].y; wt[(c + 2) * NP + n] = wv[k].z; wt[(c + 3) * NP + n] = wv[k].w; }
+        }
     }
-    const long m0 = (long)blockIdx.x * TP;
-    load_tile(x, cs, co, m0, M, xs);
-    __syncthreads();
     float2 acc[NP / 2];
 #pragma unroll
     for (int j = 0; j < NP / 2; ++j) acc[j] = make_float2(2 * j < NH ? __ldg(bias + 2 * j) : 0.f, 2 * j + 1 < NH ? __ldg(bias + 2 * j + 1) : 0.f);
+    const long m0 = (long)blockIdx.x * TP;
+    load_tile<16>(x, cs, co, m0, M, xs);
+    __syncthreads();
     const float* xr = xs + threadIdx.x * XP;
 #pragma unroll 4
     for (int c4 = 0; c4 < C / 4; ++c4) {
@@ -98,7 +120,8 @@ __global__ void __launch_bounds__(TP, 4) heads_bwd_kernel(const float* __restric
     extern __shared__ __align__(16) float hsm[];
     float* xs = hsm;                                             // [TP][XP] pixel tile
     float* ds = xs + TP * XP;                                    // [TP][NP] dY tile
-    float* ws = ds + TP * NP;                                    // [NH][C]  W
+    float* dT = ds + TP * NP;                                    // [NH][TP] dY tile, head-major (the d_x phase reads 4 pixels per 128-bit load)
+    float* ws = dT + NH * TP;                                    // [NH][C]  W
     for (int i = threadIdx.x; i < NH * C; i += TP) ws[i] = __ldg(Wt + i);
     const int cg = threadIdx.x & 15, half = (threadIdx.x >> 4) & 1, pq = threadIdx.x >> 5;
     float2 aw[NB][2];
@@ -109,7 +132,7 @@ __global__ void __launch_bounds__(TP, 4) heads_bwd_kernel(const float* __restric
     for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long m0 = (long)tile * TP;
         __syncthreads();                                          // previous tile's readers are done
-        load_tile(x, cs, co, m0, M, xs);
+        load_tile<8>(x, cs, co, m0, M, xs);
         {
             const long m = m0 + threadIdx.x;
             const long b = m / HW, p = m - b * HW;
@@ -122,6 +145,8 @@ __global__ void __launch_bounds__(TP, 4) heads_bwd_kernel(const float* __restric
 #pragma unroll
             for (int n4 = 0; n4 < NP / 4; ++n4)
                 *reinterpret_cast<float4*>(ds + threadIdx.x * NP + 4 * n4) = make_float4(v[4 * n4], v[4 * n4 + 1], v[4 * n4 + 2], v[4 * n4 + 3]);
+#pragma unroll
+            for (int n = 0; n < NH; ++n) dT[n * TP + threadIdx.x] = v[n];
         }
         __syncthreads();
         // ---- dW[n][c] += sum_p dY[p][n] x[p][c]   (this thread: 32 pixels, 4 channels, NB heads) -- packed FFMA2, broadcast dY
@@ -144,33 +169,39 @@ __global__ void __launch_bounds__(TP, 4) heads_bwd_kernel(const float* __restric
                 }
             }
         }
-        // ---- d_x[c] = sum_n dY[n] W[n][c] for this thread's pixel
-        float2 acc[C / 2];
-#pragma unroll
-        for (int j = 0; j < C / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+        // ---- d_x[p][c] = sum_n dY[p][n] W[n][c]: thread = 4 pixels x 16 channels, so one W row quarter (4 x 128 bit) serves 4 pixels
+        // (one pixel x 64 channels per thread re-read all of W per pixel: 228 shared-memory loads per thread and tile, now 70)
         {
-            float dmy[NP];
+            const int q = threadIdx.x & 3, pg = threadIdx.x >> 2;
+            float2 acc[4][8];
 #pragma unroll
-            for (int n4 = 0; n4 < NP / 4; ++n4) {
-                const float4 d4 = *reinterpret_cast<const float4*>(ds + threadIdx.x * NP + 4 * n4);
-                dmy[4 * n4] = d4.x; dmy[4 * n4 + 1] = d4.y; dmy[4 * n4 + 2] = d4.z; dmy[4 * n4 + 3] = d4.w;
-            }
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = make_float2(0.f, 0.f);
 #pragma unroll
             for (int n = 0; n < NH; ++n) {
-                const float d = dmy[n];
-                const float4* wr = reinterpret_cast<const float4*>(ws + n * C);
+                const float4 d4 = *reinterpret_cast<const float4*>(dT + n * TP + 4 * pg);
+                const float dd[4] = {d4.x, d4.y, d4.z, d4.w};
+                const float4* wr = reinterpret_cast<const float4*>(ws + n * C + 16 * q);
 #pragma unroll
-                for (int j = 0; j < C / 4; ++j) {
+                for (int j = 0; j < 4; ++j) {
                     const float4 w4 = wr[j];
-                    acc[2 * j] = ffma2(make_float2(d, d), make_float2(w4.x, w4.y), acc[2 * j]);
-                    acc[2 * j + 1] = ffma2(make_float2(d, d), make_float2(w4.z, w4.w), acc[2 * j + 1]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        acc[i][2 * j] = ffma2(make_float2(dd[i], dd[i]), make_float2(w4.x, w4.y), acc[i][2 * j]);
+                        acc[i][2 * j + 1] = ffma2(make_float2(dd[i], dd[i]), make_float2(w4.z, w4.w), acc[i][2 * j + 1]);
+                    }
                 }
             }
-        }
-        __syncthreads();                                          // everyone has finished reading the x tile
-        float* xr = xs + threadIdx.x * XP;
+            __syncthreads();                                      // everyone has finished reading the x tile (weight-gradient phase)
 #pragma unroll
-        for (int j = 0; j < C / 4; ++j) *reinterpret_cast<float4*>(xr + 4 * j) = make_float4(acc[2 * j].x, acc[2 * j].y, acc[2 * j + 1].x, acc[2 * j + 1].y);
+            for (int i = 0; i < 4; ++i) {
+                float* xr = xs + (4 * pg + i) * XP + 16 * q;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<float4*>(xr + 4 * j) = make_float4(acc[i][2 * j].x, acc[i][2 * j].y, acc[i][2 * j + 1].x, acc[i][2 * j + 1].y);
+            }
+        }
         __syncthreads();
         for (int i = threadIdx.x; i < TP * (C / 4); i += TP) {
             const int r = i >> 4, c4 = i & 15;
@@ -231,11 +262,11 @@ int pivp_heads_bwd(const float* x, int x_cs, int x_co, const float* W, const flo
     int grid = 148 * 4;
     if (grid > ntiles) grid = ntiles;
     const int NB = ((NH + 1) / 2 + 3) / 4 * 4;
-    const size_t smem = sizeof(float) * ((size_t)hd::TP * hd::XP + (size_t)hd::TP * 2 * NB + (size_t)NH * hd::C);
+    const size_t smem = sizeof(float) * ((size_t)hd::TP * hd::XP + (size_t)hd::TP * 2 * NB + (size_t)NH * hd::TP + (size_t)NH * hd::C);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(hd::heads_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
-        cudaFuncSetAttribute(hd::heads_bwd_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+        cudaFuncSetAttribute(hd::heads_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+        cudaFuncSetAttribute(hd::heads_bwd_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
         attr_set = true;
     }
     if (NH == 14) hd::heads_bwd_kernel<14><<<grid, hd::TP, smem, (cudaStream_t)stream>>>(x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
