@@ -31,6 +31,7 @@ struct Geom {
     int H, W, Kc, N, BN, stages, tmem_cols;
     int pair;                                     // 8 x 8 maps: one tile = two images (see the header)
     int patch_bytes;
+    int cb_per_split;                             // split-K: blockIdx.z owns 64-channel blocks [z * cb_per_split, ...) and adds its partial atomically
     int npatch;                                   // patch buffers (1..3): the next 64-channel block's patch loads under this block's MMAs
     long long* dbg;                               // optional per-CTA clock64 stamps [grid][8] (pivp_tc_set_debug_buffer), else null
 };
@@ -73,7 +74,8 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tile = blockIdx.y;
     const int n0 = n_tile * g.BN;
-    const int ncb = g.Kc / 64;
+    const int cb_first = blockIdx.z * g.cb_per_split;
+    const int ncb = min(g.Kc / 64 - cb_first, g.cb_per_split);        // 64-channel blocks of this CTA (local index cb, global cb_first + cb)
     const int tiles_x = g.W / TW, tiles_y = g.H / TH;
     if (warp == 0) HALO_STAMP(0);
 
@@ -89,7 +91,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 2 && ep.bias) {
+    if (warp >= 2 && ep.bias && blockIdx.z == 0) {
         for (int i = threadIdx.x - 64; i < g.BN; i += 256 * MS) bias_s[i] = ep.bias[n0 + i];
     }
     tc_fence_before();
@@ -119,10 +121,10 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     const int mt = blockIdx.x * MS + i;
                     const uint32_t dst = smem_u32(patch) + slot * pbuf_bytes + (uint32_t)(i * g.patch_bytes);
                     if (g.pair) {
-                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, n * 64, -2, 2 * mt, -2);
+                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, (cb_first + n) * 64, -2, 2 * mt, -2);
                     } else {
                         const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
-                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, n * 64, tx * TW - 2, ty * TH - 2, tb);
+                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, (cb_first + n) * 64, tx * TW - 2, ty * TH - 2, tb);
                     }
                 }
             }
@@ -142,7 +144,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 mbar_wait(empty0 + 8 * st, ph);
                 if (elect_one()) {
                     mbar_expect_tx(full0 + 8 * st, b_bytes);
-                    tma_load_2d(ring0 + st * b_bytes, &map_b, full0 + 8 * st, tap * g.Kc + cb * 64, n0);
+                    tma_load_2d(ring0 + st * b_bytes, &map_b, full0 + 8 * st, tap * g.Kc + (cb_first + cb) * 64, n0);
                 }
                 __syncwarp();
                 if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; }
@@ -345,7 +347,15 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             // plain epilogue: the two warps of a lane quarter split the columns
             const int hc = (g.BN / 2 + 7) / 8 * 8;
             const int cbeg = half ? hc : 0, cend = half ? g.BN : hc;
-            if (cend > cbeg) tc_epilogue_row(ep, trow + (uint32_t)cbeg, m, m, n0 + cbeg, cend - cbeg, n_tile, bias_s + cbeg);
+            if (cend > cbeg) {
+                if (blockIdx.z == 0) {
+                    tc_epilogue_row(ep, trow + (uint32_t)cbeg, m, m, n0 + cbeg, cend - cbeg, n_tile, bias_s + cbeg);
+                } else {                                   // split-K partial: the bias belongs to split 0
+                    TcEpilogue epz = ep;
+                    epz.bias = nullptr;
+                    tc_epilogue_row(epz, trow + (uint32_t)cbeg, m, m, n0 + cbeg, cend - cbeg, n_tile, bias_s + cbeg);
+                }
+            }
         }
         tc_fence_before();
         if (warp == 2) HALO_STAMP(5);
@@ -358,25 +368,44 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 }
 
 template <int MS, int NP>
-static int launch_ms_np(const CUtensorMap& map_a, const CUtensorMap& map_b, const Geom& g, const TcEpilogue& ep, int tiles, size_t smem, void* stream,
-                        const char* who) {
+static int launch_ms_np(const CUtensorMap& map_a, const CUtensorMap& map_b, const Geom& g, const TcEpilogue& ep, int tiles, int splits, size_t smem,
+                        void* stream, const char* who) {
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(conv5x5_halo_tc_kernel<MS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("%s(halo): cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
         attr_set = true;
     }
-    dim3 grid((unsigned)(tiles / MS), (unsigned)(g.N / g.BN));
+    dim3 grid((unsigned)(tiles / MS), (unsigned)(g.N / g.BN), (unsigned)splits);
     conv5x5_halo_tc_kernel<MS, NP><<<grid, 64 + 256 * MS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
     return check_launch(who);
 }
 
 template <int MS>
-static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g, const TcEpilogue& ep, int tiles, void* stream, const char* who) {
+static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g, TcEpilogue ep, int tiles, long M, void* stream, const char* who) {
     const int b_bytes = g.BN * 128;
     // one CTA per SM.  Patch buffers: up to 3 (never more than the 64-channel blocks), as long as the weight ring keeps >= 8 stages and
     // the staged gate epilogue still fits; the ring takes what the patches leave.
-    const int ncb = g.Kc / 64;
+    // Split-K: a plain-epilogue launch that would leave most SMs idle (the 8x8-map input gradient: 16 pixel tiles, K = 25 x 512)
+    // spreads its 64-channel blocks over blockIdx.z; every split adds its partial tile with vector atomics into the zeroed output.
+    int ncb = g.Kc / 64, splits = 1;
+    const long ctas = (long)(tiles / MS) * (g.N / g.BN);
+    const char* env_sk = getenv("PIVP_TC_HALO_SPLITK");
+    if (ep.mode == 0 && ep.out && !ep.out_bf16 && !ep.relu && ncb >= 4 && 2 * ctas <= 148 && (!env_sk || atoi(env_sk) != 0)) {
+        splits = (int)(148 / ctas);
+        if (splits > ncb / 2) splits = ncb / 2;
+        if (env_sk && atoi(env_sk) > 1) splits = atoi(env_sk) < ncb ? atoi(env_sk) : ncb;
+    }
+    g.cb_per_split = (ncb + splits - 1) / splits;
+    splits = (ncb + g.cb_per_split - 1) / g.cb_per_split;
+    if (splits > 1) {
+        if (!ep.accumulate) {
+            cudaError_t e = cudaMemset2DAsync(ep.out + ep.out_co, (size_t)ep.out_cs * 4, 0, (size_t)g.N * 4, (size_t)M, (cudaStream_t)stream);
+            if (e != cudaSuccess) { set_error("%s(halo): cudaMemset2DAsync: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
+        }
+        ep.atomic = 1;
+        ncb = g.cb_per_split;
+    }
     const char* env_np = getenv("PIVP_TC_HALO_NP");
     int np = env_np ? atoi(env_np) : 3;
     if (MS > 1) np = 1;                                  // two-tile CTAs: 80 KB per buffer, the ring needs the rest
@@ -393,9 +422,9 @@ static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g,
     const size_t smem = 1024 + (size_t)np * MS * g.patch_bytes + (size_t)stages * b_bytes + (2 * stages + 7) * 8 + 16 + (size_t)g.BN * 4;
     PIVP_REQUIRE(ep.mode != 1 || (size_t)np * MS * g.patch_bytes + (size_t)stages * b_bytes >= (size_t)MS * STG_FLOATS * 4 + 256,
                  "%s(halo): operand ring too small to stage the gate epilogue", who);
-    if (MS == 1 && np == 3) return launch_ms_np<1, 3>(map_a, map_b, g, ep, tiles, smem, stream, who);
-    if (MS == 1 && np == 2) return launch_ms_np<1, 2>(map_a, map_b, g, ep, tiles, smem, stream, who);
-    return launch_ms_np<MS, 1>(map_a, map_b, g, ep, tiles, smem, stream, who);
+    if (MS == 1 && np == 3) return launch_ms_np<1, 3>(map_a, map_b, g, ep, tiles, splits, smem, stream, who);
+    if (MS == 1 && np == 2) return launch_ms_np<1, 2>(map_a, map_b, g, ep, tiles, splits, smem, stream, who);
+    return launch_ms_np<MS, 1>(map_a, map_b, g, ep, tiles, splits, smem, stream, who);
 }
 
 }  // namespace halo
@@ -449,7 +478,8 @@ int launch_conv5x5_halo(const void* in_bf16, int in_cs, int B, int H, int W, int
     // two pixel tiles per CTA halve the weight traffic per FLOP; only worth it while the grid still covers most of the SMs
     const int force = tc_halo_mode();
     const bool two = (force == 3) ? false : (tiles % 2 == 0 && 2 * BN <= 512 && ((tiles / 2) * (N / BN) >= 96 || force == 4));
-    return two ? launch_ms<2>(map_a, map_b, g, ep, tiles, stream, who) : launch_ms<1>(map_a, map_b, g, ep, tiles, stream, who);
+    const long M = (long)B * H * W;
+    return two ? launch_ms<2>(map_a, map_b, g, ep, tiles, M, stream, who) : launch_ms<1>(map_a, map_b, g, ep, tiles, M, stream, who);
 }
 
 }  // namespace pivp

@@ -20,6 +20,7 @@ struct TcEpilogue {
     __nv_bfloat16* out_bf16; int ob_cs, ob_co;   // mode 0: optional bf16 copy (next GEMM's operand), same row mapping
     int relu;                                    // mode 0: ReLU after bias
     int accumulate;                              // mode 0: out += D (fp32 view only)
+    int atomic;                                  // mode 0: out += D with vector atomics (split-K CTAs of the halo kernel share an output tile)
     float* gates;                                // mode 1: activated gates [M][N] (saved for backward); bf16 storage when gates_bf16
     int gates_bf16;
     float2* ln_partial;                          // mode 1, halo kernel only: per-tile (mean, M2) of h for the LayerNorm that follows
@@ -61,6 +62,11 @@ __device__ __forceinline__ void tc_epilogue_row(const TcEpilogue& ep, uint32_t t
             }
             if (ep.out) {
                 float* dst = ep.out + orow * ep.out_cs + ep.out_co + n0 + c0;
+                if (ep.atomic) {
+                    atomicAdd(reinterpret_cast<float4*>(dst), make_float4(v[0], v[1], v[2], v[3]));
+                    atomicAdd(reinterpret_cast<float4*>(dst + 4), make_float4(v[4], v[5], v[6], v[7]));
+                    continue;
+                }
                 if (ep.accumulate) {
                     const float4 o0 = *reinterpret_cast<const float4*>(dst), o1 = *reinterpret_cast<const float4*>(dst + 4);
                     v[0] += o0.x; v[1] += o0.y; v[2] += o0.z; v[3] += o0.w; v[4] += o1.x; v[5] += o1.y; v[6] += o1.z; v[7] += o1.w;

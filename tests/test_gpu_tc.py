@@ -35,7 +35,8 @@ def stream():
     (2, 32, 32, 64, 128, 128),     # lstm1/2 forward shape
     (2, 16, 16, 128, 256, 128),    # lstm4 forward
     (2, 8, 8, 192, 512, 128),      # lstm5 forward (two images per 128-pixel tile: the halo kernel's pair geometry)
-    (6, 8, 8, 512, 192, 64),       # lstm5 input-gradient, three pair tiles x three N tiles
+    (6, 8, 8, 512, 192, 64),       # lstm5 input-gradient, three pair tiles x three N tiles (x four K splits, atomic epilogue)
+    (2, 16, 16, 256, 96, 96),      # few tiles, K = 25 x 256: split-K on the tiled geometry
     (4, 8, 8, 64, 64, 32),         # narrow N tile (the ConvLSTM-5 input gradient runs BN = 32)
     (4, 32, 32, 128, 64, 64),      # lstm1 input-gradient shape (N = Cin + C)
     (2, 16, 16, 256, 96, 96),      # lstm3 input-gradient
@@ -49,7 +50,7 @@ def test_tc_conv5x5_plain_matches_simt(pk, B, H, W, Kc, N, BN):
     x = torch.from_numpy(rs.standard_normal((M, Kc)).astype(np.float32)).cuda().bfloat16()
     w = torch.from_numpy((rs.standard_normal((N, 25, Kc)) / np.sqrt(25 * Kc)).astype(np.float32)).cuda().bfloat16()
     bias = torch.from_numpy(rs.standard_normal(N).astype(np.float32)).cuda()
-    out = torch.zeros(M, N, device="cuda")
+    out = torch.full((M, N), 3.0, device="cuda")          # accumulate = 0: whatever is there is overwritten (split-K launches zero it first)
     L.call("pivp_tc_conv5x5", x.data_ptr(), Kc, B, H, W, Kc, w.data_ptr(), N, BN, 0, bias.data_ptr(),
            out.data_ptr(), N, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0.0, 0, 0, stream())
     ref = torch.zeros(M, N, device="cuda")
