@@ -282,7 +282,7 @@ def main():
                         "kernel": "conv5x5_halo_tc_kernel (tcgen05 ConvLSTM implicit GEMM with halo-patch A operand; forward + fused gates, "
                                   "and input gradient; the 8x8 maps of layer 5 in the two-image pair geometry)",
                         "achieved": ach, "peak": pk_["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / pk_["bf16_tflops"],
-                        "frac_of_sustained": ach / pk_["bf16_tflops_sustained"], "traffic": traffic_from_profile(),
+                        "frac_of_sustained": ach / pk_["bf16_tflops_sustained"], "traffic": traffic_from_profile(), "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)",
                         "peak_source": src + " (burst figure: the step's %d launches are replayed back to back as one CUDA graph, "
                                              "about 3 ms, outside the long step)" % len(conv_calls),
                         "launches": len(conv_calls), "avg_launch_us": per * 1e6,
