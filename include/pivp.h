@@ -39,6 +39,9 @@ int pivp_abi_version(void);
 int pivp_device_sync_check(void);
 /* number of CUDA kernels this library has launched in this process (every successful launch is counted once) */
 long pivp_launch_count(void);
+/* programmatic dependent launch (kernel N+1's CTAs become resident and run their prologue while kernel N drains; every kernel waits
+ * for its predecessor before its first global access) on / off for subsequent launches; default on, PIVP_PDL=0 in the environment = off */
+int pivp_set_pdl(int on);
 
 /* ---- Convolution2D / Deconvolution2D (train_model.py:224,500-507,527; Chainer A.2/A.3) --------------- */
 /* y = conv(x, w) + bias [, relu]  -- L.Convolution2D forward; Deconvolution2D input-gradient */

@@ -227,6 +227,7 @@ template <int P>
 __global__ void __launch_bounds__(W*(R / P), 2) cdna_band_fwd_kernel(const float* __restrict__ prev, const float* __restrict__ e_pre,
                                                                       const float* __restrict__ a_pre, const float* __restrict__ kraw,
                                                                       float* __restrict__ out, int H, int nitems) {
+    pdl_enter();
     constexpr int NT = W * (R / P), STF = st_floats<false>();
     static_assert(NT >= 125, "raw-kernel staging uses one thread per 8 bytes");
     extern __shared__ __align__(16) float sm[];
@@ -388,6 +389,7 @@ __global__ void __launch_bounds__(W*(R / P), MINB)
     cdna_band_bwd_kernel(const float* __restrict__ gout, const float* __restrict__ prev, const float* __restrict__ e_pre,
                          const float* __restrict__ a_pre, const float* __restrict__ kraw, float* __restrict__ d_e,
                          float* __restrict__ d_a, float* __restrict__ dKp, int H) {
+    pdl_enter();
     constexpr int NT = W * (R / P), NWARP = NT / 32;
     extern __shared__ __align__(16) float sm[];
     float* mu = sm;
@@ -585,6 +587,7 @@ __global__ void __launch_bounds__(W*(R / P), MINB)
 // One warp per (sample, kernel): lane = tap, so the band partials are read coalesced and the two 25-term sums are warp shuffles.
 __global__ void __launch_bounds__(128) cdna_band_kern_bwd_kernel(const float* __restrict__ kraw, const float* __restrict__ dKp,
                                                                  float* __restrict__ d_kraw, int B, int nbands) {
+    pdl_enter();
     const int i = blockIdx.x * 4 + (threadIdx.x >> 5), t = threadIdx.x & 31;       // i over B*M kernels
     if (i >= B * M) return;
     const int b = i / M, m = i - b * M;
@@ -630,7 +633,7 @@ static int launch_fwd(const float* prev, const float* e_pre, const float* a_pre,
     const int nitems = B * (H / R);
     int grid = 2 * sm_count();                                // 2 x 85 KB of shared memory per SM
     if (grid > nitems) grid = nitems;
-    cdna_band_fwd_kernel<P><<<grid, W*(R / P), smem, st>>>(prev, e_pre, a_pre, kraw, out, H, nitems);
+    launch_k(cdna_band_fwd_kernel<P>, dim3(grid), dim3(W*(R / P)), smem, st, prev, e_pre, a_pre, kraw, out, H, nitems);
     return check_launch("cdna_fused_fwd(band)");
 }
 template <int P, int MINB>
@@ -638,7 +641,7 @@ static int launch_bwd(const float* gout, const float* prev, const float* e_pre, 
                       float* d_a, float* dKp, int B, int H, cudaStream_t st) {
     const size_t smem = sizeof(float) * bwd_smem_floats();
     if (int e = allow_smem(cdna_band_bwd_kernel<P, MINB>, smem)) return e;
-    cdna_band_bwd_kernel<P, MINB><<<dim3(H / R, B), W*(R / P), smem, st>>>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, H);
+    launch_k(cdna_band_bwd_kernel<P, MINB>, dim3(H / R, B), dim3(W*(R / P)), smem, st, gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, H);
     return check_launch("cdna_fused_bwd(band)");
 }
 
@@ -666,7 +669,7 @@ int cdna_band_bwd(const float* gout, const float* prev, const float* e_pre, cons
                  : P == 43 ? cb::launch_bwd<4, 3>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)
                            : cb::launch_bwd<4, 2>(gout, prev, e_pre, a_pre, kraw, d_e, d_a, dKp, B, H, st)))
         return e;
-    cb::cdna_band_kern_bwd_kernel<<<(B * cb::M + 3) / 4, 128, 0, st>>>(kraw, dKp, d_kraw, B, H / cb::R);
+    launch_k(cb::cdna_band_kern_bwd_kernel, dim3((B * cb::M + 3) / 4), dim3(128), 0, st, kraw, dKp, d_kraw, B, H / cb::R);
     return check_launch("cdna_fused_bwd(kern)");
 }
 

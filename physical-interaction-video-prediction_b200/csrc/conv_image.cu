@@ -33,6 +33,7 @@ __device__ __forceinline__ float4 load_pixel(const CView& x, const Geom& g, int 
 // thread = one output pixel x 16 channels (warps 0-3: channels 0-15, warps 4-7: 16-31, so weight reads stay warp-wide broadcasts)
 __global__ void __launch_bounds__(FWD_THREADS) conv_image_fwd_kernel(Geom g, CView x, const float* __restrict__ w,
                                                                      const float* __restrict__ bias, View y, int relu) {
+    pdl_enter();
     __shared__ float4 patch[PH * PW];
     __shared__ __align__(16) float wS[J * N];            // [j][n]
     const int b = blockIdx.z, oy0 = blockIdx.y * TH, ox0 = blockIdx.x * TW;
@@ -100,6 +101,7 @@ __global__ void __launch_bounds__(FWD_THREADS) conv_image_fwd_kernel(Geom g, CVi
 
 // Persistent CTAs; the next tile's patch and dY are fetched into registers while the current tile is contracted.
 __global__ void __launch_bounds__(WG_THREADS) conv_image_wgrad_kernel(Geom g, CView x, CView dy, float* __restrict__ dw, int tiles) {
+    pdl_enter();
     __shared__ float4 patch[PH * PW];
     __shared__ float4 dyS[TH * TW * (N / 4)];            // [pixel][n quad]
     constexpr int NP = (PH * PW + WG_THREADS - 1) / WG_THREADS, ND = (TH * TW * (N / 4) + WG_THREADS - 1) / WG_THREADS;
@@ -171,7 +173,7 @@ int launch_fwd(const float* x, int x_cs, int x_co, int B, int H, int W, const fl
                int Ho, int Wo, int relu, void* stream) {
     Geom g{B, H, W, Ho, Wo, Wo / TW, Ho / TH};
     dim3 grid((unsigned)g.tiles_x, (unsigned)g.tiles_y, (unsigned)B);
-    conv_image_fwd_kernel<<<grid, FWD_THREADS, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, w, bias, View{y, y_cs, y_co}, relu);
+    launch_k(conv_image_fwd_kernel, dim3(grid), dim3(FWD_THREADS), 0, (cudaStream_t)stream, g, CView{x, x_cs, x_co}, w, bias, View{y, y_cs, y_co}, relu);
     return check_launch("conv2d_fwd(image)");
 }
 
@@ -180,7 +182,7 @@ int launch_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, const 
     Geom g{B, H, W, Ho, Wo, Wo / TW, Ho / TH};
     const int tiles = B * g.tiles_x * g.tiles_y;
     const int grid = tiles < 148 * 4 ? tiles : 148 * 4;
-    conv_image_wgrad_kernel<<<grid, WG_THREADS, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, tiles);
+    launch_k(conv_image_wgrad_kernel, dim3(grid), dim3(WG_THREADS), 0, (cudaStream_t)stream, g, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, tiles);
     return check_launch("conv2d_wgrad(image)");
 }
 

@@ -38,6 +38,7 @@ __device__ __forceinline__ void mma_tile(const float (*As)[BM + PADS], const flo
 // ------------------------------------------------------------------------------------------ fwd
 __global__ void __launch_bounds__(NT) conv_fwd_kernel(ConvGeom g, CView x, const float* __restrict__ w,
                                                       const float* __restrict__ bias, View y, int relu, int accumulate) {
+    pdl_enter();
     __shared__ __align__(16) float As[BK][BM + PADS];
     __shared__ __align__(16) float Bs[BK][BN + PADS];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -106,6 +107,7 @@ __global__ void __launch_bounds__(NT) conv_fwd_kernel(ConvGeom g, CView x, const
 // GEMM: M = B*H*W (input pixels), N = C, K = KH*KW*Nout with k = tap*Nout + n.
 __global__ void __launch_bounds__(NT) conv_dgrad_kernel(ConvGeom g, CView dy, const float* __restrict__ w,
                                                         const float* __restrict__ bias, View dx, int relu, int accumulate) {
+    pdl_enter();
     __shared__ __align__(16) float As[BK][BM + PADS];
     __shared__ __align__(16) float Bs[BK][BN + PADS];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -186,6 +188,7 @@ __global__ void __launch_bounds__(NT) conv_dgrad_kernel(ConvGeom g, CView dy, co
 // ---------------------------------------------------------------------------------------- wgrad
 // GEMM: M' = Nout, N' = J = KH*KW*C, K' = P = B*Ho*Wo split over blockIdx.z; atomicAdd epilogue.
 __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvGeom g, CView x, CView dy, float* __restrict__ dw, int pchunk) {
+    pdl_enter();
     __shared__ __align__(16) float As[BK][BM + PADS];
     __shared__ __align__(16) float Bs[BK][BN + PADS];
     const int t = threadIdx.x, tx = t & 15, ty = t >> 4;
@@ -241,6 +244,7 @@ __global__ void __launch_bounds__(NT) conv_wgrad_kernel(ConvGeom g, CView x, CVi
 
 // db[n] += sum_p v[p][n]   (bias gradients; p over all pixels of the batch)
 __global__ void colsum_kernel(CView v, int P, int N, float* __restrict__ db, int pchunk) {
+    pdl_enter();
     __shared__ float red[8][33];
     const int lane = threadIdx.x, row = threadIdx.y;
     const int n = blockIdx.x * 32 + lane;
@@ -292,7 +296,7 @@ int pivp_conv2d_fwd(const float* x, int x_cs, int x_co, int B, int H, int W, int
         return img::launch_fwd(x, x_cs, x_co, B, H, W, w, bias, y, y_cs, y_co, Ho, Wo, relu, stream);
     const long M = (long)B * Ho * Wo;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
-    conv_fwd_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, w, bias, View{y, y_cs, y_co}, relu, accumulate);
+    launch_k(conv_fwd_kernel, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, g, CView{x, x_cs, x_co}, w, bias, View{y, y_cs, y_co}, relu, accumulate);
     return check_launch("conv2d_fwd");
 }
 
@@ -305,7 +309,7 @@ int pivp_conv2d_dgrad(const float* dy, int dy_cs, int dy_co, int B, int Ho, int 
     PIVP_REQUIRE(dy_cs >= dy_co + N && dx_cs >= dx_co + C, "conv2d_dgrad: channel slice exceeds row stride");
     const long M = (long)B * H * W;
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((C + BN - 1) / BN));
-    conv_dgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(g, CView{dy, dy_cs, dy_co}, w, bias, View{dx, dx_cs, dx_co}, relu, accumulate);
+    launch_k(conv_dgrad_kernel, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, g, CView{dy, dy_cs, dy_co}, w, bias, View{dx, dx_cs, dx_co}, relu, accumulate);
     return check_launch("conv2d_dgrad");
 }
 
@@ -327,14 +331,14 @@ int pivp_conv2d_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, i
         if (int e = img::launch_wgrad(x, x_cs, x_co, B, H, W, dy, dy_cs, dy_co, Ho, Wo, dw, stream)) return e;
     } else {
         dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((J + BN - 1) / BN), (unsigned)split);
-        conv_wgrad_kernel<<<grid, NT, 0, (cudaStream_t)stream>>>(g, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, pchunk);
+        launch_k(conv_wgrad_kernel, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, g, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, pchunk);
         if (int e = check_launch("conv2d_wgrad")) return e;
     }
     if (dbias) {
         int s2 = (P + 255) / 256;
         int pc = (P + s2 - 1) / s2;
         dim3 g2((unsigned)((N + 31) / 32), (unsigned)s2);
-        colsum_kernel<<<g2, dim3(32, 8), 0, (cudaStream_t)stream>>>(CView{dy, dy_cs, dy_co}, P, N, dbias, pc);
+        launch_k(colsum_kernel, dim3(g2), dim3(32, 8), 0, (cudaStream_t)stream, CView{dy, dy_cs, dy_co}, P, N, dbias, pc);
         return check_launch("conv2d_wgrad(colsum)");
     }
     return PIVP_OK;
@@ -345,7 +349,7 @@ int pivp_colsum(const float* v, int v_cs, int v_co, int P, int N, float* out, vo
     int s2 = (P + 255) / 256;
     int pc = (P + s2 - 1) / s2;
     dim3 g2((unsigned)((N + 31) / 32), (unsigned)s2);
-    colsum_kernel<<<g2, dim3(32, 8), 0, (cudaStream_t)stream>>>(CView{v, v_cs, v_co}, P, N, out, pc);
+    launch_k(colsum_kernel, dim3(g2), dim3(32, 8), 0, (cudaStream_t)stream, CView{v, v_cs, v_co}, P, N, out, pc);
     return check_launch("colsum");
 }
 

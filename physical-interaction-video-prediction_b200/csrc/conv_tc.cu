@@ -78,6 +78,7 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();                                      // everything above is independent of the previous kernel's output
     if (warp >= 2 && ep.bias) {
         for (int i = threadIdx.x - 64; i < g.BN; i += 128) bias_s[i] = ep.bias[n0 + i];
     }
@@ -161,6 +162,7 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 //                                    ->  bf16 dgrad operand    Wd[c][tap'][n] = W[n][24 - tap'][c]
 __global__ void tc_prep_weights_kernel(const float* __restrict__ W, int N, int Cx, int Kpad, __nv_bfloat16* __restrict__ Wf,
                                        __nv_bfloat16* __restrict__ Wd) {
+    pdl_enter();
     const long total_f = (long)N * 25 * Kpad;
     const long total_d = (long)Cx * 25 * N;
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total_f + total_d; i += (long)gridDim.x * blockDim.x) {
@@ -197,6 +199,7 @@ static int pick_pixel_box(int B, int H, int W, int* TW, int* TH, int* TB) {
 
 // dst[i] = bf16(src[idx[i]]), idx < 0 -> 0.  Builds any permuted / zero-padded bf16 weight operand from the fp32 master.
 __global__ void gather_bf16_kernel(const float* __restrict__ src, const int* __restrict__ idx, long n, __nv_bfloat16* __restrict__ dst) {
+    pdl_enter();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const int j = idx[i];
         dst[i] = __float2bfloat16(j >= 0 ? src[j] : 0.f);
@@ -269,7 +272,7 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
     }
     const long M = (long)B * H * W;
     dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN), (unsigned)nph);
-    conv_taps_tc_kernel<<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(map_a, mb, gp, ep);
+    launch_k(conv_taps_tc_kernel, grid, dim3(TC_THREADS), smem, stream, map_a, mb, gp, ep);
     return check_launch(who);
 }
 
@@ -298,7 +301,7 @@ int pivp_tc_set_debug_buffer(void* p) { tc_halo_set_debug((long long*)p); return
 
 int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream) {
     PIVP_REQUIRE(W && N > 0 && Cx > 0 && Kpad >= Cx && (w_fwd_bf16 || w_dgrad_bf16), "tc_prep_weights: bad argument");
-    tc_prep_weights_kernel<<<148 * 4, 256, 0, (cudaStream_t)stream>>>(W, N, Cx, Kpad, (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
+    launch_k(tc_prep_weights_kernel, dim3(148 * 4), dim3(256), 0, (cudaStream_t)stream, W, N, Cx, Kpad, (__nv_bfloat16*)w_fwd_bf16, (__nv_bfloat16*)w_dgrad_bf16);
     return check_launch("tc_prep_weights");
 }
 
@@ -306,7 +309,7 @@ int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, v
     PIVP_REQUIRE(src && idx && dst_bf16 && n > 0, "gather_bf16: bad argument");
     unsigned gb = (unsigned)((n + 255) / 256);
     if (gb > 148 * 8) gb = 148 * 8;
-    gather_bf16_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(src, idx, n, (__nv_bfloat16*)dst_bf16);
+    launch_k(gather_bf16_kernel, dim3(gb), dim3(256), 0, (cudaStream_t)stream, src, idx, n, (__nv_bfloat16*)dst_bf16);
     return check_launch("gather_bf16");
 }
 

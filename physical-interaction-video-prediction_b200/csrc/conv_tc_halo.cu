@@ -91,6 +91,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    pdl_wait();                                      // barrier init / TMEM allocation above overlap the previous kernel's tail
     if (warp >= 2 && ep.bias && blockIdx.z == 0) {
         for (int i = threadIdx.x - 64; i < g.BN; i += 256 * MS) bias_s[i] = ep.bias[n0 + i];
     }
@@ -377,7 +378,7 @@ static int launch_ms_np(const CUtensorMap& map_a, const CUtensorMap& map_b, cons
         attr_set = true;
     }
     dim3 grid((unsigned)(tiles / MS), (unsigned)(g.N / g.BN), (unsigned)splits);
-    conv5x5_halo_tc_kernel<MS, NP><<<grid, 64 + 256 * MS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, ep);
+    launch_k(conv5x5_halo_tc_kernel<MS, NP>, grid, dim3(64 + 256 * MS), smem, stream, map_a, map_b, g, ep);
     return check_launch(who);
 }
 

@@ -49,6 +49,7 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
 conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, WgGeom g, float* __restrict__ part) {
+    pdl_enter();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     const uint32_t chunk_bytes = 64 * 128;                        // 64 pixel rows x 128 B
@@ -179,6 +180,7 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
 
 // dW[i] += sum_s part[s*stride + i]   (i < n: the valid rows of every split's partial tile come first)
 __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __restrict__ out, long n, long stride, int splits) {
+    pdl_enter();
     const long i4 = ((long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (i4 >= n) return;
     float4 acc = *reinterpret_cast<const float4*>(out + i4);
@@ -192,6 +194,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ part, float* __re
 // out[c] += sum_p src[p][c]  (bf16 in, fp32 accumulate): the ConvLSTM bias gradient over all time steps.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int ld, long P, int C, long pchunk,
                                                           float* __restrict__ out) {
+    pdl_enter();
     __shared__ float red[8][66];
     const int cp = threadIdx.x & 31, row = threadIdx.x >> 5;          // channel pair, row phase
     const int c = blockIdx.x * 64 + 2 * cp;
@@ -232,7 +235,7 @@ int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out,
     if (splits > 148 * 8) splits = 148 * 8;
     const long pchunk = (P + splits - 1) / splits;
     dim3 grid((unsigned)((C + 63) / 64), (unsigned)splits);
-    colsum_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src_bf16, ld, P, C, pchunk, out);
+    launch_k(colsum_bf16_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src_bf16, ld, P, C, pchunk, out);
     return check_launch("tc_colsum_bf16");
 }
 
@@ -321,11 +324,11 @@ static int launch_wgrad(const void* dg_bf16, int dg_cs, const void* xh_bf16, int
         attr_set = true;
     }
     dim3 grid((unsigned)(g.Mrows / 128), (unsigned)groups, (unsigned)splits);
-    conv5x5_wgrad_tc_kernel<<<grid, WG_THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, (float*)workspace);
+    launch_k(conv5x5_wgrad_tc_kernel, dim3(grid), dim3(WG_THREADS), smem, (cudaStream_t)stream, map_a, map_b, g, (float*)workspace);
     if (int e = check_launch(who)) return e;
     const long n = (long)N4 * ntaps * Cx;
     const long stride = (long)g.Mrows * ntaps * Cx;
-    splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dW, n, stride, splits);
+    launch_k(splitk_reduce_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const float*)workspace, dW, n, stride, splits);
     return check_launch(who);
 }
 
@@ -338,7 +341,7 @@ int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB
         const int splits = launch_wgrad5x5_halo(dg_bf16, N4, xh_bf16, xh_cs, SB, H, W, Cx, N4, (float*)workspace, ws_bytes, stream, "tc_wgrad5x5");
         if (splits < 0) return splits;
         const long n = (long)N4 * 25 * Cx, stride = (long)((N4 + 127) / 128 * 128) * 25 * Cx;
-        splitk_reduce_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, dW, n, stride, splits);
+        launch_k(splitk_reduce_kernel, dim3((unsigned)((n / 4 + 255) / 256)), dim3(256), 0, (cudaStream_t)stream, (const float*)workspace, dW, n, stride, splits);
         return check_launch("tc_wgrad5x5(reduce)");
     }
     int dy[25], dx[25], co[25];

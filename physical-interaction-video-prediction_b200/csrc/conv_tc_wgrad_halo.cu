@@ -34,6 +34,7 @@ struct Geom {
 
 __global__ void __launch_bounds__(THREADS, 1)
 wgrad5x5_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Geom g, float* __restrict__ part) {
+    pdl_enter();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + (size_t)STAGES * STAGE);
@@ -212,7 +213,7 @@ int launch_wgrad5x5_halo(const void* dg_bf16, int dg_cs, const void* xh_bf16, in
         attr_set = true;
     }
     dim3 grid((unsigned)(g.Mrows / 128), (unsigned)(g.chunks * g.groups), (unsigned)splits);
-    wgrad5x5_halo_kernel<<<grid, THREADS, smem, (cudaStream_t)stream>>>(map_a, map_b, g, part);
+    launch_k(wgrad5x5_halo_kernel, dim3(grid), dim3(THREADS), smem, (cudaStream_t)stream, map_a, map_b, g, part);
     if (int e = check_launch(who)) return e;
     return splits;
 }

@@ -13,6 +13,7 @@ __device__ __forceinline__ int gate_col(int ch, int gate) { return (ch >> 5) * 1
 __global__ void lstm_gates_fwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, float* __restrict__ c_out,
                                       View h_out, __nv_bfloat16* __restrict__ h_bf16, int hb_cs, int hb_co,
                                       long M, int C, float forget_bias) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C) return;
     const long m = idx / C;
@@ -35,6 +36,7 @@ __global__ void lstm_gates_fwd_kernel(float* __restrict__ gates, const float* __
 __global__ void lstm_gates_bwd_kernel(float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c_cur,
                                       const float* __restrict__ dh_a, CView dh_b, float* __restrict__ dc, int dc_valid,
                                       __nv_bfloat16* __restrict__ dg_bf16, long M, int C) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C) return;
     const long m = idx / C;
@@ -78,6 +80,7 @@ __global__ void __launch_bounds__(256) lstm_gates_bwd_bf16_kernel(const __nv_bfl
                                                                   const float* __restrict__ c_cur, const float* __restrict__ dh_a, CView dh_b,
                                                                   float* __restrict__ dc, int dc_valid, __nv_bfloat16* __restrict__ dg,
                                                                   long M, int C) {
+    pdl_enter();
     const int c8 = C >> 3;
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * c8) return;
@@ -146,6 +149,7 @@ __device__ __forceinline__ long ln_addr(const CView& v, long b, int HW, int C, i
 }
 
 __global__ void __launch_bounds__(LN_T) ln_stats_kernel(CView x, int n, int C, int chunk, float2* __restrict__ partial) {
+    pdl_enter();
     __shared__ float red[32];
     const int s = blockIdx.x, S = gridDim.x;
     const long b = blockIdx.y;
@@ -193,6 +197,7 @@ __global__ void __launch_bounds__(LN_T) ln_apply_kernel(CView x, const float* __
                                                         int n, int C, const float2* __restrict__ partial, int S, int chunk, float eps,
                                                         View y, View y2, __nv_bfloat16* __restrict__ y_bf16, int yb_cs, int yb_co,
                                                         int relu, float2* __restrict__ stats) {
+    pdl_enter();
     const long b = blockIdx.y;
     const int HW = n / C;
     const float2 st = ln_combine(partial, b, S, n, chunk, eps);
@@ -212,6 +217,7 @@ __global__ void __launch_bounds__(LN_T) ln_apply_kernel(CView x, const float* __
 __global__ void __launch_bounds__(LN_T) ln_bwd_stats_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
                                                             const float* __restrict__ beta, const float2* __restrict__ stats,
                                                             int n, int C, int chunk, int relu, float2* __restrict__ partial) {
+    pdl_enter();
     __shared__ float red[32];
     const int s = blockIdx.x, S = gridDim.x;
     const long b = blockIdx.y;
@@ -241,6 +247,7 @@ __global__ void __launch_bounds__(LN_T) ln_bwd_apply_kernel(CView x, CView g1, C
                                                             const float* __restrict__ beta, const float2* __restrict__ stats,
                                                             const float2* __restrict__ partial, int S, int B, int n, int C, int relu,
                                                             View dx, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    pdl_enter();
     extern __shared__ float2 tot[];      // [B] : (mean q, mean q*xhat)
     for (int b = threadIdx.x; b < B; b += LN_T) {
         float a = 0.f, c = 0.f;
@@ -273,6 +280,7 @@ __global__ void __launch_bounds__(LN_T) ln_bwd_apply_kernel(CView x, CView g1, C
 // ----------------------------------------------------------------------------- small view kernels
 // dst = (ga + gb) * [out > 0]
 __global__ void relu_bwd_kernel(CView out, CView ga, CView gb, View dst, long M, int C) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C) return;
     const long m = idx / C;
@@ -283,6 +291,7 @@ __global__ void relu_bwd_kernel(CView out, CView ga, CView gb, View dst, long M,
 }
 
 __global__ void copy_view_kernel(CView src, View dst, __nv_bfloat16* __restrict__ dst_bf16, int db_cs, int db_co, long M, int C) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C) return;
     const long m = idx / C;
@@ -301,6 +310,7 @@ __device__ __forceinline__ uint2 pack4_bf16(float4 v) {
     return u;
 }
 __global__ void relu_bwd_v4_kernel(CView out, CView ga, CView gb, View dst, long M, int C4) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C4) return;
     const long m = idx / C4;
@@ -315,6 +325,7 @@ __global__ void relu_bwd_v4_kernel(CView out, CView ga, CView gb, View dst, long
         make_float4(o.x > 0.f ? g.x : 0.f, o.y > 0.f ? g.y : 0.f, o.z > 0.f ? g.z : 0.f, o.w > 0.f ? g.w : 0.f);
 }
 __global__ void copy_view_v4_kernel(CView src, View dst, __nv_bfloat16* __restrict__ dst_bf16, int db_cs, int db_co, long M, int C4) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C4) return;
     const long m = idx / C4;
@@ -324,6 +335,7 @@ __global__ void copy_view_v4_kernel(CView src, View dst, __nv_bfloat16* __restri
     if (dst_bf16) *reinterpret_cast<uint2*>(dst_bf16 + m * db_cs + db_co + ch) = pack4_bf16(v);
 }
 __global__ void cast_bf16_v4_kernel(CView src, __nv_bfloat16* __restrict__ dst, int d_cs, int d_co, long M, int C4, int H, int W, int s2d, int cblk) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C4) return;
     const long m = idx / C4;
@@ -347,6 +359,7 @@ __global__ void cast_bf16_v4_kernel(CView src, __nv_bfloat16* __restrict__ dst, 
 __global__ void __launch_bounds__(256) grad_handover_kernel(CView out, CView ga, CView gb, View dst, __nv_bfloat16* __restrict__ dst_bf16,
                                                             int b_cs, int b_co, int H, int W, int s2d, int cblk, float* __restrict__ db,
                                                             long M, int C4, int RPB) {
+    pdl_enter();
     __shared__ float4 red[256];
     const int c4 = threadIdx.x % C4, ty = threadIdx.x / C4;
     const int ch = c4 * 4;
@@ -393,6 +406,7 @@ static inline bool v4ok(const void* p, int cs, int co) { return !p || (!((uintpt
 
 // planar (B,C,HW) <-> NHWC view rows (b*HW + pix)
 __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, View dst, int B, int C, int HW) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;     // over B*HW pixels
     if (idx >= (long)B * HW) return;
     const long b = idx / HW;
@@ -401,6 +415,7 @@ __global__ void nchw_to_nhwc_kernel(const float* __restrict__ src, View dst, int
 }
 
 __global__ void nhwc_to_nchw_kernel(CView src, float* __restrict__ dst, int B, int C, int HW, int accumulate) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= (long)B * HW) return;
     const long b = idx / HW;
@@ -415,6 +430,7 @@ __global__ void nhwc_to_nchw_kernel(CView src, float* __restrict__ dst, int B, i
 // fp32 NHWC view (rows on a B x H x W grid) -> bf16.  s2d = 0: dst[m][co + ch].  s2d = 1: space-to-depth for the stride-2
 // layers: dst row = (b, y/2, x/2) on the half grid, channel = co + ((y&1)*2 + (x&1))*cblk + ch  (cblk >= C, pad stays untouched).
 __global__ void cast_bf16_kernel(CView src, __nv_bfloat16* __restrict__ dst, int d_cs, int d_co, long M, int C, int H, int W, int s2d, int cblk) {
+    pdl_enter();
     const long idx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= M * C) return;
     const long m = idx / C;
@@ -433,6 +449,7 @@ __global__ void cast_bf16_kernel(CView src, __nv_bfloat16* __restrict__ dst, int
 }
 
 __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, long n) {
+    pdl_enter();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] += x[i];
 }
@@ -441,6 +458,7 @@ __global__ void axpy_kernel(const float* __restrict__ x, float* __restrict__ y, 
 // one block per sample: sa = [action, cur]; next = Wc sa + bc; smear sa over npix rows of `smear`.
 __global__ void state_fwd_kernel(const float* __restrict__ action, const float* __restrict__ cur, const float* __restrict__ Wc,
                                  const float* __restrict__ bc, float* __restrict__ sa, float* __restrict__ next, View smear, int npix) {
+    pdl_enter();
     __shared__ float s[10];
     const int b = blockIdx.x, t = threadIdx.x;
     if (t < 5) s[t] = action[b * 5 + t];
@@ -465,6 +483,7 @@ __global__ void state_fwd_kernel(const float* __restrict__ action, const float* 
 __global__ void state_bwd_kernel(const float* __restrict__ dn_a, const float* __restrict__ dn_b, const float* __restrict__ sa,
                                  const float* __restrict__ Wc, CView dsmear, int npix, int B,
                                  float* __restrict__ d_cur_prev, float* __restrict__ dWc, float* __restrict__ dbc) {
+    pdl_enter();
     __shared__ float dn[5];
     __shared__ float sm[5][64];
     const int b = blockIdx.x, t = threadIdx.x;
@@ -495,6 +514,7 @@ __global__ void state_bwd_kernel(const float* __restrict__ dn_a, const float* __
 constexpr int LIN_BB = 8, LIN_NN = 4;
 __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict__ x, int xs, const float* __restrict__ W,
                                                          const float* __restrict__ bias, float* __restrict__ y, int B, int K, int N, int relu) {
+    pdl_enter();
     __shared__ float red[32];
     const int n0 = blockIdx.x * LIN_NN, b0 = blockIdx.y * LIN_BB;
     float acc[LIN_NN][LIN_BB] = {};
@@ -524,6 +544,7 @@ __global__ void __launch_bounds__(256) linear_fwd_kernel(const float* __restrict
 // dx[b][k] (+)= sum_n dy[b][n] W[n][k]
 __global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* __restrict__ W, float* __restrict__ dx, int dxs,
                                      int B, int K, int N, int accumulate) {
+    pdl_enter();
     const int k = blockIdx.x * blockDim.x + threadIdx.x, b = blockIdx.y;
     if (k >= K) return;
     float a = 0.f;
@@ -535,6 +556,7 @@ __global__ void linear_bwd_dx_kernel(const float* __restrict__ dy, const float* 
 // dW[n][k] += sum_b dy[b][n] x[b][k];  db[n] += sum_b dy[b][n]
 __global__ void linear_bwd_dw_kernel(const float* __restrict__ dy, const float* __restrict__ x, int xs, float* __restrict__ dW,
                                      float* __restrict__ db, int B, int K, int N) {
+    pdl_enter();
     const int k = blockIdx.x * blockDim.x + threadIdx.x, n = blockIdx.y;
     if (k < K) {
         float a = 0.f;
@@ -583,6 +605,7 @@ __device__ __forceinline__ float warp_reduce_scatter32(const float (&v)[LW_B], i
 
 __global__ void __launch_bounds__(128) linear_fwd_wide_kernel(const float* __restrict__ x, int xs, const float* __restrict__ W,
                                                               float* __restrict__ part, int B, int K, int N, int kchunk, int KS) {
+    pdl_enter();
     const int lane = threadIdx.x & 31;
     const int wid = blockIdx.x * 4 + (threadIdx.x >> 5);           // warp id over (n group, K slice), K slice fastest
     const int ng = wid / KS, ks = wid - ng * KS;
@@ -616,6 +639,7 @@ __global__ void __launch_bounds__(128) linear_fwd_wide_kernel(const float* __res
 }
 __global__ void linear_fwd_finish_kernel(const float* __restrict__ part, const float* __restrict__ bias, float* __restrict__ y, int BN_, int N,
                                          int KS, int relu) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= BN_) return;
     float v = bias ? bias[i % N] : 0.f;
@@ -626,6 +650,7 @@ __global__ void linear_fwd_finish_kernel(const float* __restrict__ part, const f
 // dx[b][k4] += sum_{n in chunk} dy[b][n] W[n][k4]   grid (K/4/LW_T, n chunks); 128-bit reductions into a zeroed / accumulated dx
 __global__ void __launch_bounds__(LW_T) linear_bwd_dx_wide_kernel(const float* __restrict__ dy, const float* __restrict__ W,
                                                                   float* __restrict__ dx, int dxs, int B, int K, int N, int nchunk) {
+    pdl_enter();
     extern __shared__ __align__(16) float dys[];                 // [nchunk][LW_B]
     const int na = blockIdx.y * nchunk, nb = min(N, na + nchunk);
     for (int i = threadIdx.x; i < (nb - na) * LW_B; i += LW_T) {
@@ -662,6 +687,7 @@ __global__ void __launch_bounds__(LW_T) linear_bwd_dx_wide_kernel(const float* _
 __global__ void __launch_bounds__(LW_T) linear_bwd_dw_wide_kernel(const float* __restrict__ dy, const float* __restrict__ x, int xs,
                                                                   float* __restrict__ dW, float* __restrict__ db, int B, int K, int N,
                                                                   int nchunk) {
+    pdl_enter();
     extern __shared__ __align__(16) float dys[];                 // [nchunk][LW_B]
     const int na = blockIdx.y * nchunk, nb = min(N, na + nchunk);
     for (int i = threadIdx.x; i < (nb - na) * LW_B; i += LW_T) {
@@ -702,6 +728,7 @@ __global__ void __launch_bounds__(LW_T) linear_bwd_dw_wide_kernel(const float* _
 
 // relu'(y) applied in place to a dense gradient (y is the saved post-ReLU output)
 __global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict__ g, long n) {
+    pdl_enter();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n && y[i] <= 0.f) g[i] = 0.f;
 }
@@ -710,6 +737,7 @@ __global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict_
 // *loss_slot += sum (a-b)^2 ; dgen = gscale * (a-b)   (a = generated, b = target)
 __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ a, const float* __restrict__ b, long n, float gscale,
                                                   float* __restrict__ dgen, float* __restrict__ loss_slot) {
+    pdl_enter();
     __shared__ float red[32];
     float s = 0.f;
     for (long i = (long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long)gridDim.x * 256) {
@@ -724,6 +752,7 @@ __global__ void __launch_bounds__(256) mse_kernel(const float* __restrict__ a, c
 // out[b] = take[b] ? gt[b] : gen[b]   (train_model.py:73-122 reduces to this select)
 __global__ void sched_select_kernel(const float* __restrict__ gt, const float* __restrict__ gen, const int* __restrict__ take,
                                     float* __restrict__ out, int per_sample, long n) {
+    pdl_enter();
     const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     out[i] = take[i / per_sample] ? gt[i] : gen[i];
@@ -733,6 +762,7 @@ __global__ void sched_select_kernel(const float* __restrict__ gt, const float* _
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                                                    float* __restrict__ v, long n, const int* __restrict__ step, float alpha, float b1,
                                                    float b2, float eps, float gscale) {
+    pdl_enter();
     __shared__ float lr_s;
     if (threadIdx.x == 0) {
         const double t = (double)(step[0] + 1);
@@ -750,9 +780,11 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     }
 }
 
-__global__ void counter_inc_kernel(int* c) { c[0] += 1; }
+__global__ void counter_inc_kernel(int* c) {
+    pdl_enter(); c[0] += 1; }
 
 __global__ void fill_kernel(float* __restrict__ p, float v, long n) {
+    pdl_enter();
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) p[i] = v;
 }
 
@@ -776,7 +808,7 @@ extern "C" {
 int pivp_lstm_gates_fwd(float* gates, const float* c_prev, float* c_out, float* h_out, int h_cs, int h_co,
                         void* h_bf16, int hb_cs, int hb_co, long M, int C, float forget_bias, void* stream) {
     PIVP_REQUIRE(gates && c_out && h_out && M > 0 && C > 0 && C % 32 == 0, "lstm_gates_fwd: bad argument (C must be a multiple of 32)");
-    lstm_gates_fwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_out, View{h_out, h_cs, h_co},
+    launch_k(lstm_gates_fwd_kernel, dim3(nblk(M * C, 256)), dim3(256), 0, (cudaStream_t)stream, gates, c_prev, c_out, View{h_out, h_cs, h_co},
                                                                               (__nv_bfloat16*)h_bf16, hb_cs, hb_co, M, C, forget_bias);
     return check_launch("lstm_gates_fwd");
 }
@@ -785,7 +817,7 @@ int pivp_lstm_gates_bwd(float* gates, const float* c_prev, const float* c_cur, c
                         const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid, void* dg_bf16,
                         long M, int C, void* stream) {
     PIVP_REQUIRE(gates && c_cur && dc && (dh_a || dh_b) && M > 0 && C % 32 == 0, "lstm_gates_bwd: bad argument");
-    lstm_gates_bwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(gates, c_prev, c_cur, dh_a, CView{dh_b, dhb_cs, dhb_co},
+    launch_k(lstm_gates_bwd_kernel, dim3(nblk(M * C, 256)), dim3(256), 0, (cudaStream_t)stream, gates, c_prev, c_cur, dh_a, CView{dh_b, dhb_cs, dhb_co},
                                                                               dc, dc_valid, (__nv_bfloat16*)dg_bf16, M, C);
     return check_launch("lstm_gates_bwd");
 }
@@ -797,7 +829,7 @@ int pivp_lstm_gates_bwd_bf16(const void* gates_bf16, const float* c_prev, const 
                              long M, int C, void* stream) {
     PIVP_REQUIRE(gates_bf16 && dg_bf16 && c_cur && dc && (dh_a || dh_b) && M > 0 && C % 32 == 0, "lstm_gates_bwd_bf16: bad argument");
     PIVP_REQUIRE(!dh_b || (dhb_cs % 4 == 0 && dhb_co % 4 == 0), "lstm_gates_bwd_bf16: dh view must be 16-byte aligned");
-    lstm_gates_bwd_bf16_kernel<<<nblk(M * (C / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(lstm_gates_bwd_bf16_kernel, dim3(nblk(M * (C / 8), 256)), dim3(256), 0, (cudaStream_t)stream, 
         (const __nv_bfloat16*)gates_bf16, c_prev, c_cur, dh_a, CView{dh_b, dhb_cs, dhb_co}, dc, dc_valid, (__nv_bfloat16*)dg_bf16, M, C);
     return check_launch("lstm_gates_bwd_bf16");
 }
@@ -828,10 +860,10 @@ int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, c
                            workspace, S, chunk, (cudaStream_t)stream))
         return r < 0 ? r : PIVP_OK;
     PIVP_REQUIRE(!(relu & 2), "layernorm_fwd: precomputed partials are only supported by the vectorised path");
-    ln_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, n, C, chunk, (float2*)workspace);
+    launch_k(ln_stats_kernel, dim3(S, B), dim3(LN_T), 0, (cudaStream_t)stream, CView{x, x_cs, x_co}, n, C, chunk, (float2*)workspace);
     if (int e = check_launch("layernorm_fwd(stats)")) return e;
     int gx = (n + LN_T * 4 - 1) / (LN_T * 4);
-    ln_apply_kernel<<<dim3(gx, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, gamma, beta, n, C, (const float2*)workspace, S, chunk,
+    launch_k(ln_apply_kernel, dim3(gx, B), dim3(LN_T), 0, (cudaStream_t)stream, CView{x, x_cs, x_co}, gamma, beta, n, C, (const float2*)workspace, S, chunk,
                                                                      eps, View{y, y_cs, y_co}, View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16,
                                                                      yb_cs, yb_co, relu, (float2*)stats);
     return check_launch("layernorm_fwd(apply)");
@@ -849,10 +881,10 @@ int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int 
     if (int r = ln_vec_bwd(x, x_cs, x_co, g1, g1_cs, g1_co, g2, g2_cs, g2_co, gamma, beta, stats, B, HW, C, relu, dx, dx_cs, dx_co, dgamma,
                            dbeta, workspace, S, chunk, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, 0))
         return r < 0 ? r : PIVP_OK;
-    ln_bwd_stats_kernel<<<dim3(S, B), LN_T, 0, (cudaStream_t)stream>>>(CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co},
+    launch_k(ln_bwd_stats_kernel, dim3(S, B), dim3(LN_T), 0, (cudaStream_t)stream, CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co},
                                                                         gamma, beta, (const float2*)stats, n, C, chunk, relu, (float2*)workspace);
     if (int e = check_launch("layernorm_bwd(stats)")) return e;
-    ln_bwd_apply_kernel<<<nblk(n, LN_T), LN_T, (size_t)B * sizeof(float2), (cudaStream_t)stream>>>(
+    launch_k(ln_bwd_apply_kernel, dim3(nblk(n, LN_T)), dim3(LN_T), (size_t)B * sizeof(float2), (cudaStream_t)stream, 
         CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
         (const float2*)workspace, S, B, n, C, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta);
     return check_launch("layernorm_bwd(apply)");
@@ -883,11 +915,11 @@ int pivp_relu_bwd(const float* out, int o_cs, int o_co, const float* ga, int ga_
                   float* dst, int d_cs, int d_co, long M, int C, void* stream) {
     PIVP_REQUIRE(out && ga && dst && M > 0 && C > 0, "relu_bwd: bad argument");
     if (C % 4 == 0 && v4ok(out, o_cs, o_co) && v4ok(ga, ga_cs, ga_co) && v4ok(gb, gb_cs, gb_co) && v4ok(dst, d_cs, d_co)) {
-        relu_bwd_v4_kernel<<<nblk(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co},
+        launch_k(relu_bwd_v4_kernel, dim3(nblk(M * (C / 4), 256)), dim3(256), 0, (cudaStream_t)stream, CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co},
                                                                                     CView{gb, gb_cs, gb_co}, View{dst, d_cs, d_co}, M, C / 4);
         return check_launch("relu_bwd");
     }
-    relu_bwd_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
+    launch_k(relu_bwd_kernel, dim3(nblk(M * C, 256)), dim3(256), 0, (cudaStream_t)stream, CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
                                                                         View{dst, d_cs, d_co}, M, C);
     return check_launch("relu_bwd");
 }
@@ -907,7 +939,7 @@ int pivp_grad_handover(const float* out, int o_cs, int o_co, const float* ga, in
     if (RPB < 1) RPB = 1;
     long blocks = (M + RPB - 1) / RPB;
     if (blocks > 148 * 8) blocks = 148 * 8;
-    grad_handover_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
+    launch_k(grad_handover_kernel, dim3((unsigned)blocks), dim3(256), 0, (cudaStream_t)stream, CView{out, o_cs, o_co}, CView{ga, ga_cs, ga_co}, CView{gb, gb_cs, gb_co},
                                                                            View{dst, d_cs, d_co}, (__nv_bfloat16*)dst_bf16, b_cs, b_co, H, W, s2d,
                                                                            cblk, db, M, C4, RPB);
     return check_launch("grad_handover");
@@ -917,24 +949,24 @@ int pivp_copy_view(const float* src, int s_cs, int s_co, float* dst, int d_cs, i
                    long M, int C, void* stream) {
     PIVP_REQUIRE(src && (dst || dst_bf16) && M > 0 && C > 0, "copy_view: bad argument");
     if (C % 4 == 0 && v4ok(src, s_cs, s_co) && v4ok(dst, d_cs, d_co) && (!dst_bf16 || (!((uintptr_t)dst_bf16 & 7) && db_cs % 4 == 0 && db_co % 4 == 0))) {
-        copy_view_v4_kernel<<<nblk(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, View{dst, d_cs, d_co},
+        launch_k(copy_view_v4_kernel, dim3(nblk(M * (C / 4), 256)), dim3(256), 0, (cudaStream_t)stream, CView{src, s_cs, s_co}, View{dst, d_cs, d_co},
                                                                                      (__nv_bfloat16*)dst_bf16, db_cs, db_co, M, C / 4);
         return check_launch("copy_view");
     }
-    copy_view_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, View{dst, d_cs, d_co},
+    launch_k(copy_view_kernel, dim3(nblk(M * C, 256)), dim3(256), 0, (cudaStream_t)stream, CView{src, s_cs, s_co}, View{dst, d_cs, d_co},
                                                                          (__nv_bfloat16*)dst_bf16, db_cs, db_co, M, C);
     return check_launch("copy_view");
 }
 
 int pivp_nchw_to_nhwc(const float* src, float* dst, int d_cs, int d_co, int B, int C, int HW, void* stream) {
     PIVP_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nchw_to_nhwc: bad argument");
-    nchw_to_nhwc_kernel<<<nblk((long)B * HW, 256), 256, 0, (cudaStream_t)stream>>>(src, View{dst, d_cs, d_co}, B, C, HW);
+    launch_k(nchw_to_nhwc_kernel, dim3(nblk((long)B * HW, 256)), dim3(256), 0, (cudaStream_t)stream, src, View{dst, d_cs, d_co}, B, C, HW);
     return check_launch("nchw_to_nhwc");
 }
 
 int pivp_nhwc_to_nchw(const float* src, int s_cs, int s_co, float* dst, int B, int C, int HW, int accumulate, void* stream) {
     PIVP_REQUIRE(src && dst && B > 0 && C > 0 && HW > 0, "nhwc_to_nchw: bad argument");
-    nhwc_to_nchw_kernel<<<nblk((long)B * HW, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, dst, B, C, HW, accumulate);
+    launch_k(nhwc_to_nchw_kernel, dim3(nblk((long)B * HW, 256)), dim3(256), 0, (cudaStream_t)stream, CView{src, s_cs, s_co}, dst, B, C, HW, accumulate);
     return check_launch("nhwc_to_nchw");
 }
 
@@ -943,37 +975,37 @@ int pivp_cast_bf16(const float* src, int s_cs, int s_co, void* dst_bf16, int d_c
     PIVP_REQUIRE(src && dst_bf16 && M > 0 && C > 0, "cast_bf16: bad argument");
     PIVP_REQUIRE(!s2d || (H > 0 && W > 0 && H % 2 == 0 && W % 2 == 0 && M % ((long)H * W) == 0 && cblk >= C), "cast_bf16: bad space-to-depth geometry");
     if (C % 4 == 0 && v4ok(src, s_cs, s_co) && !((uintptr_t)dst_bf16 & 7) && d_cs % 4 == 0 && d_co % 4 == 0 && cblk % 4 == 0) {
-        cast_bf16_v4_kernel<<<nblk(M * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, (__nv_bfloat16*)dst_bf16, d_cs, d_co, M,
+        launch_k(cast_bf16_v4_kernel, dim3(nblk(M * (C / 4), 256)), dim3(256), 0, (cudaStream_t)stream, CView{src, s_cs, s_co}, (__nv_bfloat16*)dst_bf16, d_cs, d_co, M,
                                                                                      C / 4, H, W, s2d, cblk);
         return check_launch("cast_bf16");
     }
-    cast_bf16_kernel<<<nblk(M * C, 256), 256, 0, (cudaStream_t)stream>>>(CView{src, s_cs, s_co}, (__nv_bfloat16*)dst_bf16, d_cs, d_co, M, C, H, W, s2d, cblk);
+    launch_k(cast_bf16_kernel, dim3(nblk(M * C, 256)), dim3(256), 0, (cudaStream_t)stream, CView{src, s_cs, s_co}, (__nv_bfloat16*)dst_bf16, d_cs, d_co, M, C, H, W, s2d, cblk);
     return check_launch("cast_bf16");
 }
 
 int pivp_axpy(const float* x, float* y, long n, void* stream) {
     PIVP_REQUIRE(x && y && n > 0, "axpy: bad argument");
-    axpy_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(x, y, n);
+    launch_k(axpy_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, x, y, n);
     return check_launch("axpy");
 }
 
 int pivp_state_fwd(const float* action, const float* cur, const float* Wc, const float* bc, float* sa, float* next,
                    float* smear, int sm_cs, int sm_co, int npix, int B, void* stream) {
     PIVP_REQUIRE(action && cur && Wc && bc && sa && next && B > 0, "state_fwd: bad argument");
-    state_fwd_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(action, cur, Wc, bc, sa, next, View{smear, sm_cs, sm_co}, npix);
+    launch_k(state_fwd_kernel, dim3(B), dim3(64), 0, (cudaStream_t)stream, action, cur, Wc, bc, sa, next, View{smear, sm_cs, sm_co}, npix);
     return check_launch("state_fwd");
 }
 
 int pivp_state_bwd(const float* dn_a, const float* dn_b, const float* sa, const float* Wc, const float* dsmear, int ds_cs, int ds_co,
                    int npix, int B, float* d_cur_prev, float* dWc, float* dbc, void* stream) {
     PIVP_REQUIRE(sa && Wc && d_cur_prev && dWc && dbc && B > 0, "state_bwd: bad argument");
-    state_bwd_kernel<<<B, 64, 0, (cudaStream_t)stream>>>(dn_a, dn_b, sa, Wc, CView{dsmear, ds_cs, ds_co}, npix, B, d_cur_prev, dWc, dbc);
+    launch_k(state_bwd_kernel, dim3(B), dim3(64), 0, (cudaStream_t)stream, dn_a, dn_b, sa, Wc, CView{dsmear, ds_cs, ds_co}, npix, B, d_cur_prev, dWc, dbc);
     return check_launch("state_bwd");
 }
 
 int pivp_linear_fwd(const float* x, int xs, const float* W, const float* bias, float* y, int B, int K, int N, int relu, void* stream) {
     PIVP_REQUIRE(x && W && y && B > 0 && K > 0 && N > 0 && xs >= K, "linear_fwd: bad argument");
-    linear_fwd_kernel<<<dim3((N + LIN_NN - 1) / LIN_NN, (B + LIN_BB - 1) / LIN_BB), 256, 0, (cudaStream_t)stream>>>(x, xs, W, bias, y, B, K, N, relu);
+    launch_k(linear_fwd_kernel, dim3((N + LIN_NN - 1) / LIN_NN, (B + LIN_BB - 1) / LIN_BB), dim3(256), 0, (cudaStream_t)stream, x, xs, W, bias, y, B, K, N, relu);
     return check_launch("linear_fwd");
 }
 
@@ -993,9 +1025,9 @@ int pivp_linear_fwd_splitk(const float* x, int xs, const float* W, const float* 
     const int kchunk = ((K / KS) + 3) / 4 * 4;
     float* part = (float*)workspace;
     const int warps = ((N + 3) / 4) * KS;
-    linear_fwd_wide_kernel<<<(warps + 3) / 4, 128, 0, (cudaStream_t)stream>>>(x, xs, W, part, B, K, N, kchunk, KS);
+    launch_k(linear_fwd_wide_kernel, dim3((warps + 3) / 4), dim3(128), 0, (cudaStream_t)stream, x, xs, W, part, B, K, N, kchunk, KS);
     if (int e = check_launch("linear_fwd(wide)")) return e;
-    linear_fwd_finish_kernel<<<(B * N + 255) / 256, 256, 0, (cudaStream_t)stream>>>(part, bias, y, B * N, N, KS, relu);
+    launch_k(linear_fwd_finish_kernel, dim3((B * N + 255) / 256), dim3(256), 0, (cudaStream_t)stream, part, bias, y, B * N, N, KS, relu);
     return check_launch("linear_fwd(finish)");
 }
 
@@ -1014,28 +1046,28 @@ int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, flo
             int nsplit = (296 + kblocks - 1) / kblocks;
             if (nsplit > N) nsplit = N;
             const int nchunk = (N + nsplit - 1) / nsplit;
-            linear_bwd_dx_wide_kernel<<<dim3(kblocks, (N + nchunk - 1) / nchunk), LW_T, sizeof(float) * nchunk * LW_B, st>>>(dy, W, dx, dxs, B, K, N,
+            launch_k(linear_bwd_dx_wide_kernel, dim3(kblocks, (N + nchunk - 1) / nchunk), dim3(LW_T), sizeof(float) * nchunk * LW_B, st, dy, W, dx, dxs, B, K, N,
                                                                                                                           nchunk);
             if (int e = check_launch("linear_bwd(dx wide)")) return e;
         }
         int nsplit = (444 + kblocks - 1) / kblocks;
         if (nsplit > N) nsplit = N;
         const int nchunk = (N + nsplit - 1) / nsplit;
-        linear_bwd_dw_wide_kernel<<<dim3(kblocks, (N + nchunk - 1) / nchunk), LW_T, sizeof(float) * nchunk * LW_B, st>>>(dy, x, xs, dW, db, B, K, N,
+        launch_k(linear_bwd_dw_wide_kernel, dim3(kblocks, (N + nchunk - 1) / nchunk), dim3(LW_T), sizeof(float) * nchunk * LW_B, st, dy, x, xs, dW, db, B, K, N,
                                                                                                                       nchunk);
         return check_launch("linear_bwd(dw wide)");
     }
     if (dx) {
-        linear_bwd_dx_kernel<<<dim3((K + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(dy, W, dx, dxs, B, K, N, accumulate_dx);
+        launch_k(linear_bwd_dx_kernel, dim3((K + 255) / 256, B), dim3(256), 0, (cudaStream_t)stream, dy, W, dx, dxs, B, K, N, accumulate_dx);
         if (int e = check_launch("linear_bwd(dx)")) return e;
     }
-    linear_bwd_dw_kernel<<<dim3((K + 255) / 256, N), 256, 0, (cudaStream_t)stream>>>(dy, x, xs, dW, db, B, K, N);
+    launch_k(linear_bwd_dw_kernel, dim3((K + 255) / 256, N), dim3(256), 0, (cudaStream_t)stream, dy, x, xs, dW, db, B, K, N);
     return check_launch("linear_bwd(dw)");
 }
 
 int pivp_relu_mask(const float* y, float* g, long n, void* stream) {
     PIVP_REQUIRE(y && g && n > 0, "relu_mask: bad argument");
-    relu_mask_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(y, g, n);
+    launch_k(relu_mask_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, y, g, n);
     return check_launch("relu_mask");
 }
 
@@ -1043,14 +1075,14 @@ int pivp_mse(const float* gen, const float* target, long n, float gscale, float*
     PIVP_REQUIRE(gen && target && loss_slot && n > 0, "mse: bad argument");
     unsigned g = nblk(n, 256 * 4);
     if (g > 592) g = 592;
-    mse_kernel<<<g, 256, 0, (cudaStream_t)stream>>>(gen, target, n, gscale, dgen, loss_slot);
+    launch_k(mse_kernel, dim3(g), dim3(256), 0, (cudaStream_t)stream, gen, target, n, gscale, dgen, loss_slot);
     return check_launch("mse");
 }
 
 int pivp_sched_select(const float* gt, const float* gen, const int* take, float* out, int B, int per_sample, void* stream) {
     PIVP_REQUIRE(gt && gen && take && out && B > 0 && per_sample > 0, "sched_select: bad argument");
     const long n = (long)B * per_sample;
-    sched_select_kernel<<<nblk(n, 256), 256, 0, (cudaStream_t)stream>>>(gt, gen, take, out, per_sample, n);
+    launch_k(sched_select_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, gt, gen, take, out, per_sample, n);
     return check_launch("sched_select");
 }
 
@@ -1059,9 +1091,9 @@ int pivp_adam_step(float* p, const float* g, float* m, float* v, long n, int* st
     PIVP_REQUIRE(p && g && m && v && step && n > 0, "adam_step: bad argument");
     unsigned gb = nblk(n, 256 * 4);
     if (gb > 148 * 8) gb = 148 * 8;
-    adam_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, step, alpha, beta1, beta2, eps, gscale);
+    launch_k(adam_kernel, dim3(gb), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, step, alpha, beta1, beta2, eps, gscale);
     if (int e = check_launch("adam_step")) return e;
-    counter_inc_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step);
+    launch_k(counter_inc_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step);
     return check_launch("adam_step(counter)");
 }
 
@@ -1069,7 +1101,7 @@ int pivp_fill(float* p, float value, long n, void* stream) {
     PIVP_REQUIRE(p && n > 0, "fill: bad argument");
     unsigned gb = nblk(n, 256 * 4);
     if (gb > 148 * 8) gb = 148 * 8;
-    fill_kernel<<<gb, 256, 0, (cudaStream_t)stream>>>(p, value, n);
+    launch_k(fill_kernel, dim3(gb), dim3(256), 0, (cudaStream_t)stream, p, value, n);
     return check_launch("fill");
 }
 

@@ -80,6 +80,7 @@ __device__ void cdna_normalise(const float* __restrict__ kraw_sample, int M, flo
 __global__ void __launch_bounds__(FT) cdna_fwd_kernel(const float* __restrict__ prev, const float* __restrict__ e_pre,
                                                       const float* __restrict__ a_pre, const float* __restrict__ kraw,
                                                       float* __restrict__ out, Band bd, int M) {
+    pdl_enter();
     extern __shared__ float sm[];
     __shared__ int shift[MAXM1];
     const int b = blockIdx.y, r0 = blockIdx.x * bd.R;
@@ -123,6 +124,7 @@ __global__ void __launch_bounds__(FT) cdna_bwd_kernel(const float* __restrict__ 
                                                       const float* __restrict__ e_pre, const float* __restrict__ a_pre,
                                                       const float* __restrict__ kraw, float* __restrict__ wq, float* __restrict__ d_e,
                                                       float* __restrict__ dK, Band bd, int M) {
+    pdl_enter();
     extern __shared__ float sm[];
     __shared__ int shift[MAXM1];
     const int b = blockIdx.y, r0 = blockIdx.x * bd.R;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(FT) cdna_bwd_kernel(const float* __restrict__ 
 __global__ void __launch_bounds__(FT) cdna_dprev_kernel(const float* __restrict__ gout, const float* __restrict__ a_pre,
                                                         const float* __restrict__ kraw, float* __restrict__ dprev, Band bd, int M,
                                                         int accumulate) {
+    pdl_enter();
     extern __shared__ float sm[];
     __shared__ int shift[MAXM1];
     const int b = blockIdx.y, r0 = blockIdx.x * bd.R;
@@ -234,6 +237,7 @@ __global__ void __launch_bounds__(FT) cdna_dprev_kernel(const float* __restrict_
 // thread per flat group: d_a = (wq - mu * sum(wq)) * [a > 0]
 __global__ void mask_softmax_bwd_kernel(const float* __restrict__ a_pre, const float* __restrict__ wq, float* __restrict__ d_a,
                                         long ngroups, int M1) {
+    pdl_enter();
     const long gidx = (long)blockIdx.x * blockDim.x + threadIdx.x;
     if (gidx >= ngroups) return;
     const float* a = a_pre + gidx * M1;
@@ -248,6 +252,7 @@ __global__ void mask_softmax_bwd_kernel(const float* __restrict__ a_pre, const f
 
 // d_kraw from dK: dkt = (dK - sum_t K_t dK_t) / s ; d_r = dkt * [r - eps > 0]     (D.1)
 __global__ void cdna_kern_bwd_kernel(const float* __restrict__ kraw, const float* __restrict__ dK, float* __restrict__ d_kraw, int BM_) {
+    pdl_enter();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;       // over B*M kernels
     if (i >= BM_) return;
     float kt[25], s = 0.f, dot = 0.f;
@@ -265,6 +270,7 @@ __global__ void __launch_bounds__(FT) dna_kernel(const float* __restrict__ prev,
                                                  const float* __restrict__ a_pre, const float* __restrict__ gout,
                                                  float* __restrict__ out, float* __restrict__ wq, float* __restrict__ d_e,
                                                  float* __restrict__ dprev, int dprev_acc, Band bd, int backward) {
+    pdl_enter();
     extern __shared__ float sm[];
     __shared__ int shift[MAXM1];
     const int b = blockIdx.y, r0 = blockIdx.x * bd.R;
@@ -340,6 +346,7 @@ __global__ void __launch_bounds__(FT) stp_kernel(const float* __restrict__ prev,
                                                  const float* __restrict__ gout, float* __restrict__ out, float* __restrict__ wq,
                                                  float* __restrict__ d_e, float* __restrict__ d_theta, float* __restrict__ dprev,
                                                  Band bd, int M, int oob, int backward) {
+    pdl_enter();
     extern __shared__ float sm[];
     __shared__ int shift[MAXM1];
     __shared__ float red[32];
@@ -483,7 +490,7 @@ int pivp_cdna_fused_fwd(const float* prev, const float* enc7_pre, const float* m
     if (int e = make_band(H, W, num_masks + 1, 0, &bd)) return e;
     const size_t smem = sizeof(float) * ((size_t)bd.M1 * bd.L + 3 * (bd.R + 4) * (W + 4) + num_masks * 25);
     if (int e = allow_smem(cdna_fwd_kernel, smem)) return e;
-    cdna_fwd_kernel<<<dim3((H + bd.R - 1) / bd.R, B), FT, smem, (cudaStream_t)stream>>>(prev, enc7_pre, mask_pre, kern_raw, out, bd, num_masks);
+    launch_k(cdna_fwd_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, (cudaStream_t)stream, prev, enc7_pre, mask_pre, kern_raw, out, bd, num_masks);
     return check_launch("cdna_fused_fwd");
 }
 
@@ -511,7 +518,7 @@ int pivp_cdna_fused_bwd(const float* g_out, const float* prev, const float* enc7
             if (int e = make_band(H, W, num_masks + 1, 4, &be)) return e;
             const size_t sm2 = sizeof(float) * ((size_t)be.M1 * be.L + 3 * (be.R + 8) * (W + 4) + num_masks * 25);
             if (int e = allow_smem(cdna_dprev_kernel, sm2)) return e;
-            cdna_dprev_kernel<<<dim3((H + be.R - 1) / be.R, B), FT, sm2, st>>>(g_out, mask_pre, kern_raw, d_prev, be, num_masks, accumulate_dprev);
+            launch_k(cdna_dprev_kernel, dim3((H + be.R - 1) / be.R, B), dim3(FT), sm2, st, g_out, mask_pre, kern_raw, d_prev, be, num_masks, accumulate_dprev);
             return check_launch("cdna_fused_bwd(dprev)");
         }
         return PIVP_OK;
@@ -521,19 +528,19 @@ int pivp_cdna_fused_bwd(const float* g_out, const float* prev, const float* enc7
     cudaMemsetAsync(dK, 0, sizeof(float) * (size_t)B * num_masks * 25, st);
     const size_t smem = sizeof(float) * ((size_t)bd.M1 * bd.L + 3 * (bd.R + 4) * (W + 4) + num_masks * 25 + 25 * (size_t)bd.R * W);
     if (int e = allow_smem(cdna_bwd_kernel, smem)) return e;
-    cdna_bwd_kernel<<<dim3((H + bd.R - 1) / bd.R, B), FT, smem, st>>>(g_out, prev, enc7_pre, mask_pre, kern_raw, wq, d_enc7_pre, dK, bd, num_masks);
+    launch_k(cdna_bwd_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, st, g_out, prev, enc7_pre, mask_pre, kern_raw, wq, d_enc7_pre, dK, bd, num_masks);
     if (int e = check_launch("cdna_fused_bwd(k1)")) return e;
     const long ngroups = (long)B * H * W;
-    mask_softmax_bwd_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, st>>>(mask_pre, wq, d_mask_pre, ngroups, num_masks + 1);
+    launch_k(mask_softmax_bwd_kernel, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, st, mask_pre, wq, d_mask_pre, ngroups, num_masks + 1);
     if (int e = check_launch("cdna_fused_bwd(softmax)")) return e;
-    cdna_kern_bwd_kernel<<<(B * num_masks + 127) / 128, 128, 0, st>>>(kern_raw, dK, d_kern_raw, B * num_masks);
+    launch_k(cdna_kern_bwd_kernel, dim3((B * num_masks + 127) / 128), dim3(128), 0, st, kern_raw, dK, d_kern_raw, B * num_masks);
     if (int e = check_launch("cdna_fused_bwd(kern)")) return e;
     if (d_prev) {
         Band be;
         if (int e = make_band(H, W, num_masks + 1, 4, &be)) return e;
         const size_t sm2 = sizeof(float) * ((size_t)be.M1 * be.L + 3 * (be.R + 8) * (W + 4) + num_masks * 25);
         if (int e = allow_smem(cdna_dprev_kernel, sm2)) return e;
-        cdna_dprev_kernel<<<dim3((H + be.R - 1) / be.R, B), FT, sm2, st>>>(g_out, mask_pre, kern_raw, d_prev, be, num_masks, accumulate_dprev);
+        launch_k(cdna_dprev_kernel, dim3((H + be.R - 1) / be.R, B), dim3(FT), sm2, st, g_out, mask_pre, kern_raw, d_prev, be, num_masks, accumulate_dprev);
         return check_launch("cdna_fused_bwd(dprev)");
     }
     return PIVP_OK;
@@ -545,7 +552,7 @@ int pivp_dna_fused_fwd(const float* prev, const float* enc7_pre, const float* ma
     if (int e = make_band(H, W, 2, 0, &bd)) return e;
     const size_t smem = sizeof(float) * ((size_t)2 * bd.L + 3 * (bd.R + 4) * (W + 4));
     if (int e = allow_smem(dna_kernel, smem)) return e;
-    dna_kernel<<<dim3((H + bd.R - 1) / bd.R, B), FT, smem, (cudaStream_t)stream>>>(prev, enc7_pre, mask_pre, nullptr, out, nullptr, nullptr,
+    launch_k(dna_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, (cudaStream_t)stream, prev, enc7_pre, mask_pre, nullptr, out, nullptr, nullptr,
                                                                                   nullptr, 0, bd, 0);
     return check_launch("dna_fused_fwd");
 }
@@ -563,11 +570,11 @@ int pivp_dna_fused_bwd(const float* g_out, const float* prev, const float* enc7_
     float* wq = (float*)workspace;
     const size_t smem = sizeof(float) * ((size_t)2 * bd.L + 3 * (bd.R + 4) * (W + 4));
     if (int e = allow_smem(dna_kernel, smem)) return e;
-    dna_kernel<<<dim3((H + bd.R - 1) / bd.R, B), FT, smem, st>>>(prev, enc7_pre, mask_pre, g_out, nullptr, wq, d_enc7_pre, d_prev,
+    launch_k(dna_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, st, prev, enc7_pre, mask_pre, g_out, nullptr, wq, d_enc7_pre, d_prev,
                                                                 accumulate_dprev, bd, 1);
     if (int e = check_launch("dna_fused_bwd(k1)")) return e;
     const long ngroups = (long)B * H * W;
-    mask_softmax_bwd_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, st>>>(mask_pre, wq, d_mask_pre, ngroups, 2);
+    launch_k(mask_softmax_bwd_kernel, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, st, mask_pre, wq, d_mask_pre, ngroups, 2);
     return check_launch("dna_fused_bwd(softmax)");
 }
 
@@ -578,7 +585,7 @@ int pivp_stp_fused_fwd(const float* prev, const float* enc7_pre, const float* ma
     if (int e = make_band(H, W, num_masks + 1, 0, &bd)) return e;
     const size_t smem = sizeof(float) * ((size_t)bd.M1 * bd.L);
     if (int e = allow_smem(stp_kernel, smem)) return e;
-    stp_kernel<<<dim3((H + bd.R - 1) / bd.R, B), FT, smem, (cudaStream_t)stream>>>(prev, enc7_pre, mask_pre, theta_raw, nullptr, out, nullptr,
+    launch_k(stp_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, (cudaStream_t)stream, prev, enc7_pre, mask_pre, theta_raw, nullptr, out, nullptr,
                                                                                   nullptr, nullptr, nullptr, bd, num_masks, oob_border, 0);
     return check_launch("stp_fused_fwd");
 }
@@ -601,11 +608,11 @@ int pivp_stp_fused_bwd(const float* g_out, const float* prev, const float* enc7_
     cudaMemsetAsync(d_theta, 0, sizeof(float) * (size_t)B * 6, st);
     const size_t smem = sizeof(float) * ((size_t)bd.M1 * bd.L);
     if (int e = allow_smem(stp_kernel, smem)) return e;
-    stp_kernel<<<dim3((H + bd.R - 1) / bd.R, B), FT, smem, st>>>(prev, enc7_pre, mask_pre, theta_raw, g_out, nullptr, wq, d_enc7_pre, d_theta,
+    launch_k(stp_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, st, prev, enc7_pre, mask_pre, theta_raw, g_out, nullptr, wq, d_enc7_pre, d_theta,
                                                                 d_prev, bd, num_masks, oob_border, 1);
     if (int e = check_launch("stp_fused_bwd(k1)")) return e;
     const long ngroups = (long)B * H * W;
-    mask_softmax_bwd_kernel<<<(unsigned)((ngroups + 255) / 256), 256, 0, st>>>(mask_pre, wq, d_mask_pre, ngroups, num_masks + 1);
+    launch_k(mask_softmax_bwd_kernel, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, st, mask_pre, wq, d_mask_pre, ngroups, num_masks + 1);
     return check_launch("stp_fused_bwd(softmax)");
 }
 

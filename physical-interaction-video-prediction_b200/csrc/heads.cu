@@ -57,6 +57,7 @@ template <int NH>
 __global__ void __launch_bounds__(TP) heads_fwd_kernel(const float* __restrict__ x, int cs, int co, const float* __restrict__ Wt,
                                                        const float* __restrict__ bias, float* __restrict__ out_a, int Na,
                                                        float* __restrict__ out_b, long M, int HW) {
+    pdl_enter();
     constexpr int NP = (NH + 3) / 4 * 4;                         // padded to float4
     __shared__ __align__(16) float xs[TP * XP];
     __shared__ __align__(16) float wt[C * NP];                   // W transposed: wt[c][n]
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(TP, 4) heads_bwd_kernel(const float* __restric
                                                           const float* __restrict__ dy_a, int Na, const float* __restrict__ dy_b,
                                                           float* __restrict__ dx, int dcs, int dco, float* __restrict__ dW,
                                                           float* __restrict__ db, long M, int HW, int ntiles) {
+    pdl_enter();
     constexpr int NB = ((NH + 1) / 2 + 3) / 4 * 4;               // heads per thread half, padded to float4 (8 for 14, 16 for 27)
     constexpr int NP = 2 * NB;                                   // dY tile pitch: [pixel][NP], heads >= NH are zero
     extern __shared__ __align__(16) float hsm[];
@@ -246,8 +248,8 @@ int pivp_heads_fwd(const float* x, int x_cs, int x_co, const float* W, const flo
     PIVP_REQUIRE(hd::a16(x) && x_cs % 4 == 0 && x_co % 4 == 0, "heads_fwd: rows must be 16-byte aligned");
     const long M = (long)B * HW;
     const unsigned grid = (unsigned)((M + hd::TP - 1) / hd::TP);
-    if (NH == 14) hd::heads_fwd_kernel<14><<<grid, hd::TP, 0, (cudaStream_t)stream>>>(x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
-    else if (NH == 27) hd::heads_fwd_kernel<27><<<grid, hd::TP, 0, (cudaStream_t)stream>>>(x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
+    if (NH == 14) launch_k(hd::heads_fwd_kernel<14>, dim3(grid), dim3(hd::TP), 0, (cudaStream_t)stream, x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
+    else if (NH == 27) launch_k(hd::heads_fwd_kernel<27>, dim3(grid), dim3(hd::TP), 0, (cudaStream_t)stream, x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
     else { set_error("heads_fwd: %d heads not instantiated (14 or 27)", NH); return PIVP_EUNSUPPORTED; }
     return check_launch("heads_fwd");
 }
@@ -269,8 +271,8 @@ int pivp_heads_bwd(const float* x, int x_cs, int x_co, const float* W, const flo
         cudaFuncSetAttribute(hd::heads_bwd_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
         attr_set = true;
     }
-    if (NH == 14) hd::heads_bwd_kernel<14><<<grid, hd::TP, smem, (cudaStream_t)stream>>>(x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
-    else if (NH == 27) hd::heads_bwd_kernel<27><<<grid, hd::TP, smem, (cudaStream_t)stream>>>(x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
+    if (NH == 14) launch_k(hd::heads_bwd_kernel<14>, dim3(grid), dim3(hd::TP), smem, (cudaStream_t)stream, x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
+    else if (NH == 27) launch_k(hd::heads_bwd_kernel<27>, dim3(grid), dim3(hd::TP), smem, (cudaStream_t)stream, x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
     else { set_error("heads_bwd: %d heads not instantiated (14 or 27)", NH); return PIVP_EUNSUPPORTED; }
     return check_launch("heads_bwd");
 }

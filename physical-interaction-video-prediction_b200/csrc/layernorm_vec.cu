@@ -24,6 +24,7 @@ __device__ __forceinline__ float4 ld4(const float* p) { return __ldg(reinterpret
 __device__ __forceinline__ float hsum(float4 v) { return (v.x + v.y) + (v.z + v.w); }
 
 __global__ void __launch_bounds__(T) stats_kernel(CView x, Geo g, int n, int chunk, float2* __restrict__ partial) {
+    pdl_enter();
     __shared__ float red[32];
     const int s = blockIdx.x, S = gridDim.x;
     const long b = blockIdx.y;
@@ -69,6 +70,7 @@ __global__ void __launch_bounds__(T) apply_kernel(CView x, const float* __restri
                                                   const float2* __restrict__ partial, int S, int chunk, float eps, View y, View y2,
                                                   __nv_bfloat16* __restrict__ y_bf16, int yb_cs, int yb_co, int relu,
                                                   float2* __restrict__ stats) {
+    pdl_enter();
     __shared__ float2 st_s;
     const long b = blockIdx.y;
     if (threadIdx.x < 32) {
@@ -125,6 +127,7 @@ __device__ __forceinline__ void load_g_xh(const CView& x, const CView& g1, const
 __global__ void __launch_bounds__(T) bwd_stats_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
                                                       const float* __restrict__ beta, const float2* __restrict__ stats, Geo g, int n,
                                                       int chunk, int relu, float2* __restrict__ partial) {
+    pdl_enter();
     __shared__ float red[32];
     const int s = blockIdx.x, S = gridDim.x;
     const long b = blockIdx.y;
@@ -213,6 +216,7 @@ __global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView 
                                                        const float* __restrict__ beta, const float2* __restrict__ stats,
                                                        const float2* __restrict__ partial, int S, int B, int bchunk, Geo g, int n,
                                                        int relu, View dx, float* __restrict__ dgamma, float* __restrict__ dbeta, GateFuse gf) {
+    pdl_enter();
     extern __shared__ float4 tot[];              // [bchunk] : (mean, rstd, mean q, mean q*xhat)
     const int b0 = blockIdx.y * bchunk, nb = min(bchunk, B - b0);
     for (int i = threadIdx.x; i < nb; i += TB) {
@@ -276,12 +280,12 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
     const int have_stats = relu & 2;                           // the producer's epilogue already wrote the (mean, M2) partials
     relu &= 1;
     if (!have_stats) {
-        stats_kernel<<<dim3(S, B), T, 0, st>>>(CView{x, x_cs, x_co}, g, n, chunk, (float2*)workspace);
+        launch_k(stats_kernel, dim3(S, B), dim3(T), 0, st, CView{x, x_cs, x_co}, g, n, chunk, (float2*)workspace);
         if (int e = check_launch("layernorm_fwd(stats)")) return e;
     }
     int gx = (n / 4 + T - 1) / T;
     if (gx > 64) gx = 64;
-    apply_kernel<<<dim3(gx, B), T, 0, st>>>(CView{x, x_cs, x_co}, gamma, beta, g, n, (const float2*)workspace, S, chunk, eps,
+    launch_k(apply_kernel, dim3(gx, B), dim3(T), 0, st, CView{x, x_cs, x_co}, gamma, beta, g, n, (const float2*)workspace, S, chunk, eps,
                                            View{y, y_cs, y_co}, View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16, yb_cs, yb_co, relu,
                                            (float2*)stats);
     if (int e = check_launch("layernorm_fwd(apply)")) return e;
@@ -299,7 +303,7 @@ int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, i
         !view_ok(dx, dx_cs, dx_co) || !a16(gamma) || !a16(beta) || !a16(dgamma) || !a16(dbeta))
         return 0;
     const Geo g = make_geo(HW, C);
-    bwd_stats_kernel<<<dim3(S, B), T, 0, st>>>(CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta,
+    launch_k(bwd_stats_kernel, dim3(S, B), dim3(T), 0, st, CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta,
                                               (const float2*)stats, g, n, chunk, relu, (float2*)workspace);
     if (int e = check_launch("layernorm_bwd(stats)")) return e;
     const int gx = (n / 4 + TB - 1) / TB;
@@ -308,7 +312,7 @@ int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, i
     if (nby < 1) nby = 1;
     const int bchunk = (B + nby - 1) / nby;
     nby = (B + bchunk - 1) / bchunk;
-    bwd_apply_kernel<<<dim3(gx, nby), TB, (size_t)bchunk * sizeof(float4), st>>>(
+    launch_k(bwd_apply_kernel, dim3(gx, nby), dim3(TB), (size_t)bchunk * sizeof(float4), st, 
         CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
         (const float2*)workspace, S, B, bchunk, g, n, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta, gf);
     if (int e = check_launch("layernorm_bwd(apply)")) return e;
