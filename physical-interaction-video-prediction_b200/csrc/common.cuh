@@ -37,7 +37,8 @@ struct CView {
 // stable, against 9.48 / 9.78 ms (two modes) with plain launches.  An explicit early trigger (griddepcontrol.launch_dependents at the
 // top of every kernel) was measured too and is WORSE (10.03 ms): CTAs of the next kernel become resident on whichever SMs free up
 // first and pack depth-first, so multi-CTA-per-SM kernels start unbalanced; a late trigger in the GEMM epilogues gave 9.56 ms.  The
-// trigger is therefore left implicit (at kernel completion).  PIVP_PDL=0 or pivp_set_pdl(0) launches plainly.
+// trigger is therefore left implicit (at kernel completion); an early trigger in the LayerNorm kernels alone (so that the one-CTA-per-SM
+// GEMM that follows could run its prologue early) changed nothing (9.30 vs 9.29 ms).  PIVP_PDL=0 or pivp_set_pdl(0) launches plainly.
 bool pdl_enabled();
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_enter() { pdl_wait(); }

@@ -47,7 +47,7 @@ class TensorCorePlan(object):
         self.wgrad_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         self.accurate = 0
         import os
-        self.split_n = int(os.environ.get("PIVP_TC_SPLIT_N", "1"))       # tuning switch for the input-gradient N split
+        self.split_n = int(os.environ.get("PIVP_TC_SPLIT_N", "0"))       # tuning switch for the input-gradient N split
         self.pair_bn = int(os.environ.get("PIVP_TC_PAIR_BN", "96"))      # N tile of the 8x8-map input gradient (0: per-tap kernel's choice)
         # layers whose maps the halo-patch kernel tiles (H % 16 == 0, W % 8 == 0): its epilogue also produces the LayerNorm statistics
         self.ln_fused = [(eng.H // lv) % 16 == 0 and (eng.W // lv) % 8 == 0 and ((eng.H // lv) * (eng.W // lv) * c) % 4096 == 0
