@@ -123,6 +123,11 @@ int pivp_linear_fwd_splitk(const float* x, int xs, const float* W, const float* 
                            void* workspace, size_t ws_bytes, void* stream);
 int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, float* dx, int dxs, int accumulate_dx,
                     float* dW, float* db, int B, int K, int N, void* stream);
+/* The weight / bias gradient of pivp_linear_bwd over S stacked time steps in one pass (dy [S][B][N] with step stride dy_step elements,
+ * x [S][B rows of stride xs] with step stride x_step): dW [N][K] and db [N] are accumulated into.  pivp_linear_bwd with dW = NULL
+ * computes dx only, so a caller can defer the weight gradient of a time loop to one launch (train_model.py:321-322 backward). */
+int pivp_linear_wgrad_steps(const float* dy, long dy_step, const float* x, long x_step, int xs, float* dW, float* db, int S, int B, int K, int N,
+                            void* stream);
 
 /* ---- loss, scheduled sampling, optimizer --------------------------------------------------------------- */
 /* F.mean_squared_error pieces (train_model.py:741,751): *loss_slot += sum (gen-target)^2 ; dgen = gscale*(gen-target) */

@@ -726,6 +726,63 @@ __global__ void __launch_bounds__(LW_T) linear_bwd_dw_wide_kernel(const float* _
     }
 }
 
+// The same weight gradient over S time steps in ONE pass: dW[n][k4] += sum_s sum_b dy[s][b][n] x[s][b][k4].  The per-step kernel
+// re-reads and re-writes all of dW (8 MB for the 8192 -> 250 kernel Linear) every step; here a thread keeps its NCH x 4 partial sums
+// in registers across the steps and touches dW once.   grid (K/4/LW_T, n chunks of NCH)
+template <int NCH>
+__global__ void __launch_bounds__(LW_T) linear_dw_steps_kernel(const float* __restrict__ dy, long dy_ss, const float* __restrict__ x, long x_ss,
+                                                               int xs, float* __restrict__ dW, float* __restrict__ db, int S, int B, int K,
+                                                               int N) {
+    pdl_enter();
+    extern __shared__ __align__(16) float dys[];                 // [S][NCH][LW_B]
+    const int na = blockIdx.y * NCH;
+    for (int i = threadIdx.x; i < S * NCH * LW_B; i += LW_T) {
+        const int s = i / (NCH * LW_B), r = i - s * NCH * LW_B, n = r / LW_B, b = r - n * LW_B;
+        dys[i] = (b < B && na + n < N) ? __ldg(dy + s * dy_ss + (long)b * N + na + n) : 0.f;
+    }
+    __syncthreads();
+    if (db && blockIdx.x == 0 && threadIdx.x < NCH && na + threadIdx.x < N) {
+        float sum = 0.f;
+        for (int s = 0; s < S; ++s)
+            for (int b = 0; b < LW_B; ++b) sum += dys[(s * NCH + threadIdx.x) * LW_B + b];
+        db[na + threadIdx.x] += sum;
+    }
+    const int k = 4 * (blockIdx.x * LW_T + threadIdx.x);
+    if (k >= K) return;
+    float4 acc[NCH];
+#pragma unroll
+    for (int n = 0; n < NCH; ++n) acc[n] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int s = 0; s < S; ++s) {
+        float4 xv[LW_B];
+#pragma unroll
+        for (int b = 0; b < LW_B; ++b)
+            xv[b] = b < B ? __ldg(reinterpret_cast<const float4*>(x + s * x_ss + (long)b * xs + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int n = 0; n < NCH; ++n) {
+            const float4* dr = reinterpret_cast<const float4*>(dys + (s * NCH + n) * LW_B);
+#pragma unroll
+            for (int b4 = 0; b4 < LW_B / 4; ++b4) {
+                const float4 d = dr[b4];
+                const float dd[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const float4 v = xv[4 * b4 + j];
+                    acc[n].x = fmaf(dd[j], v.x, acc[n].x); acc[n].y = fmaf(dd[j], v.y, acc[n].y);
+                    acc[n].z = fmaf(dd[j], v.z, acc[n].z); acc[n].w = fmaf(dd[j], v.w, acc[n].w);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int n = 0; n < NCH; ++n)
+        if (na + n < N) {
+            float4* dst = reinterpret_cast<float4*>(dW + (long)(na + n) * K + k);
+            float4 o = *dst;
+            o.x += acc[n].x; o.y += acc[n].y; o.z += acc[n].z; o.w += acc[n].w;
+            *dst = o;
+        }
+}
+
 // relu'(y) applied in place to a dense gradient (y is the saved post-ReLU output)
 __global__ void relu_mask_kernel(const float* __restrict__ y, float* __restrict__ g, long n) {
     pdl_enter();
@@ -1033,7 +1090,7 @@ int pivp_linear_fwd_splitk(const float* x, int xs, const float* W, const float* 
 
 int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, float* dx, int dxs, int accumulate_dx,
                     float* dW, float* db, int B, int K, int N, void* stream) {
-    PIVP_REQUIRE(dy && x && W && dW && B > 0 && K > 0 && N > 0, "linear_bwd: bad argument");
+    PIVP_REQUIRE(dy && x && W && (dW || dx) && B > 0 && K > 0 && N > 0, "linear_bwd: bad argument");
     if (B <= LW_B && K >= 1024 && K % 4 == 0 && xs % 4 == 0 && !(((uintptr_t)x | (uintptr_t)W | (uintptr_t)dW) & 15) &&
         (!dx || (dxs % 4 == 0 && !((uintptr_t)dx & 15)))) {
         cudaStream_t st = (cudaStream_t)stream;
@@ -1050,6 +1107,7 @@ int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, flo
                                                                                                                           nchunk);
             if (int e = check_launch("linear_bwd(dx wide)")) return e;
         }
+        if (!dW) return PIVP_OK;                      // weight gradient deferred (pivp_linear_wgrad_steps)
         int nsplit = (444 + kblocks - 1) / kblocks;
         if (nsplit > N) nsplit = N;
         const int nchunk = (N + nsplit - 1) / nsplit;
@@ -1061,8 +1119,27 @@ int pivp_linear_bwd(const float* dy, const float* x, int xs, const float* W, flo
         launch_k(linear_bwd_dx_kernel, dim3((K + 255) / 256, B), dim3(256), 0, (cudaStream_t)stream, dy, W, dx, dxs, B, K, N, accumulate_dx);
         if (int e = check_launch("linear_bwd(dx)")) return e;
     }
+    if (!dW) return PIVP_OK;
     launch_k(linear_bwd_dw_kernel, dim3((K + 255) / 256, N), dim3(256), 0, (cudaStream_t)stream, dy, x, xs, dW, db, B, K, N);
     return check_launch("linear_bwd(dw)");
+}
+
+int pivp_linear_wgrad_steps(const float* dy, long dy_step, const float* x, long x_step, int xs, float* dW, float* db, int S, int B, int K, int N,
+                            void* stream) {
+    PIVP_REQUIRE(dy && x && dW && S > 0 && B > 0 && K > 0 && N > 0, "linear_wgrad_steps: bad argument");
+    constexpr int NCH = 9;
+    if (B <= LW_B && K % 4 == 0 && xs % 4 == 0 && x_step % 4 == 0 && !(((uintptr_t)x | (uintptr_t)dW) & 15) &&
+        (size_t)S * NCH * LW_B * sizeof(float) <= 48 * 1024) {
+        const int kblocks = (K / 4 + LW_T - 1) / LW_T;
+        launch_k(linear_dw_steps_kernel<NCH>, dim3(kblocks, (N + NCH - 1) / NCH), dim3(LW_T), sizeof(float) * S * NCH * LW_B, stream, dy, dy_step, x,
+                 x_step, xs, dW, db, S, B, K, N);
+        return check_launch("linear_wgrad_steps");
+    }
+    for (int s = 0; s < S; ++s) {                   // shapes outside the fast kernel: the per-step path
+        launch_k(linear_bwd_dw_kernel, dim3((K + 255) / 256, N), dim3(256), 0, stream, dy + s * dy_step, x + s * x_step, xs, dW, db, B, K, N);
+        if (int e = check_launch("linear_wgrad_steps(dw)")) return e;
+    }
+    return PIVP_OK;
 }
 
 int pivp_relu_mask(const float* y, float* g, long n, void* stream) {

@@ -128,7 +128,7 @@ class Engine(object):
         ws["hid2"] = stack(Mr[2], 32)
         ws["hid4"] = stack(Mr[4], 64)
         ws["in3"] = stack(Mr[8], self.cs3)
-        ws["hid5"] = [A(Mr[8], 128) for _ in range(S)]
+        ws["hid5"] = stack(Mr[8], 128)                 # stacked over time: operand of the deferred kernel-Linear weight gradient
         ws["cat5"] = [A(Mr[4], 96) for _ in range(S)]
         ws["cat6"] = [A(Mr[2], 64) for _ in range(S)]
         ws["e6pre"] = [A(Mr[1], 64) for _ in range(S)]
@@ -177,7 +177,7 @@ class Engine(object):
         ws["d_hid2"] = A(Mr[2], 32)
         ws["d_enc0pre"] = stack(Mr[2], 32)
         if self.model_type == "CDNA":
-            ws["d_kern_raw"] = A(B, 25 * self.M)
+            ws["d_kern_raw"] = stack(B, 25 * self.M)   # kept per time step for the deferred kernel-Linear weight gradient
             nb = self.L.query("pivp_cdna_fused_bwd_workspace_bytes", B, H, W, self.M)
         elif self.model_type == "DNA":
             nb = self.L.query("pivp_dna_fused_bwd_workspace_bytes", B, H, W)
@@ -476,10 +476,10 @@ class Engine(object):
             # ---- fused transform backward
             if self.model_type == "CDNA":
                 L.call("pivp_cdna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
-                       _ptr(ws["kern_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_kern_raw"]),
+                       _ptr(ws["kern_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_kern_raw"][t]),
                        _ptr(d_prev), 0, B, H, W, self.M, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
-                L.call("pivp_linear_bwd", _ptr(ws["d_kern_raw"]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]),
-                       _ptr(ws["d_hid5"]), K5, 0, _ptr(g["model/cdna_kerns/W"]), _ptr(g["model/cdna_kerns/b"]), B, K5, 25 * self.M, s)
+                L.call("pivp_linear_bwd", _ptr(ws["d_kern_raw"][t]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]),
+                       _ptr(ws["d_hid5"]), K5, 0, 0, 0, B, K5, 25 * self.M, s)       # dx only; dW / db after the time loop
                 hid5_has_grad = True
             elif self.model_type == "DNA":
                 L.call("pivp_dna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
@@ -595,6 +595,10 @@ class Engine(object):
             S = T - 1
             first = lambda lst: lst[0]
             cin3 = 64 + self.sa
+            if self.model_type == "CDNA":              # kernel Linear 8192 -> 250: one pass over all steps instead of T-1 read-modify-writes of dW
+                NK = 25 * self.M
+                L.call("pivp_linear_wgrad_steps", _ptr(first(ws["d_kern_raw"])), B * NK, _ptr(first(ws["hid5"])), Mr[8] * 128, 128 * HW[8],
+                       _ptr(g["model/cdna_kerns/W"]), _ptr(g["model/cdna_kerns/b"]), S, B, 128 * HW[8], NK, s)
             self._conv_wgrad(View(first(ws["img_nhwc"]), 3, 0, 3), S * B, H, W, View(first(ws["d_enc0pre"]), 32, 0, 32), H // 2, W // 2, 5, 2, 2,
                              g["enc0/W"], g["enc0/b"])
             if self.tc is None:                # bf16 mode: tcgen05 weight-gradient GEMMs in tc.wgrad_all(), bias gradients from the hand-over
