@@ -277,6 +277,15 @@ int launch_fwd(const float* x, int x_cs, int x_co, int B, int H, int W, const fl
 int launch_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, const float* dy, int dy_cs, int dy_co, int Ho, int Wo, float* dw,
                  void* stream);
 }  // namespace img
+namespace pw {    // conv_pointwise.cu: 1x1 convolutions staged in shared memory (the implicit-GEMM kernels are latency chains at this size)
+bool supported(int C, int N, int KH, int KW, int stride, int pad);
+bool wgrad_supported(int C, int N, int KH, int KW, int stride, int pad);
+int launch_fwd(const float* x, int x_cs, int x_co, long M, int C, const float* w, const float* bias, int N, float* y, int y_cs, int y_co, int relu,
+               int accumulate, void* stream);
+int launch_dgrad(const float* dy, int dy_cs, int dy_co, long M, int N, const float* w, const float* bias, int C, float* dx, int dx_cs, int dx_co,
+                 int relu, int accumulate, void* stream);
+int launch_wgrad(const float* x, int x_cs, int x_co, long M, int C, const float* dy, int dy_cs, int dy_co, int N, float* dw, void* stream);
+}  // namespace pw
 static inline bool vec4_view(const void* p, int cs, int co) { return !((uintptr_t)p & 15) && cs % 4 == 0 && co % 4 == 0; }
 
 }  // namespace pivp
@@ -292,6 +301,8 @@ int pivp_conv2d_fwd(const float* x, int x_cs, int x_co, int B, int H, int W, int
     ConvGeom g{B, H, W, C, Ho, Wo, N, KH, KW, stride, pad};
     if (int e = check_geom(g)) return e;
     PIVP_REQUIRE(x_cs >= x_co + C && y_cs >= y_co + N, "conv2d_fwd: channel slice exceeds row stride");
+    if (pw::supported(C, N, KH, KW, stride, pad))
+        return pw::launch_fwd(x, x_cs, x_co, (long)B * H * W, C, w, bias, N, y, y_cs, y_co, relu, accumulate, stream);
     if (!accumulate && vec4_view(y, y_cs, y_co) && img::supported(H, W, C, Ho, Wo, N, KH, KW, stride, pad))
         return img::launch_fwd(x, x_cs, x_co, B, H, W, w, bias, y, y_cs, y_co, Ho, Wo, relu, stream);
     const long M = (long)B * Ho * Wo;
@@ -308,6 +319,8 @@ int pivp_conv2d_dgrad(const float* dy, int dy_cs, int dy_co, int B, int Ho, int 
     if (int e = check_geom(g)) return e;
     PIVP_REQUIRE(dy_cs >= dy_co + N && dx_cs >= dx_co + C, "conv2d_dgrad: channel slice exceeds row stride");
     const long M = (long)B * H * W;
+    if (pw::supported(C, N, KH, KW, stride, pad))
+        return pw::launch_dgrad(dy, dy_cs, dy_co, M, N, w, bias, C, dx, dx_cs, dx_co, relu, accumulate, stream);
     dim3 grid((unsigned)((M + BM - 1) / BM), (unsigned)((C + BN - 1) / BN));
     launch_k(conv_dgrad_kernel, dim3(grid), dim3(NT), 0, (cudaStream_t)stream, g, CView{dy, dy_cs, dy_co}, w, bias, View{dx, dx_cs, dx_co}, relu, accumulate);
     return check_launch("conv2d_dgrad");
@@ -327,7 +340,9 @@ int pivp_conv2d_wgrad(const float* x, int x_cs, int x_co, int B, int H, int W, i
     if (split < 1) split = 1;
     int pchunk = ((P + split - 1) / split + BK - 1) / BK * BK;
     split = (P + pchunk - 1) / pchunk;
-    if (vec4_view(dy, dy_cs, dy_co) && img::supported(H, W, C, Ho, Wo, N, KH, KW, stride, pad)) {
+    if (pw::wgrad_supported(C, N, KH, KW, stride, pad)) {
+        if (int e = pw::launch_wgrad(x, x_cs, x_co, (long)B * H * W, C, dy, dy_cs, dy_co, N, dw, stream)) return e;
+    } else if (vec4_view(dy, dy_cs, dy_co) && img::supported(H, W, C, Ho, Wo, N, KH, KW, stride, pad)) {
         if (int e = img::launch_wgrad(x, x_cs, x_co, B, H, W, dy, dy_cs, dy_co, Ho, Wo, dw, stream)) return e;
     } else {
         dim3 grid((unsigned)((N + BM - 1) / BM), (unsigned)((J + BN - 1) / BN), (unsigned)split);

@@ -215,28 +215,40 @@ static void launch_splitk_reduce(const float* part, float* out, long n, long str
 }
 
 // out[c] += sum_p src[p][c]  (bf16 in, fp32 accumulate): the ConvLSTM bias gradient over all time steps.
+// Thread = 8 channels (one 128-bit load per row), 256 threads = (C8 channel groups) x (256 / C8 row phases); four rows in flight.
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ src, int ld, long P, int C, long pchunk,
                                                           float* __restrict__ out) {
     pdl_enter();
-    __shared__ float red[8][66];
-    const int cp = threadIdx.x & 31, row = threadIdx.x >> 5;          // channel pair, row phase
-    const int c = blockIdx.x * 64 + 2 * cp;
+    __shared__ float red[256][9];
+    const int C8 = C >> 3, cg = threadIdx.x % C8, row = threadIdx.x / C8, rows = 256 / C8;
     const long p0 = (long)blockIdx.y * pchunk, p1 = min(P, p0 + pchunk);
-    float s0 = 0.f, s1 = 0.f;
-    if (c < C)
-        for (long p = p0 + row; p < p1; p += 8) {
-            const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(src + p * ld + c);
-            s0 += __low2float(v);
-            s1 += __high2float(v);
-        }
-    red[row][2 * cp] = s0;
-    red[row][2 * cp + 1] = s1;
-    __syncthreads();
-    if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < C) {
-        float t = 0.f;
+    float s[8];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) t += red[r][threadIdx.x];
-        atomicAdd(out + blockIdx.x * 64 + threadIdx.x, t);
+    for (int k = 0; k < 8; ++k) s[k] = 0.f;
+    auto add = [&](const uint4& u) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const float2 f = __bfloat1622float2(h[k]); s[2 * k] += f.x; s[2 * k + 1] += f.y; }
+    };
+    if (row < rows) {
+        long p = p0 + row;
+        for (; p + 3L * rows < p1; p += 4L * rows) {
+            uint4 u[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) u[j] = __ldg(reinterpret_cast<const uint4*>(src + (p + (long)j * rows) * ld + 8 * cg));
+#pragma unroll
+            for (int j = 0; j < 4; ++j) add(u[j]);
+        }
+        for (; p < p1; p += rows) add(__ldg(reinterpret_cast<const uint4*>(src + p * ld + 8 * cg)));
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) red[threadIdx.x][k] = (row < rows) ? s[k] : 0.f;
+    __syncthreads();
+    if (threadIdx.x < C) {                                        // channel c = 8 * cg + k: sum the row phases
+        const int g8 = threadIdx.x >> 3, k = threadIdx.x & 7;
+        float tot = 0.f;
+        for (int r = 0; r < rows; ++r) tot += red[r * C8 + g8][k];
+        atomicAdd(out + threadIdx.x, tot);
     }
 }
 
@@ -253,13 +265,21 @@ using namespace pivp;
 extern "C" {
 
 int pivp_tc_colsum_bf16(const void* src_bf16, int ld, long P, int C, float* out, void* stream) {
-    PIVP_REQUIRE(src_bf16 && out && P > 0 && C > 0 && (C % 2) == 0 && (ld % 2) == 0, "tc_colsum_bf16: bad argument (C and ld must be even)");
-    int splits = (int)((P + 511) / 512);
+    PIVP_REQUIRE(src_bf16 && out && P > 0 && C > 0 && C % 8 == 0 && C <= 2048 && ld % 8 == 0 && !((uintptr_t)src_bf16 & 15),
+                 "tc_colsum_bf16: bad argument (C and ld must be multiples of 8, C <= 2048, rows 16-byte aligned)");
+    // channel slabs of <= 256 channels (one CTA column each), row chunks over blockIdx.y
+    int slab = C;
+    while (slab > 256 || (256 % (slab / 8))) slab -= 8;          // largest slab whose channel groups divide the 256 threads
+    PIVP_REQUIRE(C % slab == 0, "tc_colsum_bf16: %d channels cannot be cut into equal slabs of <= 256", C);
+    int splits = (int)((P + 255) / 256);                          // enough CTAs to keep ~100 KB per SM in flight
     if (splits > 148 * 8) splits = 148 * 8;
     const long pchunk = (P + splits - 1) / splits;
-    dim3 grid((unsigned)((C + 63) / 64), (unsigned)splits);
-    launch_k(colsum_bf16_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, (const __nv_bfloat16*)src_bf16, ld, P, C, pchunk, out);
-    return check_launch("tc_colsum_bf16");
+    for (int c0 = 0; c0 < C; c0 += slab) {
+        launch_k(colsum_bf16_kernel, dim3(1, (unsigned)splits), dim3(256), 0, stream, (const __nv_bfloat16*)src_bf16 + c0, ld, P, slab, pchunk,
+                 out + c0);
+        if (int e = check_launch("tc_colsum_bf16")) return e;
+    }
+    return PIVP_OK;
 }
 
 static void wgrad_plan(int Cx, int Mrows, int ntaps_total, int kb_total, int* tpg, int* groups, int* splits, int* kbps) {

@@ -52,6 +52,9 @@ class TensorCorePlan(object):
         # layers whose maps the halo-patch kernel tiles (H % 16 == 0, W % 8 == 0): its epilogue also produces the LayerNorm statistics
         self.ln_fused = [(eng.H // lv) % 16 == 0 and (eng.W // lv) % 8 == 0 and ((eng.H // lv) * (eng.W // lv) * c) % 4096 == 0
                          for c, lv in zip(LSTM_SIZES, LSTM_LEVEL)]
+        # bf16 weight operands of the tap GEMMs live in ONE flat buffer filled by ONE gather launch per parameter update
+        self._wflat = torch.zeros(2 << 20, dtype=torch.bfloat16, device=dev)
+        self._wofs, self._widx = 0, []
         # ---- stride-2 Deconvolution2D layers enc4/enc5/enc6 (train_model.py:505-507) as 4 output phases each
         M8, M4, M2 = ws["Mr"][8], ws["Mr"][4], ws["Mr"][2]
         self.hid5_b = [torch.zeros(M8, 128, dtype=torch.bfloat16, device=dev) for _ in range(S)]
@@ -84,7 +87,20 @@ class TensorCorePlan(object):
             allt = torch.zeros(S, old[0].shape[0], old[0].shape[1], dtype=torch.bfloat16, device=dev)
             setattr(self, nm + "_all", allt)
             setattr(self, nm, [allt[t] for t in range(S)])
+        self._widx_all = torch.from_numpy(np.concatenate(self._widx)).to(dev)
         self.refresh_weights()
+
+    def _walloc(self, idx, shape):
+        """Carve a bf16 operand of `shape` out of the flat weight buffer; idx (int32, flat parameter offsets, -1 = zero) says how to fill it."""
+        idx = np.ascontiguousarray(idx, np.int32).reshape(-1)
+        n = idx.size
+        npad = (n + 63) // 64 * 64                       # 128-byte aligned operands (TMA global addresses)
+        if self._wofs + npad > self._wflat.numel():
+            raise PivpError("tensor-core weight buffer too small")
+        view = self._wflat[self._wofs:self._wofs + n].view(*shape)
+        self._widx.append(np.concatenate([idx, np.full(npad - n, -1, np.int32)]))
+        self._wofs += npad
+        return view
 
     def _plan_conv_s2_fwd(self, name, cin, cout, lv_in):
         """out[oy,ox][n] = sum_{ky,kx,c} W[n][ky][kx][c] in[2oy+ky-1, 2ox+kx-1][c]: on the space-to-depth input (pixel (y', x') of the half
@@ -108,7 +124,7 @@ class TensorCorePlan(object):
                 idx[n, tp, :cin] = base + (n * 9 + tp) * cin + c
         arr = lambda v: (ctypes.c_int * 9)(*v)
         return dict(cin=cin, cout=cout, cb=cb, lv=lv, dy=arr([q[0] for q in taps]), dx=arr([q[1] for q in taps]), co=arr([q[2] for q in taps]),
-                    idx=torch.from_numpy(idx.reshape(-1)).to(dev), wt=torch.empty(cout, 9 * cb, dtype=torch.bfloat16, device=dev),
+                    wt=self._walloc(idx, (cout, 9 * cb)),
                     xs=torch.zeros(self.S, M, 4 * cb, dtype=torch.bfloat16, device=dev))      # kept per time step for the weight gradient
 
     def conv_s2_fwd(self, name, t, x_f32, x_cs, out, out_cs, out_bf16, ob_cs):
@@ -147,8 +163,7 @@ class TensorCorePlan(object):
         if (M // 128) * (cin // bn) < 64 and cin % 64 == 0:
             bn = 64
         return dict(cin=cin, cout=cout, cb=cb, lv=lv, bn=bn, dy=arr([t[0] for t in taps]), dx=arr([t[1] for t in taps]),
-                    co=arr([t[2] for t in taps]), idx=torch.from_numpy(idx.reshape(-1)).to(dev),
-                    wt=torch.empty(cin, 9 * cb, dtype=torch.bfloat16, device=dev),
+                    co=arr([t[2] for t in taps]), wt=self._walloc(idx, (cin, 9 * cb)),
                     dys=torch.zeros(S, M, 4 * cb, dtype=torch.bfloat16, device=dev))
 
     def _plan_deconv(self, name, cin, cout, lv):
@@ -170,8 +185,7 @@ class TensorCorePlan(object):
                         idx[co, t, :cin] = base + ((ci * 3 + ky) * 3 + kx) * cout + co
                 arr = lambda v: (ctypes.c_int * len(taps))(*v)
                 phases.append(dict(a=a, b=b, n=len(taps), dy=arr([t[0] for t in taps]), dx=arr([t[1] for t in taps]),
-                                   co=arr([0] * len(taps)), idx=torch.from_numpy(idx.reshape(-1)).to(dev),
-                                   wt=torch.empty(cout, len(taps) * kc, dtype=torch.bfloat16, device=dev)))
+                                   co=arr([0] * len(taps)), wt=self._walloc(idx, (cout, len(taps) * kc))))
         bn = cout if cout <= 128 else 128
         if 4 * (self.ws["Mr"][lv] // 128) * (cout // bn) < 120 and cout % 64 == 0:      # the four phases share one launch
             bn = 64
@@ -187,11 +201,8 @@ class TensorCorePlan(object):
         for li, (cin, c) in enumerate(zip(LSTM_IN, LSTM_SIZES)):
             e.L.call("pivp_tc_prep_weights", _ptr(e.p["lstm%d/conv/W" % (li + 1)]), 4 * c, cin + c, self.Kpad[li],
                      _ptr(self.Wf[li]), _ptr(self.Wd[li]), e._s())
-        for d in getattr(self, "dec", {}).values():
-            for ph in d["phases"]:
-                e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(ph["idx"]), ph["idx"].numel(), _ptr(ph["wt"]), e._s())
-        for d in list(getattr(self, "dbw", {}).values()) + list(getattr(self, "s2f", {}).values()):
-            e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(d["idx"]), d["idx"].numel(), _ptr(d["wt"]), e._s())
+        if getattr(self, "_widx_all", None) is not None:
+            e.L.call("pivp_gather_bf16", _ptr(e.flat_p), _ptr(self._widx_all), self._wofs, _ptr(self._wflat), e._s())
 
     def deconv_bwd_data(self, name, t, dy_f32, out, accumulate):
         """dY (fp32, big grid, dense rows of cout) -> space-to-depth bf16 (kept for wgrad) -> d_in (fp32, dense rows of cin)."""
