@@ -345,17 +345,18 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
             mbar_wait(smem_u32(accum_full), 0);
             tc_fence_after();
             if (warp == 2) HALO_STAMP(4);
-            // plain epilogue: the two warps of a lane quarter split the columns
+            // plain epilogue: the two warps of a lane quarter split the columns; rows are staged in the dead operand ring and written
+            // out whole (tc_epilogue_staged).  Split-K partials (blockIdx.z > 0) carry no bias.
             const int hc = (g.BN / 2 + 7) / 8 * 8;
             const int cbeg = half ? hc : 0, cend = half ? g.BN : hc;
-            if (cend > cbeg) {
-                if (blockIdx.z == 0) {
-                    tc_epilogue_row(ep, trow + (uint32_t)cbeg, m, m, n0 + cbeg, cend - cbeg, n_tile, bias_s + cbeg);
-                } else {                                   // split-K partial: the bias belongs to split 0
-                    TcEpilogue epz = ep;
-                    epz.bias = nullptr;
-                    tc_epilogue_row(epz, trow + (uint32_t)cbeg, m, m, n0 + cbeg, cend - cbeg, n_tile, bias_s + cbeg);
-                }
+            TcEpilogue epz = ep;
+            if (blockIdx.z != 0) epz.bias = nullptr;
+            const size_t stage_floats = (size_t)128 * (g.BN + 4) + 256;           // tile + the 128-entry output-row table
+            if ((size_t)MS * stage_floats * sizeof(float) <= (size_t)NP * pbuf_bytes + (size_t)g.stages * b_bytes) {
+                float* stage = reinterpret_cast<float*>(smem) + (size_t)sub * stage_floats;
+                tc_epilogue_staged(epz, trow, stage, row, m, cbeg, cend, n0, g.BN, bias_s, (ew & 7) * 32 + lane, 256, 1 + sub);
+            } else if (cend > cbeg) {                          // two wide tiles do not fit the dead operand area: row stores
+                tc_epilogue_row(epz, trow + (uint32_t)cbeg, m, m, n0 + cbeg, cend - cbeg, n_tile, bias_s + cbeg);
             }
         }
         tc_fence_before();

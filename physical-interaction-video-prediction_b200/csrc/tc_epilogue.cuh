@@ -44,6 +44,60 @@ __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
     return pk;
 }
 
+// Plain (mode 0) epilogue, staged: tcgen05.ld hands every thread one accumulator ROW, but the output is row-major, so storing
+// straight from registers writes 16-byte pieces of 32 different rows per instruction.  The rows go through shared memory instead
+// (`stage`: [128][NP] floats, NP = BN + 4: conflict-free for 128-bit accesses; the operand ring is dead once the accumulator is complete)
+// and leave as whole rows: consecutive lanes write consecutive 16 bytes.  `nthr` threads (thread index `t`, named barrier `bar_id`) own
+// the tile; this thread converts columns [cbeg, cend) of accumulator row `row`, whose output row is `orow` (kept in a 128-entry table
+// behind the staged tile, so the write-out loop does no index arithmetic beyond one 32-bit division).  Needs 128*(BN+4)*4 + 1024 bytes.
+__device__ __forceinline__ void tc_epilogue_staged(const TcEpilogue& ep, uint32_t trow, float* stage, int row, long orow, int cbeg, int cend, int n0,
+                                                   int BN, const float* bias_s, int t, int nthr, int bar_id) {
+    const int NP = BN + 4;
+    long* rowmap = reinterpret_cast<long*>(stage + 128 * NP);
+    rowmap[row] = orow;
+    for (int c0 = cbeg; c0 < cend; c0 += 8) {
+        float v[8];
+        tc_ld8(trow + (uint32_t)c0, v);
+        tc_ld_wait();
+        if (ep.bias) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] += bias_s[c0 + i];
+        }
+        if (ep.relu) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+        }
+        float* s = stage + row * NP + c0;
+        *reinterpret_cast<float4*>(s) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(s + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+    asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(nthr) : "memory");
+    const int q4 = BN >> 2, total = 128 * q4;
+    for (int e = t; e < total; e += nthr) {
+        const int r = e / q4, c = 4 * (e - r * q4);
+        float4 v = *reinterpret_cast<const float4*>(stage + r * NP + c);
+        const long orow = rowmap[r];
+        if (ep.out) {
+            float* dst = ep.out + orow * ep.out_cs + ep.out_co + n0 + c;
+            if (ep.atomic) {
+                atomicAdd(reinterpret_cast<float4*>(dst), v);
+            } else {
+                if (ep.accumulate) {
+                    const float4 o = *reinterpret_cast<const float4*>(dst);
+                    v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+                }
+                *reinterpret_cast<float4*>(dst) = v;
+            }
+        }
+        if (ep.out_bf16) {
+            __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+            *reinterpret_cast<uint2*>(ep.out_bf16 + orow * ep.ob_cs + ep.ob_co + n0 + c) = pk;
+        }
+    }
+}
+
 // trow: TMEM address of this thread's lane at the tile's first column; n0 = first output channel of the tile; bias_s: BN floats in smem
 __device__ __forceinline__ void tc_epilogue_row(const TcEpilogue& ep, uint32_t trow, long m, long orow, int n0, int BN, int n_tile,
                                                 const float* bias_s) {
