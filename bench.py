@@ -40,12 +40,12 @@ class ClockSampler(object):
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.t0 = gpu_index, None, [], None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "25"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
@@ -53,16 +53,24 @@ class ClockSampler(object):
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.monotonic(), line.strip()))
+
+    def mark(self):
+        """Start of the timed region: the process is started earlier (before the warm-up), because nvidia-smi needs a few hundred ms
+        to print its first line and a short timed region would otherwise end without a sample."""
+        self.t0 = time.monotonic()
 
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        t1 = time.monotonic()
+        time.sleep(0.05)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
+        t0 = self.t0 if self.t0 is not None else 0.0
+        window = [ln for ts, ln in self.lines if t0 <= ts <= t1 + 0.03]           # a line printed just after the region was sampled inside it
+        for ln in window:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -179,13 +187,14 @@ def main():
         if world > 1:
             torch.distributed.barrier()
 
+    sampler = ClockSampler(local)
+    sampler.start()                         # running before the warm-up; only lines inside the timed region are used (mark())
     for _ in range(W_):
         step(it); it += 1
     torch.cuda.synchronize()
     # ---------------- timed region: inputs resident, device time, max over ranks
-    sampler = ClockSampler(local)
     barrier(); torch.cuda.synchronize()
-    sampler.start()
+    sampler.mark()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = pk.lib().query("pivp_launch_count")
     ev0.record()
