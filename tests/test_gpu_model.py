@@ -190,3 +190,35 @@ def test_data_parallel_shards_equal_full_batch(pk):
     assert abs(0.5 * (losses[0] + losses[1]) - lf) < 1e-5 * lf
     den = float(gfull.abs().max())
     assert float((acc - gfull).abs().max()) / den < 1e-4
+
+
+@pytest.mark.parametrize("compute", ["f32", "bf16"])
+def test_programmatic_dependent_launch_changes_nothing(pk, compute):
+    """Every kernel is launched with the programmatic-stream-serialization attribute and waits (griddepcontrol.wait) for its
+    predecessor before its first global access: a step launched that way must equal the plainly launched step -- eagerly and as a
+    captured CUDA graph -- up to the summation order of the atomics both variants share."""
+    cfg = OM.Config("CDNA", 10, schedsamp_k=900.0, height=64, width=64)
+    params = perturbed(cfg)
+    B, T = 2, 4
+    batch = [torch.from_numpy(a) for a in OM.concat_examples(OM.synthetic_sequences(B, T, cfg))]
+    L = pk.lib()
+    res = {}
+    try:
+        for pdl in (0, 1):
+            L.call("pivp_set_pdl", pdl)
+            m = pk.Model(10, is_cdna=True, scheduled_sampling_k=900.0, prefix="q", height=64, width=64, compute=compute)
+            m.load_params(params)
+            opt = pk.Adam().setup(m)
+            step = pk.TrainStep(m, opt, B, T, graph=True)
+            step.load_batch(*batch)
+            np.random.seed(5)
+            losses = [float(step(6000 + i)) for i in range(3)]            # three Adam updates through the captured graph
+            torch.cuda.synchronize()
+            res[pdl] = (losses, m.engine.flat_p.clone(), m.engine.flat_g.clone())
+    finally:
+        L.call("pivp_set_pdl", 1)
+    (l0, p0, g0), (l1, p1, g1) = res[0], res[1]
+    tol = 1e-5 if compute == "f32" else 2e-3          # bf16: an atomics-order ulp can flip a bf16 rounding downstream
+    assert max(abs(a - b) for a, b in zip(l0, l1)) <= tol * abs(l0[0])
+    assert float((g1 - g0).abs().max()) <= 10 * tol * float(g0.abs().max())
+    assert float((p1 - p0).abs().max()) <= 10 * tol * float(p0.abs().max())
