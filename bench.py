@@ -216,8 +216,10 @@ def main():
     # ---------------- end to end: H2D of the batch from pinned memory + step + D2H loss read, every step
     barrier(); torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step.load_batch(*host)
+    # the public data path: BatchPrefetcher copies batch k+1 from pinned host memory while step k computes (every batch is still
+    # copied host -> device inside this timed region), TrainStep runs the step, float(loss) is the device -> host read
+    pf = pk.BatchPrefetcher(step, (host for _ in range(args.steps)))
+    while pf.load_next():
         loss = float(step(it)); it += 1
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0

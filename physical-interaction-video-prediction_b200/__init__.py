@@ -20,4 +20,7 @@ def __getattr__(name):
     if name == "TrainStep":
         from .train import TrainStep
         return TrainStep
+    if name == "BatchPrefetcher":
+        from .train import BatchPrefetcher
+        return BatchPrefetcher
     raise AttributeError(name)

@@ -112,3 +112,49 @@ class TrainStep(object):
                 self._update()
         self.launches_per_step = lib().query("pivp_launch_count") - n0
         self.graph = (ga, gb)
+
+
+class BatchPrefetcher(object):
+    """Double-buffered host -> device staging in front of a TrainStep (the reference copies the batch synchronously at
+    train_model.py:950, `xp.array`).  While step k computes, the batch of step k+1 travels from pinned host memory into a device
+    staging buffer on a side stream; `load_next()` waits for that copy, moves it into the step's static input buffers with a
+    stream-ordered device-to-device copy and starts the copy of the following batch.
+
+        pf = BatchPrefetcher(step, batches)        # batches: iterable of (images, actions, states) pinned host tensors
+        while pf.load_next():
+            loss = step(iter_num)"""
+
+    def __init__(self, step, batches):
+        self.step = step
+        dev = step.images.device
+        self.stream = torch.cuda.Stream(device=dev)
+        self.bufs = [tuple(torch.empty_like(x) for x in (step.images, step.actions, step.states)) for _ in range(2)]
+        self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.ready = [False, False]
+        self.it = iter(batches)
+        self.k = 0
+        self._issue(0)
+
+    def _issue(self, slot):
+        batch = next(self.it, None)
+        self.ready[slot] = batch is not None
+        if batch is None:
+            return
+        cur = torch.cuda.current_stream(self.stream.device)
+        self.stream.wait_stream(cur)               # the device-to-device copy that last read this slot is already queued on `cur`
+        with torch.cuda.stream(self.stream):
+            for dst, src in zip(self.bufs[slot], batch):
+                dst.copy_(src, non_blocking=True)
+            self.events[slot].record(self.stream)
+
+    def load_next(self):
+        """Put the next batch into the step's input buffers; False when the iterable is exhausted."""
+        slot = self.k & 1
+        if not self.ready[slot]:
+            return False
+        torch.cuda.current_stream(self.stream.device).wait_event(self.events[slot])
+        self.step.load_batch(*self.bufs[slot])
+        self.k += 1
+        self._issue(self.k & 1)
+        return True
+

@@ -222,3 +222,23 @@ def test_programmatic_dependent_launch_changes_nothing(pk, compute):
     assert max(abs(a - b) for a, b in zip(l0, l1)) <= tol * abs(l0[0])
     assert float((g1 - g0).abs().max()) <= 10 * tol * float(g0.abs().max())
     assert float((p1 - p0).abs().max()) <= 10 * tol * float(p0.abs().max())
+
+
+def test_batch_prefetcher_delivers_batches_in_order(pk):
+    """BatchPrefetcher: the step's static input buffers hold batch k when load_next() has returned for the k-th time (the copy of
+    batch k+1 is already in flight on the side stream), and the iterable's end is reported."""
+    B, T, H, W = 2, 3, 64, 64
+    m = pk.Model(10, is_cdna=True, scheduled_sampling_k=900.0, prefix="pf", height=H, width=W)
+    opt = pk.Adam().setup(m)
+    step = pk.TrainStep(m, opt, B, T, graph=False)
+    rs = np.random.RandomState(0)
+    batches = [(torch.from_numpy(rs.rand(T, B, 3, H, W).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rs.rand(T, B, 5).astype(np.float32)).pin_memory(),
+                torch.from_numpy(rs.rand(T, B, 5).astype(np.float32)).pin_memory()) for _ in range(5)]
+    pf = pk.BatchPrefetcher(step, batches)
+    for k in range(5):
+        assert pf.load_next()
+        torch.cuda.synchronize()
+        assert torch.equal(step.images.cpu(), batches[k][0]) and torch.equal(step.actions.cpu(), batches[k][1])
+        assert torch.equal(step.states.cpu(), batches[k][2])
+    assert not pf.load_next()
