@@ -355,6 +355,9 @@ def main():
                 tm = cdna_time(Bc, max(2, int(600e6 // per) + 1))
                 cdna_op["b%d" % Bc] = {d: {"avg_launch_us": tm[d] * 1e6, "achieved": cdna_op["bytes_per_sample"][d] * Bc / tm[d] / 1e9,
                                            "frac": cdna_op["bytes_per_sample"][d] * Bc / tm[d] / 1e9 / pk_["hbm_gbs"]} for d in ("fwd", "bwd")}
+            tw = cdna_time(B, 1)              # warm: one input set, resident in L2 after the first launch (what the op sees inside the step)
+            cdna_op["b%d_warm_l2" % B] = {d: {"avg_launch_us": tw[d] * 1e6, "achieved": cdna_op["bytes_per_sample"][d] * B / tw[d] / 1e9}
+                                          for d in ("fwd", "bwd")}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
