@@ -35,6 +35,17 @@ def test_library_exports_every_declared_symbol(pk):
     assert L.query("pivp_cdna_fused_bwd_workspace_bytes", 32, 64, 64, 10) == 4 * (32 * 11 * 4096 + 32 * 250)
 
 
+def test_every_entry_point_is_documented():
+    """INTEGRATION.md section D names every `pivp_*` prototype of include/pivp.h with the reference lines it replaces."""
+    import re
+    header = open(os.path.join(ROOT, "include", "pivp.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = sorted(set(re.findall(r"\b(pivp_[a-z0-9_]+)\s*\(", header)))
+    assert len(names) > 50
+    missing = [n for n in names if ("`%s`" % n) not in doc]
+    assert not missing, missing
+
+
 def test_symbols_are_sm100a_only(pk):
     out = subprocess.run(["cuobjdump", "--list-elf", pk.LIBPATH], stdout=subprocess.PIPE, stderr=subprocess.STDOUT).stdout.decode()
     archs = set(l.split(".")[-2] for l in out.splitlines() if l.strip().endswith(".cubin"))
