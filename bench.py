@@ -226,7 +226,7 @@ def main():
     except RuntimeError as exc:               # keep the line valid if the side-stream path is unavailable: synchronous copy, and say so
         sys.stderr.write("bench: BatchPrefetcher failed (%s); timing the synchronous copy path\n" % exc)
         e2e_path = "load_batch (synchronous H2D)"
-        torch.cuda.synchronize(); barrier()
+        torch.cuda.synchronize()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step.load_batch(*host)
