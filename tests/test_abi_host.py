@@ -166,3 +166,12 @@ def test_data_parallel_world2_gloo(pk, tmp_path):
     flat_ref = np.concatenate([ref["grads"][k].reshape(-1) for k in sorted(ref["grads"])])
     got = np.load(out + ".grads.npy")
     assert np.abs(got - flat_ref).max() <= 1e-9 * np.abs(flat_ref).max()
+
+
+def test_profile_tooling_reads_the_committed_launch_list():
+    """scripts/summarize_launches.py turns the committed ncu launch list into the per-kernel table of profiles/ (tooling must not rot)."""
+    src = os.path.join(ROOT, "profiles", "r01_launches_step_session3.csv")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "summarize_launches.py"), src, "3", "title", "cmd"],
+                         stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    assert "conv5x5_halo_tc_kernel" in out.stdout and "| kernel | launches / step |" in out.stdout
