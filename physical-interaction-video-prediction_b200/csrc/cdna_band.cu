@@ -604,11 +604,10 @@ __global__ void __launch_bounds__(128) cdna_band_kern_bwd_kernel(const float* __
 
 template <typename K>
 static int allow_smem(K kernel, size_t bytes) {
-    static size_t granted = 48 * 1024;
-    if (bytes > granted) {
+    static PerDeviceOnce granted;              // per device and per kernel instantiation
+    if (bytes > 48 * 1024 && granted.need(bytes)) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e)); return PIVP_ECUDA; }
-        granted = bytes;
     }
     return PIVP_OK;
 }

@@ -66,6 +66,20 @@ static inline int check_launch(const char* what) {
     return PIVP_OK;
 }
 
+// cudaFuncSetAttribute (the > 48 KB dynamic shared-memory opt-in) is PER DEVICE: a process that drives several GPUs must apply it on each
+// one.  `need()` is true the first time it is asked on the calling thread's current device (and for a larger size than granted before).
+struct PerDeviceOnce {
+    size_t granted[64] = {};
+    bool need(size_t bytes = 1) {
+        int d = 0;
+        cudaGetDevice(&d);
+        d &= 63;
+        if (bytes <= granted[d]) return false;
+        granted[d] = bytes;
+        return true;
+    }
+};
+
 #define PIVP_REQUIRE(cond, ...)                  \
     do {                                         \
         if (!(cond)) {                           \

@@ -159,11 +159,10 @@ static size_t rows_smem(int K, int J) { return sizeof(float) * ((size_t)ROWS * (
 
 int launch_fwd(const float* x, int x_cs, int x_co, long M, int C, const float* w, const float* bias, int N, float* y, int y_cs, int y_co, int relu,
                int accumulate, void* stream) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaFuncSetAttribute(pw_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(pw_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
     }
     launch_k(pw_rows_kernel<false>, dim3((unsigned)((M + ROWS - 1) / ROWS)), dim3(T), rows_smem(C, N), stream, CView{x, x_cs, x_co}, w, bias,
              View{y, y_cs, y_co}, M, C, N, relu, accumulate);
@@ -172,11 +171,10 @@ int launch_fwd(const float* x, int x_cs, int x_co, long M, int C, const float* w
 
 int launch_dgrad(const float* dy, int dy_cs, int dy_co, long M, int N, const float* w, const float* bias, int C, float* dx, int dx_cs, int dx_co,
                  int relu, int accumulate, void* stream) {
-    static bool attr = false;
-    if (!attr) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaFuncSetAttribute(pw_rows_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         cudaFuncSetAttribute(pw_rows_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
     }
     launch_k(pw_rows_kernel<true>, dim3((unsigned)((M + ROWS - 1) / ROWS)), dim3(T), rows_smem(N, C), stream, CView{dy, dy_cs, dy_co}, w, bias,
              View{dx, dx_cs, dx_co}, M, N, C, relu, accumulate);
@@ -187,8 +185,8 @@ bool wgrad_supported(int C, int N, int KH, int KW, int stride, int pad) { return
 
 int launch_wgrad(const float* x, int x_cs, int x_co, long M, int C, const float* dy, int dy_cs, int dy_co, int N, float* dw, void* stream) {
     const size_t smem = sizeof(float) * ((size_t)WROWS * ((C + 3) & ~3) + (size_t)WROWS * (N | 1));
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024); attr = true; }
+    static PerDeviceOnce attr;
+    if (attr.need()) cudaFuncSetAttribute(pw_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
     launch_k(pw_wgrad_kernel, dim3((unsigned)((M + WROWS - 1) / WROWS)), dim3(T), smem, stream, CView{x, x_cs, x_co}, CView{dy, dy_cs, dy_co}, dw, M, C, N);
     return check_launch("conv2d_wgrad(1x1)");
 }

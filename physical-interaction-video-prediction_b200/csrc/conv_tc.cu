@@ -266,11 +266,10 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
         if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B%d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
     }
     const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)BN * 4;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;            // the opt-in is per device
+    if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
-        attr_set = true;
     }
     const long M = (long)B * H * W;
     dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN), (unsigned)nph);

@@ -372,11 +372,10 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 template <int MS, int NP>
 static int launch_ms_np(const CUtensorMap& map_a, const CUtensorMap& map_b, const Geom& g, const TcEpilogue& ep, int tiles, int splits, size_t smem,
                         void* stream, const char* who) {
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;            // the opt-in is per device
+    if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv5x5_halo_tc_kernel<MS, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         if (e != cudaSuccess) { set_error("%s(halo): cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
-        attr_set = true;
     }
     dim3 grid((unsigned)(tiles / MS), (unsigned)(g.N / g.BN), (unsigned)splits);
     launch_k(conv5x5_halo_tc_kernel<MS, NP>, grid, dim3(64 + 256 * MS), smem, stream, map_a, map_b, g, ep);

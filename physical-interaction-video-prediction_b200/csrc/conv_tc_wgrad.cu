@@ -360,11 +360,10 @@ static int launch_wgrad(const void* dg_bf16, int dg_cs, const void* xh_bf16, int
         if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B) failed (%d)", who, (int)r); return PIVP_ECUDA; }
     }
     const size_t smem = 1024 + (size_t)WG_ASTAGES * 16384 + (size_t)bst * chunks * 8192 + (2 * WG_ASTAGES + 2 * bst + 1) * 8 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;            // the opt-in is per device
+    if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv5x5_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
-        attr_set = true;
     }
     dim3 grid((unsigned)(g.Mrows / 128), (unsigned)groups, (unsigned)splits);
     launch_k(conv5x5_wgrad_tc_kernel, dim3(grid), dim3(WG_THREADS), smem, (cudaStream_t)stream, map_a, map_b, g, (float*)workspace);

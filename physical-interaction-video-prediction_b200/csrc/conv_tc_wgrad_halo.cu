@@ -206,11 +206,10 @@ int launch_wgrad5x5_halo(const void* dg_bf16, int dg_cs, const void* xh_bf16, in
         if (r != CUDA_SUCCESS) { set_error("%s(halo): cuTensorMapEncodeTiled(B) failed (%d)", who, (int)r); return PIVP_ECUDA; }
     }
     const size_t smem = 1024 + (size_t)STAGES * STAGE + (2 * STAGES + 1) * 8 + 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;            // the opt-in is per device
+    if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(wgrad5x5_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
         if (e != cudaSuccess) { set_error("%s(halo): cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
-        attr_set = true;
     }
     dim3 grid((unsigned)(g.Mrows / 128), (unsigned)(g.chunks * g.groups), (unsigned)splits);
     launch_k(wgrad5x5_halo_kernel, dim3(grid), dim3(THREADS), smem, (cudaStream_t)stream, map_a, map_b, g, part);

@@ -459,11 +459,10 @@ static int make_band(int H, int W, int M1, int extra_rows, Band* bd) {
 // capture -- issue no attribute call.  Every kernel in this file has a distinct signature, hence a distinct instantiation.
 template <typename K>
 static int allow_smem(K kernel, size_t bytes) {
-    static size_t granted = 48 * 1024;
-    if (bytes > granted) {
+    static PerDeviceOnce granted;              // per device and per kernel instantiation
+    if (bytes > 48 * 1024 && granted.need(bytes)) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
         if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem=%zu): %s", bytes, cudaGetErrorString(e)); return PIVP_ECUDA; }
-        granted = bytes;
     }
     return PIVP_OK;
 }

@@ -265,11 +265,10 @@ int pivp_heads_bwd(const float* x, int x_cs, int x_co, const float* W, const flo
     if (grid > ntiles) grid = ntiles;
     const int NB = ((NH + 1) / 2 + 3) / 4 * 4;
     const size_t smem = sizeof(float) * ((size_t)hd::TP * hd::XP + (size_t)hd::TP * 2 * NB + (size_t)NH * hd::TP + (size_t)NH * hd::C);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr_once;            // the opt-in is per device
+    if (attr_once.need()) {
         cudaFuncSetAttribute(hd::heads_bwd_kernel<14>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
         cudaFuncSetAttribute(hd::heads_bwd_kernel<27>, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
-        attr_set = true;
     }
     if (NH == 14) launch_k(hd::heads_bwd_kernel<14>, dim3(grid), dim3(hd::TP), smem, (cudaStream_t)stream, x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);
     else if (NH == 27) launch_k(hd::heads_bwd_kernel<27>, dim3(grid), dim3(hd::TP), smem, (cudaStream_t)stream, x, x_cs, x_co, W, dy_a, Na, dy_b, dx, dx_cs, dx_co, dW, db, M, HW, ntiles);

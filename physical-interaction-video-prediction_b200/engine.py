@@ -148,8 +148,17 @@ class Engine(object):
             ws["stp_s"] = [A(B, 100) for _ in range(S)]
             ws["theta_raw"] = [A(B, 6) for _ in range(S)]
         ws["take"] = torch.zeros(S, B, dtype=torch.int32, device=self.dev)
-        ws["take_host"] = torch.zeros(S, B, dtype=torch.int32).pin_memory()
+        # Per-step host <-> device hand-over goes through RINGS of pinned slots, one slot per step in flight, each guarded by an event:
+        # the scheduled-sampling select travels host -> device (a stream-ordered copy in front of the step, NOT a node of the captured
+        # graph, so the host may write step k+1's select while step k still runs) and the loss sums travel device -> host behind the
+        # step (so every loss handle is bound to the numbers of ITS step, train_model.py:951-956).
+        ws["take_host"] = torch.zeros(self.RING, S, B, dtype=torch.int32).pin_memory()
+        ws["take_event"] = [None] * self.RING
         ws["loss_slots"] = A(2 * S, zero=True)
+        ws["loss_host"] = torch.zeros(self.RING, 2 * S, dtype=torch.float32).pin_memory()
+        ws["loss_event"] = [None] * self.RING
+        ws["loss_owner"] = [None] * self.RING          # weak reference to the report that reads slot i (materialised before the slot is reused)
+        ws["step_no"] = 0
         # ---- backward temporaries
         ws["dxh"] = [A(Mr[lv], cin + c) for cin, c, lv in zip(LSTM_IN, LSTM_SIZES, LSTM_LEVEL)]
         ws["dln"] = [A(Mr[lv], c) for c, lv in zip(LSTM_SIZES, LSTM_LEVEL)]
@@ -291,9 +300,49 @@ class Engine(object):
             self._conv_dgrad(dG, B, h, w, self.p[name + "/W"], None, 5, 1, 2, View(dxh, cin + C, 0, cin + C), h, w)
 
     # ------------------------------------------------------------------ forward
+    RING = 4                                            # steps that may be in flight between the host and the device
+
     def stage_schedule(self, take_gt):
-        """Host part of a step: put the scheduled-sampling select (int32 (T-1,B)) into the pinned staging buffer."""
-        self.ws["take_host"].copy_(torch.from_numpy(np.ascontiguousarray(take_gt, dtype=np.int32)))
+        """Host part of a step: put the scheduled-sampling select (int32 (T-1,B)) into the next pinned ring slot and queue its copy
+        into the device buffer the step reads, on the current stream.  The slot is reused RING steps later, after the event recorded
+        behind its copy has fired, so a caller that does not synchronise every step can never overwrite a select that is still to be read."""
+        ws = self.ws
+        slot = ws["step_no"] % self.RING
+        ev = ws["take_event"][slot]
+        if ev is not None:
+            ev.synchronize()
+        else:
+            ev = ws["take_event"][slot] = torch.cuda.Event()
+        ws["take_host"][slot].copy_(torch.from_numpy(np.ascontiguousarray(take_gt, dtype=np.int32)))
+        ws["take"].copy_(ws["take_host"][slot], non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.dev))
+
+    def snapshot_loss(self, owner=None):
+        """Device -> host copy of this step's loss sums into a pinned ring slot (stream-ordered behind the step, no synchronisation here).
+        Returns a reader ``() -> (loss, psnr_all, recon_costs)`` bound to THIS step's numbers: it waits for the slot's event only."""
+        import weakref
+        ws = self.ws
+        slot = ws["step_no"] % self.RING
+        ws["step_no"] += 1
+        old = ws["loss_owner"][slot]
+        old = old() if old is not None else None
+        if old is not None:
+            old()                                       # a report RING steps old that nobody read yet: materialise it before its slot is reused
+        ev = ws["loss_event"][slot]
+        if ev is None:
+            ev = ws["loss_event"][slot] = torch.cuda.Event()
+        ws["loss_host"][slot].copy_(ws["loss_slots"], non_blocking=True)
+        ev.record(torch.cuda.current_stream(self.dev))
+        T, B = self.T, self.B
+        cache = {}
+
+        def read():
+            if not cache:
+                ev.synchronize()
+                cache["v"] = self.loss_values(ws["loss_host"][slot].numpy().copy(), T, B)
+            return cache["v"]
+        ws["loss_owner"][slot] = weakref.ref(read)
+        return read
 
     def forward(self, images, actions, states, take_gt=None, feedself=True):
         """images (T,B,3,H,W), actions/states (T,B,5) fp32 CUDA tensors.  ``take_gt``: int32 (T-1,B) host array with the
@@ -313,8 +362,6 @@ class Engine(object):
         HW, Mr = ws["HW"], ws["Mr"]
         self.feedself = bool(feedself)
         self.images, self.states = images, states
-        if not feedself:
-            ws["take"].copy_(ws["take_host"], non_blocking=True)
         ws["cur"][0].copy_(states[0])
         ws["loss_slots"].zero_()
         self.prev = []
@@ -441,23 +488,34 @@ class Engine(object):
         self.T, self.B = T, B
         return ws["gen"]
 
-    def loss_values(self):
-        """Host-side finish of train_model.py:739-758 (forces a D2H sync, like ref:955-956).  Returns (loss, psnr_all, recon)."""
-        ws, T, B = self.ws, self.T, self.B
-        slots = ws["loss_slots"].cpu().numpy()
+    def loss_values(self, slots=None, T=None, B=None):
+        """Host-side finish of train_model.py:739-758.  ``slots``: the step's loss sums on the host (snapshot_loss); None reads the
+        device buffer directly (a D2H sync, like ref:955-956).  Returns (loss, psnr_all, recon_costs, state_costs)."""
+        ws = self.ws
+        T, B = (self.T if T is None else T), (self.B if B is None else B)
+        if slots is None:
+            slots = ws["loss_slots"].cpu().numpy()
         n_img, n_sta = np.float32(B * 3 * self.H * self.W), np.float32(B * 5)
-        loss, psnr, recon = np.float32(0), 0.0, []
+        loss, psnr, recon, state = np.float32(0), 0.0, [], []
         for t in range(self.ctx - 1, T - 1):
             c = np.float32(slots[t]) / n_img
             recon.append(float(c))
-            psnr += 10.0 * math.log(1.0 / float(c)) / math.log(10.0)
+            # ref:124-134: 10 log10(1 / MSE); an exact match (MSE == 0) is +inf there too (NumPy division), not an exception
+            psnr += 10.0 * math.log(1.0 / float(c)) / math.log(10.0) if c > 0 else float("inf")
             loss = np.float32(loss + c)
         for t in range(self.ctx - 1, T - 1):
-            loss = np.float32(loss + np.float32(slots[T - 1 + t]) / n_sta * np.float32(1e-4))
+            sc = np.float32(slots[T - 1 + t]) / n_sta * np.float32(1e-4)
+            state.append(float(sc))
+            loss = np.float32(loss + sc)
         loss = np.float32(loss / np.float32(T - self.ctx))
-        return float(loss), psnr, recon
+        return float(loss), psnr, recon, state
 
     # ------------------------------------------------------------------ backward (BPTT)
+    def _stop_after_step(self, t):
+        """Hook for the stage-by-stage gradient diagnostics (scripts/dbg_bwd_stage.py subclasses Engine and overrides this to leave one
+        step's backward temporaries in place).  The production engine never stops early."""
+        return False
+
     def cleargrads(self):
         self.flat_g.zero_()
 
@@ -587,11 +645,11 @@ class Engine(object):
                 self._conv_dgrad(de0, B, H // 2, W // 2, p["enc0/W"], None, 5, 2, 2, View(ws["d_img_nhwc"], 3, 0, 3), H, W)
                 L.call("pivp_nhwc_to_nchw", _ptr(ws["d_img_nhwc"]), 3, 0, _ptr(d_prev), B, 3, HW[1], 1, s)
                 L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)
-            if getattr(self, "debug_stop_t", None) == t:
-                return                             # scripts/dbg_bwd_stage.py: leave this step's backward temporaries in place
+            if self._stop_after_step(t):
+                return
         # ---- deferred weight gradients of enc0..enc3: the per-step tensors are stacked over time, so each is ONE launch with
         # S*B "images" (9x longer reduction per launch instead of 9 launches that cannot fill the GPU)
-        if getattr(self, "debug_stop_t", None) is None:
+        if True:
             S = T - 1
             first = lambda lst: lst[0]
             cin3 = 64 + self.sa

@@ -197,7 +197,37 @@ class Model(object):
         self.loss = 0.0
         self.psnr_all = 0.0
         self.summaries = []
-        self.conv_res = []
+        self._conv_res = []
+
+    @property
+    def conv_res(self):
+        """ref:734 ``self.conv_res = encs``: the eight encoder outputs [enc0 .. enc6, enc7] of the LAST time step, (B,C,h,w) NCHW like the
+        reference (visualize.py:443 reads them).  The engine keeps them as NHWC channel slices of the ConvLSTM input buffers, so the
+        NCHW copies are made when the attribute is first looked at after a forward pass."""
+        if callable(self._conv_res):
+            self._conv_res = self._conv_res()
+        return self._conv_res
+
+    @conv_res.setter
+    def conv_res(self, v):
+        self._conv_res = v
+
+    def _make_conv_res(self):
+        e = self.engine
+        ws, t, B, H, W = e.ws, e.T - 2, e.B, e.H, e.W
+        src = [(ws["xh"][0][t], 64, 0, 32, 2), (ws["xh"][2][t], 96, 0, 32, 4), (ws["in3"][t], e.cs3, 0, 64, 8), (ws["xh"][4][t], 192, 0, 64, 8),
+               (ws["xh"][5][t], 192, 0, 128, 4), (ws["xh"][6][t], 128, 0, 96, 2), (ws["e6"][t], 64, 0, 64, 1)]
+        s = torch.cuda.current_stream(e.dev).cuda_stream
+        out = []
+        for buf, cs, co, C, lv in src:
+            y = torch.empty(B, C, H // lv, W // lv, dtype=torch.float32, device=e.dev)
+            lib().call("pivp_nhwc_to_nchw", buf.data_ptr(), cs, co, y.data_ptr(), B, C, (H // lv) * (W // lv), 0, s)
+            out.append(y)
+        enc7 = ws["enc7_pre"][t].clone()
+        if e.model_type != "STP":                      # ref:315,388 relu(enc7) for CDNA / DNA; ref:454 STP keeps the raw deconvolution
+            enc7.clamp_(min=0)
+        out.append(enc7)
+        return out
 
     # parameters in Chainer layout (npz-compatible, A.9)
     def params(self):
@@ -232,29 +262,27 @@ class Model(object):
         return self.loss
 
     def _bind_loss(self):
-        """Lazy handles for .loss / .psnr_all: the D2H read (ref:955-956) happens when they are first looked at."""
+        """Handles for .loss / .psnr_all bound to THIS step: the loss sums leave the device behind the step (a stream-ordered copy into
+        a pinned ring slot, Engine.snapshot_loss), and the host read (ref:955-956) happens when a handle is first looked at -- it waits
+        for that copy only, so step k's loss can be read after step k+1 was launched and still reports step k."""
         e = self.engine
-        T = e.T
         self.gen_states = e.ws["cur"][1:]
-        self.conv_res = [e.ws["xh"][0][T - 2], e.ws["e6"][T - 2]]
-        cache = {}
-
-        def values():
-            if not cache:
-                cache["v"] = e.loss_values()
-            return cache["v"]
+        self._conv_res = self._make_conv_res
+        values = e.snapshot_loss()
         self.loss = _Scalar(lambda: values()[0])
         self.psnr_all = _Scalar(lambda: values()[1])
         self._values = values
 
     def make_summaries(self):
-        """ref:744-759 strings (forces the D2H read)."""
-        loss, psnr, recon = self._values()
+        """ref:744-759 strings, same order: recon_cost / psnr per predicted frame, state_cost per predicted state, psnr_all, loss."""
+        loss, psnr, recon, state = self._values()
         p = self.prefix or ""
         out = []
         for i, c in enumerate(recon):
             out.append("%s_recon_cost%d: %s" % (p, i, c))
-            out.append("%s_psnr%d: %s" % (p, i, 10.0 * math.log(1.0 / c) / math.log(10.0)))
+            out.append("%s_psnr%d: %s" % (p, i, 10.0 * math.log(1.0 / c) / math.log(10.0) if c > 0 else float("inf")))
+        for i, c in enumerate(state):
+            out.append("%s_state_cost%d: %s" % (p, i, c))
         out.append("%s_psnr_all: %s" % (p, psnr))
         out.append("%s_loss: %s" % (p, loss))
         self.summaries = out

@@ -20,7 +20,8 @@ model = TM.make_model(pk, mt, nm, k, H, W, oob, use_state=use_state)
 model.load_params(params)
 np.random.seed(99)
 loss = model([torch.from_numpy(a) for a in batch], 6000)
-model.cleargrads(); model.engine.debug_stop_t = T - 2; model.backward(); torch.cuda.synchronize()
+model.engine._stop_after_step = lambda t: t == T - 2      # diagnostics hook: leave step T-2's backward temporaries in place
+model.cleargrads(); model.backward(); torch.cuda.synchronize()
 ws = model.engine.ws
 tr = ref["trace"][T - 2]
 def nhwc(t, C): return t.reshape(B, H, W, C).permute(0, 3, 1, 2)

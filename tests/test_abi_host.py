@@ -175,3 +175,18 @@ def test_profile_tooling_reads_the_committed_launch_list():
                          stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
     assert "conv5x5_halo_tc_kernel" in out.stdout and "| kernel | launches / step |" in out.stdout
+
+
+def test_concat_examples_matches_reference_form(pk):
+    """train_model.py:51-71: np.split on axis 1 + np.rollaxis(img, 3, 1) == the transpose the package does; also vs the oracle."""
+    rs = np.random.RandomState(0)
+    B, T, H, W = 3, 4, 8, 6
+    seqs = [[rs.rand(T, H, W, 3).astype(np.float32), rs.rand(T, 5).astype(np.float32), rs.rand(T, 5).astype(np.float32)] for _ in range(B)]
+    img, act, sta = pk.concat_examples(seqs)
+    # the reference's literal form
+    x = np.array([s[0] for s in seqs])
+    ref_img = np.array([np.rollaxis(np.squeeze(a, 1), 3, 1) for a in np.split(x, T, axis=1)])
+    ref_act = np.array([np.squeeze(a, 1) for a in np.split(np.array([s[1] for s in seqs]), T, axis=1)])
+    assert img.shape == (T, B, 3, H, W) and np.array_equal(img, ref_img) and np.array_equal(act, ref_act)
+    o = OM.concat_examples(seqs)
+    assert all(np.array_equal(a, b) for a, b in zip((img, act, sta), o))

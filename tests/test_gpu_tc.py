@@ -42,6 +42,11 @@ def stream():
     (2, 16, 16, 256, 96, 96),      # lstm3 input-gradient
     (2, 16, 16, 256, 192, 192),    # lstm6 input-gradient
     (2, 64, 64, 64, 128, 128),     # 128x128 images, level 2
+    # ---- the launches of the b32 benchmark step (BASELINE config 2): two pixel tiles per CTA, conv5x5_halo_tc_kernel<2, 1>
+    (32, 32, 32, 128, 64, 64),     # lstm1/2 input gradient at B=32: 256 tiles -> 128 two-tile CTAs
+    (32, 32, 32, 128, 128, 128),   # lstm7 input gradient at B=32
+    (32, 16, 16, 256, 128, 128),   # lstm4 input gradient at B=32 (64 tiles, one tile per CTA, two patch buffers)
+    (32, 8, 8, 512, 192, 96),      # lstm5 input gradient at B=32: 16 pair tiles x 2 N tiles x 4 K splits (atomic epilogue)
 ])
 def test_tc_conv5x5_plain_matches_simt(pk, B, H, W, Kc, N, BN):
     L = pk.lib()
@@ -67,7 +72,10 @@ def test_tc_conv5x5_plain_matches_simt(pk, B, H, W, Kc, N, BN):
     assert rel(got, yo) < 2e-3
 
 
-@pytest.mark.parametrize("B,H,W,cin,C,t0", [(2, 32, 32, 32, 32, True), (2, 16, 16, 64, 64, False), (2, 8, 8, 64, 128, False)])
+@pytest.mark.parametrize("B,H,W,cin,C,t0", [(2, 32, 32, 32, 32, True), (2, 16, 16, 64, 64, False), (2, 8, 8, 64, 128, False),
+                                            # b32 benchmark shapes: lstm1/2 and lstm7 forward run two pixel tiles per CTA (fused gates + LN partials)
+                                            (32, 32, 32, 32, 32, False), (32, 32, 32, 96, 32, False), (32, 32, 32, 32, 32, True),
+                                            (32, 16, 16, 128, 64, False), (32, 8, 8, 64, 128, False)])
 def test_tc_convlstm_fused_matches_simt_and_gate_kernel(pk, B, H, W, cin, C, t0):
     L = pk.lib()
     rs = np.random.RandomState(1)
