@@ -35,7 +35,9 @@ struct Geom {
     int npatch;                                   // patch buffers (1..3): the next 64-channel block's patch loads under this block's MMAs
     long long* dbg;                               // optional per-CTA clock64 stamps [grid][8] (pivp_tc_set_debug_buffer), else null
 };
-#define HALO_STAMP(i) do { if (g.dbg && lane == 0) g.dbg[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 8 + (i)] = clock64(); } while (0)
+#define HALO_ROW ((size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 8)
+#define HALO_STAMP(i) do { if (g.dbg && lane == 0) g.dbg[HALO_ROW + (i)] = clock64(); } while (0)
+__device__ __forceinline__ long long global_ns() { long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
 
 // K-major SW128 descriptor with an explicit stride between 8-row groups.  The swizzle XOR is taken from the shared-memory ADDRESS
 // bits [7,10) (measured on B200: a start address moved by whole 128-byte rows needs no base-offset field; setting it breaks the result).
@@ -77,7 +79,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int cb_first = blockIdx.z * g.cb_per_split;
     const int ncb = min(g.Kc / 64 - cb_first, g.cb_per_split);        // 64-channel blocks of this CTA (local index cb, global cb_first + cb)
     const int tiles_x = g.W / TW, tiles_y = g.H / TH;
-    if (warp == 0) HALO_STAMP(0);
+    if (warp == 0) { HALO_STAMP(0); if (g.dbg && lane == 0) g.dbg[HALO_ROW + 6] = global_ns(); }
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
@@ -366,6 +368,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     if (warp == 1) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)g.tmem_cols) : "memory");
+        if (g.dbg && lane == 0) g.dbg[HALO_ROW + 7] = global_ns();
     }
 }
 
@@ -430,8 +433,11 @@ static int launch_ms(const CUtensorMap& map_a, const CUtensorMap& map_b, Geom g,
 
 }  // namespace halo
 
-static long long* g_halo_dbg = nullptr;          // set through pivp_tc_set_debug_buffer (scripts/dbg_halo_timeline.py)
-void tc_halo_set_debug(long long* p) { g_halo_dbg = p; }
+// Diagnostics (scripts/halo_timeline_all.py): while a buffer is set, launch number k since the call writes its per-CTA stamps
+// ([0..5] clock64 of the phases, [6] / [7] %globaltimer at CTA start / end) to rows [256 k, 256 k + CTAs); at most 512 launches.
+static long long* g_halo_dbg = nullptr;
+static int g_halo_dbg_launch = 0;
+void tc_halo_set_debug(long long* p) { g_halo_dbg = p; g_halo_dbg_launch = 0; }
 
 // PIVP_TC_HALO: 0 = use the per-tap kernel of conv_tc.cu, 1 = default, 3 = always one tile per CTA, 4 = always two (tuning switches)
 int tc_halo_mode() {
@@ -451,7 +457,7 @@ int launch_conv5x5_halo(const void* in_bf16, int in_cs, int B, int H, int W, int
     PIVP_REQUIRE(in_bf16 && wt_bf16 && in_cs % 8 == 0 && N % BN == 0, "%s(halo): bad operand", who);
     Geom g;
     g.H = H; g.W = W; g.Kc = Kc; g.N = N; g.BN = BN;
-    g.dbg = g_halo_dbg;
+    g.dbg = (g_halo_dbg && g_halo_dbg_launch < 512) ? g_halo_dbg + (size_t)256 * 8 * g_halo_dbg_launch++ : nullptr;
     g.pair = (H == 8 && W == 8) ? 1 : 0;
     g.patch_bytes = g.pair ? PAIR_PATCH_BYTES : PATCH_BYTES;
     PIVP_REQUIRE(!g.pair || !ep.ln_partial, "%s(halo): no LayerNorm partials in the 8x8 pair geometry (a tile spans two samples)", who);

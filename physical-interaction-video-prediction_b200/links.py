@@ -243,6 +243,16 @@ class Model(object):
     def cleargrads(self):
         self.engine.cleargrads()
 
+    def save(self, filename):
+        """``serializers.save_npz(filename, model)`` (ref:1035)."""
+        from .serializers import save_npz
+        save_npz(filename, self)
+
+    def load(self, filename):
+        """``serializers.load_npz(filename, model)`` (ref:865)."""
+        from .serializers import load_npz
+        load_npz(filename, self)
+
     def schedule(self, batch_size_global, T, iter_num):
         """Scheduled-sampling plan for one step (ref:649-657, 663-673): returns (feedself, take[T-1, B_local], n_gt).
         Every rank draws the SAME global permutations and keeps its slice."""
@@ -298,6 +308,10 @@ class Adam(object):
     def __init__(self, alpha=0.001, beta1=0.9, beta2=0.999, eps=1e-8):
         self.alpha, self.beta1, self.beta2, self.eps = alpha, beta1, beta2, eps
         self.target = None
+        self.epoch = 0                         # chainer.Optimizer.epoch (serialised in the state file, ref:1037)
+
+    def new_epoch(self):
+        self.epoch += 1
 
     def setup(self, model):
         self.target = model

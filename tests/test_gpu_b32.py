@@ -25,7 +25,7 @@ pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 sys.path.insert(0, GOLD)
 
-GRAD_L2_BF16, GRAD_COS_BF16 = 0.25, 0.97
+GRAD_L2_BF16, GRAD_COS_BF16 = 0.12, 0.99        # measured at B=32, T=10: worst tensor lstm1/conv/W 0.089 / 0.9962
 
 
 @pytest.fixture(scope="module")
@@ -93,7 +93,7 @@ def test_b32_t10_train_step_matches_frozen_oracle(pk, compute, capsys):
     for key in sorted(grads):
         g = grads[key].astype(np.float64).reshape(-1)
         ref = gold["gsub/" + key].astype(np.float64)
-        sub = g[::MG.STRIDE]
+        sub = g[::MG.stride_of(g.size)]
         err = np.linalg.norm(sub - ref) / (np.linalg.norm(ref) + 1e-30)
         cos = float((sub * ref).sum() / (np.linalg.norm(sub) * np.linalg.norm(ref) + 1e-30))
         nrm = np.sqrt((g * g).sum()) / (float(gold["gl2/" + key]) + 1e-30)
