@@ -166,11 +166,24 @@ int pivp_stp_fused_bwd(const float* g_out, const float* prev, const float* enc7_
                        float* d_enc7_pre, float* d_mask_pre, float* d_theta, float* d_prev,
                        int B, int H, int W, int num_masks, int oob_border, void* workspace, size_t ws_bytes, void* stream);
 
+/* ---- un-fused transformation lists: the reference call surface of the Stateless* links returns (transformed_list, enc7)
+ *      (train_model.py:293-351, 368-417, 434-475).  out = [L][B][3][H][W]:
+ *      CDNA  L = num_masks + 1: sigmoid(relu(enc7_pre)) (:315-317), then the num_masks per-sample cross-correlations (:326-347)
+ *      DNA   L = 1: the 25-tap per-pixel transform with the truncated windows of :395-405
+ *      STP   L = num_masks: sigmoid(enc7_pre) (:454-455), then num_masks - 1 samplings with the one shared theta (:465-470)
+ *      Forward only; training goes through the fused entry points above. */
+int pivp_cdna_transform(const float* prev, const float* enc7_pre, const float* kern_raw, float* out, int B, int H, int W, int num_masks,
+                        void* stream);
+int pivp_dna_transform(const float* prev, const float* enc7_pre, float* out, int B, int H, int W, void* stream);
+int pivp_stp_transform(const float* prev, const float* enc7_pre, const float* theta_raw, float* out, int B, int H, int W, int num_masks,
+                       int oob_border, void* stream);
+
 /* ---- tcgen05 / TMEM / TMA path for the seven ConvLSTM 5x5 convolutions (bf16 operands, fp32 accumulate) ---------- */
 /* fp32 master W[n][tap][c] -> bf16 forward operand Wf[n][tap][Kpad] and tap-flipped dgrad operand Wd[c][tap'][n] */
 int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream);
-/* Debugging aid (scripts/dbg_halo_timeline.py): device buffer of [CTAs][8] 64-bit slots the halo-patch convolution kernel fills
- * with clock64() stamps (0 launch, 1 set-up done, 2 first operands landed, 3 last MMA issued, 4 accumulator ready, 5 epilogue done);
+/* Debugging aid (scripts/halo_timeline_all.py): device buffer of [512 launches][256 CTAs][8] 64-bit slots; launch k after the call fills
+ * rows [256 k, 256 k + CTAs) with clock64() stamps (0 launch, 1 set-up done, 2 first operands landed, 3 last MMA issued, 4 accumulator
+ * ready, 5 epilogue done) and %globaltimer at CTA start / end (6, 7);
  * null switches it off.  Process-wide, not thread-safe. */
 int pivp_tc_set_debug_buffer(void* device_buffer);
 /* D[m,n] = sum_{tap,c} In[pixel(m)+tap-2, c] * Wt[n][tap][c]  (In bf16 NHWC with row stride in_cs; Wt bf16 [N][25][Kc]).

@@ -142,31 +142,127 @@ class BasicConvLSTMCell(object):
 
 
 class _Stateless(object):
+    """Common part of StatelessCDNA / DNA / STP (train_model.py:278-475).
+
+    Two call forms:
+      * the REFERENCE form ``link(encs, hiddens, batch_size, prev_image, num_masks, color_channels) -> (transformed_list, enc7)``
+        (ref:293, 368, 434).  The link owns the reference's parameters (``enc7`` 1x1 Deconvolution2D, ``cdna_kerns`` / ``stp_input`` /
+        ``identity_params`` Linear) in Chainer layout as attributes ``<name>_W`` / ``<name>_b``, created lazily with Chainer's default
+        initialisers like ``L.Linear(in_size=None)``, or set by the caller (``load(params, prefix="model/")`` takes a checkpoint dict).
+        ``transformed_list`` is the un-fused list Model.__call__ composites at ref:725-728.
+      * the FUSED form ``link.fused(prev_image, enc7_pre, mask_pre, ...) -> gen_image``: transform + mask softmax + composite in one
+        kernel, which is what ``Model`` runs (the list never reaches memory).  A call with the fused arity is routed there.
+    """
+    NE = 3
+
     def __init__(self, num_masks):
         self.num_masks = num_masks
+        self.enc7_W = self.enc7_b = None
+
+    def load(self, params, prefix="model/"):
+        """Take this link's parameters (Chainer layout) from a checkpoint-style dict: ``model/enc7/W`` -> ``self.enc7_W`` ..."""
+        for k, v in params.items():
+            if k.startswith(prefix):
+                setattr(self, k[len(prefix):].replace("/", "_"), torch.as_tensor(np.asarray(v), dtype=torch.float32))
+        return self
+
+    def _param(self, name, shape, dev, fan_in=None):
+        v = getattr(self, name, None)
+        if v is None:
+            v = torch.randn(*shape) * math.sqrt(1.0 / fan_in) if fan_in else torch.zeros(*shape)      # LeCunNormal / zeros (A.1)
+        v = v.to(dev).float().contiguous()
+        setattr(self, name, v)
+        return v
+
+    def _enc7(self, enc6):
+        """ref:314 / 387 / 454: 1x1 Deconvolution2D(64 -> NE) on enc6 (B,64,H,W) -> pre-activation (B,NE,H,W)."""
+        B, C, H, W = enc6.shape
+        Wt = self._param("enc7_W", (C, self.NE, 1, 1), enc6.device, fan_in=self.NE)
+        b = self._param("enc7_b", (self.NE,), enc6.device)
+        return Fn.Deconvolution2DFunction(1, 0, (H, W)).forward((enc6.contiguous(), Wt, b))[0]
+
+    def _linear(self, name, x, out_size, relu=0):
+        B, K = x.shape
+        Wt = self._param(name + "_W", (out_size, K), x.device, fan_in=K)
+        b = self._param(name + "_b", (out_size,), x.device)
+        y = torch.empty(B, out_size, dtype=torch.float32, device=x.device)
+        lib().call("pivp_linear_fwd", x.data_ptr(), K, Wt.data_ptr(), b.data_ptr(), y.data_ptr(), B, K, out_size, relu,
+                   torch.cuda.current_stream(x.device).cuda_stream)
+        return y
 
 
 class StatelessCDNA(_Stateless):
-    """train_model.py:278-351 as a fused op: call with the 1x1 outputs and the kernel Linear output."""
+    """train_model.py:278-351."""
 
-    def __call__(self, prev_image, enc7_pre, mask_pre, kern_raw):
+    def __init__(self, num_masks):
+        super(StatelessCDNA, self).__init__(num_masks)
+        self.cdna_kerns_W = self.cdna_kerns_b = None
+
+    def fused(self, prev_image, enc7_pre, mask_pre, kern_raw):
         return Fn.CDNACompositeFunction(self.num_masks).forward((prev_image, enc7_pre, mask_pre, kern_raw))[0]
+
+    def __call__(self, *args):
+        if len(args) == 4:
+            return self.fused(*args)
+        encs, hiddens, batch_size, prev_image, num_masks, color_channels = args
+        B, _, H, W = prev_image.shape
+        enc7_pre = self._enc7(encs[6])
+        kern_raw = self._linear("cdna_kerns", hiddens[4].reshape(int(batch_size), -1).contiguous(), DNA_KERN_SIZE * DNA_KERN_SIZE * self.num_masks)
+        out = torch.empty(self.num_masks + 1, B, 3, H, W, dtype=torch.float32, device=prev_image.device)
+        lib().call("pivp_cdna_transform", prev_image.contiguous().data_ptr(), enc7_pre.data_ptr(), kern_raw.data_ptr(), out.data_ptr(), B, H, W,
+                   self.num_masks, torch.cuda.current_stream(out.device).cuda_stream)
+        self.enc7_pre, self.kern_raw = enc7_pre, kern_raw
+        return [out[i] for i in range(self.num_masks + 1)], enc7_pre.clamp(min=0)          # ref:315 enc7 = relu(enc7)
 
 
 class StatelessDNA(_Stateless):
     """train_model.py:354-417."""
+    NE = DNA_KERN_SIZE * DNA_KERN_SIZE
 
-    def __call__(self, prev_image, enc7_pre, mask_pre):
+    def fused(self, prev_image, enc7_pre, mask_pre):
         if self.num_masks != 1:
             raise ValueError("Only one mask is supported for DNA model.")
         return Fn.DNACompositeFunction().forward((prev_image, enc7_pre, mask_pre))[0]
+
+    def __call__(self, *args):
+        if len(args) == 3:
+            return self.fused(*args)
+        encs, hiddens, batch_size, prev_image, num_masks, color_channels = args
+        if self.num_masks != 1:
+            raise ValueError("Only one mask is supported for DNA model.")                # ref:389-390
+        B, _, H, W = prev_image.shape
+        enc7_pre = self._enc7(encs[6])
+        out = torch.empty(1, B, 3, H, W, dtype=torch.float32, device=prev_image.device)
+        lib().call("pivp_dna_transform", prev_image.contiguous().data_ptr(), enc7_pre.data_ptr(), out.data_ptr(), B, H, W,
+                   torch.cuda.current_stream(out.device).cuda_stream)
+        self.enc7_pre = enc7_pre
+        return [out[0]], enc7_pre.clamp(min=0)
 
 
 class StatelessSTP(_Stateless):
     """train_model.py:419-475."""
 
-    def __call__(self, prev_image, enc7_pre, mask_pre, theta_raw, oob="zeros"):
+    def __init__(self, num_masks):
+        super(StatelessSTP, self).__init__(num_masks)
+        self.stp_input_W = self.stp_input_b = self.identity_params_W = self.identity_params_b = None
+
+    def fused(self, prev_image, enc7_pre, mask_pre, theta_raw, oob="zeros"):
         return Fn.STPCompositeFunction(self.num_masks, oob).forward((prev_image, enc7_pre, mask_pre, theta_raw))[0]
+
+    def __call__(self, *args, **kw):
+        if len(args) in (4, 5) and not isinstance(args[0], (list, tuple)):
+            return self.fused(*args, **kw)
+        encs, hiddens, batch_size, prev_image, num_masks, color_channels = args
+        B, _, H, W = prev_image.shape
+        enc7 = self._enc7(encs[6])                                                       # ref:454 no ReLU
+        s_ = self._linear("stp_input", hiddens[4].reshape(int(batch_size), -1).contiguous(), 100, relu=1)
+        theta_raw = self._linear("identity_params", s_, 6)                               # ONE Linear shared by all transformers (B.4)
+        n = max(int(num_masks), 1)                                                       # ref:463 loops over the ARGUMENT num_masks - 1
+        out = torch.empty(n, B, 3, H, W, dtype=torch.float32, device=prev_image.device)
+        lib().call("pivp_stp_transform", prev_image.contiguous().data_ptr(), enc7.data_ptr(), theta_raw.data_ptr(), out.data_ptr(), B, H, W,
+                   n, 1 if kw.get("oob", "zeros") == "border" else 0, torch.cuda.current_stream(out.device).cuda_stream)
+        self.enc7_pre, self.theta_raw = enc7, theta_raw
+        return [out[i] for i in range(n)], enc7
 
 
 # ----------------------------------------------------------------------------- Model

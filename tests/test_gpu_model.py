@@ -220,8 +220,11 @@ def test_programmatic_dependent_launch_changes_nothing(pk, compute):
     (l0, p0, g0), (l1, p1, g1) = res[0], res[1]
     tol = 1e-5 if compute == "f32" else 2e-3          # bf16: an atomics-order ulp can flip a bf16 rounding downstream
     assert max(abs(a - b) for a, b in zip(l0, l1)) <= tol * abs(l0[0])
-    assert float((g1 - g0).abs().max()) <= 10 * tol * float(g0.abs().max())
-    assert float((p1 - p0).abs().max()) <= 10 * tol * float(p0.abs().max())
+    # gradients after the third update: the fp32 atomics of both variants (split-K, bias sums) are unordered, and Adam turns an ulp on a
+    # near-zero gradient into a +-alpha step, so two runs of the SAME variant already differ by ~3e-4 of max|g| here; a missing
+    # dependency (what this test is for) produces garbage, orders of magnitude above these bounds
+    assert float((g1 - g0).abs().max()) <= max(10 * tol, 1e-3) * float(g0.abs().max())
+    assert float((p1 - p0).abs().max()) <= 3 * 2 * 1e-3 + 10 * tol * float(p0.abs().max())
 
 
 def test_batch_prefetcher_delivers_batches_in_order(pk):
