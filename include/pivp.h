@@ -178,6 +178,11 @@ int pivp_dna_transform(const float* prev, const float* enc7_pre, float* out, int
 int pivp_stp_transform(const float* prev, const float* enc7_pre, const float* theta_raw, float* out, int B, int H, int W, int num_masks,
                        int oob_border, void* stream);
 
+/* ---- inference preprocessing (predict_model.py:118-123): F.resize_images (bilinear, positions linspace(0, W-1, OW) in float64, corner
+ *      indices clipped to [0, W-2]) fused with the cast and the division: y = resize(x) / scale (divide != 0) or * scale.
+ *      x: (BC, H, W) float32 or uint8 planes (x_is_u8), y: (BC, OH, OW) float32. */
+int pivp_resize_images(const void* x, int x_is_u8, float* y, int BC, int H, int W, int OH, int OW, float scale, int divide, void* stream);
+
 /* ---- tcgen05 / TMEM / TMA path for the seven ConvLSTM 5x5 convolutions (bf16 operands, fp32 accumulate) ---------- */
 /* fp32 master W[n][tap][c] -> bf16 forward operand Wf[n][tap][Kpad] and tap-flipped dgrad operand Wd[c][tap'][n] */
 int pivp_tc_prep_weights(const float* W, int N, int Cx, int Kpad, void* w_fwd_bf16, void* w_dgrad_bf16, void* stream);

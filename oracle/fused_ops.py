@@ -88,3 +88,24 @@ def stp_fused(prev, enc7_pre, mask_pre, theta, num_masks, oob="zeros"):
         layers.append(G.spatial_transformer_sampler(iv["prev"], grid, oob))
     out, m = _masks_and_composite(iv["prev"], layers, iv["mask_pre"], M)
     return _finish(out, m, iv, dict(warped=layers[1].data if M > 1 else None))
+
+
+def resize_images(x, out_hw):
+    """chainer.functions.resize_images (Chainer 2.0.1 ResizeImages.forward) as predict_model.py:120 calls it: bilinear, sample positions
+    ``linspace(0, W-1, out_W)`` in float64, corner indices clipped to ``[0, W-2]``, weights cast to the input dtype."""
+    B, C, H, W = x.shape
+    out_H, out_W = out_hw
+    u_1d = np.linspace(0, W - 1, num=out_W)
+    v_1d = np.linspace(0, H - 1, num=out_H)
+    grid = np.meshgrid(u_1d, v_1d)
+    u, v = grid[0].ravel(), grid[1].ravel()
+    u0 = np.floor(u).astype(np.int32).clip(0, W - 2)
+    v0 = np.floor(v).astype(np.int32).clip(0, H - 2)
+    u1, v1 = u0 + 1, v0 + 1
+    w1 = ((u1 - u) * (v1 - v)).astype(x.dtype)
+    w2 = ((u - u0) * (v1 - v)).astype(x.dtype)
+    w3 = ((u1 - u) * (v - v0)).astype(x.dtype)
+    w4 = ((u - u0) * (v - v0)).astype(x.dtype)
+    y = (w1[None, None, :] * x[:, :, v0, u0] + w2[None, None, :] * x[:, :, v0, u1] +
+         w3[None, None, :] * x[:, :, v1, u0] + w4[None, None, :] * x[:, :, v1, u1])
+    return y.reshape(B, C, out_H, out_W)

@@ -9,7 +9,7 @@ from . import layout                                                      # noqa
 
 def __getattr__(name):
     # torch-dependent modules are imported lazily so that `import pivp_b200` works in a build-only environment
-    if name in ("functions", "links", "engine", "tensorcore", "parallel", "train", "data"):
+    if name in ("functions", "links", "engine", "tensorcore", "parallel", "train", "data", "serializers", "rollout", "train_loop"):
         import importlib
         return importlib.import_module("." + name, __name__)
     if name in ("Model", "Adam", "BasicConvLSTMCell", "LayerNormalizationConv2D", "StatelessCDNA", "StatelessDNA",
@@ -20,6 +20,12 @@ def __getattr__(name):
     if name == "TrainStep":
         from .train import TrainStep
         return TrainStep
+    if name in ("Rollout", "predict"):
+        from . import rollout
+        return getattr(rollout, name)
+    if name in ("save_npz", "load_npz"):
+        from . import serializers
+        return getattr(serializers, name)
     if name == "BatchPrefetcher":
         from .train import BatchPrefetcher
         return BatchPrefetcher

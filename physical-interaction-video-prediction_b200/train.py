@@ -130,6 +130,7 @@ class BatchPrefetcher(object):
         self.stream = torch.cuda.Stream(device=dev)
         self.bufs = [tuple(torch.empty_like(x) for x in (step.images, step.actions, step.states)) for _ in range(2)]
         self.events = [torch.cuda.Event(), torch.cuda.Event()]
+        self.drained = [None, None]                # event behind the device-to-device copy that last read the slot
         self.ready = [False, False]
         self.it = iter(batches)
         self.k = 0
@@ -140,21 +141,35 @@ class BatchPrefetcher(object):
         self.ready[slot] = batch is not None
         if batch is None:
             return
-        cur = torch.cuda.current_stream(self.stream.device)
-        self.stream.wait_stream(cur)               # the device-to-device copy that last read this slot is already queued on `cur`
+        if self.drained[slot] is not None:         # wait for the copy that last read this slot -- not for the steps queued behind it
+            self.stream.wait_event(self.drained[slot])
         with torch.cuda.stream(self.stream):
             for dst, src in zip(self.bufs[slot], batch):
                 dst.copy_(src, non_blocking=True)
             self.events[slot].record(self.stream)
 
-    def load_next(self):
-        """Put the next batch into the step's input buffers; False when the iterable is exhausted."""
+    def load_next(self, prefetch=True):
+        """Put the next batch into the step's input buffers; False when the iterable is exhausted.  ``prefetch=False`` leaves the
+        following batch un-requested until ``prefetch()`` is called: a caller whose batch source and scheduled-sampling both draw from
+        the global NumPy stream (train_loop.py, like train_model.py:939-950) asks for batch k+1 only AFTER step k drew its selects, so
+        the stream is consumed in the reference's order; the copy still overlaps step k on the device."""
         slot = self.k & 1
         if not self.ready[slot]:
             return False
-        torch.cuda.current_stream(self.stream.device).wait_event(self.events[slot])
+        cur = torch.cuda.current_stream(self.stream.device)
+        cur.wait_event(self.events[slot])
         self.step.load_batch(*self.bufs[slot])
+        if self.drained[slot] is None:
+            self.drained[slot] = torch.cuda.Event()
+        self.drained[slot].record(cur)
         self.k += 1
-        self._issue(self.k & 1)
+        self.ready[self.k & 1] = False
+        if prefetch:
+            self._issue(self.k & 1)
         return True
+
+    def prefetch(self):
+        """Request the batch after the current one (see ``load_next(prefetch=False)``)."""
+        if not self.ready[self.k & 1]:
+            self._issue(self.k & 1)
 
