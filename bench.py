@@ -102,8 +102,20 @@ def run_reference(args, rank):
     NumPy restatement (oracle/), all host threads the BLAS will use, on a bounded sample: ONE sequence of the b32 workload."""
     if rank != 0:
         return
+    cores = len(os.sched_getaffinity(0))
+    # torchrun exports OMP_NUM_THREADS=1 to its workers, which would silently single-thread the BLAS under the CPU arm: the reference
+    # arm is ONE process and gets every host core, whatever launched it (must be set before NumPy loads its BLAS)
+    for var in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[var] = str(cores)
     import numpy as np
     from oracle import model as OM
+    blas_threads = None
+    try:
+        from threadpoolctl import threadpool_info, threadpool_limits
+        threadpool_limits(cores)
+        blas_threads = max([p_.get("num_threads", 0) for p_ in threadpool_info()] or [0]) or None
+    except Exception:
+        pass
     cfg = OM.Config("CDNA", MASKS, schedsamp_k=K_SCHED, height=H, width=W)
     params = OM.init_params(cfg)
     adam = OM.Adam()
@@ -116,13 +128,12 @@ def run_reference(args, rank):
     for i in range(steps):
         OM.train_step(params, adam, batch, ITER0 + warm + i, cfg)
     dt = (time.perf_counter() - t0) / steps
-    cores = len(os.sched_getaffinity(0))
     val = 1 * T_SEQ / dt
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "frames/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "CDNA 64x64 T=10 10 masks train step (fwd+bwd+Adam), CPU NumPy restatement of the Chainer path",
                        "sample": "1 sequence of the b32 batch per step"},
-            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "kind": "port",
+            "cpu_baseline": {"value": val, "unit": "frames/s", "cores": cores, "blas_threads": blas_threads, "kind": "port",
                              "sample": "CDNA b1 T=10 fwd+bwd+Adam, %d steps after %d warm-up" % (steps, warm)},
             "e2e": {"value": val, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -141,7 +152,13 @@ def cpu_baseline():
         t0 = time.perf_counter()
         OM.loss_and_grads(params, batch, ITER0, cfg)
         best = min(best, time.perf_counter() - t0)
-    return {"value": T_SEQ / best, "unit": "frames/s", "cores": len(os.sched_getaffinity(0)), "kind": "port",
+    blas_threads = None
+    try:
+        from threadpoolctl import threadpool_info
+        blas_threads = max([p_.get("num_threads", 0) for p_ in threadpool_info()] or [0]) or None
+    except Exception:
+        pass
+    return {"value": T_SEQ / best, "unit": "frames/s", "cores": len(os.sched_getaffinity(0)), "blas_threads": blas_threads, "kind": "port",
             "sample": "oracle (NumPy restatement of the Chainer CPU path; Chainer 2.0.1 not installable): CDNA b1 T=10 fwd+bwd, best of 3 after 1 warm-up"}
 
 
@@ -155,6 +172,8 @@ def main():
     ap.add_argument("--compute", default="bf16", choices=["bf16", "f32"])
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--global-batch", type=int, default=0, help="strong scaling: fixed GLOBAL batch split over the ranks (BASELINE config 3: 256)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the DNA-op (config 4) and STP 128x128 (config 5) measurements")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
@@ -172,6 +191,9 @@ def main():
     torch.cuda.set_device(dev)
     W_ = max(3, args.warmup)
     B, T = args.batch, T_SEQ
+    if args.global_batch:
+        assert args.global_batch % world == 0, "--global-batch must be divisible by the number of ranks"
+        B = args.global_batch // world
 
     model = pk.Model(MASKS, is_cdna=True, scheduled_sampling_k=K_SCHED, prefix="train", height=H, width=W, device=str(dev),
                      compute=args.compute, rank=rank, world_size=world)
@@ -221,8 +243,13 @@ def main():
     e2e_path = "BatchPrefetcher"
     try:
         pf = pk.BatchPrefetcher(step, (host for _ in range(args.steps)))
+        pending = None
         while pf.load_next():
-            loss = float(step(it)); it += 1
+            handle = step(it); it += 1
+            if pending is not None:
+                loss = float(pending)         # device -> host read of step k's loss, issued while step k+1 runs (every step's loss is read)
+            pending = handle
+        loss = float(pending)
     except RuntimeError as exc:               # keep the line valid if the side-stream path is unavailable: synchronous copy, and say so
         sys.stderr.write("bench: BatchPrefetcher failed (%s); timing the synchronous copy path\n" % exc)
         e2e_path = "load_batch (synchronous H2D)"
@@ -369,9 +396,85 @@ def main():
             cdna_op["b%d_warm_l2" % B] = {d: {"avg_launch_us": tw[d] * 1e6, "achieved": cdna_op["bytes_per_sample"][d] * B / tw[d] / 1e9}
                                           for d in ("fwd", "bwd")}
 
+    # ---------------- BASELINE config 4: DNA fused transform + composite (num_masks = 1), b32, forward / backward GB/s on cold inputs
+    dna_op, stp_step = None, None
+    if rank == 0 and world == 1 and not args.no_extras:
+        L = pk.lib()
+        pk_, src = peaks()
+
+        def op_time(fn, nsets, iters=20):
+            for i in range(nsets):
+                fn(i, torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(iters):
+                    fn(i % nsets, torch.cuda.current_stream().cuda_stream)
+            g.replay(); torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            best = 1e9
+            for _ in range(5):
+                e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+                best = min(best, e0.elapsed_time(e1) * 1e-3 / iters)
+            return best
+        HWc = H * W
+        dna_bytes = {"fwd": (25 + 3 + 2 + 3) * HWc * 4, "bwd": (3 + 3 + 25 + 2 + 25 + 2) * HWc * 4}
+        dna_op = {"bound": "hbm", "unit": "GB/s", "peak": pk_["hbm_gbs"], "peak_source": src, "bytes_per_sample": dna_bytes,
+                  "note": "BASELINE config 4. Algorithmic bytes (SURVEY 8d): fwd reads enc7_pre (25 planes), prev (3), mask_pre (2) and writes gen (3) = "
+                          "540,672 B/sample; bwd reads g, prev, enc7_pre, mask_pre and writes d_enc7_pre, d_mask_pre (the taps are detached, "
+                          "train_model.py:404, and prev is detached under scheduled sampling: no d_prev).  Cold = 20 launches walking input sets "
+                          "that together exceed the 126 MB L2."}
+        for Bc in sorted({args.batch, 256}):
+            nsets = max(2, int(600e6 // (Bc * 60 * HWc * 4)) + 1)
+            sets = [dict(prev=torch.rand(Bc, 3, H, W, device=dev), e=torch.randn(Bc, 25, H, W, device=dev), a=2 * torch.randn(Bc, 2, H, W, device=dev),
+                         g=torch.randn(Bc, 3, H, W, device=dev)) for _ in range(nsets)]
+            for t_ in sets:
+                t_.update(out=torch.empty_like(t_["prev"]), de=torch.empty_like(t_["e"]), da=torch.empty_like(t_["a"]))
+            nb = L.query("pivp_dna_fused_bwd_workspace_bytes", Bc, H, W)
+            wsb = torch.empty(max(nb, 16), dtype=torch.uint8, device=dev)
+
+            def fwd(i, st, sets=sets, Bc=Bc):
+                t_ = sets[i]
+                L.call("pivp_dna_fused_fwd", t_["prev"].data_ptr(), t_["e"].data_ptr(), t_["a"].data_ptr(), t_["out"].data_ptr(), Bc, H, W, st)
+
+            def bwd(i, st, sets=sets, Bc=Bc, wsb=wsb, nb=nb):
+                t_ = sets[i]
+                L.call("pivp_dna_fused_bwd", t_["g"].data_ptr(), t_["prev"].data_ptr(), t_["e"].data_ptr(), t_["a"].data_ptr(), t_["de"].data_ptr(),
+                       t_["da"].data_ptr(), 0, 0, Bc, H, W, wsb.data_ptr(), nb, st)
+            tm = {"fwd": op_time(fwd, nsets), "bwd": op_time(bwd, nsets)}
+            dna_op["b%d" % Bc] = {d: {"avg_launch_us": tm[d] * 1e6, "achieved": dna_bytes[d] * Bc / tm[d] / 1e9,
+                                      "frac": dna_bytes[d] * Bc / tm[d] / 1e9 / pk_["hbm_gbs"]} for d in ("fwd", "bwd")}
+            del sets
+        # ------------ BASELINE config 5: STP, 10 transformers, 128x128, 20-frame sequences, scheduled sampling: whole training step
+        try:
+            Hs, Ts, Bs = 128, 20, 16
+            m5 = pk.Model(MASKS, is_cdna=False, is_stp=True, scheduled_sampling_k=K_SCHED, prefix="stp", height=Hs, width=Hs, device=str(dev),
+                          compute=args.compute)
+            o5 = pk.Adam(alpha=0.001).setup(m5)
+            s5 = pk.TrainStep(m5, o5, Bs, Ts, graph=not args.no_graph)
+            s5.load_batch(*[torch.from_numpy(a) for a in pk.concat_examples(pk.data.synthetic_sequences(Bs, Ts, Hs, Hs, seed=77))])
+            np.random.seed(7)
+            for i in range(3):
+                s5(ITER0 + i)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n5 = 5
+            e0.record()
+            for i in range(n5):
+                s5(ITER0 + 3 + i)
+            e1.record(); torch.cuda.synchronize()
+            ms5 = e0.elapsed_time(e1) / n5
+            stp_step = {"workload": "STP, 10 transformers, 128x128 RGB, T=20 (19 recurrent steps, 18 loss terms), batch %d, scheduled sampling k=900 at iter %d; "
+                                    "forward + BPTT + Adam as one CUDA graph" % (Bs, ITER0), "value": Bs * Ts / (ms5 * 1e-3), "unit": "frames/s",
+                        "ms_per_step": ms5, "steps": n5, "warmup": 3, "loss": float(m5.loss), "gpu_launches_per_step": s5.launches_per_step,
+                        "stp_out_of_range_rule": "zeros (SURVEY A.7; the other rule is implemented and tested)"}
+            del m5, o5, s5
+        except Exception as exc:              # keep the headline line valid whatever happens in the extra configuration
+            stp_step = {"error": "%s: %s" % (type(exc).__name__, exc)}
+
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": W_,
-                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if args.global_batch else "weak", "vs_baseline": None,
                 "dtype": "bf16" if args.compute == "bf16" else "f32", "data": "synthetic",
                 "config": {"workload": "CDNA 64x64 RGB, batch %d per GPU, T=10, 10 masks, scheduled sampling k=900 at iter %d; "
                                        "one step = forward + BPTT + grad all-reduce + Adam" % (B, ITER0),
@@ -386,6 +489,10 @@ def main():
             line["roofline_wgrad"] = roof_wgrad
         if cdna_op:
             line["cdna_op"] = cdna_op
+        if dna_op:
+            line["dna_op"] = dna_op
+        if stp_step:
+            line["stp_step"] = stp_step
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
