@@ -288,7 +288,7 @@ def main():
         recs = []
 
         def recording_call(name, *a):
-            if name in ("pivp_tc_conv5x5", "pivp_tc_wgrad5x5"):
+            if name in ("pivp_tc_conv5x5", "pivp_tc_conv5x5_ln", "pivp_tc_wgrad5x5"):
                 recs.append((name, a))
             orig(name, *a)
         L.call = recording_call
@@ -321,7 +321,7 @@ def main():
             for li, f in enumerate(fl):
                 by_ptr[tcp.Wf[li].data_ptr()] = f          # forward launch of layer li
                 by_ptr[tcp.Wd[li].data_ptr()] = f          # input-gradient launch: same 2*M*N*K
-            conv_calls = [(n, a) for n, a in recs if n == "pivp_tc_conv5x5"]
+            conv_calls = [(n, a) for n, a in recs if n in ("pivp_tc_conv5x5", "pivp_tc_conv5x5_ln")]      # weights pointer = argument 6 of both
             if conv_calls:
                 per = replay_time(conv_calls)
                 flops = sum(by_ptr[a[6]] for _, a in conv_calls) / len(conv_calls)

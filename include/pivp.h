@@ -209,6 +209,18 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     void* h_t, long h_t_ld, int hT_co,
                     int C, float forget_bias, int flags, float* ln_partial, void* stream);
 
+/* The ConvLSTM cell of pivp_tc_conv5x5 (mode 1, bf16 gate storage) with the LayerNormalizationConv2D that follows it (train_model.py:203-208,
+ * 596-601) applied in the SAME kernel: the CTAs of a sample meet at a per-sample arrival counter once their statistics partials are
+ * written, then every thread normalises the h values it still holds in registers: y = (h - mean) * rstd * gamma + beta -> fp32 view `y`
+ * (+ optional bf16 view), stats[b] = (mean, rstd) for the LayerNorm backward.  gamma / beta in the sample's H*W*C order.
+ * counter: B unsigned ints owned by this layer, zeroed once (never reset: every launch adds the same number of arrivals per sample).
+ * Needs the halo-patch geometry (H % 16 == 0, W % 8 == 0), H*W*C % 4096 == 0 and at most 148 CTAs (all resident at once). */
+int pivp_tc_conv5x5_ln(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, const void* wt_bf16, int C, const float* bias,
+                       void* gates_bf16, const float* c_prev, float* c_out, float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
+                       float forget_bias, int flags, float* ln_partial,
+                       const float* gamma, const float* beta, float eps, float* y, int y_cs, int y_co, void* y_bf16, int yb_cs, int yb_co,
+                       float* stats, void* counter, void* stream);
+
 /* dst[i] = bf16(src[idx[i]]) (idx < 0 -> 0): builds permuted / zero-padded bf16 weight operands from the fp32 master parameters */
 int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, void* stream);
 /* General tap-list implicit GEMM on tcgen05: D[m,n] = sum_t sum_c In[pixel(m)+(dy_t,dx_t), coff_t+c] * Wt[n][t*Kc+c];

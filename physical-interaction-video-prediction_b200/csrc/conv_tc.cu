@@ -314,14 +314,20 @@ int pivp_gather_bf16(const float* src, const int* idx, long n, void* dst_bf16, v
     return check_launch("gather_bf16");
 }
 
-int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
+}  // extern "C"
+
+struct LnFuse {                 // LayerNorm applied inside the gate epilogue (pivp_tc_conv5x5_ln); all null / zero = not fused
+    const float* gamma; const float* beta; float* y; int y_cs, y_co; void* y_bf16; int yb_cs, yb_co; float* stats; unsigned* counter; float eps;
+};
+
+static int tc_conv5x5_impl(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
                     const void* wt_bf16, int N, int BN,
                     int mode, const float* bias,
                     float* out, int out_cs, int out_co,
                     float* gates, const float* c_prev, float* c_out,
                     float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
                     void* h_t, long h_t_ld, int hT_co,
-                    int C, float forget_bias, int flags, float* ln_partial, void* stream) {
+                    int C, float forget_bias, int flags, float* ln_partial, const LnFuse& lf, void* stream) {
     PIVP_REQUIRE(in_cs >= Kc, "tc_conv5x5: row stride smaller than Kc");
     if (mode == 1) {
         PIVP_REQUIRE(BN == 128 && N == 4 * C && C % 32 == 0 && gates && c_out && h_out && bias, "tc_conv5x5: gate epilogue needs BN=128, N=4C, bias");
@@ -343,8 +349,45 @@ int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
         ep.ln_partial = reinterpret_cast<float2*>(ln_partial);
         ep.ln_S = (H * W / 128) * (C / 32);
     }
+    if (lf.gamma) {
+        PIVP_REQUIRE(ln_partial && lf.beta && lf.y && lf.stats && lf.counter, "tc_conv5x5_ln: the fused LayerNorm needs ln_partial, beta, y, stats and counter");
+        ep.ln_gamma = lf.gamma; ep.ln_beta = lf.beta; ep.ln_y = lf.y; ep.ln_y_cs = lf.y_cs; ep.ln_y_co = lf.y_co;
+        ep.ln_yb = (__nv_bfloat16*)lf.y_bf16; ep.ln_yb_cs = lf.yb_cs; ep.ln_yb_co = lf.yb_co;
+        ep.ln_stats = reinterpret_cast<float2*>(lf.stats); ep.ln_counter = lf.counter; ep.ln_eps = lf.eps;
+    }
     if (tc_halo_supported(B, H, W, Kc, BN)) return launch_conv5x5_halo(in_bf16, in_cs, B, H, W, Kc, wt_bf16, N, BN, ep, stream, "tc_conv5x5");
+    PIVP_REQUIRE(!lf.gamma, "tc_conv5x5_ln: the fused LayerNorm exists in the halo-patch kernel only");
     return launch_conv_taps(in_bf16, in_cs, B, H, W, Kc, 25, dy, dx, co, wt_bf16, N, BN, ep, H, W, 1, 0, 0, stream, "tc_conv5x5");
+}
+
+extern "C" {
+
+int pivp_tc_conv5x5(const void* in_bf16, int in_cs, int B, int H, int W, int Kc,
+                    const void* wt_bf16, int N, int BN,
+                    int mode, const float* bias,
+                    float* out, int out_cs, int out_co,
+                    float* gates, const float* c_prev, float* c_out,
+                    float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
+                    void* h_t, long h_t_ld, int hT_co,
+                    int C, float forget_bias, int flags, float* ln_partial, void* stream) {
+    LnFuse none;
+    memset(&none, 0, sizeof(none));
+    return tc_conv5x5_impl(in_bf16, in_cs, B, H, W, Kc, wt_bf16, N, BN, mode, bias, out, out_cs, out_co, gates, c_prev, c_out, h_out, h_cs, h_co,
+                           h_bf16, hb_cs, hb_co, h_t, h_t_ld, hT_co, C, forget_bias, flags, ln_partial, none, stream);
+}
+
+/* ConvLSTM cell (mode 1 of pivp_tc_conv5x5, bf16 gate storage) with the LayerNorm of its output applied in the same kernel:
+ * y = LN(h_t) * gamma + beta -> fp32 view (and optional bf16 view); stats[b] = (mean, rstd) for the backward pass.
+ * counter: B unsigned ints owned by this layer, zeroed once at allocation (per-sample arrival counters, never reset). */
+int pivp_tc_conv5x5_ln(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, const void* wt_bf16, int C, const float* bias,
+                       void* gates_bf16, const float* c_prev, float* c_out, float* h_out, int h_cs, int h_co, void* h_bf16, int hb_cs, int hb_co,
+                       float forget_bias, int flags, float* ln_partial,
+                       const float* gamma, const float* beta, float eps, float* y, int y_cs, int y_co, void* y_bf16, int yb_cs, int yb_co,
+                       float* stats, void* counter, void* stream) {
+    LnFuse lf{gamma, beta, y, y_cs, y_co, y_bf16, yb_cs, yb_co, stats, (unsigned*)counter, eps};
+    PIVP_REQUIRE(gamma, "tc_conv5x5_ln: gamma is null");
+    return tc_conv5x5_impl(in_bf16, in_cs, B, H, W, Kc, wt_bf16, 4 * C, 128, 1, bias, nullptr, 0, 0, (float*)gates_bf16, c_prev, c_out, h_out, h_cs, h_co,
+                           h_bf16, hb_cs, hb_co, nullptr, 0, 0, C, forget_bias, flags | 2, ln_partial, lf, stream);
 }
 
 // General tap-list convolution with a plain epilogue:  D[m,n] = sum_t sum_c In[pixel(m)+(dy_t,dx_t), coff_t + c] * Wt[n][t*Kc + c],

@@ -30,10 +30,42 @@ struct TcEpilogue {
     __nv_bfloat16* h_bf16; int hb_cs, hb_co;     // bf16 shadow (GEMM operand of the next step)
     __nv_bfloat16* h_t; long h_t_ld;             // optional channel-major bf16 copy  h_t[(hT_co + ch) * h_t_ld + m]  (wgrad operand)
     int hT_co;
+    // mode 1, halo kernel with TMA stores only: the LayerNorm that follows the cell (train_model.py:203-208, 596-601) applied in the SAME
+    // kernel.  The CTAs of a sample meet at a per-sample arrival counter once their (mean, M2) partials are written; every thread then
+    // normalises the h values it still holds in registers.  ln_gamma == null: no fusion (the separate LayerNorm kernel reads ln_partial).
+    const float* ln_gamma; const float* ln_beta; // per-element affine in the sample's H*W*C order
+    float* ln_y; int ln_y_cs, ln_y_co;           // fp32 output view (the next layer's x slot)
+    __nv_bfloat16* ln_yb; int ln_yb_cs, ln_yb_co;   // optional bf16 copy (the next GEMM's operand)
+    float2* ln_stats;                            // [B] (mean, rstd) saved for the LayerNorm backward
+    unsigned* ln_counter;                        // [B] arrival counters, never reset: every launch adds exactly ln_S per sample
+    float ln_eps;
     int C;                                       // LSTM channels (N = 4C)
     float forget_bias;
     int accurate;                                // 1: expf/tanhf, 0: tanh.approx
 };
+
+// Gate non-linearities + cell update of 8 channels (train_model.py:269-272): gj/gi/gf/go hold the accumulator on entry and the ACTIVATED
+// gates on exit.  ACC is a template parameter on purpose: with a run-time flag inside the element loop ptxas keeps one basic block per
+// element (branch, 4 MUFU, branch, MUFU ...) and the eight independent dependency chains run one after the other.
+template <bool ACC>
+__device__ __forceinline__ void gate_math8(float (&gj)[8], float (&gi)[8], float (&gf)[8], float (&go)[8], const float* cp, const float* bias_s,
+                                           int c0, float forget_bias, float (&cn)[8], float (&hn)[8]) {
+    const float4 bj0 = *reinterpret_cast<const float4*>(bias_s + c0), bj1 = *reinterpret_cast<const float4*>(bias_s + c0 + 4);
+    const float4 bi0 = *reinterpret_cast<const float4*>(bias_s + 32 + c0), bi1 = *reinterpret_cast<const float4*>(bias_s + 32 + c0 + 4);
+    const float4 bf0 = *reinterpret_cast<const float4*>(bias_s + 64 + c0), bf1 = *reinterpret_cast<const float4*>(bias_s + 64 + c0 + 4);
+    const float4 bo0 = *reinterpret_cast<const float4*>(bias_s + 96 + c0), bo1 = *reinterpret_cast<const float4*>(bias_s + 96 + c0 + 4);
+    const float bj[8] = {bj0.x, bj0.y, bj0.z, bj0.w, bj1.x, bj1.y, bj1.z, bj1.w}, bi[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+    const float bf[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w}, bo[8] = {bo0.x, bo0.y, bo0.z, bo0.w, bo1.x, bo1.y, bo1.z, bo1.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        float j = gj[i] + bj[i], ii = gi[i] + bi[i], f = gf[i] + bf[i] + forget_bias, o = go[i] + bo[i];
+        if (ACC) { j = tanhf(j); ii = sigmoid_acc(ii); f = sigmoid_acc(f); o = sigmoid_acc(o); }
+        else { j = tanh_fast(j); ii = sigmoid_fast(ii); f = sigmoid_fast(f); o = sigmoid_fast(o); }
+        cn[i] = cp[i] * f + ii * j;
+        hn[i] = (ACC ? tanhf(cn[i]) : tanh_fast(cn[i])) * o;
+        gj[i] = j; gi[i] = ii; gf[i] = f; go[i] = o;
+    }
+}
 
 __device__ __forceinline__ uint4 pack8_bf16(const float (&v)[8]) {
     __nv_bfloat162 p0 = __floats2bfloat162_rn(v[0], v[1]), p1 = __floats2bfloat162_rn(v[2], v[3]);

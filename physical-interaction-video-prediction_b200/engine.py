@@ -73,6 +73,7 @@ class Engine(object):
         self.g = {s.name: self.flat_g[s.offset:s.offset + s.size] for s in self.specs}
         self.ws = None
         self.tc = None                                   # tensor-core (bf16) plan, created lazily
+        self.grad_sync = None                            # parallel.GradSync when the all-reduce is overlapped with the deferred weight gradients
         self.load_chainer_params(layout.lecun_normal_init(self.specs))
 
     # ------------------------------------------------------------------ parameters
@@ -261,6 +262,19 @@ class Engine(object):
                     0 if gb is None else gb.cs, 0 if gb is None else gb.co, dst.ptr, dst.cs, dst.co, M, dst.C, self._s())
 
     # ------------------------------------------------------------------ ConvLSTM layer (fwd / bwd)
+    def _lstm_ln_fwd(self, li, t, B, name, y, y_bf16=None):
+        """ConvLSTM layer li at step t followed by the LayerNorm `name` of its output h_t (train_model.py:596-601): one kernel on the tensor-core
+        path when the launch fits (TensorCorePlan.ln_fusable), else the cell and then the LayerNorm kernel(s)."""
+        ws = self.ws
+        cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
+        stats = ws["ln_stats"][name][t]
+        if self.tc is not None and self.tc.ln_fusable(li):
+            self.tc.lstm_fwd(li, t, ln=(name, y, y_bf16, stats))
+            return
+        self._lstm_fwd(li, t, B)
+        self._ln_fwd(name, View(ws["xh"][li][t + 1], cin + C, cin, C), B, ws["HW"][lv], y, None, 0, stats, y_bf16,
+                     have_stats=self.tc is not None and self.tc.ln_fused[li])
+
     def _lstm_fwd(self, li, t, B):
         ws = self.ws
         cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
@@ -386,12 +400,8 @@ class Engine(object):
             if self.tc is not None:
                 L.call("pivp_copy_view", _ptr(ws["cat6"][t]), 64, 32, 0, 0, 0, _ptr(self.tc.cat6_b[t]), 64, 32, Mr[2], 32, s)
             # ---- group 1
-            self._lstm_fwd(0, t, B)
-            self._ln_fwd("hidden1", View(ws["xh"][0][t + 1], 64, 32, 32), B, HW[2], View(ws["xh"][1][t], 64, 0, 32), None, 0,
-                         ws["ln_stats"]["hidden1"][t], None if self.tc is None else self.tc.xview(1, t), have_stats=self.tc is not None and self.tc.ln_fused[0])
-            self._lstm_fwd(1, t, B)
-            self._ln_fwd("hidden2", View(ws["xh"][1][t + 1], 64, 32, 32), B, HW[2], View(ws["hid2"][t], 32, 0, 32), None, 0,
-                         ws["ln_stats"]["hidden2"][t], have_stats=self.tc is not None and self.tc.ln_fused[1])
+            self._lstm_ln_fwd(0, t, B, "hidden1", View(ws["xh"][1][t], 64, 0, 32), None if self.tc is None else self.tc.xview(1, t))
+            self._lstm_ln_fwd(1, t, B, "hidden2", View(ws["hid2"][t], 32, 0, 32))
             if self.tc is not None:       # stride-2 conv as a 9-tap tcgen05 GEMM on the space-to-depth bf16 input; bf16 x slot from the epilogue
                 self.tc.conv_s2_fwd("enc1", t, ws["hid2"][t], 32, ws["xh"][2][t], 96, self.tc.xview(2, t).t, self.tc.Kpad[2])
                 L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, s)
@@ -400,12 +410,8 @@ class Engine(object):
                                View(ws["xh"][2][t], 96, 0, 32), relu=1)
                 L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, 0, 0, 0, Mr[4], 32, s)
             # ---- group 2
-            self._lstm_fwd(2, t, B)
-            self._ln_fwd("hidden3", View(ws["xh"][2][t + 1], 96, 32, 64), B, HW[4], View(ws["xh"][3][t], 128, 0, 64), None, 0,
-                         ws["ln_stats"]["hidden3"][t], None if self.tc is None else self.tc.xview(3, t), have_stats=self.tc is not None and self.tc.ln_fused[2])
-            self._lstm_fwd(3, t, B)
-            self._ln_fwd("hidden4", View(ws["xh"][3][t + 1], 128, 64, 64), B, HW[4], View(ws["hid4"][t], 64, 0, 64), None, 0,
-                         ws["ln_stats"]["hidden4"][t], have_stats=self.tc is not None and self.tc.ln_fused[3])
+            self._lstm_ln_fwd(2, t, B, "hidden3", View(ws["xh"][3][t], 128, 0, 64), None if self.tc is None else self.tc.xview(3, t))
+            self._lstm_ln_fwd(3, t, B, "hidden4", View(ws["hid4"][t], 64, 0, 64))
             if self.tc is not None:
                 self.tc.conv_s2_fwd("enc2", t, ws["hid4"][t], 64, ws["in3"][t], self.cs3, None, 0)
             else:
@@ -420,27 +426,21 @@ class Engine(object):
             if self.tc is not None:
                 L.call("pivp_copy_view", _ptr(ws["xh"][4][t]), 192, 0, 0, 0, 0, self.tc.xview(4, t).ptr, self.tc.Kpad[4], 0, Mr[8], 64, s)
             # ---- group 4
-            self._lstm_fwd(4, t, B)
-            self._ln_fwd("hidden5", View(ws["xh"][4][t + 1], 192, 64, 128), B, HW[8], View(ws["hid5"][t], 128, 0, 128), None, 0,
-                         ws["ln_stats"]["hidden5"][t], None if self.tc is None else View(self.tc.hid5_b[t], 128, 0, 128), have_stats=self.tc is not None and self.tc.ln_fused[4])
+            self._lstm_ln_fwd(4, t, B, "hidden5", View(ws["hid5"][t], 128, 0, 128), None if self.tc is None else View(self.tc.hid5_b[t], 128, 0, 128))
             if self.tc is not None:
                 self.tc.deconv_fwd("enc4", self.tc.hid5_b[t], ws["xh"][5][t], 192, self.tc.xh_bf16[5][t], self.tc.Kpad[5], 1)
             else:
                 self._conv_dgrad(View(ws["hid5"][t], 128, 0, 128), B, H // 8, W // 8, p["enc4/W"], p["enc4/b"], 3, 2, 1,
                                  View(ws["xh"][5][t], 192, 0, 128), H // 4, W // 4, relu=1)
             # ---- group 5
-            self._lstm_fwd(5, t, B)
-            self._ln_fwd("hidden6", View(ws["xh"][5][t + 1], 192, 128, 64), B, HW[4], View(ws["cat5"][t], 96, 0, 64), None, 0,
-                         ws["ln_stats"]["hidden6"][t], None if self.tc is None else View(self.tc.cat5_b[t], 128, 0, 64), have_stats=self.tc is not None and self.tc.ln_fused[5])
+            self._lstm_ln_fwd(5, t, B, "hidden6", View(ws["cat5"][t], 96, 0, 64), None if self.tc is None else View(self.tc.cat5_b[t], 128, 0, 64))
             if self.tc is not None:
                 self.tc.deconv_fwd("enc5", self.tc.cat5_b[t], ws["xh"][6][t], 128, self.tc.xh_bf16[6][t], self.tc.Kpad[6], 1)
             else:
                 self._conv_dgrad(View(ws["cat5"][t], 96, 0, 96), B, H // 4, W // 4, p["enc5/W"], p["enc5/b"], 3, 2, 1,
                                  View(ws["xh"][6][t], 128, 0, 96), H // 2, W // 2, relu=1)
             # ---- group 6
-            self._lstm_fwd(6, t, B)
-            self._ln_fwd("hidden7", View(ws["xh"][6][t + 1], 128, 96, 32), B, HW[2], View(ws["cat6"][t], 64, 0, 32), None, 0,
-                         ws["ln_stats"]["hidden7"][t], None if self.tc is None else View(self.tc.cat6_b[t], 64, 0, 32), have_stats=self.tc is not None and self.tc.ln_fused[6])
+            self._lstm_ln_fwd(6, t, B, "hidden7", View(ws["cat6"][t], 64, 0, 32), None if self.tc is None else View(self.tc.cat6_b[t], 64, 0, 32))
             if self.tc is not None:
                 self.tc.deconv_fwd("enc6", self.tc.cat6_b[t], ws["e6pre"][t], 64, None, 0, 0)
             else:
@@ -649,6 +649,9 @@ class Engine(object):
                 return
         # ---- deferred weight gradients of enc0..enc3: the per-step tensors are stacked over time, so each is ONE launch with
         # S*B "images" (9x longer reduction per launch instead of 9 launches that cannot fill the GPU)
+        gs = self.grad_sync
+        if gs is not None:
+            gs.ready("tail")                   # LayerNorm / heads / state-predictor gradients are final: their all-reduce runs under the GEMMs below
         if True:
             S = T - 1
             first = lambda lst: lst[0]
@@ -666,5 +669,9 @@ class Engine(object):
                                  3, 2, 1, g["enc2/W"], g["enc2/b"])
             self._conv_wgrad(View(first(ws["in3"]), self.cs3, 0, cin3), S * B, H // 8, W // 8, View(first(ws["d_e3pre"]), 64, 0, 64), H // 8, W // 8,
                              1, 1, 0, g["enc3/W"], g["enc3/b"])
+        if gs is not None:
+            gs.ready("xform")
         if self.tc is not None:
-            self.tc.wgrad_all()                # ConvLSTM weight/bias gradients: one tcgen05 GEMM per layer over all time steps
+            self.tc.wgrad_all(gs)              # ConvLSTM weight/bias gradients: one tcgen05 GEMM per layer over all time steps
+        if gs is not None:
+            gs.finish()

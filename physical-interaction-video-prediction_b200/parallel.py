@@ -71,3 +71,70 @@ def allreduce_sum_(flat):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
         dist.all_reduce(flat)
     return flat
+
+
+class GradSync(object):
+    """Gradient all-reduce overlapped with the tail of the backward pass (the reference has no multi-GPU path).
+
+    The flat gradient buffer is cut into UNITS, each a contiguous range that becomes final at one point of ``Engine.backward``:
+    ``tail`` (LayerNorm, heads, state predictor -- accumulated step by step, final when the reverse time loop ends), ``enc`` (enc0 .. enc6,
+    final after their deferred weight-gradient launches), ``lstm1`` .. ``lstm7`` (final after that layer's weight-gradient GEMM) and
+    ``xform`` (cdna_kerns / stp Linears).  ``ready(unit)`` is called on the compute stream right after the launches that finish the
+    unit: the side stream waits for that point and sums the unit over the ranks (NCCL over NVLink) while the compute stream goes on with
+    the next weight-gradient GEMM.  ``finish()`` reduces whatever is left and makes the compute stream wait for the side stream, so the
+    fused 1/N + Adam kernel that follows sees the complete sum.  Everything is stream-ordered (``wait_stream`` only), hence capturable
+    in the step's CUDA graph."""
+
+    def __init__(self, engine):
+        import torch
+        self.e = engine
+        self.side = torch.cuda.Stream(device=engine.dev)
+        rng = {}
+        for s in engine.specs:
+            top = s.name.split("/")[0]
+            if top.startswith("lstm"):
+                unit = top
+            elif top.startswith("enc"):
+                unit = "enc"
+            elif top == "model" and not s.name.startswith("model/enc7"):
+                unit = "xform"
+            else:
+                unit = "tail"
+            lo, hi = rng.get(unit, (s.offset, s.offset + s.size))
+            rng[unit] = (min(lo, s.offset), max(hi, s.offset + s.size))
+        # units must not interleave in the flat buffer (layout.param_specs orders them so); pad bytes between specs belong to nobody
+        spans = sorted(rng.values())
+        assert all(a[1] <= b[0] for a, b in zip(spans, spans[1:])), "gradient units interleave in the flat buffer"
+        self.range = rng
+        self.done = set()
+
+    def begin(self):
+        self.done = set()
+
+    def _reduce(self, units):
+        import torch
+        import torch.distributed as dist
+        units = [u for u in units if u in self.range and u not in self.done]
+        if not units:
+            return
+        self.done.update(units)
+        spans = sorted(self.range[u] for u in units)
+        merged = [list(spans[0])]
+        for a, b in spans[1:]:
+            if a - merged[-1][1] <= 4:                     # adjacent up to alignment padding
+                merged[-1][1] = b
+            else:
+                merged.append([a, b])
+        cur = torch.cuda.current_stream(self.e.dev)
+        self.side.wait_stream(cur)
+        with torch.cuda.stream(self.side):
+            for a, b in merged:
+                dist.all_reduce(self.e.flat_g[a:b])
+
+    def ready(self, *units):
+        self._reduce(units)
+
+    def finish(self):
+        import torch
+        self._reduce(list(self.range))
+        torch.cuda.current_stream(self.e.dev).wait_stream(self.side)

@@ -47,6 +47,9 @@ class TensorCorePlan(object):
         self.wgrad_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         self.accurate = 0
         import os
+        # LayerNorm of the ConvLSTM output applied inside the gate epilogue (pivp_tc_conv5x5_ln): per-layer arrival counters, zeroed once
+        self.ln_counter = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in LSTM_SIZES]
+        self.fuse_ln = os.environ.get("PIVP_TC_FUSE_LN", "1") != "0"
         self.split_n = int(os.environ.get("PIVP_TC_SPLIT_N", "0"))       # tuning switch for the input-gradient N split
         self.pair_bn = int(os.environ.get("PIVP_TC_PAIR_BN", "96"))      # N tile of the 8x8-map input gradient (0: per-tap kernel's choice)
         # layers whose maps the halo-patch kernel tiles (H % 16 == 0, W % 8 == 0): its epilogue also produces the LayerNorm statistics
@@ -272,11 +275,31 @@ class TensorCorePlan(object):
         """bf16 x-slot of layer li at time t (what the producer of the layer input also writes)."""
         return View(self.xh_bf16[li][t], self.Kpad[li], 0, LSTM_IN[li])
 
-    def lstm_fwd(self, li, t):
-        """conv + bias + gates + cell + h of BasicConvLSTMCell (train_model.py:262-272) in ONE tcgen05 kernel."""
+    def ln_fusable(self, li):
+        """The LayerNorm behind ConvLSTM layer li can run inside the layer's gate epilogue: halo geometry with fused statistics and a launch
+        of at most 148 CTAs (one per SM: the per-sample rendezvous needs all of them resident)."""
+        e = self.eng
+        C, lv = LSTM_SIZES[li], LSTM_LEVEL[li]
+        h, w = e.H // lv, e.W // lv
+        tiles = self.ws["B"] * (h // 16) * (w // 8) if self.ln_fused[li] else 0
+        ctas_one, ctas_two = tiles * (C // 32), (tiles // 2) * (C // 32)
+        ctas = ctas_two if (tiles % 2 == 0 and ctas_two >= 96) else ctas_one          # launch_conv5x5_halo's choice of tiles per CTA
+        return self.fuse_ln and self.ln_fused[li] and 0 < ctas <= 148
+
+    def lstm_fwd(self, li, t, ln=None):
+        """conv + bias + gates + cell + h of BasicConvLSTMCell (train_model.py:262-272) in ONE tcgen05 kernel.
+        ``ln`` = (name, y View, y_bf16 View or None, stats): also apply the LayerNorm of the layer's output there (train_model.py:596-601)."""
         e, ws = self.eng, self.ws
         cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
         h, w = e.H // lv, e.W // lv
+        if ln is not None:
+            name, y, yb, stats = ln
+            e.L.call("pivp_tc_conv5x5_ln", _ptr(self.xh_bf16[li][t]), self.Kpad[li], ws["B"], h, w, self.Kpad[li], _ptr(self.Wf[li]), C,
+                     _ptr(e.p["lstm%d/conv/b" % (li + 1)]), _ptr(self.dg_bf16[li][t]), _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]),
+                     _ptr(ws["xh"][li][t + 1]), cin + C, cin, _ptr(self.xh_bf16[li][t + 1]), self.Kpad[li], cin, 1.0, self.accurate, _ptr(ws["ln_ws"]),
+                     _ptr(e.p[name + "/norm/gamma"]), _ptr(e.p[name + "/norm/beta"]), 1e-6, y.ptr, y.cs, y.co,
+                     0 if yb is None else yb.ptr, 0 if yb is None else yb.cs, 0 if yb is None else yb.co, _ptr(stats), _ptr(self.ln_counter[li]), e._s())
+            return
         e.L.call("pivp_tc_conv5x5", _ptr(self.xh_bf16[li][t]), self.Kpad[li], ws["B"], h, w, self.Kpad[li],
                  _ptr(self.Wf[li]), 4 * C, 128, 1, _ptr(e.p["lstm%d/conv/b" % (li + 1)]),
                  0, 0, 0,
@@ -313,11 +336,21 @@ class TensorCorePlan(object):
                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
                  C, 0.0, 0, 0, e._s())
 
-    def wgrad_all(self):
-        """After BPTT: weight and bias gradients of all seven ConvLSTM convolutions, each as ONE GEMM over all time steps."""
+    def wgrad_all(self, grad_sync=None):
+        """After BPTT: weight and bias gradients of all seven ConvLSTM convolutions, each as ONE GEMM over all time steps.
+        Data parallel (``grad_sync``): the small encoder / decoder gradients go first and are all-reduced as one block, then the ConvLSTM
+        layers from the largest parameter tensor to the smallest, each layer's all-reduce running under the next layer's GEMM, so only the
+        smallest tensor's reduction (0.8 MB) is exposed behind the last GEMM."""
         e, ws = self.eng, self.ws
         S, B = self.S, ws["B"]
-        for li, (cin, C, lv) in enumerate(zip(LSTM_IN, LSTM_SIZES, LSTM_LEVEL)):
+        order = range(7)
+        if grad_sync is not None:
+            self.deconv_wgrad_all()
+            self.conv_s2_wgrad_all()
+            grad_sync.ready("enc")
+            order = sorted(range(7), key=lambda li: -(LSTM_IN[li] + LSTM_SIZES[li]) * LSTM_SIZES[li])
+        for li in order:
+            cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
             M = ws["Mr"][lv]
             h, w = e.H // lv, e.W // lv
             cx = cin + C
@@ -325,5 +358,8 @@ class TensorCorePlan(object):
             e.L.call("pivp_tc_colsum_bf16", _ptr(self.dg_all[li]), 4 * C, S * M, 4 * C, _ptr(e.g[name + "/b"]), e._s())
             e.L.call("pivp_tc_wgrad5x5", _ptr(self.dg_all[li]), _ptr(self.xh_all[li]), self.Kpad[li], S * B, h, w, cx, 4 * C,
                      _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
-        self.deconv_wgrad_all()
-        self.conv_s2_wgrad_all()
+            if grad_sync is not None:
+                grad_sync.ready("lstm%d" % (li + 1))
+        if grad_sync is None:
+            self.deconv_wgrad_all()
+            self.conv_s2_wgrad_all()

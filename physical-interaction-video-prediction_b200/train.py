@@ -51,11 +51,25 @@ class TrainStep(object):
                    torch.cuda.current_stream(e.dev).cuda_stream)
         e.params_changed()
 
+    def _overlap(self):
+        """Data parallel, tensor-core mode: the gradient all-reduce runs unit by unit on a side stream under the deferred weight-gradient
+        GEMMs (parallel.GradSync) and the whole step -- collective included -- is ONE CUDA graph.  PIVP_DP_OVERLAP=0 keeps the plain
+        form: graph (forward + BPTT), one all-reduce of the flat buffer, graph (Adam)."""
+        import os
+        return self.model.world_size > 1 and self.e.compute == "bf16" and os.environ.get("PIVP_DP_OVERLAP", "1") != "0"
+
     def _eager_step(self):
-        self._fwd_bwd()
-        if self.model.world_size > 1:
-            from .parallel import allreduce_sum_
-            allreduce_sum_(self.e.flat_g)          # the step's only collective: NCCL sum of 36.8 MB over NVLink
+        if self._overlap():
+            from .parallel import GradSync
+            if self.e.grad_sync is None:
+                self.e.grad_sync = GradSync(self.e)
+            self.e.grad_sync.begin()
+            self._fwd_bwd()                        # backward() hands each finished unit to the side stream and joins it at the end
+        else:
+            self._fwd_bwd()
+            if self.model.world_size > 1:
+                from .parallel import allreduce_sum_
+                allreduce_sum_(self.e.flat_g)      # the step's only collective: NCCL sum of 36.8 MB over NVLink
         self._update()
 
     def __call__(self, iter_num):
@@ -73,10 +87,9 @@ class TrainStep(object):
             if self.graph is None:
                 self._capture()
             self.graph[0].replay()
-            if m.world_size > 1:
+            if self.graph[1] is not None:          # plain data-parallel form: the all-reduce sits between the two graphs, on the same stream
                 from .parallel import allreduce_sum_
-                allreduce_sum_(e.flat_g)           # between the two graphs, on the same stream
-            if self.graph[1] is not None:
+                allreduce_sum_(e.flat_g)
                 self.graph[1].replay()
         m.gen_images = e.ws["gen"]
         m._bind_loss()
@@ -100,7 +113,10 @@ class TrainStep(object):
         n0 = lib().query("pivp_launch_count")
         ga = torch.cuda.CUDAGraph()
         gb = None
-        if self.model.world_size > 1:
+        if self._overlap():
+            with torch.cuda.graph(ga):             # NCCL collectives on the forked side stream are captured with the kernels
+                self._eager_step()
+        elif self.model.world_size > 1:
             with torch.cuda.graph(ga):
                 self._fwd_bwd()
             gb = torch.cuda.CUDAGraph()

@@ -32,7 +32,7 @@ orig, recs = L.call, []
 
 
 def rec(name, *a):
-    if name in ("pivp_tc_conv5x5", "pivp_tc_wgrad5x5"):
+    if name in ("pivp_tc_conv5x5", "pivp_tc_conv5x5_ln", "pivp_tc_wgrad5x5"):
         recs.append((name, a))
     orig(name, *a)
 
@@ -66,7 +66,7 @@ rows = []
 tot = {"fwd": 0.0, "dgrad": 0.0, "wgrad": 0.0}
 for li in range(7):
     for kind, ptr in (("fwd", tc.Wf[li].data_ptr()), ("dgrad", tc.Wd[li].data_ptr())):
-        calls = [(n, a) for n, a in recs if n == "pivp_tc_conv5x5" and a[6] == ptr]
+        calls = [(n, a) for n, a in recs if n in ("pivp_tc_conv5x5", "pivp_tc_conv5x5_ln") and a[6] == ptr]
         per = replay(calls)
         tot[kind] += per * len(calls)
         rows.append(dict(layer=li + 1, kind=kind, launches=len(calls), us=per * 1e6, tflops=flops[li] / per / 1e12,
@@ -81,7 +81,7 @@ print("|---|---|---:|---:|---:|---:|")
 for r in rows:
     print("| lstm%d | %s | %d | %.2f | %.0f | %.3f |" % (r["layer"], r["kind"], r["launches"], r["us"], r["tflops"], r["frac"]))
 print("per step: fwd %.3f ms, dgrad %.3f ms, wgrad %.3f ms" % (tot["fwd"] * 1e3, tot["dgrad"] * 1e3, tot["wgrad"] * 1e3))
-allc = [(n, a) for n, a in recs if n == "pivp_tc_conv5x5"]
+allc = [(n, a) for n, a in recs if n in ("pivp_tc_conv5x5", "pivp_tc_conv5x5_ln")]
 per = replay(allc)
 fl = sum(flops) * 2 * (T - 1) / len(allc)
 print("all %d fwd+dgrad launches in one graph: %.2f us/launch, %.0f TFLOP/s, frac %.3f" % (len(allc), per * 1e6, fl / per / 1e12, fl / per / 1e12 / peaks["bf16_tflops"]))

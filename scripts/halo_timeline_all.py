@@ -7,7 +7,6 @@ import numpy as np, torch
 import pivp_b200 as pk
 ap = argparse.ArgumentParser(); ap.add_argument("--batch", type=int, default=32); args = ap.parse_args()
 L = pk.lib()
-st = torch.cuda.current_stream().cuda_stream
 B = args.batch
 LS, LI, LV = (32, 32, 64, 64, 128, 64, 32), (32, 32, 32, 64, 64, 128, 96), (2, 2, 4, 4, 8, 4, 2)
 print("cycles since CTA start: mean (max) over CTAs; graph columns: 8 back-to-back launches of the same call in one CUDA graph, %globaltimer per CTA")
@@ -22,9 +21,18 @@ def run(name, H, W, Kc, C, mode, N, BN, ln):
     h = torch.empty(M, Kc, device="cuda"); hb = torch.empty(M, Kc, device="cuda", dtype=torch.bfloat16)
     out = torch.empty(M, N, device="cuda")
     part = torch.zeros(B * 64 * 2 + 16, device="cuda")
+    n = H * W * C
+    gamma, beta = torch.ones(n, device="cuda"), torch.zeros(n, device="cuda")
+    y, yb = torch.empty(M, C, device="cuda"), torch.empty(M, 64, device="cuda", dtype=torch.bfloat16)
+    stats, counter = torch.zeros(B, 2, device="cuda"), torch.zeros(B, dtype=torch.int32, device="cuda")
     dbg = torch.zeros(4096, 8, dtype=torch.int64, device="cuda")
     def call():
-        if mode == 1:
+        st = torch.cuda.current_stream().cuda_stream          # looked up per call: under graph capture the current stream is the capture stream
+        if mode == 1 and ln and os.environ.get("PIVP_TC_FUSE_LN", "1") != "0":        # the production launch: cell + LayerNorm in one kernel
+            L.call("pivp_tc_conv5x5_ln", x.data_ptr(), Kc, B, H, W, Kc, w.data_ptr(), C, bias.data_ptr(), gates.data_ptr(), cp.data_ptr(), co.data_ptr(),
+                   h.data_ptr(), Kc, Kc - C, hb.data_ptr(), Kc, Kc - C, 1.0, 0, part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-6,
+                   y.data_ptr(), C, 0, yb.data_ptr(), 64, 0, stats.data_ptr(), counter.data_ptr(), st)
+        elif mode == 1:
             L.call("pivp_tc_conv5x5", x.data_ptr(), Kc, B, H, W, Kc, w.data_ptr(), N, 128, 1, bias.data_ptr(), 0, 0, 0,
                    gates.data_ptr(), cp.data_ptr(), co.data_ptr(), h.data_ptr(), Kc, Kc - C, hb.data_ptr(), Kc, Kc - C, 0, 0, 0, C, 1.0, 2,
                    part.data_ptr() if ln else 0, st)

@@ -368,3 +368,64 @@ def test_tc_deconv_phases_match_simt(pk, B, ih, iw, cin, cout, bn, relu):
     assert rel(out[:, :cout], ref) < 2e-3
     assert torch.all(out[:, cout:] == -5.0)
     assert rel(out_b, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,cin,C,with_bf16", [(2, 32, 32, 32, 32, True), (32, 32, 32, 32, 32, True), (32, 32, 32, 96, 32, True),
+                                                   (32, 16, 16, 32, 64, True), (32, 16, 16, 128, 64, False), (6, 16, 16, 64, 64, False)])
+def test_tc_convlstm_with_fused_layernorm_equals_cell_then_layernorm(pk, B, H, W, cin, C, with_bf16):
+    """pivp_tc_conv5x5_ln (ConvLSTM cell + the LayerNorm of its output in ONE kernel, per-sample rendezvous of the CTAs) ==
+    pivp_tc_conv5x5 (bf16 gate storage, statistics partials) followed by pivp_layernorm_fwd.  Launched three times on the same
+    arrival counters (they are never reset); includes the b32 launches of the benchmark step (128 CTAs, one and two tiles per CTA)."""
+    L = pk.lib()
+    rs = np.random.RandomState(5)
+    M, cx = B * H * W, cin + C
+    Kp = (cx + 63) // 64 * 64
+    n = H * W * C
+    xh = torch.zeros(M, Kp, device="cuda")
+    xh[:, :cx] = torch.from_numpy(rs.standard_normal((M, cx)).astype(np.float32)).cuda()
+    xh_b = xh.bfloat16()
+    Wm = torch.from_numpy((rs.standard_normal((4 * C, 25, cx)) / np.sqrt(25 * cx)).astype(np.float32)).cuda()
+    bias = torch.from_numpy((0.1 * rs.standard_normal(4 * C)).astype(np.float32)).cuda()
+    Wf = torch.empty(4 * C, 25, Kp, dtype=torch.bfloat16, device="cuda")
+    Wd = torch.empty(cx, 25, 4 * C, dtype=torch.bfloat16, device="cuda")
+    L.call("pivp_tc_prep_weights", Wm.data_ptr(), 4 * C, cx, Kp, Wf.data_ptr(), Wd.data_ptr(), stream())
+    gamma = torch.from_numpy((1 + 0.2 * rs.standard_normal(n)).astype(np.float32)).cuda()
+    beta = torch.from_numpy((0.2 * rs.standard_normal(n)).astype(np.float32)).cuda()
+    nb = max(16, L.query("pivp_layernorm_workspace_bytes", B, n))
+    counter = torch.zeros(B, dtype=torch.int32, device="cuda")
+    ycs, yco = C + 32, 16                                         # y is a channel slice of a wider buffer, like the next layer's x slot
+
+    def run(fused, c_prev):
+        gates = torch.empty(M, 4 * C, dtype=torch.bfloat16, device="cuda")
+        c_out, h_out = torch.empty(M, C, device="cuda"), torch.zeros(M, cx, device="cuda")
+        h_b = torch.zeros(M, Kp, dtype=torch.bfloat16, device="cuda")
+        y = torch.full((M, ycs), -7.0, device="cuda")
+        yb = torch.zeros(M, 64 + C, dtype=torch.bfloat16, device="cuda") if with_bf16 else None
+        stats = torch.zeros(B, 2, device="cuda")
+        ws = torch.zeros(nb, dtype=torch.uint8, device="cuda")
+        cp = 0 if c_prev is None else c_prev.data_ptr()
+        if fused:
+            L.call("pivp_tc_conv5x5_ln", xh_b.data_ptr(), Kp, B, H, W, Kp, Wf.data_ptr(), C, bias.data_ptr(), gates.data_ptr(), cp, c_out.data_ptr(),
+                   h_out.data_ptr(), cx, cin, h_b.data_ptr(), Kp, cin, 1.0, 0, ws.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-6,
+                   y.data_ptr(), ycs, yco, 0 if yb is None else yb.data_ptr(), 64 + C, 64, stats.data_ptr(), counter.data_ptr(), stream())
+        else:
+            L.call("pivp_tc_conv5x5", xh_b.data_ptr(), Kp, B, H, W, Kp, Wf.data_ptr(), 4 * C, 128, 1, bias.data_ptr(), 0, 0, 0, gates.data_ptr(), cp,
+                   c_out.data_ptr(), h_out.data_ptr(), cx, cin, h_b.data_ptr(), Kp, cin, 0, 0, 0, C, 1.0, 2, ws.data_ptr(), stream())
+            L.call("pivp_layernorm_fwd", h_out.data_ptr(), cx, cin, gamma.data_ptr(), beta.data_ptr(), B, H * W, C, 1e-6, y.data_ptr(), ycs, yco,
+                   0, 0, 0, 0 if yb is None else yb.data_ptr(), 64 + C, 64, 2, stats.data_ptr(), ws.data_ptr(), nb, stream())
+        torch.cuda.synchronize()
+        return gates, c_out, h_out, h_b, y, yb, stats
+
+    c_prev = None
+    for rep in range(3):
+        a = run(False, c_prev)
+        b = run(True, c_prev)
+        for i in range(4):                                         # the cell's own outputs: same arithmetic, identical bits
+            assert torch.equal(a[i], b[i]), (rep, i)
+        assert rel(b[4][:, yco:yco + C], a[4][:, yco:yco + C]) < 1e-5
+        assert torch.all(b[4][:, :yco] == -7.0) and torch.all(b[4][:, yco + C:] == -7.0)      # only the slice is written
+        if with_bf16:
+            assert rel(b[5][:, 64:64 + C], a[5][:, 64:64 + C]) < 2 ** -7 and float(b[5][:, :64].abs().max()) == 0.0
+        assert rel(b[6], a[6]) < 1e-5                              # (mean, rstd) saved for the backward pass
+        c_prev = a[1]
+    assert int(counter.min()) == int(counter.max()) == 3 * (H * W // 128) * (C // 32)
