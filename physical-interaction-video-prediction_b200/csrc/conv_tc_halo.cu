@@ -115,62 +115,6 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     pdl_wait();                                      // barrier init / TMEM allocation above overlap the previous kernel's tail
-
-    // ===================== TMA producer (warp 0) =====================
-    // Producer and MMA issuer run warp-uniform loops (every operand derives from kernel parameters and loop counters, the TMEM
-    // base is broadcast with a shuffle) and one elected lane issues: otherwise the compiler cannot keep descriptors in uniform
-    // registers and wraps every tcgen05.mma in a per-lane waterfall loop -- ~20 issue slots per MMA, which is what bounded the
-    // per-tap kernel at ~25 % tensor-pipe utilisation (profiles/r01_ncu_halo_issue_bound.md).
-    // (Measured and dropped: running the first `stages` iterations of this loop BEFORE the CTA-wide set-up barrier.  The TMA issue path
-    // costs ~300 cycles per stage (try_wait + elect + expect_tx + UTMALDG), so the barrier -- and with it the MMA warp -- waited 3.6k
-    // cycles for the producer: first operands at 5.0k cycles instead of 3.6k.)
-    const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), ring0 = smem_u32(bring);
-    const uint32_t pfull0 = smem_u32(patch_full), pempty0 = smem_u32(patch_empty);
-    uint32_t p_st = 0, p_ph = 1;                                  // waits on `empty` start with parity 1 (fresh barrier)
-    int p_next = 0;                                               // next 64-channel block whose patch has not been requested yet
-    int p_cb = 0, p_tap = 0;
-    constexpr int np = NP;
-    // patch n goes to buffer n % np once the MMAs of block n - np have drained it (use count u = n / np -> parity (u & 1) ^ 1)
-    auto issue_patch = [&](int n) {
-        const uint32_t slot = (uint32_t)(n % np);
-        if (elect_one()) {
-            mbar_expect_tx(pfull0 + 8 * slot, pbuf_bytes);
-#pragma unroll
-            for (int i = 0; i < MS; ++i) {
-                const int mt = blockIdx.x * MS + i;
-                const uint32_t dst = smem_u32(patch) + slot * pbuf_bytes + (uint32_t)(i * g.patch_bytes);
-                if (g.pair) {
-                    tma_load_4d(dst, &map_a, pfull0 + 8 * slot, (cb_first + n) * 64, -2, 2 * mt, -2);
-                } else {
-                    const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
-                    tma_load_4d(dst, &map_a, pfull0 + 8 * slot, (cb_first + n) * 64, tx * TW - 2, ty * TH - 2, tb);
-                }
-            }
-        }
-        __syncwarp();
-    };
-    auto produce = [&](int count) {
-        for (int n = 0; n < count; ++n) {
-            if (p_tap == 0 && p_next == p_cb) {                       // this block's patch must be on its way before its weights fill the ring
-                mbar_wait(pempty0 + 8 * (uint32_t)(p_next % np), (uint32_t)((p_next / np) & 1) ^ 1u);
-                issue_patch(p_next++);
-            }
-            // prefetch later patches as soon as their buffer is free (non-blocking test), after this block's first weight tiles
-            if (NP > 1 && p_tap >= 2 && p_next < ncb && p_next < p_cb + np) {
-                const int freed = (int)mbar_test(pempty0 + 8 * (uint32_t)(p_next % np), (uint32_t)((p_next / np) & 1) ^ 1u);
-                if (__all_sync(0xffffffffu, freed)) issue_patch(p_next++);      // a vote keeps the branch (and with it the whole kernel) warp-uniform for ptxas
-            }
-            mbar_wait(empty0 + 8 * p_st, p_ph);
-            if (elect_one()) {
-                mbar_expect_tx(full0 + 8 * p_st, b_bytes);
-                tma_load_2d(ring0 + p_st * b_bytes, &map_b, full0 + 8 * p_st, p_tap * g.Kc + (cb_first + p_cb) * 64, n0);
-            }
-            __syncwarp();
-            if (++p_st == (uint32_t)g.stages) { p_st = 0; p_ph ^= 1u; }
-            if (++p_tap == 25) { p_tap = 0; ++p_cb; }
-        }
-    };
-    const int p_total = ncb * 25;
     if (warp >= 2 && ep.bias && blockIdx.z == 0) {
         for (int i = threadIdx.x - 64; i < g.BN; i += 256 * MS) bias_s[i] = ep.bias[n0 + i];
     }
@@ -180,8 +124,60 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const uint32_t tmem_base = *tmem_slot;
     if (warp == 1) HALO_STAMP(1);
 
+    // Producer and MMA issuer run warp-uniform loops (every operand derives from kernel parameters and loop counters, the TMEM
+    // base is broadcast with a shuffle) and one elected lane issues: otherwise the compiler cannot keep descriptors in uniform
+    // registers and wraps every tcgen05.mma in a per-lane waterfall loop -- ~20 issue slots per MMA, which is what bounded the
+    // per-tap kernel at ~25 % tensor-pipe utilisation (profiles/r01_ncu_halo_issue_bound.md).
+    // (Measured and dropped in round 2: running the first `stages` iterations of the producer loop BEFORE the CTA-wide set-up barrier -- the
+    // TMA issue path costs ~300 cycles per stage (try_wait + elect + expect_tx + UTMALDG), so the barrier, and with it the MMA warp, waited
+    // 3.6k cycles for the producer: first operands at 5.0k cycles instead of 3.6k.  Also measured: the same loop written as a resumable
+    // lambda over captured state ran at 356 instead of 294 cycles per stage and made the one-tile launches producer-bound.)
     if (warp == 0) {
-        produce(p_total);
+        // ===================== TMA producer =====================
+        const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), ring0 = smem_u32(bring);
+        uint32_t st = 0, ph = 1;                                  // waits on `empty` start with parity 1 (fresh barrier)
+        const uint32_t pfull0 = smem_u32(patch_full), pempty0 = smem_u32(patch_empty);
+        constexpr int np = NP;
+        int next = 0;                                             // next 64-channel block whose patch has not been requested yet
+        // patch n goes to buffer n % np once the MMAs of block n - np have drained it (use count u = n / np -> parity (u & 1) ^ 1)
+        auto issue_patch = [&](int n) {
+            const uint32_t slot = (uint32_t)(n % np);
+            if (elect_one()) {
+                mbar_expect_tx(pfull0 + 8 * slot, pbuf_bytes);
+#pragma unroll
+                for (int i = 0; i < MS; ++i) {
+                    const int mt = blockIdx.x * MS + i;
+                    const uint32_t dst = smem_u32(patch) + slot * pbuf_bytes + (uint32_t)(i * g.patch_bytes);
+                    if (g.pair) {
+                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, (cb_first + n) * 64, -2, 2 * mt, -2);
+                    } else {
+                        const int tx = mt % tiles_x, ty = (mt / tiles_x) % tiles_y, tb = mt / (tiles_x * tiles_y);
+                        tma_load_4d(dst, &map_a, pfull0 + 8 * slot, (cb_first + n) * 64, tx * TW - 2, ty * TH - 2, tb);
+                    }
+                }
+            }
+            __syncwarp();
+        };
+        for (int cb = 0; cb < ncb; ++cb) {
+            if (next == cb) {                                     // this block's patch must be on its way before its weights fill the ring
+                mbar_wait(pempty0 + 8 * (uint32_t)(next % np), (uint32_t)((next / np) & 1) ^ 1u);
+                issue_patch(next++);
+            }
+            for (int tap = 0; tap < 25; ++tap) {
+                // prefetch later patches as soon as their buffer is free (non-blocking test), after this block's first weight tiles
+                if (NP > 1 && tap >= 2 && next < ncb && next < cb + np) {
+                    const int freed = (int)mbar_test(pempty0 + 8 * (uint32_t)(next % np), (uint32_t)((next / np) & 1) ^ 1u);
+                    if (__all_sync(0xffffffffu, freed)) issue_patch(next++);      // a vote keeps the branch (and with it the whole kernel) warp-uniform for ptxas
+                }
+                mbar_wait(empty0 + 8 * st, ph);
+                if (elect_one()) {
+                    mbar_expect_tx(full0 + 8 * st, b_bytes);
+                    tma_load_2d(ring0 + st * b_bytes, &map_b, full0 + 8 * st, tap * g.Kc + (cb_first + cb) * 64, n0);
+                }
+                __syncwarp();
+                if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; }
+            }
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(g.BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
@@ -289,7 +285,7 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                 st_shared_v4(sH + r128 + (((k4 + 1u) ^ rsw) << 4), __float_as_uint(hn[4]), __float_as_uint(hn[5]), __float_as_uint(hn[6]), __float_as_uint(hn[7]));
                 pk = pack8_bf16(hn); st_shared_v4(sHB + r64 + ((k8 ^ rsw64) << 4), pk.x, pk.y, pk.z, pk.w);
             }
-            float2* red = reinterpret_cast<float2*>(smem + (size_t)MS * STG_TMA) + sub * 8;
+            float2* red = reinterpret_cast<float2*>(smem + (size_t)MS * STG_TMA) + sub * 12;        // 8 warp pairs + the sample's (mean, rstd)
             const bool fuse_ln = ep.ln_gamma != nullptr;
             float ga[16], be[16];
             if (fuse_ln) {                                   // affine parameters of this thread's 16 elements: in flight across the barriers below
@@ -327,34 +323,39 @@ conv5x5_halo_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
                     tma_store_commit();
                 }
                 __syncwarp();
-            } else if (lw == 1 && lane == 0 && ep.ln_partial) {
-                float mean = 0.f;
+            } else if (lw == 1 && ep.ln_partial) {
+                if (lane == 0) {
+                    float mean = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) mean += red[i].x;
-                mean *= 0.125f;
-                float t2 = 0.f;
+                    for (int i = 0; i < 8; ++i) mean += red[i].x;
+                    mean *= 0.125f;
+                    float t2 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; ++i) { const float d = red[i].x - mean; t2 += red[i].y + 512.f * d * d; }
-                ep.ln_partial[(long)tb * ep.ln_S + (mt - tb * tiles_per_img) * (ep.C >> 5) + n_tile] = make_float2(mean, t2);
+                    for (int i = 0; i < 8; ++i) { const float d = red[i].x - mean; t2 += red[i].y + 512.f * d * d; }
+                    ep.ln_partial[(long)tb * ep.ln_S + (mt - tb * tiles_per_img) * (ep.C >> 5) + n_tile] = make_float2(mean, t2);
+                    if (fuse_ln) {
+                        // arrive at the sample's counter; the launch adds exactly ln_S arrivals per sample, so the target is the next multiple
+                        __threadfence();
+                        const unsigned old = atomicAdd(ep.ln_counter + tb, 1u);
+                        const unsigned target = (old / (unsigned)ep.ln_S + 1u) * (unsigned)ep.ln_S;
+                        unsigned spins = 0;
+                        while ((int)(ld_acquire_u32(ep.ln_counter + tb) - target) < 0 && ++spins < (1u << 22)) { }       // bounded: never hangs the GPU
+                    }
+                }
                 if (fuse_ln) {
-                    // arrive at the sample's counter; the launch adds exactly ln_S arrivals per sample, so the target is the next multiple
-                    __threadfence();
-                    const unsigned old = atomicAdd(ep.ln_counter + tb, 1u);
-                    const unsigned target = (old / (unsigned)ep.ln_S + 1u) * (unsigned)ep.ln_S;
-                    unsigned spins = 0;
-                    while ((int)(ld_acquire_u32(ep.ln_counter + tb) - target) < 0 && ++spins < (1u << 22)) { }       // bounded: never hangs the GPU
+                    // every tile of the sample has published its pair: lane i fetches pair i (ONE L2 round trip for the whole merge), Chan merge
+                    // of the ln_S <= 32 equal-sized chunks with two warp reductions, result to shared memory for the tile's threads
+                    __syncwarp();
+                    const float2 p = lane < ep.ln_S ? __ldcg(ep.ln_partial + (long)tb * ep.ln_S + lane) : make_float2(0.f, 0.f);
+                    const float mu = warp_sum(p.x) / (float)ep.ln_S;
+                    const float d = p.x - mu;
+                    const float m2 = warp_sum(lane < ep.ln_S ? p.y + 4096.f * d * d : 0.f);
+                    if (lane == 0) red[8] = make_float2(mu, 1.f / sqrtf(m2 / (4096.f * (float)ep.ln_S) + ep.ln_eps));
                 }
             }
             if (fuse_ln) {
-                asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");      // every tile of the sample has published its partial
-                // Chan merge of the sample's ln_S partials of 4096 values each (same arithmetic as layernorm_vec.cu's combine)
-                const float2* part = ep.ln_partial + (long)tb * ep.ln_S;
-                float mu = 0.f;
-                for (int i = 0; i < ep.ln_S; ++i) mu += __ldcg(part + i).x;
-                mu /= (float)ep.ln_S;
-                float m2 = 0.f;
-                for (int i = 0; i < ep.ln_S; ++i) { const float2 p = __ldcg(part + i); const float d = p.x - mu; m2 += p.y + 4096.f * d * d; }
-                const float rstd = 1.f / sqrtf(m2 / (4096.f * (float)ep.ln_S) + ep.ln_eps);
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + sub) : "memory");      // the sample's (mean, rstd) is in shared memory
+                const float mu = red[8].x, rstd = red[8].y;
                 const uint32_t sY = sHB + 8192u, sYB = sY + 16384u;
                 float yv[16];
 #pragma unroll

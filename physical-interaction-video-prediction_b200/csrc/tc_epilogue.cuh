@@ -50,15 +50,16 @@ struct TcEpilogue {
 template <bool ACC>
 __device__ __forceinline__ void gate_math8(float (&gj)[8], float (&gi)[8], float (&gf)[8], float (&go)[8], const float* cp, const float* bias_s,
                                            int c0, float forget_bias, float (&cn)[8], float (&hn)[8]) {
-    const float4 bj0 = *reinterpret_cast<const float4*>(bias_s + c0), bj1 = *reinterpret_cast<const float4*>(bias_s + c0 + 4);
-    const float4 bi0 = *reinterpret_cast<const float4*>(bias_s + 32 + c0), bi1 = *reinterpret_cast<const float4*>(bias_s + 32 + c0 + 4);
-    const float4 bf0 = *reinterpret_cast<const float4*>(bias_s + 64 + c0), bf1 = *reinterpret_cast<const float4*>(bias_s + 64 + c0 + 4);
-    const float4 bo0 = *reinterpret_cast<const float4*>(bias_s + 96 + c0), bo1 = *reinterpret_cast<const float4*>(bias_s + 96 + c0 + 4);
-    const float bj[8] = {bj0.x, bj0.y, bj0.z, bj0.w, bj1.x, bj1.y, bj1.z, bj1.w}, bi[8] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
-    const float bf[8] = {bf0.x, bf0.y, bf0.z, bf0.w, bf1.x, bf1.y, bf1.z, bf1.w}, bo[8] = {bo0.x, bo0.y, bo0.z, bo0.w, bo1.x, bo1.y, bo1.z, bo1.w};
+    // bias one gate at a time (8 transient registers instead of 32 live ones)
+    auto add_bias = [&](float (&g)[8], int off, float extra) {
+        const float4 b0 = *reinterpret_cast<const float4*>(bias_s + off + c0), b1 = *reinterpret_cast<const float4*>(bias_s + off + c0 + 4);
+        g[0] += b0.x + extra; g[1] += b0.y + extra; g[2] += b0.z + extra; g[3] += b0.w + extra;
+        g[4] += b1.x + extra; g[5] += b1.y + extra; g[6] += b1.z + extra; g[7] += b1.w + extra;
+    };
+    add_bias(gj, 0, 0.f); add_bias(gi, 32, 0.f); add_bias(gf, 64, forget_bias); add_bias(go, 96, 0.f);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        float j = gj[i] + bj[i], ii = gi[i] + bi[i], f = gf[i] + bf[i] + forget_bias, o = go[i] + bo[i];
+        float j = gj[i], ii = gi[i], f = gf[i], o = go[i];
         if (ACC) { j = tanhf(j); ii = sigmoid_acc(ii); f = sigmoid_acc(f); o = sigmoid_acc(o); }
         else { j = tanh_fast(j); ii = sigmoid_fast(ii); f = sigmoid_fast(f); o = sigmoid_fast(o); }
         cn[i] = cp[i] * f + ii * j;

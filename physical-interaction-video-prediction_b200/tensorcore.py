@@ -47,9 +47,12 @@ class TensorCorePlan(object):
         self.wgrad_ws = torch.empty(wsb, dtype=torch.uint8, device=dev)
         self.accurate = 0
         import os
-        # LayerNorm of the ConvLSTM output applied inside the gate epilogue (pivp_tc_conv5x5_ln): per-layer arrival counters, zeroed once
+        # LayerNorm of the ConvLSTM output applied inside the gate epilogue (pivp_tc_conv5x5_ln): per-layer arrival counters, zeroed once.
+        # OFF by default: measured on the b32 step (profiles/r02_halo_epilogue.md) the per-sample rendezvous (publish, atomic arrival, poll,
+        # fetch of the sample's pairs: three dependent L2 round trips behind the slowest tile of the sample) adds 4.2 us to each forward
+        # launch, while the LayerNorm kernel it removes costs 3.1 us inside the graph: 8.81 ms per step fused against 8.75 ms unfused.
         self.ln_counter = [torch.zeros(B, dtype=torch.int32, device=dev) for _ in LSTM_SIZES]
-        self.fuse_ln = os.environ.get("PIVP_TC_FUSE_LN", "1") != "0"
+        self.fuse_ln = os.environ.get("PIVP_TC_FUSE_LN", "0") != "0"
         self.split_n = int(os.environ.get("PIVP_TC_SPLIT_N", "0"))       # tuning switch for the input-gradient N split
         self.pair_bn = int(os.environ.get("PIVP_TC_PAIR_BN", "96"))      # N tile of the 8x8-map input gradient (0: per-tap kernel's choice)
         # layers whose maps the halo-patch kernel tiles (H % 16 == 0, W % 8 == 0): its epilogue also produces the LayerNorm statistics

@@ -28,7 +28,7 @@ def run(name, H, W, Kc, C, mode, N, BN, ln):
     dbg = torch.zeros(4096, 8, dtype=torch.int64, device="cuda")
     def call():
         st = torch.cuda.current_stream().cuda_stream          # looked up per call: under graph capture the current stream is the capture stream
-        if mode == 1 and ln and os.environ.get("PIVP_TC_FUSE_LN", "1") != "0":        # the production launch: cell + LayerNorm in one kernel
+        if mode == 1 and ln and os.environ.get("PIVP_TC_FUSE_LN", "0") != "0":        # the production launch: cell + LayerNorm in one kernel
             L.call("pivp_tc_conv5x5_ln", x.data_ptr(), Kc, B, H, W, Kc, w.data_ptr(), C, bias.data_ptr(), gates.data_ptr(), cp.data_ptr(), co.data_ptr(),
                    h.data_ptr(), Kc, Kc - C, hb.data_ptr(), Kc, Kc - C, 1.0, 0, part.data_ptr(), gamma.data_ptr(), beta.data_ptr(), 1e-6,
                    y.data_ptr(), C, 0, yb.data_ptr(), 64, 0, stats.data_ptr(), counter.data_ptr(), st)
