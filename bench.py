@@ -275,13 +275,14 @@ def main():
 
     def traffic_from_profile():
         """DRAM bytes (read + write) per launch of the dominant kernel from the committed `ncu --set full` capture of one step
-        (profiles/r01_ncu_full_halo_traffic.json, written by scripts/ncu_traffic_summary.py); None when the summary is absent."""
-        f = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_ncu_full_halo_traffic.json")
-        try:
-            with open(f) as fh:
-                return json.load(fh)["dram_bytes_per_launch"]
-        except (OSError, KeyError, ValueError):
-            return None
+        (profiles/r02_ncu_full_halo_traffic.json, else the round-1 file; written by scripts/ncu_traffic_summary.py); None when absent."""
+        for nm in ("r02_ncu_full_halo_traffic.json", "r01_ncu_full_halo_traffic.json"):
+            try:
+                with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", nm)) as fh:
+                    return json.load(fh)["dram_bytes_per_launch"]
+            except (OSError, KeyError, ValueError):
+                continue
+        return None
     if True:                                  # every rank runs the instrumented step (it contains the all-reduce); rank 0 reports
         L = pk.lib()
         orig = L.call

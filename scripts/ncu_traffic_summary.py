@@ -1,7 +1,7 @@
-"""Summarise an `ncu --set full` capture of the tcgen05 ConvLSTM kernel into profiles/r01_ncu_full_halo_traffic.json.
+"""Summarise an `ncu --set full` capture of the tcgen05 ConvLSTM kernel into profiles/<name>.json (default r02_ncu_full_halo_traffic.json).
 
     ncu -i gpurun_out/halo_full.ncu-rep --page raw --csv > gpurun_out/halo_full_raw.csv
-    python scripts/ncu_traffic_summary.py gpurun_out/halo_full_raw.csv
+    python scripts/ncu_traffic_summary.py gpurun_out/halo_full_raw.csv [r02_ncu_full_halo_traffic.json]
 
 Writes, per launch (mean over the captured launches of one training step): DRAM bytes read + written, duration, tensor-pipe
 utilisation -- bench.py reports `dram_bytes_per_launch` as roofline.traffic next to the algorithmic bytes."""
@@ -17,7 +17,7 @@ scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-3, "us"
 
 def val(r, name):
     i = col[name]
-    return float(r[i].replace(",", "")) * scale.get(units[i], 1.0)
+    return float(r[i].replace(",", "")) * scale.get(units[i].split("/")[0], 1.0)
 
 
 launches = [r for r in rows[hdr + 2:] if len(r) > col["Kernel Name"] and "conv5x5_halo_tc_kernel" in r[col["Kernel Name"]]]
@@ -30,6 +30,6 @@ out = {"source": "ncu --set full --clock-control none, one training step (CDNA 6
 for extra in ("sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tensor.sum"):
     if extra in col:
         out[extra] = sum(val(r, extra) for r in launches) / len(launches)
-dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r01_ncu_full_halo_traffic.json")
+dst = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", sys.argv[2] if len(sys.argv) > 2 else "r02_ncu_full_halo_traffic.json")
 json.dump(out, open(dst, "w"), indent=1)
 print(json.dumps(out, indent=1))

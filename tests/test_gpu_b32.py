@@ -146,7 +146,8 @@ def test_steps_in_flight_keep_their_own_select_and_loss(pk):
     (l0, t0, p0), (l1, t1, p1) = res["synced"], res["in_flight"]
     assert all(np.array_equal(a, b) for a, b in zip(t0, t1))
     assert len(set(l0)) == N                       # the steps really differ
-    # same kernels, same inputs, same order; the only run-to-run noise is the order of the fp32 atomics (~1e-4 relative on the loss),
-    # whereas a select or loss that belongs to another step moves the loss by several percent (neighbouring steps differ by 10-40 %)
-    assert all(abs(a - b) <= 2e-3 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
+    # same kernels, same inputs, same order; the only run-to-run noise is the order of the fp32 atomics, which seven Adam updates of a
+    # two-sample bf16 model amplify to ~2e-3 relative on the later losses (measured 1e-4 ... 2.0e-3 over repeated runs), whereas a select
+    # or loss that belongs to another step moves the loss by several percent (neighbouring steps differ by 10-40 %)
+    assert all(abs(a - b) <= 1e-2 * abs(a) for a, b in zip(l0, l1)), (l0, l1)
     assert float((p0 - p1).abs().max()) <= 2e-2
