@@ -5,6 +5,7 @@
 // HBM-bound: forward reads x once per pass (second pass from L2), backward reads x, g twice; gamma/beta (per-element, shared by the
 // batch) stay in L2.  dgamma/dbeta are accumulated with 128-bit red.global.add (one per 4 elements per batch chunk).
 #include "common.cuh"
+#include <cooperative_groups.h>
 #include <stdlib.h>
 
 namespace pivp {
@@ -253,6 +254,123 @@ __global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView 
     atomicAdd(reinterpret_cast<float4*>(dbeta + e), db);
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// Backward in ONE launch: a thread-block CLUSTER owns a sample.  CTA r of the cluster keeps elements [4096 r, 4096 r + 4096) of the
+// sample in registers (masked gradient, x-hat), reduces its share of the two sums the LayerNorm backward needs (sum q, sum q * x-hat,
+// q = g * gamma), pushes the pair into the shared memory of every CTA of the cluster (distributed shared memory), and after ONE
+// cluster barrier every CTA adds up the pairs in its own shared memory and finishes dx (or, fused, the ConvLSTM gate backward)
+// from the registers it already holds.
+// Replaces bwd_stats_kernel + bwd_apply_kernel (two launches, x and g read twice) whenever the sample fits a portable cluster
+// (n = 4096 * CL, CL <= 8: every LayerNorm of the model except norm_enc6).  A CTA walks `bchunk` samples and accumulates dgamma / dbeta
+// for its 4096 elements across them before the 128-bit atomics, like bwd_apply_kernel.
+namespace cg = cooperative_groups;
+constexpr int TF = 256, EF = 4, CHUNK_F = TF * EF * 4;      // 4096 elements per CTA per sample
+
+template <bool RELU, bool MULTI>                     // RELU: the LayerNorm is followed by a ReLU (beta needed for the mask); MULTI: bchunk > 1
+__global__ void __launch_bounds__(TF, 2) bwd_fused_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, const float2* __restrict__ stats, int B, int bchunk,
+                                                       Geo g, int n, View dx, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                       GateFuse gf) {
+    pdl_enter();
+    constexpr int relu = RELU ? 1 : 0;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float2 redp[TF / 32];
+    __shared__ float2 part[2][8];                     // (sum q, sum q * x-hat) of every CTA of the cluster for the current sample (pushed by the
+                                                      // owners through distributed shared memory), double-buffered over samples
+    __shared__ float2 tot_s;
+    const int CL = gridDim.x, rank = blockIdx.x;      // cluster = the grid's x extent
+    const int b0 = blockIdx.y * bchunk, nb = min(bchunk, B - b0);
+    const int e_base = rank * CHUNK_F;
+    float4 ga[EF], be[RELU ? EF : 1], dg[MULTI ? EF : 1], db[MULTI ? EF : 1];
+    int pix[EF], ch[EF];
+#pragma unroll
+    for (int k = 0; k < EF; ++k) {
+        const int e = e_base + (k * TF + threadIdx.x) * 4;
+        pix[k] = g.cshift >= 0 ? (e >> g.cshift) : (e / g.C);
+        ch[k] = e - pix[k] * g.C;
+        ga[k] = ld4(gamma + e);
+        if (RELU) be[k] = ld4(beta + e);
+        if (MULTI) dg[k] = db[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float inv_n = 1.f / (float)n;
+    for (int i = 0; i < nb; ++i) {
+        const long b = b0 + i;
+        const float2 st = stats[b];
+        float4 gq[EF], xh[EF];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < EF; ++k) {
+            load_g_xh(x, g1, g2, b * g.HW + pix[k], ch[k], ga[k], RELU ? be[k] : zero4, st, relu, gq[k], xh[k]);
+            const float4 q = make_float4(gq[k].x * ga[k].x, gq[k].y * ga[k].y, gq[k].z * ga[k].z, gq[k].w * ga[k].w);
+            s1 += hsum(q);
+            s2 += (q.x * xh[k].x + q.y * xh[k].y) + (q.z * xh[k].z + q.w * xh[k].w);
+        }
+        // CTA sums (one pass: both sums through the same two-level reduction), then PUSH the pair into slot `rank` of every peer's shared
+        // memory and meet at ONE cluster barrier: after it each CTA reads only its own shared memory, so nobody has to wait for readers.
+        s1 = warp_sum(s1); s2 = warp_sum(s2);
+        if ((threadIdx.x & 31) == 0) redp[threadIdx.x >> 5] = make_float2(s1, s2);
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            float2 v = threadIdx.x < TF / 32 ? redp[threadIdx.x] : make_float2(0.f, 0.f);
+            v.x = warp_sum(v.x); v.y = warp_sum(v.y);
+            if ((int)threadIdx.x < CL) *cluster.map_shared_rank(&part[i & 1][rank], threadIdx.x) = v;      // lane r writes into CTA r
+        }
+        cluster.sync();                               // release / acquire: every pair of the sample has landed in this CTA's `part`
+        if (threadIdx.x < 32) {
+            const float2 p = (int)threadIdx.x < CL ? part[i & 1][threadIdx.x] : make_float2(0.f, 0.f);
+            const float a = warp_sum(p.x), c = warp_sum(p.y);
+            if (threadIdx.x == 0) tot_s = make_float2(a * inv_n, c * inv_n);
+        }
+        __syncthreads();
+        const float mq = tot_s.x, mqx = tot_s.y;
+#pragma unroll
+        for (int k = 0; k < EF; ++k) {
+            if (MULTI) {
+                dg[k].x += gq[k].x * xh[k].x; dg[k].y += gq[k].y * xh[k].y; dg[k].z += gq[k].z * xh[k].z; dg[k].w += gq[k].w * xh[k].w;
+                db[k].x += gq[k].x; db[k].y += gq[k].y; db[k].z += gq[k].z; db[k].w += gq[k].w;
+            } else {                                  // one sample per CTA: straight to the 128-bit atomics, no accumulator registers
+                const int e = e_base + (k * TF + threadIdx.x) * 4;
+                atomicAdd(reinterpret_cast<float4*>(dgamma + e), make_float4(gq[k].x * xh[k].x, gq[k].y * xh[k].y, gq[k].z * xh[k].z, gq[k].w * xh[k].w));
+                atomicAdd(reinterpret_cast<float4*>(dbeta + e), gq[k]);
+            }
+            float4 d;
+            d.x = (gq[k].x * ga[k].x - mq - xh[k].x * mqx) * st.y;
+            d.y = (gq[k].y * ga[k].y - mq - xh[k].y * mqx) * st.y;
+            d.z = (gq[k].z * ga[k].z - mq - xh[k].z * mqx) * st.y;
+            d.w = (gq[k].w * ga[k].w - mq - xh[k].w * mqx) * st.y;
+            const long row = b * g.HW + pix[k];
+            if (gf.gates) gate_backward4(gf, row, ch[k], g.C, d);
+            else *reinterpret_cast<float4*>(dx.p + row * dx.cs + dx.co + ch[k]) = d;
+        }
+        __syncthreads();                              // tot_s / redp are reused by the next sample
+    }
+    if (MULTI) {
+#pragma unroll
+        for (int k = 0; k < EF; ++k) {
+            const int e = e_base + (k * TF + threadIdx.x) * 4;
+            atomicAdd(reinterpret_cast<float4*>(dgamma + e), dg[k]);
+            atomicAdd(reinterpret_cast<float4*>(dbeta + e), db[k]);
+        }
+    }
+    // no trailing cluster barrier: remote shared memory is only WRITTEN, and every write precedes the barrier its target waits at
+}
+
+template <typename... KArgs, typename... Args>
+static inline void launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, unsigned cluster_x, void* stream, Args&&... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = 0; cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute at[2];
+    memset(at, 0, sizeof(at));
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = cluster_x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = 2;
+    cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+
 static bool a16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static bool view_ok(const float* p, int cs, int co) { return !p || (a16(p) && cs % 4 == 0 && co % 4 == 0); }
 static bool disabled() {
@@ -304,6 +422,19 @@ int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, i
         !view_ok(dx, dx_cs, dx_co) || !a16(gamma) || !a16(beta) || !a16(dgamma) || !a16(dbeta))
         return 0;
     const Geo g = make_geo(HW, C);
+    static const int fused_mode = getenv("PIVP_LN_BWD_FUSED") ? atoi(getenv("PIVP_LN_BWD_FUSED")) : 1;     // 0: two launches; k >= 1: one cluster launch, k samples per CTA
+    if (fused_mode > 0 && n % CHUNK_F == 0 && n / CHUNK_F <= 8) {
+        const int CL = n / CHUNK_F, bchunk = fused_mode < B ? fused_mode : B;
+        auto go = [&](auto kern) {
+            launch_cluster(kern, dim3(CL, (B + bchunk - 1) / bchunk), dim3(TF), (unsigned)CL, st,
+                           CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats, B, bchunk, g, n,
+                           View{dx, dx_cs, dx_co}, dgamma, dbeta, gf);
+        };
+        if (relu) { if (bchunk > 1) go(bwd_fused_kernel<true, true>); else go(bwd_fused_kernel<true, false>); }
+        else { if (bchunk > 1) go(bwd_fused_kernel<false, true>); else go(bwd_fused_kernel<false, false>); }
+        if (int e = check_launch("layernorm_bwd(cluster)")) return e;
+        return 1;
+    }
     launch_k(bwd_stats_kernel, dim3(S, B), dim3(T), 0, st, CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta,
                                               (const float2*)stats, g, n, chunk, relu, (float2*)workspace);
     if (int e = check_launch("layernorm_bwd(stats)")) return e;
