@@ -34,7 +34,14 @@ __device__ void band_softmax(const float* __restrict__ a_sample, const Band& bd,
         const int fb = (f0 / M1) * M1;                    // start of its group
         const int fe = ((f0 + np - 1) / M1 + 1) * M1;     // one past the last group
         if (threadIdx.x == 0) shift[j] = f0 - fb;
-        for (int i = threadIdx.x; i < fe - fb; i += blockDim.x) mu[j * bd.L + i] = fmaxf(__ldg(a_sample + fb + i), 0.f);
+        const int cnt = fe - fb, nt = blockDim.x;
+        for (int i0 = threadIdx.x; i0 < cnt; i0 += 4 * nt) {       // four loads in flight per thread before the first store (see load_prev_tile)
+            float v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) v[u] = (i0 + u * nt < cnt) ? __ldg(a_sample + fb + i0 + u * nt) : 0.f;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) if (i0 + u * nt < cnt) mu[j * bd.L + i0 + u * nt] = fmaxf(v[u], 0.f);
+        }
     }
     __syncthreads();
     for (int j = 0; j < M1; ++j) {
@@ -55,12 +62,46 @@ __device__ void band_softmax(const float* __restrict__ a_sample, const Band& bd,
 
 // prev tile with a 2-pixel zero halo: tile[c][(R+4)][(W+4)], rows r0-2 .. r0+nrows+1
 __device__ void load_prev_tile(const float* __restrict__ prev_sample, int H, int W, int r0, int nrows, float* tile) {
+    // One warp per tile row (channel c, row ty), lanes walk the row: no per-element integer division (the flat i / (TH*TW), r / TW form
+    // cost ~800 instructions per thread, more than the transform itself).  Every global load of the thread is issued into registers BEFORE
+    // the first shared-memory store: a `smem[i] = __ldg(...)` loop issues in order, i.e. one full memory round trip per iteration.
     const int TW = W + 4, TH = nrows + 4;
-    for (int i = threadIdx.x; i < 3 * TH * TW; i += blockDim.x) {
-        const int c = i / (TH * TW), r = i - c * TH * TW;
-        const int ty = r / TW, tx = r - ty * TW;
-        const int y = r0 - 2 + ty, x = tx - 2;
-        tile[i] = (y >= 0 && y < H && x >= 0 && x < W) ? __ldg(prev_sample + (c * H + y) * W + x) : 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    constexpr int RR = 5, JJ = 3;                        // rows per warp x 32-lane column groups held in registers
+    if (TW <= 32 * JJ && 3 * TH <= RR * nw) {
+        float v[RR][JJ];
+#pragma unroll
+        for (int rr = 0; rr < RR; ++rr) {
+            const int row = warp + rr * nw;
+            const int c = row / TH, ty = row - c * TH, y = r0 - 2 + ty;
+            const bool ok = row < 3 * TH && y >= 0 && y < H;
+            const float* src = prev_sample + (long)(c * H + y) * W - 2;
+#pragma unroll
+            for (int jj = 0; jj < JJ; ++jj) {
+                const int tx = lane + 32 * jj;
+                v[rr][jj] = (ok && tx >= 2 && tx < W + 2) ? __ldg(src + tx) : 0.f;
+            }
+        }
+#pragma unroll
+        for (int rr = 0; rr < RR; ++rr) {
+            const int row = warp + rr * nw;
+            if (row < 3 * TH) {
+#pragma unroll
+                for (int jj = 0; jj < JJ; ++jj) {
+                    const int tx = lane + 32 * jj;
+                    if (tx < TW) tile[row * TW + tx] = v[rr][jj];
+                }
+            }
+        }
+        return;
+    }
+    for (int row = warp; row < 3 * TH; row += nw) {
+        const int c = row / TH, ty = row - c * TH;
+        const int y = r0 - 2 + ty;
+        const bool yin = y >= 0 && y < H;
+        const float* src = prev_sample + (long)(c * H + y) * W - 2;
+        float* dst = tile + row * TW;
+        for (int tx = lane; tx < TW; tx += 32) dst[tx] = (yin && tx >= 2 && tx < W + 2) ? __ldg(src + tx) : 0.f;
     }
 }
 
@@ -266,17 +307,31 @@ __global__ void cdna_kern_bwd_kernel(const float* __restrict__ kraw, const float
 
 // ====================================================================================== DNA
 // tap (xk,yk) of pixel (i,j) reads prev[i+xk-2][j+yk-2] iff i+xk < H and j+yk < W (and inside the image) -- B.2
+// BWD and the image width are compile-time (WC = 0: run-time width): the forward instantiation carries none of the gradient arithmetic and the
+// pixel index splits into (row, column) with shifts.
+template <bool BWD, int WC>
 __global__ void __launch_bounds__(FT) dna_kernel(const float* __restrict__ prev, const float* __restrict__ e_pre,
                                                  const float* __restrict__ a_pre, const float* __restrict__ gout,
                                                  float* __restrict__ out, float* __restrict__ wq, float* __restrict__ d_e,
-                                                 float* __restrict__ dprev, int dprev_acc, Band bd, int backward) {
+                                                 float* __restrict__ dprev, int dprev_acc, Band bd) {
     pdl_enter();
+    constexpr bool backward = BWD;
     extern __shared__ float sm[];
     __shared__ int shift[MAXM1];
+    const int W = WC ? WC : bd.W;
     const int b = blockIdx.y, r0 = blockIdx.x * bd.R;
-    const int nrows = min(bd.R, bd.H - r0), HW = bd.H * bd.W, W = bd.W, H = bd.H;
+    const int nrows = min(bd.R, bd.H - r0), HW = bd.H * W, H = bd.H;
     float* mu = sm;
     float* tile = mu + bd.M1 * bd.L;
+    // the 25 kernel logits of this thread's first pixel are requested BEFORE the two shared-memory staging phases (each of which is a
+    // global round trip followed by a barrier): three dependent memory latencies become one
+    float kpre[25];
+    if ((int)threadIdx.x < nrows * W) {
+        const int y = threadIdx.x / W, x = threadIdx.x - y * W;
+        const float* src = e_pre + (long)b * 25 * HW + (r0 + y) * W + x;
+#pragma unroll
+        for (int t = 0; t < 25; ++t) kpre[t] = __ldg(src + (long)t * HW);
+    }
     load_prev_tile(prev + (long)b * 3 * HW, H, W, r0, nrows, tile);
     band_softmax(a_pre + (long)b * 2 * HW, bd, r0, nrows, mu, shift);
     const int TW = W + 4, TS = (nrows + 4) * TW;
@@ -285,13 +340,16 @@ __global__ void __launch_bounds__(FT) dna_kernel(const float* __restrict__ prev,
         const long ep = (long)b * 25 * HW + yi * W + x;
         float k[25], s = 0.f;
 #pragma unroll
-        for (int t = 0; t < 25; ++t) { k[t] = fmaxf(__ldg(e_pre + ep + (long)t * HW) - RELU_SHIFT, 0.f) + RELU_SHIFT; s += k[t]; }
+        for (int t = 0; t < 25; ++t) {
+            const float raw = (q == (int)threadIdx.x) ? kpre[t] : __ldg(e_pre + ep + (long)t * HW);
+            k[t] = fmaxf(raw - RELU_SHIFT, 0.f) + RELU_SHIFT; s += k[t];
+        }
         const float inv = 1.f / s;
         const float m0 = mu[shift[0] + q], m1 = mu[bd.L + shift[1] + q];
         const long gp = (long)b * 3 * HW + yi * W + x;
         float T[3] = {0.f, 0.f, 0.f};
         float g[3] = {0.f, 0.f, 0.f};
-        float dKt[25];
+        float dKt[BWD ? 25 : 1];
         if (backward) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) g[c] = __ldg(gout + gp + (long)c * HW);
@@ -306,9 +364,9 @@ __global__ void __launch_bounds__(FT) dna_kernel(const float* __restrict__ prev,
                 for (int c = 0; c < 3; ++c) {
                     const float pv = live ? tile[c * TS + (y + u) * TW + x + v] : 0.f;
                     T[c] = fmaf(k[u * 5 + v] * inv, pv, T[c]);
-                    dk = fmaf(g[c], pv, dk);
+                    if (BWD) dk = fmaf(g[c], pv, dk);
                 }
-                dKt[u * 5 + v] = dk * m1;
+                if (BWD) dKt[u * 5 + v] = dk * m1;
             }
         if (!backward) {
 #pragma unroll
@@ -326,12 +384,10 @@ __global__ void __launch_bounds__(FT) dna_kernel(const float* __restrict__ prev,
                 }
             }
 #pragma unroll
-            for (int t = 0; t < 25; ++t) dot = fmaf(k[t] * inv, dKt[t], dot);
+            for (int t = 0; t < 25; ++t) dot = fmaf(k[t] * inv, dKt[BWD ? t : 0], dot);
 #pragma unroll
-            for (int t = 0; t < 25; ++t) {
-                const float ev = __ldg(e_pre + ep + (long)t * HW);
-                d_e[ep + (long)t * HW] = (ev - RELU_SHIFT > 0.f) ? (dKt[t] - dot) * inv : 0.f;
-            }
+            for (int t = 0; t < 25; ++t)               // k[t] > eps  <=>  the ReLU of ref:408 let the logit through
+                d_e[ep + (long)t * HW] = (k[t] > RELU_SHIFT) ? (dKt[BWD ? t : 0] - dot) * inv : 0.f;
             const long wp = (long)b * 2 * HW + yi * W + x;
             wq[wp] = m0 * dmu0;
             wq[wp + HW] = m1 * dmu1;
@@ -445,9 +501,9 @@ __global__ void __launch_bounds__(FT) stp_kernel(const float* __restrict__ prev,
     }
 }
 
-static int make_band(int H, int W, int M1, int extra_rows, Band* bd) {
+static int make_band(int H, int W, int M1, int extra_rows, Band* bd, int band_pixels = 512) {
     PIVP_REQUIRE(H > 0 && W > 0 && M1 >= 2 && M1 <= MAXM1, "fused transform: bad geometry (need 2 <= masks+1 <= 16)");
-    int R = 512 / W;
+    int R = band_pixels / W;
     if (R < 1) R = 1;
     if (R > H) R = H;
     bd->H = H; bd->W = W; bd->M1 = M1; bd->R = R;
@@ -548,11 +604,14 @@ int pivp_cdna_fused_bwd(const float* g_out, const float* prev, const float* enc7
 int pivp_dna_fused_fwd(const float* prev, const float* enc7_pre, const float* mask_pre, float* out, int B, int H, int W, void* stream) {
     PIVP_REQUIRE(prev && enc7_pre && mask_pre && out && B > 0, "dna_fused_fwd: bad argument");
     Band bd;
-    if (int e = make_band(H, W, 2, 0, &bd)) return e;
+    if (int e = make_band(H, W, 2, 0, &bd)) return e;              // (measured: 256-pixel bands -- one pixel per thread, twice the CTAs -- are 1.7x slower:
+                                                                   //  the per-band staging, not the pixel loop, is what a CTA waits for)
     const size_t smem = sizeof(float) * ((size_t)2 * bd.L + 3 * (bd.R + 4) * (W + 4));
-    if (int e = allow_smem(dna_kernel, smem)) return e;
-    launch_k(dna_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, (cudaStream_t)stream, prev, enc7_pre, mask_pre, nullptr, out, nullptr, nullptr,
-                                                                                  nullptr, 0, bd, 0);
+    PIVP_REQUIRE(smem <= 48 * 1024, "dna_fused_fwd: image too wide for the band staging");
+    if (W == 64) launch_k(dna_kernel<false, 64>, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, (cudaStream_t)stream, prev, enc7_pre, mask_pre, nullptr, out,
+                          nullptr, nullptr, nullptr, 0, bd);
+    else launch_k(dna_kernel<false, 0>, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, (cudaStream_t)stream, prev, enc7_pre, mask_pre, nullptr, out,
+                  nullptr, nullptr, nullptr, 0, bd);
     return check_launch("dna_fused_fwd");
 }
 
@@ -568,9 +627,11 @@ int pivp_dna_fused_bwd(const float* g_out, const float* prev, const float* enc7_
     cudaStream_t st = (cudaStream_t)stream;
     float* wq = (float*)workspace;
     const size_t smem = sizeof(float) * ((size_t)2 * bd.L + 3 * (bd.R + 4) * (W + 4));
-    if (int e = allow_smem(dna_kernel, smem)) return e;
-    launch_k(dna_kernel, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, st, prev, enc7_pre, mask_pre, g_out, nullptr, wq, d_enc7_pre, d_prev,
-                                                                accumulate_dprev, bd, 1);
+    PIVP_REQUIRE(smem <= 48 * 1024, "dna_fused_bwd: image too wide for the band staging");
+    if (W == 64) launch_k(dna_kernel<true, 64>, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, st, prev, enc7_pre, mask_pre, g_out, nullptr, wq, d_enc7_pre,
+                          d_prev, accumulate_dprev, bd);
+    else launch_k(dna_kernel<true, 0>, dim3((H + bd.R - 1) / bd.R, B), dim3(FT), smem, st, prev, enc7_pre, mask_pre, g_out, nullptr, wq, d_enc7_pre,
+                  d_prev, accumulate_dprev, bd);
     if (int e = check_launch("dna_fused_bwd(k1)")) return e;
     const long ngroups = (long)B * H * W;
     launch_k(mask_softmax_bwd_kernel, dim3((unsigned)((ngroups + 255) / 256)), dim3(256), 0, st, mask_pre, wq, d_mask_pre, ngroups, 2);
