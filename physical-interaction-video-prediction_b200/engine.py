@@ -174,8 +174,8 @@ class Engine(object):
         ws["d_mask_pre"] = A(B, self.M1, H, W)
         ws["d_prev"] = A(B, 3, H, W)
         ws["d_img_nhwc"] = A(Mr[1], 3)
-        ws["d_hid5"] = A(Mr[8], 128)
-        ws["d_cat6"] = A(Mr[2], 64)
+        ws["d_hid5"] = [A(Mr[8], 128), A(Mr[8], 128)]      # ping-pong over time steps: HEAD(t-1) fills slot (t-1)&1 while CHAIN(t) reads slot t&1
+        ws["d_cat6"] = [A(Mr[2], 64), A(Mr[2], 64)]
         ws["d_cat5"] = A(Mr[4], 96)
         ws["d_e5pre"] = A(Mr[2], 96)
         ws["d_e4pre"] = A(Mr[4], 128)
@@ -200,11 +200,47 @@ class Engine(object):
                                    dtype=torch.uint8, device=self.dev)
         nb = self.L.query("pivp_layernorm_workspace_bytes", B, 64 * H * W)
         ws["ln_ws"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)
+        ws["ln_ws_head"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)     # LayerNorm workspace of the backward heads (side branch 3)
         self.ws = ws
         if self.compute == "bf16":
             from .tensorcore import TensorCorePlan
             self.tc = TensorCorePlan(self, ws)
         return ws
+
+    # ------------------------------------------------------------------ parallel branches
+    # The step is one dependent chain of ~780 small kernels, but a few pieces hang off it sideways: the kernel Linear (needs hidden5, is
+    # needed only by the transform at the end of the time step), its input gradient (needed only when BPTT reaches enc4), the loss
+    # reductions, the deferred weight gradients.  They are issued on forked side streams (``with self._fork(k): ...``) and joined where
+    # their result is consumed; under CUDA-graph capture fork / join become parallel branches of the graph, so these kernels fill SMs the
+    # chain leaves idle instead of lengthening it.
+    def _side(self, k):
+        if not hasattr(self, "_side_streams"):
+            import os
+            self._side_streams = {}
+            # branch ids: 0 kernel Linear (forward / backward), 1 loss terms, 2 small deferred weight gradients.  Measured on the b32 step
+            # (one id at a time, against 8.353 ms with none): 0 -> 8.248, 1 -> 8.274, 2 -> 8.280 ms.  (Also measured: the eight bf16
+            # weight-refresh launches behind Adam on three branches -> 8.57 ms, WORSE -- the forks delay the first kernels of the next
+            # step -- so they stay on the main chain.)  PIVP_BRANCHES="" keeps everything on one stream.
+            # 3: the loss-side head of backward step t-1 beside the recurrent chain of step t (Engine.backward).
+            self._branches = set(int(v) for v in os.environ.get("PIVP_BRANCHES", "0,1,2,3").split(",") if v.strip() != "")
+        if k not in self._side_streams:
+            self._side_streams[k] = torch.cuda.Stream(device=self.dev)
+        return self._side_streams[k]
+
+    def _fork(self, k):
+        """Context manager: work inside runs on side stream k, ordered after everything issued on the current stream so far."""
+        import contextlib
+        side = self._side(k)
+        if k not in self._branches:
+            return contextlib.nullcontext()
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        return torch.cuda.stream(side)
+
+    def _join(self, k):
+        """The current stream waits for side stream k."""
+        side = self._side(k)
+        if k in self._branches:
+            torch.cuda.current_stream(self.dev).wait_stream(side)
 
     # ------------------------------------------------------------------ thin kernel wrappers
     def _s(self):
@@ -231,13 +267,14 @@ class Engine(object):
                     0 if y2 is None else y2.co, 0 if y_bf16 is None else y_bf16.ptr, 0 if y_bf16 is None else y_bf16.cs,
                     0 if y_bf16 is None else y_bf16.co, relu, _ptr(stats), _ptr(ws["ln_ws"]), ws["ln_ws"].numel(), self._s())
 
-    def _ln_bwd(self, name, x, g1, g2, B, HW, relu, stats, dx):
+    def _ln_bwd(self, name, x, g1, g2, B, HW, relu, stats, dx, ln_ws=None):
         ws = self.ws
+        ln_ws = ws["ln_ws"] if ln_ws is None else ln_ws
         self.L.call("pivp_layernorm_bwd", x.ptr, x.cs, x.co, g1.ptr, g1.cs, g1.co, 0 if g2 is None else g2.ptr,
                     0 if g2 is None else g2.cs, 0 if g2 is None else g2.co, _ptr(self.p[name + "/norm/gamma"]),
                     _ptr(self.p[name + "/norm/beta"]), _ptr(stats), B, HW, x.C, relu, dx.ptr, dx.cs, dx.co,
-                    _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(ws["ln_ws"]),
-                    ws["ln_ws"].numel(), self._s())
+                    _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(ln_ws),
+                    ln_ws.numel(), self._s())
 
     def _ln_lstm_bwd(self, name, li, t, x, g1, g2, B, HW, last):
         """LayerNorm backward of ConvLSTM layer li's output at step t, then the layer's gate / input-gradient backward.
@@ -380,6 +417,8 @@ class Engine(object):
         ws["loss_slots"].zero_()
         self.prev = []
         p = self.p
+        n_img, n_sta = B * 3 * H * W, B * 5
+        div = float(T - self.ctx)
         for t in range(T - 1):
             # ---- previous frame (train_model.py:663-673)
             if t < self.ctx:
@@ -427,6 +466,18 @@ class Engine(object):
                 L.call("pivp_copy_view", _ptr(ws["xh"][4][t]), 192, 0, 0, 0, 0, self.tc.xview(4, t).ptr, self.tc.Kpad[4], 0, Mr[8], 64, s)
             # ---- group 4
             self._lstm_ln_fwd(4, t, B, "hidden5", View(ws["hid5"][t], 128, 0, 128), None if self.tc is None else View(self.tc.hid5_b[t], 128, 0, 128))
+            # the kernel / theta Linear needs hidden5 only and is consumed by the transform at the end of the step: side branch 0
+            K5 = 128 * HW[8]
+            with self._fork(0):
+                s0 = self._s()
+                if self.model_type == "CDNA":
+                    L.call("pivp_linear_fwd_splitk", _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]), _ptr(p["model/cdna_kerns/b"]),
+                           _ptr(ws["kern_raw"][t]), B, K5, 25 * self.M, 0, _ptr(ws["lin_ws"]), ws["lin_ws"].numel(), s0)
+                elif self.model_type == "STP":
+                    L.call("pivp_linear_fwd_splitk", _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]), _ptr(p["model/stp_input/b"]),
+                           _ptr(ws["stp_s"][t]), B, K5, 100, 1, _ptr(ws["lin_ws"]), ws["lin_ws"].numel(), s0)
+                    L.call("pivp_linear_fwd", _ptr(ws["stp_s"][t]), 100, _ptr(p["model/identity_params/W"]),
+                           _ptr(p["model/identity_params/b"]), _ptr(ws["theta_raw"][t]), B, 100, 6, 0, s0)
             if self.tc is not None:
                 self.tc.deconv_fwd("enc4", self.tc.hid5_b[t], ws["xh"][5][t], 192, self.tc.xh_bf16[5][t], self.tc.Kpad[5], 1)
             else:
@@ -458,33 +509,27 @@ class Engine(object):
                 L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, 0, _ptr(ws["enc7_pre"][t]), B, self.Ne, HW[1], 0, s)
                 L.call("pivp_nhwc_to_nchw", _ptr(ws["head"][t]), self.Nh, self.Ne, _ptr(ws["mask_pre"][t]), B, self.M1, HW[1], 0, s)
             # ---- transform + masks + composite
-            K5 = 128 * HW[8]
+            self._join(0)                                  # kernel / theta Linear of this step
             if self.model_type == "CDNA":
-                L.call("pivp_linear_fwd_splitk", _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]), _ptr(p["model/cdna_kerns/b"]),
-                       _ptr(ws["kern_raw"][t]), B, K5, 25 * self.M, 0, _ptr(ws["lin_ws"]), ws["lin_ws"].numel(), s)
                 L.call("pivp_cdna_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["kern_raw"][t]),
                        _ptr(ws["gen"][t]), B, H, W, self.M, s)
             elif self.model_type == "DNA":
                 L.call("pivp_dna_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["gen"][t]), B, H, W, s)
             else:
-                L.call("pivp_linear_fwd_splitk", _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]), _ptr(p["model/stp_input/b"]),
-                       _ptr(ws["stp_s"][t]), B, K5, 100, 1, _ptr(ws["lin_ws"]), ws["lin_ws"].numel(), s)
-                L.call("pivp_linear_fwd", _ptr(ws["stp_s"][t]), 100, _ptr(p["model/identity_params/W"]),
-                       _ptr(p["model/identity_params/b"]), _ptr(ws["theta_raw"][t]), B, 100, 6, 0, s)
                 L.call("pivp_stp_fused_fwd", _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]), _ptr(ws["theta_raw"][t]),
                        _ptr(ws["gen"][t]), B, H, W, self.M, self.oob, s)
-        # ---- loss (train_model.py:737-758): sums go to loss_slots, the loss gradients to d_gen / d_gs
-        n_img, n_sta = B * 3 * H * W, B * 5
-        div = float(T - self.ctx)
-        for t in range(T - 1):
-            if t >= self.ctx - 1:
-                L.call("pivp_mse", _ptr(ws["gen"][t]), _ptr(images[t + 1]), n_img, 2.0 / (n_img * div), _ptr(ws["d_gen"][t]),
-                       ws["loss_slots"][t:].data_ptr(), s)
-                L.call("pivp_mse", _ptr(ws["cur"][t + 1]), _ptr(states[t + 1]), n_sta, 1e-4 * 2.0 / (n_sta * div), _ptr(ws["d_gs"][t]),
-                       ws["loss_slots"][T - 1 + t:].data_ptr(), s)
-            else:
-                ws["d_gen"][t].zero_()
-                ws["d_gs"][t].zero_()
+            # ---- loss terms of this step (train_model.py:737-758) on side branch 1: sums to loss_slots, loss gradients to d_gen / d_gs
+            with self._fork(1):
+                s1 = self._s()
+                if t >= self.ctx - 1:
+                    L.call("pivp_mse", _ptr(ws["gen"][t]), _ptr(images[t + 1]), n_img, 2.0 / (n_img * div), _ptr(ws["d_gen"][t]),
+                           ws["loss_slots"][t:].data_ptr(), s1)
+                    L.call("pivp_mse", _ptr(ws["cur"][t + 1]), _ptr(states[t + 1]), n_sta, 1e-4 * 2.0 / (n_sta * div), _ptr(ws["d_gs"][t]),
+                           ws["loss_slots"][T - 1 + t:].data_ptr(), s1)
+                else:
+                    ws["d_gen"][t].zero_()
+                    ws["d_gs"][t].zero_()
+        self._join(1)
         self.T, self.B = T, B
         return ws["gen"]
 
@@ -519,66 +564,99 @@ class Engine(object):
     def cleargrads(self):
         self.flat_g.zero_()
 
+    def _bwd_head(self, t, slot, inline):
+        """The part of backward step t that hangs off the loss only (when the previous frame is detached, i.e. under scheduled sampling):
+        fused transform backward, kernel / theta Linear input gradient, the two 1x1 heads, LayerNorm norm_enc6 and the enc6 deconvolution
+        input gradient.  Its outputs for the recurrent chain are d_cat6[slot] (gradient of [hidden7 | enc0 skip]) and d_hid5[slot] (gradient
+        of hidden5 through the Linear); everything else it touches is private to heads, which never overlap one another.
+        ``inline``: the Linear runs on the head's own stream (the head itself is a side branch); else on side branch 0, joined at enc4."""
+        import contextlib
+        ws, L = self.ws, self.L
+        s = self._s()
+        T, B, H, W = self.T, self.B, self.H, self.W
+        HW, Mr = ws["HW"], ws["Mr"]
+        p, g = self.p, self.g
+        K5 = 128 * HW[8]
+        prev = self.prev[t]
+        need_dprev = self.feedself and t >= self.ctx          # prev_t = gen_{t-1} keeps the graph (ref:664-666)
+        d_prev = ws["d_prev"] if need_dprev else None
+        # ---- fused transform backward
+        if self.model_type == "CDNA":
+            L.call("pivp_cdna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
+                   _ptr(ws["kern_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_kern_raw"][t]),
+                   _ptr(d_prev), 0, B, H, W, self.M, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
+            with (contextlib.nullcontext() if inline else self._fork(0)):       # d hidden5 through the kernel Linear: needed only when BPTT reaches enc4
+                L.call("pivp_linear_bwd", _ptr(ws["d_kern_raw"][t]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]),
+                       _ptr(ws["d_hid5"][slot]), K5, 0, 0, 0, B, K5, 25 * self.M, self._s())       # dx only; dW / db after the time loop
+            hid5_has_grad = True
+        elif self.model_type == "DNA":
+            L.call("pivp_dna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
+                   _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(d_prev), 0, B, H, W, _ptr(ws["fused_ws"]),
+                   ws["fused_ws"].numel(), s)
+            hid5_has_grad = False
+        else:
+            if need_dprev:
+                d_prev.zero_()
+            L.call("pivp_stp_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
+                   _ptr(ws["theta_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_theta"]), _ptr(d_prev),
+                   B, H, W, self.M, self.oob, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
+            with (contextlib.nullcontext() if inline else self._fork(0)):
+                s0 = self._s()
+                L.call("pivp_linear_bwd", _ptr(ws["d_theta"]), _ptr(ws["stp_s"][t]), 100, _ptr(p["model/identity_params/W"]),
+                       _ptr(ws["d_stp_s"]), 100, 0, _ptr(g["model/identity_params/W"]), _ptr(g["model/identity_params/b"]), B, 100, 6, s0)
+                L.call("pivp_relu_mask", _ptr(ws["stp_s"][t]), _ptr(ws["d_stp_s"]), B * 100, s0)
+                L.call("pivp_linear_bwd", _ptr(ws["d_stp_s"]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]),
+                       _ptr(ws["d_hid5"][slot]), K5, 0, _ptr(g["model/stp_input/W"]), _ptr(g["model/stp_input/b"]), B, K5, 100, s0)
+            hid5_has_grad = True
+        # ---- heads backward: planes -> NHWC, then 1x1 conv dgrad / wgrad
+        if self.Nh in (14, 27):
+            L.call("pivp_heads_bwd", _ptr(ws["e6"][t]), 64, 0, _ptr(p["model/enc7/W"]), _ptr(ws["d_enc7_pre"]), self.Ne,
+                   _ptr(ws["d_mask_pre"]), self.Nh, _ptr(ws["d_e6"]), 64, 0, _ptr(g["model/enc7/W"]), _ptr(g["model/enc7/b"]),
+                   B, HW[1], s)
+        else:
+            L.call("pivp_nchw_to_nhwc", _ptr(ws["d_enc7_pre"]), _ptr(ws["d_head"]), self.Nh, 0, B, self.Ne, HW[1], s)
+            L.call("pivp_nchw_to_nhwc", _ptr(ws["d_mask_pre"]), _ptr(ws["d_head"]), self.Nh, self.Ne, B, self.M1, HW[1], s)
+            dhead = View(ws["d_head"], self.Nh, 0, self.Nh)
+            self._conv_wgrad(View(ws["e6"][t], 64, 0, 64), B, H, W, dhead, H, W, 1, 1, 0, g["model/enc7/W"], g["model/enc7/b"])
+            self._conv_dgrad(dhead, B, H, W, p["model/enc7/W"], None, 1, 1, 0, View(ws["d_e6"], 64, 0, 64), H, W)
+        # ---- norm_enc6 (+relu) and enc6 deconv
+        self._ln_bwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), View(ws["d_e6"], 64, 0, 64), None, B, HW[1], 1,
+                     ws["ln_stats"]["norm_enc6"][t], View(ws["d_e6pre"], 64, 0, 64), ln_ws=ws["ln_ws_head"])
+        de6 = View(ws["d_e6pre"], 64, 0, 64)
+        if self.tc is not None:           # bias gradient + bf16 space-to-depth operand in one hand-over launch; weight gradient deferred
+            self.tc.deconv_bwd_fused("enc6", t, None, de6, None, g["enc6/b"], ws["d_cat6"][slot], 0)
+        else:
+            L.call("pivp_colsum", de6.ptr, 64, 0, Mr[1], 64, _ptr(g["enc6/b"]), s)
+            self._conv_wgrad(de6, B, H, W, View(ws["cat6"][t], 64, 0, 64), H // 2, W // 2, 3, 2, 1, g["enc6/W"], None)
+            self._conv_fwd(de6, B, H, W, p["enc6/W"], None, 64, 3, 2, 1, View(ws["d_cat6"][slot], 64, 0, 64))
+        return hid5_has_grad
+
     def backward(self):
+        """BPTT.  Step t = HEAD(t) (see _bwd_head) + CHAIN(t) (the seven ConvLSTM layers and the encoder / decoder between them, which
+        need the recurrent gradients of step t+1).  Under scheduled sampling HEAD(t-1) depends on nothing CHAIN(t) produces, so it runs on
+        side branch 3 WHILE CHAIN(t) runs (ping-pong d_cat6 / d_hid5): the heads are whole-GPU bandwidth kernels on 64x64 maps, the chain is
+        a string of small latency-bound kernels, and the step pays max(CHAIN, HEAD) instead of their sum.  In feedself mode the previous
+        frame keeps the graph (ref:664-666), d_gen[t-1] receives d_prev at the end of CHAIN(t), and the heads stay in line."""
         ws, L, s = self.ws, self.L, self._s()
         T, B, H, W = self.T, self.B, self.H, self.W
         HW, Mr = ws["HW"], ws["Mr"]
         p, g = self.p, self.g
         K5 = 128 * HW[8]
         d_cur_in = None                       # gradient w.r.t. cur[t+1] arriving from step t+1's state_action
+        self._side(3)
+        pipelined = (not self.feedself) and 3 in self._branches
+        hid5_flags = {T - 2: self._bwd_head(T - 2, (T - 2) & 1, False)}
         for t in range(T - 2, -1, -1):
             last = (t == T - 2)
-            prev = self.prev[t]
+            slot = t & 1
             need_dprev = self.feedself and t >= self.ctx          # prev_t = gen_{t-1} keeps the graph (ref:664-666)
             d_prev = ws["d_prev"] if need_dprev else None
-            # ---- fused transform backward
-            if self.model_type == "CDNA":
-                L.call("pivp_cdna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
-                       _ptr(ws["kern_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_kern_raw"][t]),
-                       _ptr(d_prev), 0, B, H, W, self.M, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
-                L.call("pivp_linear_bwd", _ptr(ws["d_kern_raw"][t]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]),
-                       _ptr(ws["d_hid5"]), K5, 0, 0, 0, B, K5, 25 * self.M, s)       # dx only; dW / db after the time loop
-                hid5_has_grad = True
-            elif self.model_type == "DNA":
-                L.call("pivp_dna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
-                       _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(d_prev), 0, B, H, W, _ptr(ws["fused_ws"]),
-                       ws["fused_ws"].numel(), s)
-                hid5_has_grad = False
-            else:
-                if need_dprev:
-                    d_prev.zero_()
-                L.call("pivp_stp_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
-                       _ptr(ws["theta_raw"][t]), _ptr(ws["d_enc7_pre"]), _ptr(ws["d_mask_pre"]), _ptr(ws["d_theta"]), _ptr(d_prev),
-                       B, H, W, self.M, self.oob, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
-                L.call("pivp_linear_bwd", _ptr(ws["d_theta"]), _ptr(ws["stp_s"][t]), 100, _ptr(p["model/identity_params/W"]),
-                       _ptr(ws["d_stp_s"]), 100, 0, _ptr(g["model/identity_params/W"]), _ptr(g["model/identity_params/b"]), B, 100, 6, s)
-                L.call("pivp_relu_mask", _ptr(ws["stp_s"][t]), _ptr(ws["d_stp_s"]), B * 100, s)
-                L.call("pivp_linear_bwd", _ptr(ws["d_stp_s"]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]),
-                       _ptr(ws["d_hid5"]), K5, 0, _ptr(g["model/stp_input/W"]), _ptr(g["model/stp_input/b"]), B, K5, 100, s)
-                hid5_has_grad = True
-            # ---- heads backward: planes -> NHWC, then 1x1 conv dgrad / wgrad
-            if self.Nh in (14, 27):
-                L.call("pivp_heads_bwd", _ptr(ws["e6"][t]), 64, 0, _ptr(p["model/enc7/W"]), _ptr(ws["d_enc7_pre"]), self.Ne,
-                       _ptr(ws["d_mask_pre"]), self.Nh, _ptr(ws["d_e6"]), 64, 0, _ptr(g["model/enc7/W"]), _ptr(g["model/enc7/b"]),
-                       B, HW[1], s)
-            else:
-                L.call("pivp_nchw_to_nhwc", _ptr(ws["d_enc7_pre"]), _ptr(ws["d_head"]), self.Nh, 0, B, self.Ne, HW[1], s)
-                L.call("pivp_nchw_to_nhwc", _ptr(ws["d_mask_pre"]), _ptr(ws["d_head"]), self.Nh, self.Ne, B, self.M1, HW[1], s)
-                dhead = View(ws["d_head"], self.Nh, 0, self.Nh)
-                self._conv_wgrad(View(ws["e6"][t], 64, 0, 64), B, H, W, dhead, H, W, 1, 1, 0, g["model/enc7/W"], g["model/enc7/b"])
-                self._conv_dgrad(dhead, B, H, W, p["model/enc7/W"], None, 1, 1, 0, View(ws["d_e6"], 64, 0, 64), H, W)
-            # ---- norm_enc6 (+relu) and enc6 deconv
-            self._ln_bwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), View(ws["d_e6"], 64, 0, 64), None, B, HW[1], 1,
-                         ws["ln_stats"]["norm_enc6"][t], View(ws["d_e6pre"], 64, 0, 64))
-            de6 = View(ws["d_e6pre"], 64, 0, 64)
-            if self.tc is not None:           # bias gradient + bf16 space-to-depth operand in one hand-over launch; weight gradient deferred
-                self.tc.deconv_bwd_fused("enc6", t, None, de6, None, g["enc6/b"], ws["d_cat6"], 0)
-            else:
-                L.call("pivp_colsum", de6.ptr, 64, 0, Mr[1], 64, _ptr(g["enc6/b"]), s)
-                self._conv_wgrad(de6, B, H, W, View(ws["cat6"][t], 64, 0, 64), H // 2, W // 2, 3, 2, 1, g["enc6/W"], None)
-                self._conv_fwd(de6, B, H, W, p["enc6/W"], None, 64, 3, 2, 1, View(ws["d_cat6"], 64, 0, 64))
+            hid5_has_grad = hid5_flags[t]
+            if pipelined and t > 0:
+                with self._fork(3):
+                    hid5_flags[t - 1] = self._bwd_head(t - 1, (t - 1) & 1, True)
             # ---- lstm7
-            self._ln_lstm_bwd("hidden7", 6, t, View(ws["xh"][6][t + 1], 128, 96, 32), View(ws["d_cat6"], 64, 0, 32), None, B, HW[2], last)
+            self._ln_lstm_bwd("hidden7", 6, t, View(ws["xh"][6][t + 1], 128, 96, 32), View(ws["d_cat6"][slot], 64, 0, 32), None, B, HW[2], last)
             # ---- enc5 deconv (input concat(hidden6, encs[1]))
             de5 = View(ws["d_e5pre"], 96, 0, 96)
             if self.tc is not None:
@@ -591,19 +669,21 @@ class Engine(object):
                 self._conv_fwd(de5, B, H // 2, W // 2, p["enc5/W"], None, 96, 3, 2, 1, View(ws["d_cat5"], 96, 0, 96))
             # ---- lstm6
             self._ln_lstm_bwd("hidden6", 5, t, View(ws["xh"][5][t + 1], 192, 128, 64), View(ws["d_cat5"], 96, 0, 64), None, B, HW[4], last)
-            # ---- enc4 deconv (input hidden5); d_hid5 may already hold the kernel-Linear contribution
+            # ---- enc4 deconv (input hidden5); d_hid5 may already hold the kernel-Linear contribution (side branch 0)
+            if hid5_has_grad and not (pipelined and not last):       # an in-line head put the Linear on side branch 0
+                self._join(0)
             de4 = View(ws["d_e4pre"], 128, 0, 128)
             if self.tc is not None:
                 self.tc.deconv_bwd_fused("enc4", t, View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, g["enc4/b"],
-                                         ws["d_hid5"], 1 if hid5_has_grad else 0)
+                                         ws["d_hid5"][slot], 1 if hid5_has_grad else 0)
             else:
                 self._relu_bwd(View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, de4, Mr[4])
                 L.call("pivp_colsum", de4.ptr, 128, 0, Mr[4], 128, _ptr(g["enc4/b"]), s)
                 self._conv_wgrad(de4, B, H // 4, W // 4, View(ws["hid5"][t], 128, 0, 128), H // 8, W // 8, 3, 2, 1, g["enc4/W"], None)
-                self._conv_fwd(de4, B, H // 4, W // 4, p["enc4/W"], None, 128, 3, 2, 1, View(ws["d_hid5"], 128, 0, 128),
+                self._conv_fwd(de4, B, H // 4, W // 4, p["enc4/W"], None, 128, 3, 2, 1, View(ws["d_hid5"][slot], 128, 0, 128),
                                acc=1 if hid5_has_grad else 0)
             # ---- lstm5
-            self._ln_lstm_bwd("hidden5", 4, t, View(ws["xh"][4][t + 1], 192, 64, 128), View(ws["d_hid5"], 128, 0, 128), None, B, HW[8], last)
+            self._ln_lstm_bwd("hidden5", 4, t, View(ws["xh"][4][t + 1], 192, 64, 128), View(ws["d_hid5"][slot], 128, 0, 128), None, B, HW[8], last)
             # ---- enc3 (1x1 on concat(enc2 out, smear))
             self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"][t], 64, 0, 64), Mr[8])
             de3 = View(ws["d_e3pre"][t], 64, 0, 64)
@@ -638,7 +718,7 @@ class Engine(object):
             self._ln_lstm_bwd("hidden2", 1, t, View(ws["xh"][1][t + 1], 64, 32, 32), View(ws["d_hid2"], 32, 0, 32), None, B, HW[2], last)
             self._ln_lstm_bwd("hidden1", 0, t, View(ws["xh"][0][t + 1], 64, 32, 32), View(ws["dxh"][1], 64, 0, 32), None, B, HW[2], last)
             # ---- norm_enc0 (+relu): encs[0] feeds lstm1 (x slot) and the enc6 skip slot; enc0
-            self._ln_bwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), View(ws["dxh"][0], 64, 0, 32), View(ws["d_cat6"], 64, 32, 32),
+            self._ln_bwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), View(ws["dxh"][0], 64, 0, 32), View(ws["d_cat6"][slot], 64, 32, 32),
                          B, HW[2], 1, ws["ln_stats"]["norm_enc0"][t], View(ws["d_enc0pre"][t], 32, 0, 32))
             de0 = View(ws["d_enc0pre"][t], 32, 0, 32)
             if need_dprev:
@@ -647,19 +727,24 @@ class Engine(object):
                 L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)
             if self._stop_after_step(t):
                 return
+            if t > 0:
+                if pipelined:
+                    self._join(3)                  # HEAD(t-1) ran beside this step's chain
+                else:
+                    hid5_flags[t - 1] = self._bwd_head(t - 1, (t - 1) & 1, False)
         # ---- deferred weight gradients of enc0..enc3: the per-step tensors are stacked over time, so each is ONE launch with
         # S*B "images" (9x longer reduction per launch instead of 9 launches that cannot fill the GPU)
         gs = self.grad_sync
         if gs is not None:
             gs.ready("tail")                   # LayerNorm / heads / state-predictor gradients are final: their all-reduce runs under the GEMMs below
-        if True:
+        with self._fork(2):                    # small deferred weight gradients: a branch beside tc.wgrad_all()
             S = T - 1
             first = lambda lst: lst[0]
             cin3 = 64 + self.sa
             if self.model_type == "CDNA":              # kernel Linear 8192 -> 250: one pass over all steps instead of T-1 read-modify-writes of dW
                 NK = 25 * self.M
                 L.call("pivp_linear_wgrad_steps", _ptr(first(ws["d_kern_raw"])), B * NK, _ptr(first(ws["hid5"])), Mr[8] * 128, 128 * HW[8],
-                       _ptr(g["model/cdna_kerns/W"]), _ptr(g["model/cdna_kerns/b"]), S, B, 128 * HW[8], NK, s)
+                       _ptr(g["model/cdna_kerns/W"]), _ptr(g["model/cdna_kerns/b"]), S, B, 128 * HW[8], NK, self._s())
             self._conv_wgrad(View(first(ws["img_nhwc"]), 3, 0, 3), S * B, H, W, View(first(ws["d_enc0pre"]), 32, 0, 32), H // 2, W // 2, 5, 2, 2,
                              g["enc0/W"], g["enc0/b"])
             if self.tc is None:                # bf16 mode: tcgen05 weight-gradient GEMMs in tc.wgrad_all(), bias gradients from the hand-over
@@ -670,8 +755,10 @@ class Engine(object):
             self._conv_wgrad(View(first(ws["in3"]), self.cs3, 0, cin3), S * B, H // 8, W // 8, View(first(ws["d_e3pre"]), 64, 0, 64), H // 8, W // 8,
                              1, 1, 0, g["enc3/W"], g["enc3/b"])
         if gs is not None:
+            self._join(2)
             gs.ready("xform")
         if self.tc is not None:
             self.tc.wgrad_all(gs)              # ConvLSTM weight/bias gradients: one tcgen05 GEMM per layer over all time steps
+        self._join(2)
         if gs is not None:
             gs.finish()

@@ -94,6 +94,10 @@ class TensorCorePlan(object):
             setattr(self, nm + "_all", allt)
             setattr(self, nm, [allt[t] for t in range(S)])
         self._widx_all = torch.from_numpy(np.concatenate(self._widx)).to(dev)
+        # parallel branches for the deferred weight gradients (wgrad_all): PIVP_WGRAD_STREAMS = total branches (1 = one chain)
+        nbr = max(1, min(3, int(os.environ.get("PIVP_WGRAD_STREAMS", "3"))))       # measured on the b32 step: 8.61 / 8.37 / 8.31 ms with 1 / 2 / 3
+        self.wg_streams = [torch.cuda.Stream(device=dev) for _ in range(nbr - 1)]
+        self.wg_ws = [torch.empty_like(self.wgrad_ws) for _ in range(nbr - 1)]
         self.refresh_weights()
 
     def _walloc(self, idx, shape):
@@ -244,7 +248,7 @@ class TensorCorePlan(object):
                  _ptr(db), M, C, e._s())
         self.deconv_fwd(name, dy_b, d_in, d_in_cs, None, 0, 0, bias=False)
 
-    def conv_s2_wgrad_all(self):
+    def conv_s2_wgrad_all(self, wsb=None):
         """Deferred weight gradients of the stride-2 convolutions enc1 / enc2 over all time steps: dW[n][ky][kx][c] contracts the bf16
         d(pre-activation) with the tap-shifted space-to-depth input the forward already wrote (train_model.py:501-502 backward)."""
         e, S, B = self.eng, self.S, self.ws["B"]
@@ -252,17 +256,19 @@ class TensorCorePlan(object):
             d = self.s2f[name]
             h, w = e.H // d["lv"], e.W // d["lv"]
             a = self.de_b[name]
+            wsb_ = self.wgrad_ws if wsb is None else wsb
             e.L.call("pivp_tc_wgrad_taps", _ptr(a), a.shape[2], _ptr(d["xs"]), 4 * d["cb"], S * B, h, w, d["cin"], d["cout"], 9,
-                     d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
+                     d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(wsb_), wsb_.numel(), e._s())
 
-    def deconv_wgrad_all(self):
+    def deconv_wgrad_all(self, wsb=None):
         """Deferred weight gradients of enc4/5/6 over all time steps (one MN-major GEMM each)."""
         e, S, B = self.eng, self.S, self.ws["B"]
         for name, xall in (("enc4", self.hid5_b_all), ("enc5", self.cat5_b_all), ("enc6", self.cat6_b_all)):
             d = self.dbw[name]
             h, w = e.H // d["lv"], e.W // d["lv"]
+            wsb_ = self.wgrad_ws if wsb is None else wsb
             e.L.call("pivp_tc_wgrad_taps", _ptr(xall), xall.shape[2], _ptr(d["dys"]), 4 * d["cb"], S * B, h, w, d["cout"], d["cin"], 9,
-                     d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
+                     d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(wsb_), wsb_.numel(), e._s())
 
     def deconv_fwd(self, name, x_bf16, out, out_cs, out_bf16, ob_cs, relu, bias=True):
         """Deconvolution2D forward (+bias, optional ReLU) -> fp32 view `out` (row stride out_cs, channel offset 0) and an
@@ -346,13 +352,7 @@ class TensorCorePlan(object):
         smallest tensor's reduction (0.8 MB) is exposed behind the last GEMM."""
         e, ws = self.eng, self.ws
         S, B = self.S, ws["B"]
-        order = range(7)
-        if grad_sync is not None:
-            self.deconv_wgrad_all()
-            self.conv_s2_wgrad_all()
-            grad_sync.ready("enc")
-            order = sorted(range(7), key=lambda li: -(LSTM_IN[li] + LSTM_SIZES[li]) * LSTM_SIZES[li])
-        for li in order:
+        def lstm_wgrad(li, wsb):
             cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
             M = ws["Mr"][lv]
             h, w = e.H // lv, e.W // lv
@@ -360,9 +360,44 @@ class TensorCorePlan(object):
             name = "lstm%d/conv" % (li + 1)
             e.L.call("pivp_tc_colsum_bf16", _ptr(self.dg_all[li]), 4 * C, S * M, 4 * C, _ptr(e.g[name + "/b"]), e._s())
             e.L.call("pivp_tc_wgrad5x5", _ptr(self.dg_all[li]), _ptr(self.xh_all[li]), self.Kpad[li], S * B, h, w, cx, 4 * C,
-                     _ptr(e.g[name + "/W"]), _ptr(self.wgrad_ws), self.wgrad_ws.numel(), e._s())
-            if grad_sync is not None:
-                grad_sync.ready("lstm%d" % (li + 1))
-        if grad_sync is None:
+                     _ptr(e.g[name + "/W"]), _ptr(wsb), wsb.numel(), e._s())
+
+        if grad_sync is not None:
             self.deconv_wgrad_all()
             self.conv_s2_wgrad_all()
+            grad_sync.ready("enc")
+            for li in sorted(range(7), key=lambda li: -(LSTM_IN[li] + LSTM_SIZES[li]) * LSTM_SIZES[li]):
+                lstm_wgrad(li, self.wgrad_ws)
+                grad_sync.ready("lstm%d" % (li + 1))
+            return
+        if self.wg_streams:
+            # The twelve deferred weight-gradient GEMMs are independent of one another: issued on parallel branches (forked side streams,
+            # one split-K workspace each; parallel branches of the captured graph) a GEMM's tail -- its last partial wave and its split-K
+            # reduce -- overlaps the head of a GEMM on another branch instead of leaving SMs idle.  Jobs balanced by measured duration.
+            cur = torch.cuda.current_stream(e.dev)
+            branches = [[6, 0, 2], [5, 1, 4], [3, "deconv", "s2"]][:len(self.wg_streams) + 1] if len(self.wg_streams) == 2 else [[6, 0, 2, 3], [5, 1, 4, "deconv", "s2"]]
+            for sd in self.wg_streams:
+                sd.wait_stream(cur)
+            for k, jobs in enumerate(branches):
+                wsb = self.wgrad_ws if k == 0 else self.wg_ws[k - 1]
+                ctx = torch.cuda.stream(self.wg_streams[k - 1]) if k > 0 else None
+                if ctx is not None:
+                    ctx.__enter__()
+                try:
+                    for j in jobs:
+                        if j == "deconv":
+                            self.deconv_wgrad_all(wsb)
+                        elif j == "s2":
+                            self.conv_s2_wgrad_all(wsb)
+                        else:
+                            lstm_wgrad(j, wsb)
+                finally:
+                    if ctx is not None:
+                        ctx.__exit__(None, None, None)
+            for sd in self.wg_streams:
+                cur.wait_stream(sd)
+            return
+        for li in range(7):
+            lstm_wgrad(li, self.wgrad_ws)
+        self.deconv_wgrad_all()
+        self.conv_s2_wgrad_all()

@@ -37,14 +37,14 @@ show("d_mask_pre", ws["d_mask_pre"], tr["mask_pre"].saved_grad)
 show("d_enc7_pre", ws["d_enc7_pre"], tr["enc7_pre"].saved_grad)
 show("d_kern_raw", ws["d_kern_raw"], tr["kern_raw"].saved_grad)
 show("d_e6", nhwc(ws["d_e6"], 64), tr["enc6"].saved_grad)
-show("d_hid5", ws["d_hid5"].reshape(B, H // 8, W // 8, 128).permute(0, 3, 1, 2), tr["hidden5"].saved_grad) if hasattr(tr["hidden5"], "saved_grad") else None
+show("d_hid5", ws["d_hid5"][(T - 2) & 1].reshape(B, H // 8, W // 8, 128).permute(0, 3, 1, 2), tr["hidden5"].saved_grad) if hasattr(tr["hidden5"], "saved_grad") else None
 def lvl(t, lv, cs, co, C):
     h, w = H // lv, W // lv
     return t.reshape(B, h, w, cs)[..., co:co + C].permute(0, 3, 1, 2)
 hs = tr["hiddens"]
-show("g hidden7", lvl(ws["d_cat6"], 2, 64, 0, 32), hs[6].saved_grad)
+show("g hidden7", lvl(ws["d_cat6"][(T - 2) & 1], 2, 64, 0, 32), hs[6].saved_grad)
 show("g hidden6", lvl(ws["d_cat5"], 4, 96, 0, 64), hs[5].saved_grad)
-show("g hidden5", lvl(ws["d_hid5"], 8, 128, 0, 128), hs[4].saved_grad)
+show("g hidden5", lvl(ws["d_hid5"][(T - 2) & 1], 8, 128, 0, 128), hs[4].saved_grad)
 show("g hidden4", lvl(ws["d_hid4"], 4, 64, 0, 64), hs[3].saved_grad)
 show("g hidden3", lvl(ws["dxh"][3], 4, 128, 0, 64), hs[2].saved_grad)
 show("g hidden2", lvl(ws["d_hid2"], 2, 32, 0, 32), hs[1].saved_grad)

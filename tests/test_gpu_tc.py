@@ -147,7 +147,8 @@ def l2rel(a, b):
     return float(np.linalg.norm(a.astype(np.float64) - b) / (np.linalg.norm(b) + 1e-30))
 
 
-@pytest.mark.parametrize("mt,nm,k", [("CDNA", 10, 900.0), ("CDNA", 10, -1.0), ("DNA", 1, 900.0), ("STP", 10, 900.0)])
+@pytest.mark.parametrize("mt,nm,k", [("CDNA", 10, 900.0), ("CDNA", 10, -1.0), ("DNA", 1, 900.0), ("STP", 10, 900.0),
+                                     ("CDNA", 4, 900.0)])      # 4 masks: the generic heads / generic fused-transform fallbacks of the bf16 path
 def test_model_bf16_within_tolerance_of_oracle(pk, mt, nm, k):
     """bf16 compute mode end to end (64x64, B=2, T=4) against the float64 oracle.
 
