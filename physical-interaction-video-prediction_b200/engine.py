@@ -174,13 +174,14 @@ class Engine(object):
         ws["d_mask_pre"] = A(B, self.M1, H, W)
         ws["d_prev"] = A(B, 3, H, W)
         ws["d_img_nhwc"] = A(Mr[1], 3)
-        ws["d_hid5"] = [A(Mr[8], 128), A(Mr[8], 128)]      # ping-pong over time steps: HEAD(t-1) fills slot (t-1)&1 while CHAIN(t) reads slot t&1
-        ws["d_cat6"] = [A(Mr[2], 64), A(Mr[2], 64)]
-        ws["d_cat5"] = A(Mr[4], 96)
+        # what crosses the stages of the backward pipeline (Engine.backward) is multi-buffered by time step
+        ws["d_hid5"] = [A(Mr[8], 128), A(Mr[8], 128)]
+        ws["d_cat6"] = [A(Mr[2], 64), A(Mr[2], 64), A(Mr[2], 64)]
+        ws["d_cat5"] = [A(Mr[4], 96), A(Mr[4], 96)]
         ws["d_e5pre"] = A(Mr[2], 96)
         ws["d_e4pre"] = A(Mr[4], 128)
         ws["d_e3pre"] = stack(Mr[8], 64)               # d(pre-activation) of enc0..enc3 kept per time step for the deferred weight gradients
-        ws["d_in3"] = A(Mr[8], self.cs3)
+        ws["d_in3"] = [A(Mr[8], self.cs3), A(Mr[8], self.cs3)]
         ws["d_e2pre"] = stack(Mr[8], 64)
         ws["d_hid4"] = A(Mr[4], 64)
         ws["d_e1pre"] = stack(Mr[4], 32)
@@ -200,7 +201,8 @@ class Engine(object):
                                    dtype=torch.uint8, device=self.dev)
         nb = self.L.query("pivp_layernorm_workspace_bytes", B, 64 * H * W)
         ws["ln_ws"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)
-        ws["ln_ws_head"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)     # LayerNorm workspace of the backward heads (side branch 3)
+        ws["ln_ws_head"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)     # LayerNorm workspaces of the other two backward stages
+        ws["ln_ws_upper"] = torch.empty(max(nb, 16), dtype=torch.uint8, device=self.dev)
         self.ws = ws
         if self.compute == "bf16":
             from .tensorcore import TensorCorePlan
@@ -276,13 +278,14 @@ class Engine(object):
                     _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(ln_ws),
                     ln_ws.numel(), self._s())
 
-    def _ln_lstm_bwd(self, name, li, t, x, g1, g2, B, HW, last):
+    def _ln_lstm_bwd(self, name, li, t, x, g1, g2, B, HW, last, ln_ws=None):
         """LayerNorm backward of ConvLSTM layer li's output at step t, then the layer's gate / input-gradient backward.
         Tensor-core mode: ONE kernel does the LayerNorm dx and the gate backward (d h_t never reaches memory), then the tcgen05 dgrad."""
         ws = self.ws
+        ln_ws = ws["ln_ws"] if ln_ws is None else ln_ws
         cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
         if self.tc is None:
-            self._ln_bwd(name, x, g1, g2, B, HW, 0, ws["ln_stats"][name][t], View(ws["dln"][li], C, 0, C))
+            self._ln_bwd(name, x, g1, g2, B, HW, 0, ws["ln_stats"][name][t], View(ws["dln"][li], C, 0, C), ln_ws=ln_ws)
             self._lstm_bwd(li, t, B, last)
             return
         dgb = self.tc.dg_bf16[li][t]
@@ -291,7 +294,7 @@ class Engine(object):
                     _ptr(self.p[name + "/norm/beta"]), _ptr(ws["ln_stats"][name][t]), B, HW, C,
                     _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(dgb),
                     _ptr(ws["c"][li][t - 1]) if t > 0 else 0, _ptr(ws["c"][li][t]), 0 if last else _ptr(ws["dxh"][li]), cin + C, cin,
-                    _ptr(ws["dc"][li]), 0 if last else 1, _ptr(ws["ln_ws"]), ws["ln_ws"].numel(), self._s())
+                    _ptr(ws["dc"][li]), 0 if last else 1, _ptr(ln_ws), ln_ws.numel(), self._s())
         self.tc.lstm_dgrad(li, t)
 
     def _relu_bwd(self, out, ga, gb, dst, M):
@@ -564,10 +567,10 @@ class Engine(object):
     def cleargrads(self):
         self.flat_g.zero_()
 
-    def _bwd_head(self, t, slot, inline):
+    def _bwd_head(self, t, inline):
         """The part of backward step t that hangs off the loss only (when the previous frame is detached, i.e. under scheduled sampling):
         fused transform backward, kernel / theta Linear input gradient, the two 1x1 heads, LayerNorm norm_enc6 and the enc6 deconvolution
-        input gradient.  Its outputs for the recurrent chain are d_cat6[slot] (gradient of [hidden7 | enc0 skip]) and d_hid5[slot] (gradient
+        input gradient.  Its outputs for the recurrent chain are d_cat6[t % 3] (gradient of [hidden7 | enc0 skip]) and d_hid5[t & 1] (gradient
         of hidden5 through the Linear); everything else it touches is private to heads, which never overlap one another.
         ``inline``: the Linear runs on the head's own stream (the head itself is a side branch); else on side branch 0, joined at enc4."""
         import contextlib
@@ -577,6 +580,7 @@ class Engine(object):
         HW, Mr = ws["HW"], ws["Mr"]
         p, g = self.p, self.g
         K5 = 128 * HW[8]
+        s2, s3 = t & 1, t % 3
         prev = self.prev[t]
         need_dprev = self.feedself and t >= self.ctx          # prev_t = gen_{t-1} keeps the graph (ref:664-666)
         d_prev = ws["d_prev"] if need_dprev else None
@@ -587,7 +591,7 @@ class Engine(object):
                    _ptr(d_prev), 0, B, H, W, self.M, _ptr(ws["fused_ws"]), ws["fused_ws"].numel(), s)
             with (contextlib.nullcontext() if inline else self._fork(0)):       # d hidden5 through the kernel Linear: needed only when BPTT reaches enc4
                 L.call("pivp_linear_bwd", _ptr(ws["d_kern_raw"][t]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/cdna_kerns/W"]),
-                       _ptr(ws["d_hid5"][slot]), K5, 0, 0, 0, B, K5, 25 * self.M, self._s())       # dx only; dW / db after the time loop
+                       _ptr(ws["d_hid5"][s2]), K5, 0, 0, 0, B, K5, 25 * self.M, self._s())       # dx only; dW / db after the time loop
             hid5_has_grad = True
         elif self.model_type == "DNA":
             L.call("pivp_dna_fused_bwd", _ptr(ws["d_gen"][t]), _ptr(prev), _ptr(ws["enc7_pre"][t]), _ptr(ws["mask_pre"][t]),
@@ -606,7 +610,7 @@ class Engine(object):
                        _ptr(ws["d_stp_s"]), 100, 0, _ptr(g["model/identity_params/W"]), _ptr(g["model/identity_params/b"]), B, 100, 6, s0)
                 L.call("pivp_relu_mask", _ptr(ws["stp_s"][t]), _ptr(ws["d_stp_s"]), B * 100, s0)
                 L.call("pivp_linear_bwd", _ptr(ws["d_stp_s"]), _ptr(ws["hid5"][t]), K5, _ptr(p["model/stp_input/W"]),
-                       _ptr(ws["d_hid5"][slot]), K5, 0, _ptr(g["model/stp_input/W"]), _ptr(g["model/stp_input/b"]), B, K5, 100, s0)
+                       _ptr(ws["d_hid5"][s2]), K5, 0, _ptr(g["model/stp_input/W"]), _ptr(g["model/stp_input/b"]), B, K5, 100, s0)
             hid5_has_grad = True
         # ---- heads backward: planes -> NHWC, then 1x1 conv dgrad / wgrad
         if self.Nh in (14, 27):
@@ -624,114 +628,153 @@ class Engine(object):
                      ws["ln_stats"]["norm_enc6"][t], View(ws["d_e6pre"], 64, 0, 64), ln_ws=ws["ln_ws_head"])
         de6 = View(ws["d_e6pre"], 64, 0, 64)
         if self.tc is not None:           # bias gradient + bf16 space-to-depth operand in one hand-over launch; weight gradient deferred
-            self.tc.deconv_bwd_fused("enc6", t, None, de6, None, g["enc6/b"], ws["d_cat6"][slot], 0)
+            self.tc.deconv_bwd_fused("enc6", t, None, de6, None, g["enc6/b"], ws["d_cat6"][s3], 0)
         else:
             L.call("pivp_colsum", de6.ptr, 64, 0, Mr[1], 64, _ptr(g["enc6/b"]), s)
             self._conv_wgrad(de6, B, H, W, View(ws["cat6"][t], 64, 0, 64), H // 2, W // 2, 3, 2, 1, g["enc6/W"], None)
-            self._conv_fwd(de6, B, H, W, p["enc6/W"], None, 64, 3, 2, 1, View(ws["d_cat6"][slot], 64, 0, 64))
+            self._conv_fwd(de6, B, H, W, p["enc6/W"], None, 64, 3, 2, 1, View(ws["d_cat6"][s3], 64, 0, 64))
         return hid5_has_grad
 
-    def backward(self):
-        """BPTT.  Step t = HEAD(t) (see _bwd_head) + CHAIN(t) (the seven ConvLSTM layers and the encoder / decoder between them, which
-        need the recurrent gradients of step t+1).  Under scheduled sampling HEAD(t-1) depends on nothing CHAIN(t) produces, so it runs on
-        side branch 3 WHILE CHAIN(t) runs (ping-pong d_cat6 / d_hid5): the heads are whole-GPU bandwidth kernels on 64x64 maps, the chain is
-        a string of small latency-bound kernels, and the step pays max(CHAIN, HEAD) instead of their sum.  In feedself mode the previous
-        frame keeps the graph (ref:664-666), d_gen[t-1] receives d_prev at the end of CHAIN(t), and the heads stay in line."""
-        ws, L, s = self.ws, self.L, self._s()
+    def _bwd_upper(self, t, hid5_has_grad, inline_head, ln_ws):
+        """Backward step t, decoder half: lstm7, enc5, lstm6, enc4, lstm5, enc3 and the state predictor.  Reads d_cat6 / d_hid5 of HEAD(t);
+        hands d_in3 (gradient of [enc2 out | smear]) and d_cat5[:, 64:96] (the enc1 skip) to the encoder half."""
+        ws, L = self.ws, self.L
+        s = self._s()
         T, B, H, W = self.T, self.B, self.H, self.W
         HW, Mr = ws["HW"], ws["Mr"]
         p, g = self.p, self.g
-        K5 = 128 * HW[8]
-        d_cur_in = None                       # gradient w.r.t. cur[t+1] arriving from step t+1's state_action
+        last = (t == T - 2)
+        s2, s3 = t & 1, t % 3
+        # ---- lstm7
+        self._ln_lstm_bwd("hidden7", 6, t, View(ws["xh"][6][t + 1], 128, 96, 32), View(ws["d_cat6"][s3], 64, 0, 32), None, B, HW[2], last, ln_ws)
+        # ---- enc5 deconv (input concat(hidden6, encs[1]))
+        de5 = View(ws["d_e5pre"], 96, 0, 96)
+        if self.tc is not None:
+            self.tc.deconv_bwd_fused("enc5", t, View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, g["enc5/b"],
+                                     ws["d_cat5"][s2], 0)
+        else:
+            self._relu_bwd(View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, de5, Mr[2])
+            L.call("pivp_colsum", de5.ptr, 96, 0, Mr[2], 96, _ptr(g["enc5/b"]), s)
+            self._conv_wgrad(de5, B, H // 2, W // 2, View(ws["cat5"][t], 96, 0, 96), H // 4, W // 4, 3, 2, 1, g["enc5/W"], None)
+            self._conv_fwd(de5, B, H // 2, W // 2, p["enc5/W"], None, 96, 3, 2, 1, View(ws["d_cat5"][s2], 96, 0, 96))
+        # ---- lstm6
+        self._ln_lstm_bwd("hidden6", 5, t, View(ws["xh"][5][t + 1], 192, 128, 64), View(ws["d_cat5"][s2], 96, 0, 64), None, B, HW[4], last, ln_ws)
+        # ---- enc4 deconv (input hidden5); d_hid5 may already hold the kernel-Linear contribution (side branch 0)
+        if hid5_has_grad and not inline_head:                   # an in-line head put the Linear on side branch 0
+            self._join(0)
+        de4 = View(ws["d_e4pre"], 128, 0, 128)
+        if self.tc is not None:
+            self.tc.deconv_bwd_fused("enc4", t, View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, g["enc4/b"],
+                                     ws["d_hid5"][s2], 1 if hid5_has_grad else 0)
+        else:
+            self._relu_bwd(View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, de4, Mr[4])
+            L.call("pivp_colsum", de4.ptr, 128, 0, Mr[4], 128, _ptr(g["enc4/b"]), s)
+            self._conv_wgrad(de4, B, H // 4, W // 4, View(ws["hid5"][t], 128, 0, 128), H // 8, W // 8, 3, 2, 1, g["enc4/W"], None)
+            self._conv_fwd(de4, B, H // 4, W // 4, p["enc4/W"], None, 128, 3, 2, 1, View(ws["d_hid5"][s2], 128, 0, 128),
+                           acc=1 if hid5_has_grad else 0)
+        # ---- lstm5
+        self._ln_lstm_bwd("hidden5", 4, t, View(ws["xh"][4][t + 1], 192, 64, 128), View(ws["d_hid5"][s2], 128, 0, 128), None, B, HW[8], last, ln_ws)
+        # ---- enc3 (1x1 on concat(enc2 out, smear))
+        self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"][t], 64, 0, 64), Mr[8])
+        de3 = View(ws["d_e3pre"][t], 64, 0, 64)
+        cin3, cs3 = 64 + self.sa, self.cs3
+        self._conv_dgrad(de3, B, H // 8, W // 8, p["enc3/W"], None, 1, 1, 0, View(ws["d_in3"][s2], cs3, 0, cin3), H // 8, W // 8)
+        # ---- state predictor + smear backward; produces d cur[t] for step t-1
+        d_cur_out = ws["d_cur"][t & 1]
+        d_cur_in = None if last else ws["d_cur"][(t + 1) & 1]       # gradient w.r.t. cur[t+1] from step t+1's state_action
+        L.call("pivp_state_bwd", _ptr(ws["d_gs"][t]), _ptr(d_cur_in), _ptr(ws["sa"][t]), _ptr(p["current_state/W"]),
+               _ptr(ws["d_in3"][s2]) if self.use_state else 0, cs3, 64, HW[8], B, _ptr(d_cur_out),
+               _ptr(g["current_state/W"]), _ptr(g["current_state/b"]), s)
+
+    def _bwd_lower(self, t, ln_ws):
+        """Backward step t, encoder half: enc2, lstm4, lstm3, enc1, lstm2, lstm1, norm_enc0 (and, in feedself mode, enc0 back to the frame)."""
+        ws, L = self.ws, self.L
+        s = self._s()
+        T, B, H, W = self.T, self.B, self.H, self.W
+        HW, Mr = ws["HW"], ws["Mr"]
+        p, g = self.p, self.g
+        last = (t == T - 2)
+        s2, s3 = t & 1, t % 3
+        need_dprev = self.feedself and t >= self.ctx          # prev_t = gen_{t-1} keeps the graph (ref:664-666)
+        d_prev = ws["d_prev"] if need_dprev else None
+        cs3 = self.cs3
+        # ---- enc2
+        de2 = View(ws["d_e2pre"][t], 64, 0, 64)
+        if self.tc is not None:
+            self.tc.conv_s2_dgrad_fused("enc2", t, View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"][s2], cs3, 0, 64), None, g["enc2/b"],
+                                        Mr[8], 64, ws["d_hid4"], 64)
+        else:
+            self._relu_bwd(View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"][s2], cs3, 0, 64), None, de2, Mr[8])
+            self._conv_dgrad(de2, B, H // 8, W // 8, p["enc2/W"], None, 3, 2, 1, View(ws["d_hid4"], 64, 0, 64), H // 4, W // 4)
+        # ---- lstm4, lstm3
+        self._ln_lstm_bwd("hidden4", 3, t, View(ws["xh"][3][t + 1], 128, 64, 64), View(ws["d_hid4"], 64, 0, 64), None, B, HW[4], last, ln_ws)
+        self._ln_lstm_bwd("hidden3", 2, t, View(ws["xh"][2][t + 1], 96, 32, 64), View(ws["dxh"][3], 128, 0, 64), None, B, HW[4], last, ln_ws)
+        # ---- enc1: encs[1] feeds lstm3 (x slot) and the enc5 skip slot
+        de1 = View(ws["d_e1pre"][t], 32, 0, 32)
+        if self.tc is not None:
+            self.tc.conv_s2_dgrad_fused("enc1", t, View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"][s2], 96, 64, 32),
+                                        g["enc1/b"], Mr[4], 32, ws["d_hid2"], 32)
+        else:
+            self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"][s2], 96, 64, 32), de1, Mr[4])
+            self._conv_dgrad(de1, B, H // 4, W // 4, p["enc1/W"], None, 3, 2, 1, View(ws["d_hid2"], 32, 0, 32), H // 2, W // 2)
+        # ---- lstm2, lstm1
+        self._ln_lstm_bwd("hidden2", 1, t, View(ws["xh"][1][t + 1], 64, 32, 32), View(ws["d_hid2"], 32, 0, 32), None, B, HW[2], last, ln_ws)
+        self._ln_lstm_bwd("hidden1", 0, t, View(ws["xh"][0][t + 1], 64, 32, 32), View(ws["dxh"][1], 64, 0, 32), None, B, HW[2], last, ln_ws)
+        # ---- norm_enc0 (+relu): encs[0] feeds lstm1 (x slot) and the enc6 skip slot; enc0
+        self._ln_bwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), View(ws["dxh"][0], 64, 0, 32), View(ws["d_cat6"][s3], 64, 32, 32),
+                     B, HW[2], 1, ws["ln_stats"]["norm_enc0"][t], View(ws["d_enc0pre"][t], 32, 0, 32), ln_ws=ln_ws)
+        de0 = View(ws["d_enc0pre"][t], 32, 0, 32)
+        if need_dprev:
+            self._conv_dgrad(de0, B, H // 2, W // 2, p["enc0/W"], None, 5, 2, 2, View(ws["d_img_nhwc"], 3, 0, 3), H, W)
+            L.call("pivp_nhwc_to_nchw", _ptr(ws["d_img_nhwc"]), 3, 0, _ptr(d_prev), B, 3, HW[1], 1, s)
+            L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)
+
+    def backward(self):
+        """BPTT.  Backward step t = HEAD(t) (loss side: transform, heads, norm_enc6, enc6 -- see _bwd_head), UPPER(t) (lstm7 .. lstm5, enc3, state
+        predictor) and LOWER(t) (enc2 .. lstm1, norm_enc0).  UPPER(t) needs HEAD(t) and UPPER(t+1); LOWER(t) needs UPPER(t) and LOWER(t+1);
+        under scheduled sampling HEAD(t) needs nothing from the other two (the previous frame is detached).  So the three run as a software
+        pipeline over three streams -- tick k issues HEAD(T-2-k), UPPER(T-1-k), LOWER(T-k), with a cross-stream barrier between ticks -- and
+        a time step costs max(HEAD, UPPER, LOWER) (about 155 us each at b32) instead of their sum.  What crosses stages is multi-buffered by
+        time step: d_cat6 x3, d_hid5 / d_in3 / d_cat5 x2, one LayerNorm workspace per stage; everything else is private to a layer, hence to
+        a stage.  Under CUDA-graph capture the streams become parallel branches of the graph.  In feedself mode the previous frame keeps the
+        graph (ref:664-666): d_gen[t-1] receives d_prev at the end of LOWER(t), so the stages run in line on one stream."""
+        ws, T = self.ws, self.T
         self._side(3)
         pipelined = (not self.feedself) and 3 in self._branches
-        hid5_flags = {T - 2: self._bwd_head(T - 2, (T - 2) & 1, False)}
-        for t in range(T - 2, -1, -1):
-            last = (t == T - 2)
-            slot = t & 1
-            need_dprev = self.feedself and t >= self.ctx          # prev_t = gen_{t-1} keeps the graph (ref:664-666)
-            d_prev = ws["d_prev"] if need_dprev else None
-            hid5_has_grad = hid5_flags[t]
-            if pipelined and t > 0:
-                with self._fork(3):
-                    hid5_flags[t - 1] = self._bwd_head(t - 1, (t - 1) & 1, True)
-            # ---- lstm7
-            self._ln_lstm_bwd("hidden7", 6, t, View(ws["xh"][6][t + 1], 128, 96, 32), View(ws["d_cat6"][slot], 64, 0, 32), None, B, HW[2], last)
-            # ---- enc5 deconv (input concat(hidden6, encs[1]))
-            de5 = View(ws["d_e5pre"], 96, 0, 96)
-            if self.tc is not None:
-                self.tc.deconv_bwd_fused("enc5", t, View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, g["enc5/b"],
-                                         ws["d_cat5"], 0)
-            else:
-                self._relu_bwd(View(ws["xh"][6][t], 128, 0, 96), View(ws["dxh"][6], 128, 0, 96), None, de5, Mr[2])
-                L.call("pivp_colsum", de5.ptr, 96, 0, Mr[2], 96, _ptr(g["enc5/b"]), s)
-                self._conv_wgrad(de5, B, H // 2, W // 2, View(ws["cat5"][t], 96, 0, 96), H // 4, W // 4, 3, 2, 1, g["enc5/W"], None)
-                self._conv_fwd(de5, B, H // 2, W // 2, p["enc5/W"], None, 96, 3, 2, 1, View(ws["d_cat5"], 96, 0, 96))
-            # ---- lstm6
-            self._ln_lstm_bwd("hidden6", 5, t, View(ws["xh"][5][t + 1], 192, 128, 64), View(ws["d_cat5"], 96, 0, 64), None, B, HW[4], last)
-            # ---- enc4 deconv (input hidden5); d_hid5 may already hold the kernel-Linear contribution (side branch 0)
-            if hid5_has_grad and not (pipelined and not last):       # an in-line head put the Linear on side branch 0
-                self._join(0)
-            de4 = View(ws["d_e4pre"], 128, 0, 128)
-            if self.tc is not None:
-                self.tc.deconv_bwd_fused("enc4", t, View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, g["enc4/b"],
-                                         ws["d_hid5"][slot], 1 if hid5_has_grad else 0)
-            else:
-                self._relu_bwd(View(ws["xh"][5][t], 192, 0, 128), View(ws["dxh"][5], 192, 0, 128), None, de4, Mr[4])
-                L.call("pivp_colsum", de4.ptr, 128, 0, Mr[4], 128, _ptr(g["enc4/b"]), s)
-                self._conv_wgrad(de4, B, H // 4, W // 4, View(ws["hid5"][t], 128, 0, 128), H // 8, W // 8, 3, 2, 1, g["enc4/W"], None)
-                self._conv_fwd(de4, B, H // 4, W // 4, p["enc4/W"], None, 128, 3, 2, 1, View(ws["d_hid5"][slot], 128, 0, 128),
-                               acc=1 if hid5_has_grad else 0)
-            # ---- lstm5
-            self._ln_lstm_bwd("hidden5", 4, t, View(ws["xh"][4][t + 1], 192, 64, 128), View(ws["d_hid5"][slot], 128, 0, 128), None, B, HW[8], last)
-            # ---- enc3 (1x1 on concat(enc2 out, smear))
-            self._relu_bwd(View(ws["xh"][4][t], 192, 0, 64), View(ws["dxh"][4], 192, 0, 64), None, View(ws["d_e3pre"][t], 64, 0, 64), Mr[8])
-            de3 = View(ws["d_e3pre"][t], 64, 0, 64)
-            cin3, cs3 = 64 + self.sa, self.cs3
-            self._conv_dgrad(de3, B, H // 8, W // 8, p["enc3/W"], None, 1, 1, 0, View(ws["d_in3"], cs3, 0, cin3), H // 8, W // 8)
-            # ---- state predictor + smear backward; produces d cur[t] for step t-1
-            d_cur_out = ws["d_cur"][t & 1]
-            L.call("pivp_state_bwd", _ptr(ws["d_gs"][t]), _ptr(d_cur_in), _ptr(ws["sa"][t]), _ptr(p["current_state/W"]),
-                   _ptr(ws["d_in3"]) if self.use_state else 0, cs3, 64, HW[8], B, _ptr(d_cur_out),
-                   _ptr(g["current_state/W"]), _ptr(g["current_state/b"]), s)
-            d_cur_in = d_cur_out
-            # ---- enc2
-            de2 = View(ws["d_e2pre"][t], 64, 0, 64)
-            if self.tc is not None:
-                self.tc.conv_s2_dgrad_fused("enc2", t, View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, g["enc2/b"],
-                                            Mr[8], 64, ws["d_hid4"], 64)
-            else:
-                self._relu_bwd(View(ws["in3"][t], cs3, 0, 64), View(ws["d_in3"], cs3, 0, 64), None, de2, Mr[8])
-                self._conv_dgrad(de2, B, H // 8, W // 8, p["enc2/W"], None, 3, 2, 1, View(ws["d_hid4"], 64, 0, 64), H // 4, W // 4)
-            # ---- lstm4, lstm3
-            self._ln_lstm_bwd("hidden4", 3, t, View(ws["xh"][3][t + 1], 128, 64, 64), View(ws["d_hid4"], 64, 0, 64), None, B, HW[4], last)
-            self._ln_lstm_bwd("hidden3", 2, t, View(ws["xh"][2][t + 1], 96, 32, 64), View(ws["dxh"][3], 128, 0, 64), None, B, HW[4], last)
-            # ---- enc1: encs[1] feeds lstm3 (x slot) and the enc5 skip slot
-            de1 = View(ws["d_e1pre"][t], 32, 0, 32)
-            if self.tc is not None:
-                self.tc.conv_s2_dgrad_fused("enc1", t, View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32),
-                                            g["enc1/b"], Mr[4], 32, ws["d_hid2"], 32)
-            else:
-                self._relu_bwd(View(ws["xh"][2][t], 96, 0, 32), View(ws["dxh"][2], 96, 0, 32), View(ws["d_cat5"], 96, 64, 32), de1, Mr[4])
-                self._conv_dgrad(de1, B, H // 4, W // 4, p["enc1/W"], None, 3, 2, 1, View(ws["d_hid2"], 32, 0, 32), H // 2, W // 2)
-            # ---- lstm2, lstm1
-            self._ln_lstm_bwd("hidden2", 1, t, View(ws["xh"][1][t + 1], 64, 32, 32), View(ws["d_hid2"], 32, 0, 32), None, B, HW[2], last)
-            self._ln_lstm_bwd("hidden1", 0, t, View(ws["xh"][0][t + 1], 64, 32, 32), View(ws["dxh"][1], 64, 0, 32), None, B, HW[2], last)
-            # ---- norm_enc0 (+relu): encs[0] feeds lstm1 (x slot) and the enc6 skip slot; enc0
-            self._ln_bwd("norm_enc0", View(ws["enc0_pre"][t], 32, 0, 32), View(ws["dxh"][0], 64, 0, 32), View(ws["d_cat6"][slot], 64, 32, 32),
-                         B, HW[2], 1, ws["ln_stats"]["norm_enc0"][t], View(ws["d_enc0pre"][t], 32, 0, 32))
-            de0 = View(ws["d_enc0pre"][t], 32, 0, 32)
-            if need_dprev:
-                self._conv_dgrad(de0, B, H // 2, W // 2, p["enc0/W"], None, 5, 2, 2, View(ws["d_img_nhwc"], 3, 0, 3), H, W)
-                L.call("pivp_nhwc_to_nchw", _ptr(ws["d_img_nhwc"]), 3, 0, _ptr(d_prev), B, 3, HW[1], 1, s)
-                L.call("pivp_axpy", _ptr(d_prev), _ptr(ws["d_gen"][t - 1]), B * 3 * H * W, s)
-            if self._stop_after_step(t):
-                return
-            if t > 0:
-                if pipelined:
-                    self._join(3)                  # HEAD(t-1) ran beside this step's chain
-                else:
-                    hid5_flags[t - 1] = self._bwd_head(t - 1, (t - 1) & 1, False)
+        if not pipelined:
+            for t in range(T - 2, -1, -1):
+                flag = self._bwd_head(t, False)
+                self._bwd_upper(t, flag, False, ws["ln_ws"])
+                self._bwd_lower(t, ws["ln_ws"])
+                if self._stop_after_step(t):
+                    return
+        else:
+            cur = torch.cuda.current_stream(self.dev)
+            st_h, st_u = self._side(3), self._side(4)
+            flags = {}
+            streams = (cur, st_u, st_h)
+            st_u.wait_stream(cur)                      # fork: the two side streams join the (possibly capturing) current stream first --
+            st_h.wait_stream(cur)                      # a capturing stream must not wait on a stream that is not part of the capture yet
+            for k in range(T - 1 + 2):
+                for a in streams:                      # barrier between ticks: every stage waits for what the other two were given so far
+                    for b in streams:
+                        if a is not b and k > 0:
+                            a.wait_stream(b)
+                h, u, l = T - 2 - k, T - 1 - k, T - k
+                if 0 <= h <= T - 2:
+                    with torch.cuda.stream(st_h):
+                        flags[h] = self._bwd_head(h, True)
+                if 0 <= u <= T - 2:
+                    with torch.cuda.stream(st_u):
+                        self._bwd_upper(u, flags[u], True, ws["ln_ws_upper"])
+                if 0 <= l <= T - 2:
+                    self._bwd_lower(l, ws["ln_ws"])
+            cur.wait_stream(st_u)
+            cur.wait_stream(st_h)
+        L, s = self.L, self._s()
+        B, H, W = self.B, self.H, self.W
+        HW, Mr = ws["HW"], ws["Mr"]
+        p, g = self.p, self.g
         # ---- deferred weight gradients of enc0..enc3: the per-step tensors are stacked over time, so each is ONE launch with
         # S*B "images" (9x longer reduction per launch instead of 9 launches that cannot fill the GPU)
         gs = self.grad_sync

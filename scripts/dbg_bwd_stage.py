@@ -1,5 +1,6 @@
 """Compare backward intermediates of time step 0 (T=3: the last step the reverse sweep visits) with the oracle's Var.grad."""
 import sys, os
+os.environ.setdefault("PIVP_BRANCHES", "")     # stage-by-stage diagnostics: one stream, so that the stop hook leaves a consistent state
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import numpy as np, torch
