@@ -656,6 +656,7 @@ bool cdna_band_supported(int H, int W, int num_masks, const void* p0, const void
 int cdna_band_fwd(const float* prev, const float* e_pre, const float* a_pre, const float* kraw, float* out, int B, int H,
                   cudaStream_t st) {
     static const int P = getenv("PIVP_CDNA_P") ? atoi(getenv("PIVP_CDNA_P")) : 2;
+    if (P == 1) return cb::launch_fwd<1>(prev, e_pre, a_pre, kraw, out, B, H, st);
     return P == 4 ? cb::launch_fwd<4>(prev, e_pre, a_pre, kraw, out, B, H, st) : cb::launch_fwd<2>(prev, e_pre, a_pre, kraw, out, B, H, st);
 }
 
