@@ -498,6 +498,12 @@ def main():
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line))
     if world > 1:
+        # CUDA graphs that hold NCCL kernels (PIVP_DP_OVERLAP=1) must be gone before the communicator is torn down
+        step.graph = None
+        del step
+        import gc
+        gc.collect()
+        torch.cuda.synchronize()
         torch.distributed.barrier()
         torch.distributed.destroy_process_group()
 

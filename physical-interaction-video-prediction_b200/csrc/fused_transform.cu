@@ -354,20 +354,41 @@ __global__ void __launch_bounds__(FT) dna_kernel(const float* __restrict__ prev,
 #pragma unroll
             for (int c = 0; c < 3; ++c) g[c] = __ldg(gout + gp + (long)c * HW);
         }
+        // The window is truncated at i + xkern >= H / j + ykern >= W (B.2): only pixels of the last four rows / columns lose taps, so the
+        // interior runs the 75 multiply-adds without a predicate per tap; T is normalised once at the end instead of per tap.
+        const float* trow = tile + y * TW + x;
+        if (yi + 4 < H && x + 4 < W) {
 #pragma unroll
-        for (int u = 0; u < 5; ++u)
+            for (int u = 0; u < 5; ++u)
 #pragma unroll
-            for (int v = 0; v < 5; ++v) {
-                const bool live = (yi + u < H) && (x + v < W);                   // truncated window (B.2)
-                float dk = 0.f;
+                for (int v = 0; v < 5; ++v) {
+                    float dk = 0.f;
 #pragma unroll
-                for (int c = 0; c < 3; ++c) {
-                    const float pv = live ? tile[c * TS + (y + u) * TW + x + v] : 0.f;
-                    T[c] = fmaf(k[u * 5 + v] * inv, pv, T[c]);
-                    if (BWD) dk = fmaf(g[c], pv, dk);
+                    for (int c = 0; c < 3; ++c) {
+                        const float pv = trow[c * TS + u * TW + v];
+                        T[c] = fmaf(k[u * 5 + v], pv, T[c]);
+                        if (BWD) dk = fmaf(g[c], pv, dk);
+                    }
+                    if (BWD) dKt[u * 5 + v] = dk * m1;
                 }
-                if (BWD) dKt[u * 5 + v] = dk * m1;
-            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+#pragma unroll
+                for (int v = 0; v < 5; ++v) {
+                    const bool live = (yi + u < H) && (x + v < W);
+                    float dk = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) {
+                        const float pv = live ? trow[c * TS + u * TW + v] : 0.f;
+                        T[c] = fmaf(k[u * 5 + v], pv, T[c]);
+                        if (BWD) dk = fmaf(g[c], pv, dk);
+                    }
+                    if (BWD) dKt[u * 5 + v] = dk * m1;
+                }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) T[c] *= inv;
         if (!backward) {
 #pragma unroll
             for (int c = 0; c < 3; ++c) out[gp + (long)c * HW] = m0 * tile[c * TS + (y + 2) * TW + x + 2] + m1 * T[c];
