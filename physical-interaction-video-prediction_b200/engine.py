@@ -767,6 +767,8 @@ class Engine(object):
                 if 0 <= u <= T - 2:
                     with torch.cuda.stream(st_u):
                         self._bwd_upper(u, flags[u], True, ws["ln_ws_upper"])
+                if u < 0 <= l and self.tc is not None and self.grad_sync is None:
+                    self.tc.wgrad_early(st_u, st_h)    # decoder half finished: its weight gradients start beside LOWER(0)
                 if 0 <= l <= T - 2:
                     self._bwd_lower(l, ws["ln_ws"])
             cur.wait_stream(st_u)

@@ -98,6 +98,9 @@ class TensorCorePlan(object):
         nbr = max(1, min(3, int(os.environ.get("PIVP_WGRAD_STREAMS", "3"))))       # measured on the b32 step: 8.61 / 8.37 / 8.31 ms with 1 / 2 / 3
         self.wg_streams = [torch.cuda.Stream(device=dev) for _ in range(nbr - 1)]
         self.wg_ws = [torch.empty_like(self.wgrad_ws) for _ in range(nbr - 1)]
+        self.early_on = os.environ.get("PIVP_WGRAD_EARLY", "1") != "0"
+        self.wg_ws_early = [torch.empty_like(self.wgrad_ws) for _ in range(2)] if (nbr == 3 and self.early_on) else []
+        self._early = set()
         self.refresh_weights()
 
     def _walloc(self, idx, shape):
@@ -345,23 +348,49 @@ class TensorCorePlan(object):
                  0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
                  C, 0.0, 0, 0, e._s())
 
+    def _lstm_wgrad(self, li, wsb):
+        e, ws = self.eng, self.ws
+        S, B = self.S, ws["B"]
+        cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
+        M = ws["Mr"][lv]
+        h, w = e.H // lv, e.W // lv
+        cx = cin + C
+        name = "lstm%d/conv" % (li + 1)
+        e.L.call("pivp_tc_colsum_bf16", _ptr(self.dg_all[li]), 4 * C, S * M, 4 * C, _ptr(e.g[name + "/b"]), e._s())
+        e.L.call("pivp_tc_wgrad5x5", _ptr(self.dg_all[li]), _ptr(self.xh_all[li]), self.Kpad[li], S * B, h, w, cx, 4 * C,
+                 _ptr(e.g[name + "/W"]), _ptr(wsb), wsb.numel(), e._s())
+
+    def wgrad_jobs(self, jobs, wsb):
+        """Deferred weight-gradient jobs on the CURRENT stream: ConvLSTM layer index, "deconv" (enc4/5/6) or "s2" (enc1/2)."""
+        for j in jobs:
+            if j == "deconv":
+                self.deconv_wgrad_all(wsb)
+            elif j == "s2":
+                self.conv_s2_wgrad_all(wsb)
+            else:
+                self._lstm_wgrad(j, wsb)
+
+    def wgrad_early(self, stream_a, stream_b):
+        """Called by the backward pipeline when its decoder half is done (all gate gradients of lstm5-7 and the dY of enc4-6 exist) while the
+        encoder half of the last time step still runs: the decoder-side weight gradients start on the two idle pipeline streams, with
+        workspaces of their own, and are joined with the rest in wgrad_all()."""
+        if len(self.wg_streams) != 2 or not self.early_on:
+            return
+        with torch.cuda.stream(stream_a):
+            self.wgrad_jobs([6, 4], self.wg_ws_early[0])
+        with torch.cuda.stream(stream_b):
+            self.wgrad_jobs([5, "deconv"], self.wg_ws_early[1])
+        self._early = {6, 4, 5, "deconv"}
+
     def wgrad_all(self, grad_sync=None):
         """After BPTT: weight and bias gradients of all seven ConvLSTM convolutions, each as ONE GEMM over all time steps.
         Data parallel (``grad_sync``): the small encoder / decoder gradients go first and are all-reduced as one block, then the ConvLSTM
         layers from the largest parameter tensor to the smallest, each layer's all-reduce running under the next layer's GEMM, so only the
         smallest tensor's reduction (0.8 MB) is exposed behind the last GEMM."""
-        e, ws = self.eng, self.ws
-        S, B = self.S, ws["B"]
-        def lstm_wgrad(li, wsb):
-            cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
-            M = ws["Mr"][lv]
-            h, w = e.H // lv, e.W // lv
-            cx = cin + C
-            name = "lstm%d/conv" % (li + 1)
-            e.L.call("pivp_tc_colsum_bf16", _ptr(self.dg_all[li]), 4 * C, S * M, 4 * C, _ptr(e.g[name + "/b"]), e._s())
-            e.L.call("pivp_tc_wgrad5x5", _ptr(self.dg_all[li]), _ptr(self.xh_all[li]), self.Kpad[li], S * B, h, w, cx, 4 * C,
-                     _ptr(e.g[name + "/W"]), _ptr(wsb), wsb.numel(), e._s())
-
+        e = self.eng
+        lstm_wgrad = self._lstm_wgrad
+        early = self._early
+        self._early = set()
         if grad_sync is not None:
             self.deconv_wgrad_all()
             self.conv_s2_wgrad_all()
@@ -374,30 +403,27 @@ class TensorCorePlan(object):
             # The twelve deferred weight-gradient GEMMs are independent of one another: issued on parallel branches (forked side streams,
             # one split-K workspace each; parallel branches of the captured graph) a GEMM's tail -- its last partial wave and its split-K
             # reduce -- overlaps the head of a GEMM on another branch instead of leaving SMs idle.  Jobs balanced by measured duration.
+            # Jobs in `early` were already issued by the backward pipeline beside its last stage (wgrad_early).
             cur = torch.cuda.current_stream(e.dev)
-            branches = [[6, 0, 2], [5, 1, 4], [3, "deconv", "s2"]][:len(self.wg_streams) + 1] if len(self.wg_streams) == 2 else [[6, 0, 2, 3], [5, 1, 4, "deconv", "s2"]]
+            if early:
+                branches = [[0, 2], [1, "s2"], [3]] if len(self.wg_streams) == 2 else [[0, 2, 3], [1, "s2"]]
+            else:
+                branches = [[6, 0, 2], [5, 1, 4], [3, "deconv", "s2"]] if len(self.wg_streams) == 2 else [[6, 0, 2, 3], [5, 1, 4, "deconv", "s2"]]
             for sd in self.wg_streams:
                 sd.wait_stream(cur)
             for k, jobs in enumerate(branches):
                 wsb = self.wgrad_ws if k == 0 else self.wg_ws[k - 1]
-                ctx = torch.cuda.stream(self.wg_streams[k - 1]) if k > 0 else None
-                if ctx is not None:
-                    ctx.__enter__()
-                try:
-                    for j in jobs:
-                        if j == "deconv":
-                            self.deconv_wgrad_all(wsb)
-                        elif j == "s2":
-                            self.conv_s2_wgrad_all(wsb)
-                        else:
-                            lstm_wgrad(j, wsb)
-                finally:
-                    if ctx is not None:
-                        ctx.__exit__(None, None, None)
+                if k == 0:
+                    self.wgrad_jobs(jobs, wsb)
+                else:
+                    with torch.cuda.stream(self.wg_streams[k - 1]):
+                        self.wgrad_jobs(jobs, wsb)
             for sd in self.wg_streams:
                 cur.wait_stream(sd)
             return
         for li in range(7):
-            lstm_wgrad(li, self.wgrad_ws)
-        self.deconv_wgrad_all()
+            if li not in early:
+                lstm_wgrad(li, self.wgrad_ws)
+        if "deconv" not in early:
+            self.deconv_wgrad_all()
         self.conv_s2_wgrad_all()
