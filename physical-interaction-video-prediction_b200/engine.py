@@ -223,8 +223,8 @@ class Engine(object):
             # (one id at a time, against 8.353 ms with none): 0 -> 8.248, 1 -> 8.274, 2 -> 8.280 ms.  (Also measured: the eight bf16
             # weight-refresh launches behind Adam on three branches -> 8.57 ms, WORSE -- the forks delay the first kernels of the next
             # step -- so they stay on the main chain.)  PIVP_BRANCHES="" keeps everything on one stream.
-            # 3: the loss-side head of backward step t-1 beside the recurrent chain of step t (Engine.backward).
-            self._branches = set(int(v) for v in os.environ.get("PIVP_BRANCHES", "0,1,2,3").split(",") if v.strip() != "")
+            # 3: the backward pipeline (Engine.backward); 5: bf16 / fp32 copies of the two skip connections (forward).
+            self._branches = set(int(v) for v in os.environ.get("PIVP_BRANCHES", "0,1,2,3,5").split(",") if v.strip() != "")
         if k not in self._side_streams:
             self._side_streams[k] = torch.cuda.Stream(device=self.dev)
         return self._side_streams[k]
@@ -432,6 +432,12 @@ class Engine(object):
                 prev = ws["prev_buf"][t]
                 L.call("pivp_sched_select", _ptr(images[t]), _ptr(ws["gen"][t - 1]), _ptr(ws["take"][t]), _ptr(prev), B, 3 * H * W, s)
             self.prev.append(prev)
+            # state predictor + smear (train_model.py:563-565, 676, 730): needs the action and the previous state only -> side branch 5;
+            # it fills the smear columns of enc3's input, enc2 fills the others; joined in front of enc3
+            with self._fork(5):
+                L.call("pivp_state_fwd", _ptr(actions[t]), _ptr(ws["cur"][t]), _ptr(p["current_state/W"]), _ptr(p["current_state/b"]),
+                       _ptr(ws["sa"][t]), _ptr(ws["cur"][t + 1]), _ptr(ws["in3"][t]) if self.use_state else 0, self.cs3, 64,
+                       HW[8], B, self._s())
             L.call("pivp_nchw_to_nhwc", _ptr(prev), _ptr(ws["img_nhwc"][t]), 3, 0, B, 3, HW[1], s)
             # ---- group 0: enc0 -> LN -> relu  (goes to lstm1's x slot and to the enc6 skip slot)
             self._conv_fwd(View(ws["img_nhwc"][t], 3, 0, 3), B, H, W, p["enc0/W"], p["enc0/b"], 32, 5, 2, 2,
@@ -440,17 +446,20 @@ class Engine(object):
                          View(ws["cat6"][t], 64, 32, 32), 1, ws["ln_stats"]["norm_enc0"][t],
                          None if self.tc is None else self.tc.xview(0, t))
             if self.tc is not None:
-                L.call("pivp_copy_view", _ptr(ws["cat6"][t]), 64, 32, 0, 0, 0, _ptr(self.tc.cat6_b[t]), 64, 32, Mr[2], 32, s)
+                with self._fork(5):            # bf16 copy of the enc0 skip: needed by the enc6 deconvolution at the end of the step only
+                    L.call("pivp_copy_view", _ptr(ws["cat6"][t]), 64, 32, 0, 0, 0, _ptr(self.tc.cat6_b[t]), 64, 32, Mr[2], 32, self._s())
             # ---- group 1
             self._lstm_ln_fwd(0, t, B, "hidden1", View(ws["xh"][1][t], 64, 0, 32), None if self.tc is None else self.tc.xview(1, t))
             self._lstm_ln_fwd(1, t, B, "hidden2", View(ws["hid2"][t], 32, 0, 32))
             if self.tc is not None:       # stride-2 conv as a 9-tap tcgen05 GEMM on the space-to-depth bf16 input; bf16 x slot from the epilogue
                 self.tc.conv_s2_fwd("enc1", t, ws["hid2"][t], 32, ws["xh"][2][t], 96, self.tc.xview(2, t).t, self.tc.Kpad[2])
-                L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, s)
+                with self._fork(5):            # enc1 skip (fp32 + bf16): needed by the enc5 deconvolution only
+                    L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, self._s())
             else:
                 self._conv_fwd(View(ws["hid2"][t], 32, 0, 32), B, H // 2, W // 2, p["enc1/W"], p["enc1/b"], 32, 3, 2, 1,
                                View(ws["xh"][2][t], 96, 0, 32), relu=1)
-                L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, 0, 0, 0, Mr[4], 32, s)
+                with self._fork(5):
+                    L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, 0, 0, 0, Mr[4], 32, self._s())
             # ---- group 2
             self._lstm_ln_fwd(2, t, B, "hidden3", View(ws["xh"][3][t], 128, 0, 64), None if self.tc is None else self.tc.xview(3, t))
             self._lstm_ln_fwd(3, t, B, "hidden4", View(ws["hid4"][t], 64, 0, 64))
@@ -459,16 +468,15 @@ class Engine(object):
             else:
                 self._conv_fwd(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, p["enc2/W"], p["enc2/b"], 64, 3, 2, 1,
                                View(ws["in3"][t], self.cs3, 0, 64), relu=1)
-            # ---- group 3: smear + enc3; state predictor (train_model.py:676,730)
-            L.call("pivp_state_fwd", _ptr(actions[t]), _ptr(ws["cur"][t]), _ptr(p["current_state/W"]), _ptr(p["current_state/b"]),
-                   _ptr(ws["sa"][t]), _ptr(ws["cur"][t + 1]), _ptr(ws["in3"][t]) if self.use_state else 0, self.cs3, 64,
-                   HW[8], B, s)
+            # ---- group 3: enc3 on [enc2 out | smear]; the smear and the state predictor (train_model.py:676,730) ran on side branch 5
+            self._join(5)
             self._conv_fwd(View(ws["in3"][t], self.cs3, 0, 64 + self.sa), B, H // 8, W // 8, p["enc3/W"], p["enc3/b"], 64, 1, 1, 0,
                            View(ws["xh"][4][t], 192, 0, 64), relu=1)
             if self.tc is not None:
                 L.call("pivp_copy_view", _ptr(ws["xh"][4][t]), 192, 0, 0, 0, 0, self.tc.xview(4, t).ptr, self.tc.Kpad[4], 0, Mr[8], 64, s)
             # ---- group 4
             self._lstm_ln_fwd(4, t, B, "hidden5", View(ws["hid5"][t], 128, 0, 128), None if self.tc is None else View(self.tc.hid5_b[t], 128, 0, 128))
+            # (the enc0 skip copy on branch 5 is joined with the enc1 skip above: same side stream, issued earlier)
             # the kernel / theta Linear needs hidden5 only and is consumed by the transform at the end of the step: side branch 0
             K5 = 128 * HW[8]
             with self._fork(0):
@@ -488,6 +496,7 @@ class Engine(object):
                                  View(ws["xh"][5][t], 192, 0, 128), H // 4, W // 4, relu=1)
             # ---- group 5
             self._lstm_ln_fwd(5, t, B, "hidden6", View(ws["cat5"][t], 96, 0, 64), None if self.tc is None else View(self.tc.cat5_b[t], 128, 0, 64))
+            self._join(5)                              # the enc1 skip copies
             if self.tc is not None:
                 self.tc.deconv_fwd("enc5", self.tc.cat5_b[t], ws["xh"][6][t], 128, self.tc.xh_bf16[6][t], self.tc.Kpad[6], 1)
             else:
