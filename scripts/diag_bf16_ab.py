@@ -8,7 +8,7 @@ against the float64 oracle -- the attribution VERDICT r1 asked for (weak #3):
   W     : every weight the tensor-core path casts to bf16 (ConvLSTM, enc1/2, enc4/5/6) is rounded once
   all   : the four together;   bf16 : the real tensor-core engine (adds bf16 deconvolution activations and tcgen05 accumulation order)
 
-    python scripts/diag_bf16_ab.py [B=2] [T=4]        # CDNA 64x64, scheduled sampling at iteration 6000, perturbed parameters
+    python scripts/diag_bf16_ab.py [B=2] [T=4] [CDNA|DNA|STP]        # 64x64, scheduled sampling at iteration 6000, perturbed parameters
 torch is used for the roundings only (diagnostics, not the product path)."""
 import os, sys
 os.environ.setdefault("PIVP_BRANCHES", "")
@@ -20,8 +20,10 @@ from oracle import model as OM, npgrad as G
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
 T = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+MT = sys.argv[3] if len(sys.argv) > 3 else "CDNA"
+NM = 1 if MT == "DNA" else 10
 H = W = 64
-cfg = OM.Config("CDNA", 10, schedsamp_k=900.0, height=H, width=W, dtype=np.float64)
+cfg = OM.Config(MT, NM, schedsamp_k=900.0, height=H, width=W, dtype=np.float64)
 params = OM.init_params(cfg)
 rs = np.random.RandomState(7)
 for key in sorted(params):
@@ -69,7 +71,7 @@ def patched(eng, sw):
 
 
 def run(sw, compute="f32"):
-    m = pk.Model(10, is_cdna=True, scheduled_sampling_k=900.0, prefix="t", height=H, width=W, compute=compute)
+    m = pk.Model(NM, is_cdna=MT == "CDNA", is_dna=MT == "DNA", is_stp=MT == "STP", scheduled_sampling_k=900.0, prefix="t", height=H, width=W, compute=compute)
     p = dict(params)
     if "W" in sw:
         for k_ in p:
@@ -92,7 +94,7 @@ def run(sw, compute="f32"):
 
 variants = [("fp32 (no rounding)", set(), "f32"), ("gates", {"gates"}, "f32"), ("dG", {"dG"}, "f32"), ("xh", {"xh"}, "f32"), ("W", {"W"}, "f32"),
             ("all four", {"gates", "dG", "xh", "W"}, "f32"), ("bf16 engine (tcgen05)", set(), "bf16")]
-print("CDNA 64x64 B=%d T=%d, per-tensor gradient relative L2 error vs the float64 oracle" % (B, T))
+print("%s 64x64 B=%d T=%d, per-tensor gradient relative L2 error vs the float64 oracle" % (MT, B, T))
 print("| rounding switched on | frames rel L2 (worst t) | worst tensor | its error | median over tensors | lstm1/conv/W | lstm5/conv/W | enc0/W | masks/W |")
 print("|---|---:|---|---:|---:|---:|---:|---:|---:|")
 for name, sw, comp in variants:
