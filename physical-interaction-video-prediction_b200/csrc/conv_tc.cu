@@ -45,13 +45,17 @@ struct TcGeom {
 // blockIdx.z picks the weight tensor map and the geometry; the A tensor, tile counts and epilogue are common.
 constexpr int TC_MAXPH = 4;
 struct TcMapsB { CUtensorMap m[TC_MAXPH]; };
-struct TcGeomPack { TcGeom g[TC_MAXPH]; };
+struct TcGeomPack {
+    TcGeom g[TC_MAXPH];
+    int nloop;       // 1: one phase per CTA (blockIdx.z picks it).  n > 1: every CTA walks phases 0..n-1 of its pixel tile, one TMEM
+                     // accumulator of BN columns per phase (grid z = 1) -- a quarter of the CTAs, so a 64x64 deconvolution is ONE wave
+};
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ TcMapsB maps_b, const __grid_constant__ TcGeomPack gp,
                     TcEpilogue ep) {
-    const TcGeom& g = gp.g[blockIdx.z];
-    const CUtensorMap& map_b = maps_b.m[blockIdx.z];
+    const TcGeom& g = gp.g[blockIdx.z];            // fields common to all phases (tile geometry, Kc, BN, ring depth, TMEM columns)
+    const int nloop = gp.nloop;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // carve: [stages][A 16 KB | B BN*128] then barriers
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -59,19 +63,18 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     uint64_t* bars = (uint64_t*)(smem + (size_t)g.stages * stage_bytes);
     uint64_t* full = bars;
     uint64_t* empty = bars + g.stages;
-    uint64_t* accum_full = bars + 2 * g.stages;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * g.stages + 1);
+    uint64_t* accum_full = bars + 2 * g.stages;     // [TC_MAXPH]: one per phase accumulator
+    uint32_t* tmem_slot = (uint32_t*)(bars + 2 * g.stages + TC_MAXPH);
     float* bias_s = (float*)(tmem_slot + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m_tile = blockIdx.x, n_tile = blockIdx.y;
     const int n0 = n_tile * g.BN;
     const int kblocks_per_tap = g.Kc / TC_BK;
-    const int num_kb = g.ntaps * kblocks_per_tap;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
-        mbar_init(smem_u32(accum_full), 1);
+        for (int p = 0; p < TC_MAXPH; ++p) mbar_init(smem_u32(accum_full + p), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -97,18 +100,22 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const int x0 = tx * g.TW, y0 = ty * g.TH, b0 = tb * g.TB;
         const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty), ring0 = smem_u32(smem);
         uint32_t st = 0, ph = 1;
-        for (int tap = 0; tap < g.ntaps; ++tap) {
-            const int cx = x0 + g.dx[tap], cy = y0 + g.dy[tap], cc = g.coff[tap];
-            for (int cb = 0; cb < kblocks_per_tap; ++cb) {
-                mbar_wait(empty0 + 8 * st, ph);
-                if (elect_one()) {
-                    const uint32_t sa = ring0 + st * stage_bytes;
-                    mbar_expect_tx(full0 + 8 * st, stage_bytes);
-                    tma_load_4d(sa, &map_a, full0 + 8 * st, cc + cb * TC_BK, cx, cy, b0);
-                    tma_load_2d(sa + a_bytes, &map_b, full0 + 8 * st, tap * g.Kc + cb * TC_BK, n0);
+        for (int p = 0; p < nloop; ++p) {
+            const TcGeom& gq = gp.g[blockIdx.z + p];
+            const CUtensorMap& map_b = maps_b.m[blockIdx.z + p];
+            for (int tap = 0; tap < gq.ntaps; ++tap) {
+                const int cx = x0 + gq.dx[tap], cy = y0 + gq.dy[tap], cc = gq.coff[tap];
+                for (int cb = 0; cb < kblocks_per_tap; ++cb) {
+                    mbar_wait(empty0 + 8 * st, ph);
+                    if (elect_one()) {
+                        const uint32_t sa = ring0 + st * stage_bytes;
+                        mbar_expect_tx(full0 + 8 * st, stage_bytes);
+                        tma_load_4d(sa, &map_a, full0 + 8 * st, cc + cb * TC_BK, cx, cy, b0);
+                        tma_load_2d(sa + a_bytes, &map_b, full0 + 8 * st, tap * g.Kc + cb * TC_BK, n0);
+                    }
+                    __syncwarp();
+                    if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; }
                 }
-                __syncwarp();
-                if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; }
             }
         }
     } else if (warp == 1) {
@@ -120,36 +127,43 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         const uint32_t ring_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | 0x10000u, step_lo = stage_bytes >> 4, a_lo_sz = a_bytes >> 4;
         const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
         uint32_t st = 0, ph = 0, lo = ring_lo;
-        for (int kb = 0; kb < num_kb; ++kb) {
-            mbar_wait(full0 + 8 * st, ph);
-            tc_fence_after();
-            if (elect_one()) {
+        for (int p = 0; p < nloop; ++p) {
+            const int num_kb = gp.g[blockIdx.z + p].ntaps * kblocks_per_tap;
+            const uint32_t acc = tmem_u + (uint32_t)(p * g.BN);      // this phase's accumulator columns
+            for (int kb = 0; kb < num_kb; ++kb) {
+                mbar_wait(full0 + 8 * st, ph);
+                tc_fence_after();
+                if (elect_one()) {
 #pragma unroll
-                for (int k = 0; k < TC_BK / 16; ++k)      // advance 16 bf16 = 32 B = 2 (>>4 units) inside the swizzle span
-                    tc_mma_lohi(tmem_u, lo + 2 * k, lo + a_lo_sz + 2 * k, hi, hi, idesc, (k == 0) ? (kb ? 1u : 0u) : 1u);
-                tc_commit(empty0 + 8 * st);               // frees the smem slot when these MMAs retire
-                if (kb == num_kb - 1) tc_commit(smem_u32(accum_full));
+                    for (int k = 0; k < TC_BK / 16; ++k)      // advance 16 bf16 = 32 B = 2 (>>4 units) inside the swizzle span
+                        tc_mma_lohi(acc, lo + 2 * k, lo + a_lo_sz + 2 * k, hi, hi, idesc, (k == 0) ? (kb ? 1u : 0u) : 1u);
+                    tc_commit(empty0 + 8 * st);               // frees the smem slot when these MMAs retire
+                    if (kb == num_kb - 1) tc_commit(smem_u32(accum_full + p));
+                }
+                __syncwarp();
+                lo += step_lo;
+                if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; lo = ring_lo; }
             }
-            __syncwarp();
-            lo += step_lo;
-            if (++st == (uint32_t)g.stages) { st = 0; ph ^= 1u; lo = ring_lo; }
         }
     } else {
         // ===================== epilogue (warps 2..5) =====================
         const int q = warp & 3;                            // TMEM lane quarter this warp may read
         const int row = q * 32 + lane;
         const long m = (long)m_tile * TC_BM + row;
-        mbar_wait(smem_u32(accum_full), 0);
-        tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
         // output row of this A-grid pixel (identity for stride-1 convs, phase scatter for transposed convs)
         const int hw = g.H * g.W;
         const int bi = (int)(m / hw), rem = (int)(m - (long)bi * hw);
         const int iy = rem / g.W, ix = rem - iy * g.W;
-        const long orow = ((long)bi * g.OH + iy * g.os + g.oa) * g.OW + ix * g.os + g.ob;
-        // (the staged, coalesced write-out of tc_epilogue_staged was measured here too: +0.2 ms per step -- with 4 epilogue warps and
-        // rows of <= 128 channels the extra shared-memory round trip costs more than the scattered 16-byte stores)
-        tc_epilogue_row(ep, trow, m, orow, n0, g.BN, n_tile, bias_s);
+        for (int p = 0; p < nloop; ++p) {                  // phase p's epilogue overlaps phase p+1's MMAs
+            const TcGeom& gq = gp.g[blockIdx.z + p];
+            mbar_wait(smem_u32(accum_full + p), 0);
+            tc_fence_after();
+            const long orow = ((long)bi * g.OH + iy * g.os + gq.oa) * g.OW + ix * g.os + gq.ob;
+            // (the staged, coalesced write-out of tc_epilogue_staged was measured here too: +0.2 ms per step -- with 4 epilogue warps and
+            // rows of <= 128 channels the extra shared-memory round trip costs more than the scattered 16-byte stores)
+            tc_epilogue_row(ep, trow + (uint32_t)(p * g.BN), m, orow, n0, g.BN, n_tile, bias_s);
+        }
         tc_fence_before();
     }
     __syncthreads();
@@ -228,7 +242,11 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
     const int stage_bytes = TC_BM * 128 + BN * 128;
     // ring depth: at most one CTA per SM fits anyway when the grid is <= 148 CTAs, so a small launch takes the whole shared memory
     // (the 8x8-map layers were bound by 3 stages x ~1.5 us TMA round trip, not by the MMAs); larger grids leave room for two CTAs per SM
-    const long ctas = ((long)B * H * W / TC_BM) * (N / BN) * nph;
+    long ctas = ((long)B * H * W / TC_BM) * (N / BN) * nph;
+    // more than one wave of two CTAs per SM and room for every phase's accumulator: let each CTA walk all phases of its tile
+    static const int fuse_env = getenv("PIVP_TC_TAPS_FUSE_PH") ? atoi(getenv("PIVP_TC_TAPS_FUSE_PH")) : 1;
+    const bool fuse_ph = fuse_env && nph > 1 && ctas > 2 * 148 && nph * BN <= 256;
+    if (fuse_ph) ctas /= nph;
     const int env_ring = getenv("PIVP_TC_TAPS_RING_KB") ? atoi(getenv("PIVP_TC_TAPS_RING_KB")) : 0;
     int stages = ((env_ring > 0 ? env_ring : ctas <= 148 ? 190 : 100) * 1024) / stage_bytes;
     if (stages > 8) stages = 8;
@@ -258,21 +276,23 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
         }
         g.OH = OH; g.OW = OW; g.os = os; g.oa = q.oa; g.ob = q.ob;
         g.stages = stages;
-        g.tmem_cols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+        const int cols = fuse_ph ? nph * BN : BN;
+        g.tmem_cols = cols <= 32 ? 32 : cols <= 64 ? 64 : cols <= 128 ? 128 : 256;
         cuuint64_t dims[2] = {(cuuint64_t)q.ntaps * Kc, (cuuint64_t)N};
         cuuint64_t str[1] = {(cuuint64_t)q.ntaps * Kc * 2};
         cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)BN};
         CUresult r = encode_tmap(&mb.m[p], q.wt_bf16, 2, dims, str, box);
         if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B%d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
     }
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + 1) * 8 + 16 + (size_t)BN * 4;
+    gp.nloop = fuse_ph ? nph : 1;
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + TC_MAXPH) * 8 + 16 + (size_t)BN * 4;
     static PerDeviceOnce attr_once;            // the opt-in is per device
     if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
         if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
     }
     const long M = (long)B * H * W;
-    dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN), (unsigned)nph);
+    dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN), (unsigned)(fuse_ph ? 1 : nph));
     launch_k(conv_taps_tc_kernel, grid, dim3(TC_THREADS), smem, stream, map_a, mb, gp, ep);
     return check_launch(who);
 }

@@ -356,6 +356,72 @@ __global__ void __launch_bounds__(TF, 2) bwd_fused_kernel(CView x, CView g1, CVi
     // no trailing cluster barrier: remote shared memory is only WRITTEN, and every write precedes the barrier its target waits at
 }
 
+// Forward in ONE launch for the LayerNorms whose producer does not deliver statistics (norm_enc0, the 8x8 ConvLSTM layers): one cluster per
+// sample, CTA r holds elements [4096 r, 4096 (r+1)) in registers, computes its (mean, M2) partial exactly like stats_kernel with chunk = 4096,
+// pushes it into every peer's shared memory, and after one cluster barrier merges the CL partials (combine_warp's order) and normalises
+// from registers: x is read once and the stats -> apply launch boundary disappears from the forward chain.
+__global__ void __launch_bounds__(TF, 2) fwd_fused_kernel(CView x, const float* __restrict__ gamma, const float* __restrict__ beta, Geo g, int n,
+                                                          float eps, View y, View y2, __nv_bfloat16* __restrict__ y_bf16, int yb_cs, int yb_co,
+                                                          int relu, float2* __restrict__ stats) {
+    pdl_enter();
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float red[32];
+    __shared__ float2 part[8];
+    __shared__ float2 st_s;
+    const int CL = gridDim.x, rank = blockIdx.x;
+    const long b = blockIdx.y;
+    const int e_base = rank * CHUNK_F;
+    float4 v[EF];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < EF; ++k) {
+        v[k] = ld4(x.p + row_addr(g, b, e_base + (k * TF + threadIdx.x) * 4, x.cs, x.co));
+        sum += hsum(v[k]);
+    }
+    const float mean = block_sum(sum, red) / (float)CHUNK_F;
+    float m2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < EF; ++k) {
+        const float a = v[k].x - mean, bb = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+        m2 += (a * a + bb * bb) + (c * c + d * d);
+    }
+    m2 = block_sum(m2, red);
+    if ((int)threadIdx.x < CL) *cluster.map_shared_rank(&part[rank], threadIdx.x) = make_float2(mean, m2);      // thread r writes into CTA r
+    cluster.sync();
+    if (threadIdx.x < 32) {
+        const float2 st = combine_warp(part, 0, CL, n, CHUNK_F, eps, threadIdx.x);
+        if (threadIdx.x == 0) {
+            st_s = st;
+            if (rank == 0) stats[b] = st;
+        }
+    }
+    __syncthreads();
+    const float2 st = st_s;
+#pragma unroll
+    for (int k = 0; k < EF; ++k) {
+        const int e = e_base + (k * TF + threadIdx.x) * 4;
+        const int pix = g.cshift >= 0 ? (e >> g.cshift) : (e / g.C);
+        const int ch = e - pix * g.C;
+        const long row = b * g.HW + pix;
+        const float4 ga = ld4(gamma + e), be = ld4(beta + e);
+        float4 o;
+        o.x = (v[k].x - st.x) * st.y * ga.x + be.x;
+        o.y = (v[k].y - st.x) * st.y * ga.y + be.y;
+        o.z = (v[k].z - st.x) * st.y * ga.z + be.z;
+        o.w = (v[k].w - st.x) * st.y * ga.w + be.w;
+        if (relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+        *reinterpret_cast<float4*>(y.p + row * y.cs + y.co + ch) = o;
+        if (y2.p) *reinterpret_cast<float4*>(y2.p + row * y2.cs + y2.co + ch) = o;
+        if (y_bf16) {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            uint2 pk;
+            pk.x = *reinterpret_cast<unsigned*>(&lo);
+            pk.y = *reinterpret_cast<unsigned*>(&hi);
+            *reinterpret_cast<uint2*>(y_bf16 + row * yb_cs + yb_co + ch) = pk;
+        }
+    }
+}
+
 template <typename... KArgs, typename... Args>
 static inline void launch_cluster(void (*kern)(KArgs...), dim3 grid, dim3 block, unsigned cluster_x, void* stream, Args&&... args) {
     cudaLaunchConfig_t cfg;
@@ -397,6 +463,14 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
     const Geo g = make_geo(HW, C);
     const int have_stats = relu & 2;                           // the producer's epilogue already wrote the (mean, M2) partials
     relu &= 1;
+    static const int fused_fwd = getenv("PIVP_LN_FWD_FUSED") ? atoi(getenv("PIVP_LN_FWD_FUSED")) : 1;      // 0: stats + apply launches
+    if (!have_stats && fused_fwd && n % CHUNK_F == 0 && n / CHUNK_F <= 8) {
+        const int CL = n / CHUNK_F;
+        launch_cluster(fwd_fused_kernel, dim3(CL, B), dim3(TF), (unsigned)CL, st, CView{x, x_cs, x_co}, gamma, beta, g, n, eps, View{y, y_cs, y_co},
+                       View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16, yb_cs, yb_co, relu, (float2*)stats);
+        if (int e = check_launch("layernorm_fwd(cluster)")) return e;
+        return 1;
+    }
     if (!have_stats) {
         launch_k(stats_kernel, dim3(S, B), dim3(T), 0, st, CView{x, x_cs, x_co}, g, n, chunk, (float2*)workspace);
         if (int e = check_launch("layernorm_fwd(stats)")) return e;
