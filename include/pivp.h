@@ -238,6 +238,14 @@ int pivp_tc_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, int W,
                             const int* dx, const int* coff, const void* const* wt_bf16, int N, int BN, const float* bias, int relu,
                             int accumulate, float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
                             int OH, int OW, int os, const int* oa, const int* ob, void* stream);
+/* Same launch, and the epilogue also delivers the statistics of the LayerNorm that follows the deconvolution (norm_enc6 behind enc6,
+ * train_model.py:507, 601): ln_partial[b][(H*W/128) * nph * (N/32)] (mean, M2) pairs of 4096 outputs each -- exactly the workspace
+ * pivp_layernorm_fwd reads when bit 1 of its relu argument is set (no separate statistics launch).  Needs relu = accumulate = 0,
+ * N and BN multiples of 32, H*W a multiple of 128.  ln_partial = null: identical to pivp_tc_conv_taps_multi. */
+int pivp_tc_conv_taps_multi_ln(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int nph, const int* ntaps, const int* dy,
+                               const int* dx, const int* coff, const void* const* wt_bf16, int N, int BN, const float* bias, int relu,
+                               int accumulate, float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
+                               int OH, int OW, int os, const int* oa, const int* ob, float* ln_partial, void* stream);
 /* fp32 NHWC view -> bf16 copy; s2d=1 writes the space-to-depth layout the stride-2 layers contract over
  * (row = (b, y/2, x/2), channel = d_co + ((y&1)*2 + (x&1))*cblk + ch) */
 int pivp_cast_bf16(const float* src, int s_cs, int s_co, void* dst_bf16, int d_cs, int d_co, long M, int C, int H, int W, int s2d, int cblk,

@@ -162,7 +162,26 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const long orow = ((long)bi * g.OH + iy * g.os + gq.oa) * g.OW + ix * g.os + gq.ob;
             // (the staged, coalesced write-out of tc_epilogue_staged was measured here too: +0.2 ms per step -- with 4 epilogue warps and
             // rows of <= 128 channels the extra shared-memory round trip costs more than the scattered 16-byte stores)
-            tc_epilogue_row(ep, trow + (uint32_t)(p * g.BN), m, orow, n0, g.BN, n_tile, bias_s);
+            if (ep.ln_partial) {
+                // statistics of the LayerNorm behind this deconvolution: one (mean, M2) pair per (tile, phase, 32-column group)
+                float2* red = reinterpret_cast<float2*>(bias_s + g.BN) + p * 32;
+                tc_epilogue_row_ln(ep, trow + (uint32_t)(p * g.BN), orow, n0, g.BN, bias_s, red, q, lane);
+                asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps
+                const int grp = (int)threadIdx.x - 64;
+                if (grp < (g.BN >> 5)) {
+                    const float2 a = red[grp * 4], b = red[grp * 4 + 1], c = red[grp * 4 + 2], e = red[grp * 4 + 3];
+                    const float dab = b.x - a.x, dce = e.x - c.x;                // 1024 values each, then 2048 + 2048
+                    const float mab = 0.5f * (a.x + b.x), mce = 0.5f * (c.x + e.x);
+                    const float sab = (a.y + b.y) + dab * dab * 512.f, sce = (c.y + e.y) + dce * dce * 512.f;
+                    const float dd = mce - mab;
+                    const int tiles_per_img = hw / TC_BM, nphases = nloop > 1 ? nloop : (int)gridDim.z;
+                    const int tile_in = m_tile - bi * tiles_per_img;            // a tile never straddles samples (H * W is a multiple of 128)
+                    ep.ln_partial[(long)bi * ep.ln_S + ((long)(tile_in * nphases + (int)blockIdx.z + p)) * (g.N >> 5) + (n0 >> 5) + grp] =
+                        make_float2(0.5f * (mab + mce), (sab + sce) + dd * dd * 1024.f);
+                }
+            } else {
+                tc_epilogue_row(ep, trow + (uint32_t)(p * g.BN), m, orow, n0, g.BN, n_tile, bias_s);
+            }
         }
         tc_fence_before();
     }
@@ -285,7 +304,12 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
         if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B%d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
     }
     gp.nloop = fuse_ph ? nph : 1;
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + TC_MAXPH) * 8 + 16 + (size_t)BN * 4;
+    if (ep.ln_partial) {
+        PIVP_REQUIRE(ep.mode == 0 && !ep.relu && !ep.accumulate && !ep.atomic && BN % 32 == 0 && N % 32 == 0 && (H * W) % TC_BM == 0 && TB == 1,
+                     "%s: LayerNorm statistics need a plain store, 32-column groups and tiles inside one sample", who);
+        ep.ln_S = (H * W / TC_BM) * nph * (N / 32);
+    }
+    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + TC_MAXPH) * 8 + 16 + (size_t)BN * 4 + TC_MAXPH * 32 * sizeof(float2);
     static PerDeviceOnce attr_once;            // the opt-in is per device
     if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -432,10 +456,13 @@ int pivp_tc_conv_taps(const void* in_bf16, int in_cs, int B, int H, int W, int K
 /* Up to four tap lists in ONE launch (blockIdx.z = phase): the output phases (oa[p], ob[p]) of a stride-2 Deconvolution2D, or of the
  * input gradient of a stride-2 Convolution2D.  ntaps[p] <= 4 taps per phase; dy / dx / coff hold 4 slots per phase; wt[p] = bf16
  * weights [N][ntaps[p] * Kc] of phase p.  Everything else as pivp_tc_conv_taps. */
-int pivp_tc_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int nph, const int* ntaps, const int* dy,
-                            const int* dx, const int* coff, const void* const* wt_bf16, int N, int BN, const float* bias, int relu,
-                            int accumulate, float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
-                            int OH, int OW, int os, const int* oa, const int* ob, void* stream) {
+/* ln_partial != null: also write the (mean, M2) partials of the LayerNorm that follows the deconvolution (norm_enc6, train_model.py:601):
+ * per sample (H * W / 128) * nph * (N / 32) pairs of 4096 values each, the layout pivp_layernorm_fwd reads when its relu argument has
+ * bit 1 set.  Needs relu = accumulate = 0. */
+int pivp_tc_conv_taps_multi_ln(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int nph, const int* ntaps, const int* dy,
+                               const int* dx, const int* coff, const void* const* wt_bf16, int N, int BN, const float* bias, int relu,
+                               int accumulate, float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
+                               int OH, int OW, int os, const int* oa, const int* ob, float* ln_partial, void* stream) {
     PIVP_REQUIRE(ntaps && dy && dx && coff && wt_bf16 && oa && ob && nph >= 1 && nph <= TC_MAXPH, "tc_conv_taps_multi: null list or bad phase count");
     PIVP_REQUIRE(out || out_bf16, "tc_conv_taps_multi: no output");
     PIVP_REQUIRE((!out || (out_cs % 4 == 0 && out_co % 4 == 0)) && (!out_bf16 || (ob_cs % 8 == 0 && ob_co % 8 == 0)),
@@ -451,7 +478,16 @@ int pivp_tc_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, int W,
     memset(&ep, 0, sizeof(ep));
     ep.mode = 0; ep.bias = bias; ep.relu = relu; ep.accumulate = accumulate; ep.out = out; ep.out_cs = out_cs; ep.out_co = out_co;
     ep.out_bf16 = (__nv_bfloat16*)out_bf16; ep.ob_cs = ob_cs; ep.ob_co = ob_co;
+    ep.ln_partial = reinterpret_cast<float2*>(ln_partial);
     return launch_conv_taps_multi(in_bf16, in_cs, B, H, W, Kc, nph, ph, N, BN, ep, OH, OW, os, stream, "tc_conv_taps_multi");
+}
+
+int pivp_tc_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, int W, int Kc, int nph, const int* ntaps, const int* dy,
+                            const int* dx, const int* coff, const void* const* wt_bf16, int N, int BN, const float* bias, int relu,
+                            int accumulate, float* out, int out_cs, int out_co, void* out_bf16, int ob_cs, int ob_co,
+                            int OH, int OW, int os, const int* oa, const int* ob, void* stream) {
+    return pivp_tc_conv_taps_multi_ln(in_bf16, in_cs, B, H, W, Kc, nph, ntaps, dy, dx, coff, wt_bf16, N, BN, bias, relu, accumulate, out, out_cs,
+                                      out_co, out_bf16, ob_cs, ob_co, OH, OW, os, oa, ob, nullptr, stream);
 }
 
 }  // extern "C"

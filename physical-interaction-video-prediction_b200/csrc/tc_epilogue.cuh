@@ -23,8 +23,9 @@ struct TcEpilogue {
     int atomic;                                  // mode 0: out += D with vector atomics (split-K CTAs of the halo kernel share an output tile)
     float* gates;                                // mode 1: activated gates [M][N] (saved for backward); bf16 storage when gates_bf16
     int gates_bf16;
-    float2* ln_partial;                          // mode 1, halo kernel only: per-tile (mean, M2) of h for the LayerNorm that follows
-    int ln_S;                                    //   partial[b * ln_S + tile_in_sample * (C / 32) + n_tile], 4096 values each
+    float2* ln_partial;                          // per-tile (mean, M2) of the output for the LayerNorm that follows, 4096 values each:
+    int ln_S;                                    //   mode 1 (halo kernel): partial[b * ln_S + tile_in_sample * (C / 32) + n_tile];
+                                                 //   mode 0 (tap kernel, deconvolution phases): one pair per (tile, phase, 32-column group)
     const float* c_prev; float* c_out;           // [M][C]  (c_prev may be null)
     float* h_out; int h_cs, h_co;                // fp32 h view (next step's xh h-slot)
     __nv_bfloat16* h_bf16; int hb_cs, hb_co;     // bf16 shadow (GEMM operand of the next step)
@@ -132,6 +133,50 @@ __device__ __forceinline__ void tc_epilogue_staged(const TcEpilogue& ep, uint32_
 }
 
 // trow: TMEM address of this thread's lane at the tile's first column; n0 = first output channel of the tile; bias_s: BN floats in smem
+// Mode 0 with the statistics of the LayerNorm that follows (norm_enc6 behind enc6, train_model.py:507/601): bias + store as tc_epilogue_row,
+// and for every 32-column group of the tile the warp's exact (mean, M2) over its 32 rows x 32 columns -- per chunk of 8 registers in two
+// passes, chunks and lanes merged with Chan's formula -- into red[group * 4 + q] (q = the warp's TMEM lane quarter).  No ReLU, no accumulate.
+__device__ __forceinline__ void tc_epilogue_row_ln(const TcEpilogue& ep, uint32_t trow, long orow, int n0, int BN, const float* bias_s,
+                                                   float2* red, int q, int lane) {
+    for (int g0 = 0; g0 < BN; g0 += 32) {
+        float mean = 0.f, m2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c0 = g0 + 8 * k;
+            float v[8];
+            tc_ld8(trow + (uint32_t)c0, v);
+            tc_ld_wait();
+            if (ep.bias) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += bias_s[c0 + i];
+            }
+            if (ep.out) {
+                float* dst = ep.out + orow * ep.out_cs + ep.out_co + n0 + c0;
+                *reinterpret_cast<float4*>(dst) = make_float4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<float4*>(dst + 4) = make_float4(v[4], v[5], v[6], v[7]);
+            }
+            if (ep.out_bf16) *reinterpret_cast<uint4*>(ep.out_bf16 + orow * ep.ob_cs + ep.ob_co + n0 + c0) = pack8_bf16(v);
+            const float cm = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) * 0.125f;
+            float c2 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { const float d = v[i] - cm; c2 = fmaf(d, d, c2); }
+            const float d = cm - mean;                       // Chan: 8k values so far + 8 new ones
+            mean += d * (1.f / (float)(k + 1));
+            m2 += c2 + d * d * (8.f * (float)k / (float)(k + 1));
+        }
+        float cnt = 32.f;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {                   // equal counts on both sides of every merge
+            const float mo = __shfl_xor_sync(0xffffffffu, mean, o), m2o = __shfl_xor_sync(0xffffffffu, m2, o);
+            const float d = mo - mean;
+            m2 = (m2 + m2o) + d * d * (cnt * 0.5f);
+            mean = 0.5f * (mean + mo);
+            cnt *= 2.f;
+        }
+        if (lane == 0) red[(g0 >> 5) * 4 + q] = make_float2(mean, m2);
+    }
+}
+
 __device__ __forceinline__ void tc_epilogue_row(const TcEpilogue& ep, uint32_t trow, long m, long orow, int n0, int BN, int n_tile,
                                                 const float* bias_s) {
     if (ep.mode == 0) {

@@ -505,12 +505,14 @@ class Engine(object):
             # ---- group 6
             self._lstm_ln_fwd(6, t, B, "hidden7", View(ws["cat6"][t], 64, 0, 32), None if self.tc is None else View(self.tc.cat6_b[t], 64, 0, 32))
             if self.tc is not None:
-                self.tc.deconv_fwd("enc6", self.tc.cat6_b[t], ws["e6pre"][t], 64, None, 0, 0)
+                e6_stats = ((H // 2) * (W // 2)) % 128 == 0          # the deconvolution's epilogue also writes norm_enc6's (mean, M2) partials
+                self.tc.deconv_fwd("enc6", self.tc.cat6_b[t], ws["e6pre"][t], 64, None, 0, 0, ln_partial=ws["ln_ws"] if e6_stats else None)
             else:
+                e6_stats = False
                 self._conv_dgrad(View(ws["cat6"][t], 64, 0, 64), B, H // 2, W // 2, p["enc6/W"], p["enc6/b"], 3, 2, 1,
                                  View(ws["e6pre"][t], 64, 0, 64), H, W, relu=0)
             self._ln_fwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), B, HW[1], View(ws["e6"][t], 64, 0, 64), None, 1,
-                         ws["ln_stats"]["norm_enc6"][t])
+                         ws["ln_stats"]["norm_enc6"][t], have_stats=e6_stats)
             # ---- heads (enc7 + masks 1x1), NCHW planes out
             if self.Nh in (14, 27):       # fused heads: e6 read once, planes written directly (heads.cu)
                 L.call("pivp_heads_fwd", _ptr(ws["e6"][t]), 64, 0, _ptr(p["model/enc7/W"]), _ptr(p["model/enc7/b"]),

@@ -273,15 +273,16 @@ class TensorCorePlan(object):
             e.L.call("pivp_tc_wgrad_taps", _ptr(xall), xall.shape[2], _ptr(d["dys"]), 4 * d["cb"], S * B, h, w, d["cout"], d["cin"], 9,
                      d["dy"], d["dx"], d["co"], _ptr(e.g[name + "/W"]), _ptr(wsb_), wsb_.numel(), e._s())
 
-    def deconv_fwd(self, name, x_bf16, out, out_cs, out_bf16, ob_cs, relu, bias=True):
+    def deconv_fwd(self, name, x_bf16, out, out_cs, out_bf16, ob_cs, relu, bias=True, ln_partial=None):
         """Deconvolution2D forward (+bias, optional ReLU) -> fp32 view `out` (row stride out_cs, channel offset 0) and an
-        optional bf16 copy (the next ConvLSTM's x slot): four tcgen05 launches, one per output phase."""
+        optional bf16 copy (the next ConvLSTM's x slot): the four output phases in one tcgen05 launch.  ``ln_partial``: the epilogue
+        also writes the (mean, M2) partials of the LayerNorm that follows (norm_enc6), so that LayerNorm skips its statistics launch."""
         e, d = self.eng, self.dec[name]
         h, w = e.H // d["lv"], e.W // d["lv"]
-        m = d["multi"]                       # the four output phases in one launch (grid z = phase)
-        e.L.call("pivp_tc_conv_taps_multi", _ptr(x_bf16), d["kc"], self.ws["B"], h, w, d["kc"], 4, m["ntaps"], m["dy"], m["dx"], m["co"],
+        m = d["multi"]                       # the four output phases in one launch (grid z = phase, or walked inside each CTA)
+        e.L.call("pivp_tc_conv_taps_multi_ln", _ptr(x_bf16), d["kc"], self.ws["B"], h, w, d["kc"], 4, m["ntaps"], m["dy"], m["dx"], m["co"],
                  m["wt"], d["cout"], d["bn"], _ptr(e.p[name + "/b"]) if bias else 0, relu, 0,
-                 _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, 2 * h, 2 * w, 2, m["oa"], m["ob"], e._s())
+                 _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, 2 * h, 2 * w, 2, m["oa"], m["ob"], _ptr(ln_partial), e._s())
 
     def xview(self, li, t):
         """bf16 x-slot of layer li at time t (what the producer of the layer input also writes)."""

@@ -110,7 +110,9 @@ def test_conv2d_strided_views_and_errors(pk):
 
 
 # ---------------------------------------------------------------------------------------------- LayerNorm, ConvLSTM
-@pytest.mark.parametrize("B,C,H,W,relu", [(3, 32, 8, 8, False), (2, 64, 16, 16, True), (2, 128, 2, 3, False), (1, 64, 64, 64, True)])
+@pytest.mark.parametrize("B,C,H,W,relu", [(3, 32, 8, 8, False), (2, 64, 16, 16, True), (2, 128, 2, 3, False), (1, 64, 64, 64, True),
+                                           # one-launch cluster kernels both ways: n = 4096 CL, CL = 8 / 2 / 1
+                                           (2, 32, 32, 32, False), (3, 128, 8, 8, True), (2, 16, 16, 16, False)])
 def test_layernorm_fwd_bwd(pk, B, C, H, W, relu):
     rs = np.random.RandomState(3)
     n = C * H * W

@@ -267,13 +267,14 @@ def test_layernorm_bwd_lstm_equals_separate_kernels(pk, B, HW, C, cin, last):
         assert rel(b, a) < 2 ** -8 if a is outs[0][0] else rel(b, a) < 1e-5
 
 
-def test_tc_conv_taps_multi_equals_single_phase_launches(pk):
-    """The four output phases of a stride-2 deconvolution in one launch (grid z = phase) == four single-phase launches, bit for bit."""
+@pytest.mark.parametrize("B,h,w,cin,cout,kc", [(2, 16, 16, 96, 96, 128),        # 16 CTAs: grid z = phase
+                                                 (16, 32, 32, 64, 64, 64)])       # 512 CTAs > one wave: every CTA walks the four phases (enc6 at b32)
+def test_tc_conv_taps_multi_equals_single_phase_launches(pk, B, h, w, cin, cout, kc):
+    """The four output phases of a stride-2 deconvolution in one launch (grid z = phase, or all four phases inside each CTA when the
+    launch would exceed a wave) == four single-phase launches, bit for bit."""
     import ctypes
     L = pk.lib()
     rs = np.random.RandomState(4)
-    B, h, w, cin, cout = 2, 16, 16, 96, 96
-    kc = 128
     M = B * h * w
     x = torch.zeros(M, kc, device="cuda"); x[:, :cin] = torch.from_numpy(rs.standard_normal((M, cin)).astype(np.float32)).cuda()
     xb = x.bfloat16()
@@ -289,13 +290,34 @@ def test_tc_conv_taps_multi_equals_single_phase_launches(pk):
     for a, b, taps, wt in phases:
         arr = lambda v: (ctypes.c_int * len(v))(*v)
         L.call("pivp_tc_conv_taps", xb.data_ptr(), kc, B, h, w, kc, len(taps), arr([t[0] for t in taps]), arr([t[1] for t in taps]),
-               arr([0] * len(taps)), wt.data_ptr(), cout, 96, bias.data_ptr(), 1, 0, o1.data_ptr(), cout, 0, 0, 0, 0, 2 * h, 2 * w, 2, a, b, stream())
+               arr([0] * len(taps)), wt.data_ptr(), cout, cout, bias.data_ptr(), 1, 0, o1.data_ptr(), cout, 0, 0, 0, 0, 2 * h, 2 * w, 2, a, b, stream())
     flat = lambda k: (ctypes.c_int * 16)(*[(list(p[2][i] if k >= 0 else (0, 0)) + [0])[max(k, 0)] if i < len(p[2]) else 0 for p in phases for i in range(4)])
     L.call("pivp_tc_conv_taps_multi", xb.data_ptr(), kc, B, h, w, kc, 4, (ctypes.c_int * 4)(*[len(p[2]) for p in phases]), flat(0), flat(1),
-           (ctypes.c_int * 16)(*([0] * 16)), (ctypes.c_void_p * 4)(*[p[3].data_ptr() for p in phases]), cout, 96, bias.data_ptr(), 1, 0,
+           (ctypes.c_int * 16)(*([0] * 16)), (ctypes.c_void_p * 4)(*[p[3].data_ptr() for p in phases]), cout, cout, bias.data_ptr(), 1, 0,
            o2.data_ptr(), cout, 0, 0, 0, 0, 2 * h, 2 * w, 2, (ctypes.c_int * 4)(*[p[0] for p in phases]), (ctypes.c_int * 4)(*[p[1] for p in phases]), stream())
     torch.cuda.synchronize()
     assert float(o1.abs().max()) > 0 and torch.equal(o1, o2)
+    # the same launch with the LayerNorm statistics in the epilogue (pivp_tc_conv_taps_multi_ln, no ReLU): identical output, and the
+    # (mean, M2) partials -- 4096 values each -- merge to every sample's mean and variance
+    S = (h * w // 128) * 4 * (cout // 32)
+    part = torch.full((B, S, 2), float("nan"), device="cuda")
+    o3, o4 = torch.zeros(4 * M, cout, device="cuda"), torch.zeros(4 * M, cout, device="cuda")
+    common = lambda o: (xb.data_ptr(), kc, B, h, w, kc, 4, (ctypes.c_int * 4)(*[len(p[2]) for p in phases]), flat(0), flat(1),
+                        (ctypes.c_int * 16)(*([0] * 16)), (ctypes.c_void_p * 4)(*[p[3].data_ptr() for p in phases]), cout, cout, bias.data_ptr(), 0, 0,
+                        o.data_ptr(), cout, 0, 0, 0, 0, 2 * h, 2 * w, 2, (ctypes.c_int * 4)(*[p[0] for p in phases]), (ctypes.c_int * 4)(*[p[1] for p in phases]))
+    L.call("pivp_tc_conv_taps_multi", *common(o3), stream())
+    L.call("pivp_tc_conv_taps_multi_ln", *common(o4), part.data_ptr(), stream())
+    torch.cuda.synchronize()
+    assert torch.equal(o3, o4)
+    pm, pm2 = part[:, :, 0].double(), part[:, :, 1].double()
+    ref = o3.double().reshape(B, -1)
+    mean = pm.mean(1)
+    var = (pm2.sum(1) + 4096.0 * ((pm - mean[:, None]) ** 2).sum(1)) / ref.shape[1]
+    assert ref.shape[1] == S * 4096
+    assert float((mean - ref.mean(1)).abs().max()) < 1e-5 and rel(var, ref.var(1, unbiased=False)) < 1e-5
+    with pytest.raises(pk.PivpError):                     # ReLU in front of the statistics is not the reference's order of operations
+        args = list(common(o4)); args[15] = 1
+        L.call("pivp_tc_conv_taps_multi_ln", *args, part.data_ptr(), stream())
 
 
 @pytest.mark.parametrize("SB,H,W,Cx,N4", [
