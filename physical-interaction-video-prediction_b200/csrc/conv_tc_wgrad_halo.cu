@@ -30,7 +30,7 @@ struct Geom {
     int H, W, Cx, N4, Mrows;
     int chunks, tpg, groups;                     // 64-channel chunks of XH, taps per group, tap groups
     int kb_total, kb_per_split;                  // K steps = 8x8 pixel blocks over all images
-    int pair;                                    // issue adjacent taps as one N = 128 MMA (PIVP_TC_WGRAD_PAIR, default on)
+    int pair;                                    // most taps issued as one MMA of N = 64 * run columns (PIVP_TC_WGRAD_PAIR = 1, 2 or 4; default 4)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -92,14 +92,13 @@ wgrad5x5_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         // D=f32, A=B=bf16, BOTH MN-major (bits 15, 16), N>>3 at [17,23), M>>4 at [24,29)
         const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(ncol >> 3) << 17) |
                                ((uint32_t)(128 >> 4) << 24);
-        const uint32_t idesc2 = (idesc & ~(0x3Fu << 17)) | ((uint32_t)(128 >> 3) << 17);      // the same with N = 128 (two taps)
-        const bool pair_taps = g.pair && ncol == 64;
+        const int max_run = ncol == 64 ? g.pair : 1;         // taps per MMA (partial channel chunks: one, the LBO blocks are 64 wide)
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem_base, 0);
         // MN-major SW128 descriptor halves.  A: LBO = 8192 B between the two 64-n chunks, SBO = 1024 B between 8-pixel K groups.
-        // B: one 64-channel chunk (LBO unused), SBO = one patch row = 2048 B between 8-pixel K groups.
+        // B: 64-channel blocks = tap-shifted views of one patch (LBO set per MMA, see below), SBO = one patch row = 2048 B between 8-pixel K groups.
         const uint32_t hi_a = (1024u >> 4) | (1u << 14) | (2u << 29);
         const uint32_t hi_b = ((uint32_t)(PW * 128) >> 4) | (1u << 14) | (2u << 29);
-        const uint32_t lbo_a = ((8192u >> 4) & 0x3FFFu) << 16, lbo_b = 1u << 16;
+        const uint32_t lbo_a = ((8192u >> 4) & 0x3FFFu) << 16;
         const uint32_t ring_lo = (smem_u32(smem) & 0x3FFFFu) >> 4, st_step = STAGE >> 4;
         const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
         const int ky0 = tap0 / 5, kx0 = tap0 - ky0 * 5;
@@ -109,35 +108,31 @@ wgrad5x5_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             tc_fence_after();
             if (elect_one()) {
                 const uint32_t acc0 = kb > kb0 ? 1u : 0u;
-                const uint32_t a_lo = lo | lbo_a, p_lo = (lo + (A_BYTES >> 4)) | lbo_b;
+                const uint32_t a_lo = lo | lbo_a;
                 int ky = ky0, kx = kx0;
                 for (int tl = 0; tl < ntaps;) {
+                    // A RUN of taps in one MMA of N = 64 * run columns: block j of the B operand is the SAME patch seen j taps further (LBO = the
+                    // row distance between consecutive views), and the accumulators of taps tl .. tl+run-1 are adjacent column blocks.
+                    // Cuts the A reads per tap: a 128 x 64 x 16 MMA reads 6 KB of shared memory in 32 tensor cycles (port-bound at 128 B/clk),
+                    // 128 x 128 x 16 reads 8 KB in 64, 128 x 256 x 16 reads 12 KB in 128.  Runs of 3-4 need equal distances: taps of one
+                    // kernel row (distance 1 patch row); the last tap of a row pairs with the first of the next (distance 16 - 4 rows).
                     const uint32_t row = (uint32_t)(ky * PW + kx);                    // one pixel row = 128 B = 8 descriptor units
-                    int ky2 = ky, kx2 = kx + 1;
-                    if (kx2 == 5) { kx2 = 0; ++ky2; }
-                    if (pair_taps && tl + 1 < ntaps) {
-                        // TWO taps in one N = 128 MMA: the second 64-channel block of the B operand is the SAME patch seen one tap further
-                        // (LBO = the row distance between the two views), and the accumulators of taps tl, tl+1 are adjacent column blocks.
-                        // Halves the A reads per tap: a 128 x 64 x 16 MMA reads 6 KB of shared memory in 32 tensor cycles (port-bound),
-                        // a 128 x 128 x 16 one 8 KB in 64.
-                        const uint32_t lbo = (uint32_t)(ky2 * PW + kx2) - row;
-                        const uint32_t b_lo = ((lo + (A_BYTES >> 4)) + row * 8u) | ((lbo * 8u) << 16);
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            tc_mma_lohi(tmem_u + (uint32_t)(tl * 64), a_lo + 128 * k, b_lo + (uint32_t)(2 * k * PW * 8), hi_a, hi_b, idesc2,
-                                        (k == 0) ? acc0 : 1u);
-                        tl += 2;
-                        kx = kx2 + 1; ky = ky2;
-                        if (kx == 5) { kx = 0; ++ky; }
-                    } else {
-                        const uint32_t b_lo = p_lo + row * 8u;
-#pragma unroll
-                        for (int k = 0; k < 4; ++k)    // K slice k: block rows 2k, 2k+1 -> A rows 16k.. (2048 B), patch rows +2k (2k * 16 * 8 units)
-                            tc_mma_lohi(tmem_u + (uint32_t)(tl * 64), a_lo + 128 * k, b_lo + (uint32_t)(2 * k * PW * 8), hi_a, hi_b, idesc,
-                                        (k == 0) ? acc0 : 1u);
-                        ++tl;
-                        kx = kx2; ky = ky2;
+                    int run = 1;
+                    uint32_t lbo = 1;
+                    if (max_run > 1) {
+                        const int in_row = min(5 - kx, ntaps - tl);
+                        if (in_row >= 2) run = min(in_row, max_run);
+                        else if (tl + 1 < ntaps) { run = 2; lbo = (uint32_t)(PW - 4); }
                     }
+                    const uint32_t b_lo = ((lo + (A_BYTES >> 4)) + row * 8u) | ((lbo * 8u) << 16);
+                    const uint32_t id = (idesc & ~(0x3Fu << 17)) | ((uint32_t)((ncol * run) >> 3) << 17);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)        // K slice k: block rows 2k, 2k+1 -> A rows 16k.. (2048 B), patch rows +2k (2k * 16 * 8 units)
+                        tc_mma_lohi(tmem_u + (uint32_t)(tl * 64), a_lo + 128 * k, b_lo + (uint32_t)(2 * k * PW * 8), hi_a, hi_b, id,
+                                    (k == 0) ? acc0 : 1u);
+                    tl += run;
+                    kx += run;
+                    if (kx >= 5) { kx -= 5; ++ky; }
                 }
                 tc_commit(empty0 + 8 * st);
                 if (kb == kb1 - 1) tc_commit(smem_u32(accum_full));
@@ -179,8 +174,8 @@ static void plan(int Cx, int N4, int H, int W, int SB, Geom* g, int* splits) {
     g->groups = (25 + MAXTPG - 1) / MAXTPG;                       // 4
     g->tpg = (25 + g->groups - 1) / g->groups;                    // 7
     g->kb_total = SB * (H / 8) * (W / 8);
-    static const int pair_env = getenv("PIVP_TC_WGRAD_PAIR") ? atoi(getenv("PIVP_TC_WGRAD_PAIR")) : 1;
-    g->pair = pair_env;
+    static const int pair_env = getenv("PIVP_TC_WGRAD_PAIR") ? atoi(getenv("PIVP_TC_WGRAD_PAIR")) : 4;
+    g->pair = pair_env < 1 ? 1 : pair_env > 4 ? 4 : pair_env;
     const int tiles = (g->Mrows / 128) * g->chunks * g->groups;
     int s = (2 * 148 + tiles - 1) / tiles;
     int smax = g->kb_total / 8;
