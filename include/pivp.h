@@ -80,6 +80,13 @@ size_t pivp_layernorm_workspace_bytes(int B, int n);
 int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
                        float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
                        int relu, float* stats, void* workspace, size_t ws_bytes, void* stream);
+/* The same, with the bf16 copy written in the space-to-depth layout the stride-2 convolution behind this LayerNorm contracts over
+ * (hidden2 -> enc1, hidden4 -> enc2, train_model.py:597-599): s2d_w = width W of the normalised map (0 = plain rows, identical to
+ * pivp_layernorm_fwd); pixel (y, x) of sample b goes to row (b, y/2, x/2) of a [B*H/2*W/2][yb_cs] matrix, columns
+ * yb_co + ((y&1)*2 + (x&1)) * s2d_cblk + c.  Replaces a separate pivp_cast_bf16 launch. */
+int pivp_layernorm_fwd_s2d(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
+                           float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
+                           int relu, float* stats, void* workspace, size_t ws_bytes, int s2d_w, int s2d_cblk, void* stream);
 /* g = g1 + g2 (g2 may be NULL), masked by [y>0] when relu; dgamma/dbeta are accumulated into */
 int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                        const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,

@@ -850,7 +850,7 @@ static inline unsigned nblk(long n, int t) { return (unsigned)((n + t - 1) / t);
 // 128-bit vectorised LayerNorm kernels (layernorm_vec.cu): 1 = done, 0 = not applicable, < 0 = error
 int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
                float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co, int relu,
-               float* stats, void* workspace, int S, int chunk, cudaStream_t st);
+               float* stats, void* workspace, int S, int chunk, cudaStream_t st, int s2d_w, int s2d_cblk);
 int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu, float* dx, int dx_cs,
                int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st, void* gates_bf16,
@@ -903,9 +903,9 @@ size_t pivp_layernorm_workspace_bytes(int B, int n) {
     return (size_t)B * S * sizeof(float2);
 }
 
-int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
-                       float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
-                       int relu, float* stats, void* workspace, size_t ws_bytes, void* stream) {
+int pivp_layernorm_fwd_s2d(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
+                           float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
+                           int relu, float* stats, void* workspace, size_t ws_bytes, int s2d_w, int s2d_cblk, void* stream) {
     PIVP_REQUIRE(x && gamma && beta && y && stats && workspace, "layernorm_fwd: null pointer");
     PIVP_REQUIRE(B > 0 && HW > 0 && C > 0, "layernorm_fwd: bad shape");
     const int n = HW * C;
@@ -913,10 +913,14 @@ int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, c
     const int S = ln_split(n, &chunk);
     PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_fwd: workspace too small");
     PIVP_REQUIRE(!(relu & 2) || (n % 4096 == 0 && chunk == 4096), "layernorm_fwd: precomputed partials need n to be a multiple of 4096");
+    PIVP_REQUIRE(s2d_w == 0 || (y_bf16 && s2d_w > 0 && s2d_w % 2 == 0 && HW % s2d_w == 0 && (HW / s2d_w) % 2 == 0 && s2d_cblk >= C && s2d_cblk % 4 == 0 &&
+                                yb_cs >= yb_co + 4 * s2d_cblk),
+                 "layernorm_fwd: bad space-to-depth geometry for the bf16 output");
     if (int r = ln_vec_fwd(x, x_cs, x_co, gamma, beta, B, HW, C, eps, y, y_cs, y_co, y2, y2_cs, y2_co, y_bf16, yb_cs, yb_co, relu, stats,
-                           workspace, S, chunk, (cudaStream_t)stream))
+                           workspace, S, chunk, (cudaStream_t)stream, s2d_w, s2d_cblk))
         return r < 0 ? r : PIVP_OK;
     PIVP_REQUIRE(!(relu & 2), "layernorm_fwd: precomputed partials are only supported by the vectorised path");
+    PIVP_REQUIRE(!s2d_w, "layernorm_fwd: the space-to-depth bf16 output is only supported by the vectorised path");
     launch_k(ln_stats_kernel, dim3(S, B), dim3(LN_T), 0, (cudaStream_t)stream, CView{x, x_cs, x_co}, n, C, chunk, (float2*)workspace);
     if (int e = check_launch("layernorm_fwd(stats)")) return e;
     int gx = (n + LN_T * 4 - 1) / (LN_T * 4);
@@ -924,6 +928,13 @@ int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, c
                                                                      eps, View{y, y_cs, y_co}, View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16,
                                                                      yb_cs, yb_co, relu, (float2*)stats);
     return check_launch("layernorm_fwd(apply)");
+}
+
+int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
+                       float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co,
+                       int relu, float* stats, void* workspace, size_t ws_bytes, void* stream) {
+    return pivp_layernorm_fwd_s2d(x, x_cs, x_co, gamma, beta, B, HW, C, eps, y, y_cs, y_co, y2, y2_cs, y2_co, y_bf16, yb_cs, yb_co, relu, stats,
+                                  workspace, ws_bytes, 0, 0, stream);
 }
 
 int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,

@@ -70,7 +70,7 @@ __device__ __forceinline__ float2 combine_warp(const float2* __restrict__ partia
 __global__ void __launch_bounds__(T) apply_kernel(CView x, const float* __restrict__ gamma, const float* __restrict__ beta, Geo g, int n,
                                                   const float2* __restrict__ partial, int S, int chunk, float eps, View y, View y2,
                                                   __nv_bfloat16* __restrict__ y_bf16, int yb_cs, int yb_co, int relu,
-                                                  float2* __restrict__ stats) {
+                                                  float2* __restrict__ stats, int s2d_w, int s2d_cblk) {
     pdl_enter();
     __shared__ float2 st_s;
     const long b = blockIdx.y;
@@ -101,7 +101,14 @@ __global__ void __launch_bounds__(T) apply_kernel(CView x, const float* __restri
             uint2 pk;
             pk.x = *reinterpret_cast<unsigned*>(&lo);
             pk.y = *reinterpret_cast<unsigned*>(&hi);
-            *reinterpret_cast<uint2*>(y_bf16 + row * yb_cs + yb_co + ch) = pk;
+            long brow = row;
+            int bcol = yb_co + ch;
+            if (s2d_w) {                             // space-to-depth operand of the stride-2 convolution that reads this output
+                const int py = pix / s2d_w, px = pix - py * s2d_w;
+                brow = (b * (g.HW / s2d_w >> 1) + (py >> 1)) * (s2d_w >> 1) + (px >> 1);
+                bcol += ((py & 1) * 2 + (px & 1)) * s2d_cblk;
+            }
+            *reinterpret_cast<uint2*>(y_bf16 + brow * yb_cs + bcol) = pk;
         }
     }
 }
@@ -454,7 +461,7 @@ static Geo make_geo(int HW, int C) {
 // Both return 1 when the vectorised path ran, 0 when the caller must use the scalar kernels, < 0 on a launch error.
 int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, int B, int HW, int C, float eps,
                float* y, int y_cs, int y_co, float* y2, int y2_cs, int y2_co, void* y_bf16, int yb_cs, int yb_co, int relu,
-               float* stats, void* workspace, int S, int chunk, cudaStream_t st) {
+               float* stats, void* workspace, int S, int chunk, cudaStream_t st, int s2d_w, int s2d_cblk) {
     using namespace lnv;
     const int n = HW * C;
     if (disabled() || C % 4 || chunk % 4 || chunk > T * E4 * 4 || !view_ok(x, x_cs, x_co) || !view_ok(y, y_cs, y_co) || !view_ok(y2, y2_cs, y2_co) ||
@@ -464,7 +471,7 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
     const int have_stats = relu & 2;                           // the producer's epilogue already wrote the (mean, M2) partials
     relu &= 1;
     static const int fused_fwd = getenv("PIVP_LN_FWD_FUSED") ? atoi(getenv("PIVP_LN_FWD_FUSED")) : 1;      // 0: stats + apply launches
-    if (!have_stats && fused_fwd && n % CHUNK_F == 0 && n / CHUNK_F <= 8) {
+    if (!have_stats && fused_fwd && !s2d_w && n % CHUNK_F == 0 && n / CHUNK_F <= 8) {
         const int CL = n / CHUNK_F;
         launch_cluster(fwd_fused_kernel, dim3(CL, B), dim3(TF), (unsigned)CL, st, CView{x, x_cs, x_co}, gamma, beta, g, n, eps, View{y, y_cs, y_co},
                        View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16, yb_cs, yb_co, relu, (float2*)stats);
@@ -480,7 +487,7 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
     if (gx > gx_cap) gx = gx_cap;
     launch_k(apply_kernel, dim3(gx, B), dim3(T), 0, st, CView{x, x_cs, x_co}, gamma, beta, g, n, (const float2*)workspace, S, chunk, eps,
                                            View{y, y_cs, y_co}, View{y2, y2_cs, y2_co}, (__nv_bfloat16*)y_bf16, yb_cs, yb_co, relu,
-                                           (float2*)stats);
+                                           (float2*)stats, s2d_w, s2d_cblk);
     if (int e = check_launch("layernorm_fwd(apply)")) return e;
     return 1;
 }

@@ -261,13 +261,15 @@ class Engine(object):
         self.L.call("pivp_conv2d_wgrad", x.ptr, x.cs, x.co, B, H, W, x.C, dy.ptr, dy.cs, dy.co, Ho, Wo, dy.C,
                     k, k, stride, pad, _ptr(dw), _ptr(db), self._s())
 
-    def _ln_fwd(self, name, x, B, HW, y, y2, relu, stats, y_bf16=None, have_stats=False):
+    def _ln_fwd(self, name, x, B, HW, y, y2, relu, stats, y_bf16=None, have_stats=False, s2d=None):
+        """``s2d`` = (map width, channel block): the bf16 copy is written in the space-to-depth layout of the stride-2 convolution that reads it."""
         ws = self.ws
         relu = relu | (2 if have_stats else 0)          # bit 1: the producing tcgen05 epilogue already wrote the (mean, M2) partials
-        self.L.call("pivp_layernorm_fwd", x.ptr, x.cs, x.co, _ptr(self.p[name + "/norm/gamma"]), _ptr(self.p[name + "/norm/beta"]),
+        s2d_w, s2d_cb = (0, 0) if s2d is None else s2d
+        self.L.call("pivp_layernorm_fwd_s2d", x.ptr, x.cs, x.co, _ptr(self.p[name + "/norm/gamma"]), _ptr(self.p[name + "/norm/beta"]),
                     B, HW, x.C, 1e-6, y.ptr, y.cs, y.co, 0 if y2 is None else y2.ptr, 0 if y2 is None else y2.cs,
                     0 if y2 is None else y2.co, 0 if y_bf16 is None else y_bf16.ptr, 0 if y_bf16 is None else y_bf16.cs,
-                    0 if y_bf16 is None else y_bf16.co, relu, _ptr(stats), _ptr(ws["ln_ws"]), ws["ln_ws"].numel(), self._s())
+                    0 if y_bf16 is None else y_bf16.co, relu, _ptr(stats), _ptr(ws["ln_ws"]), ws["ln_ws"].numel(), s2d_w, s2d_cb, self._s())
 
     def _ln_bwd(self, name, x, g1, g2, B, HW, relu, stats, dx, ln_ws=None):
         ws = self.ws
@@ -302,18 +304,18 @@ class Engine(object):
                     0 if gb is None else gb.cs, 0 if gb is None else gb.co, dst.ptr, dst.cs, dst.co, M, dst.C, self._s())
 
     # ------------------------------------------------------------------ ConvLSTM layer (fwd / bwd)
-    def _lstm_ln_fwd(self, li, t, B, name, y, y_bf16=None):
+    def _lstm_ln_fwd(self, li, t, B, name, y, y_bf16=None, s2d=None):
         """ConvLSTM layer li at step t followed by the LayerNorm `name` of its output h_t (train_model.py:596-601): one kernel on the tensor-core
         path when the launch fits (TensorCorePlan.ln_fusable), else the cell and then the LayerNorm kernel(s)."""
         ws = self.ws
         cin, C, lv = LSTM_IN[li], LSTM_SIZES[li], LSTM_LEVEL[li]
         stats = ws["ln_stats"][name][t]
-        if self.tc is not None and self.tc.ln_fusable(li):
+        if self.tc is not None and self.tc.ln_fusable(li) and s2d is None:
             self.tc.lstm_fwd(li, t, ln=(name, y, y_bf16, stats))
             return
         self._lstm_fwd(li, t, B)
         self._ln_fwd(name, View(ws["xh"][li][t + 1], cin + C, cin, C), B, ws["HW"][lv], y, None, 0, stats, y_bf16,
-                     have_stats=self.tc is not None and self.tc.ln_fused[li])
+                     have_stats=self.tc is not None and self.tc.ln_fused[li], s2d=s2d)
 
     def _lstm_fwd(self, li, t, B):
         ws = self.ws
@@ -450,9 +452,12 @@ class Engine(object):
                     L.call("pivp_copy_view", _ptr(ws["cat6"][t]), 64, 32, 0, 0, 0, _ptr(self.tc.cat6_b[t]), 64, 32, Mr[2], 32, self._s())
             # ---- group 1
             self._lstm_ln_fwd(0, t, B, "hidden1", View(ws["xh"][1][t], 64, 0, 32), None if self.tc is None else self.tc.xview(1, t))
-            self._lstm_ln_fwd(1, t, B, "hidden2", View(ws["hid2"][t], 32, 0, 32))
+            if self.tc is not None:       # the LayerNorm writes enc1's GEMM operand itself: bf16, space-to-depth (no separate cast launch)
+                self._lstm_ln_fwd(1, t, B, "hidden2", View(ws["hid2"][t], 32, 0, 32), *self.tc.s2d_operand("enc1", t, W // 2))
+            else:
+                self._lstm_ln_fwd(1, t, B, "hidden2", View(ws["hid2"][t], 32, 0, 32))
             if self.tc is not None:       # stride-2 conv as a 9-tap tcgen05 GEMM on the space-to-depth bf16 input; bf16 x slot from the epilogue
-                self.tc.conv_s2_fwd("enc1", t, ws["hid2"][t], 32, ws["xh"][2][t], 96, self.tc.xview(2, t).t, self.tc.Kpad[2])
+                self.tc.conv_s2_fwd("enc1", t, None, 32, ws["xh"][2][t], 96, self.tc.xview(2, t).t, self.tc.Kpad[2])
                 with self._fork(5):            # enc1 skip (fp32 + bf16): needed by the enc5 deconvolution only
                     L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, _ptr(self.tc.cat5_b[t]), 128, 64, Mr[4], 32, self._s())
             else:
@@ -462,10 +467,11 @@ class Engine(object):
                     L.call("pivp_copy_view", _ptr(ws["xh"][2][t]), 96, 0, _ptr(ws["cat5"][t]), 96, 64, 0, 0, 0, Mr[4], 32, self._s())
             # ---- group 2
             self._lstm_ln_fwd(2, t, B, "hidden3", View(ws["xh"][3][t], 128, 0, 64), None if self.tc is None else self.tc.xview(3, t))
-            self._lstm_ln_fwd(3, t, B, "hidden4", View(ws["hid4"][t], 64, 0, 64))
             if self.tc is not None:
-                self.tc.conv_s2_fwd("enc2", t, ws["hid4"][t], 64, ws["in3"][t], self.cs3, None, 0)
+                self._lstm_ln_fwd(3, t, B, "hidden4", View(ws["hid4"][t], 64, 0, 64), *self.tc.s2d_operand("enc2", t, W // 4))
+                self.tc.conv_s2_fwd("enc2", t, None, 64, ws["in3"][t], self.cs3, None, 0)
             else:
+                self._lstm_ln_fwd(3, t, B, "hidden4", View(ws["hid4"][t], 64, 0, 64))
                 self._conv_fwd(View(ws["hid4"][t], 64, 0, 64), B, H // 4, W // 4, p["enc2/W"], p["enc2/b"], 64, 3, 2, 1,
                                View(ws["in3"][t], self.cs3, 0, 64), relu=1)
             # ---- group 3: enc3 on [enc2 out | smear]; the smear and the state predictor (train_model.py:676,730) ran on side branch 5

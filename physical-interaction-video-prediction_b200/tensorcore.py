@@ -140,13 +140,21 @@ class TensorCorePlan(object):
                     wt=self._walloc(idx, (cout, 9 * cb)),
                     xs=torch.zeros(self.S, M, 4 * cb, dtype=torch.bfloat16, device=dev))      # kept per time step for the weight gradient
 
+    def s2d_operand(self, name, t, width):
+        """(bf16 View, (map width, channel block)) of the space-to-depth GEMM operand of stride-2 convolution `name` at step t: what the
+        LayerNorm in front of it writes directly (Engine._ln_fwd(..., y_bf16, s2d))."""
+        d = self.s2f[name]
+        return View(d["xs"][t], 4 * d["cb"], 0, d["cin"]), (width, d["cb"])
+
     def conv_s2_fwd(self, name, t, x_f32, x_cs, out, out_cs, out_bf16, ob_cs):
-        """Stride-2 Convolution2D + bias + ReLU (train_model.py:501-502): cast the fp32 input to space-to-depth bf16, one tcgen05 launch."""
+        """Stride-2 Convolution2D + bias + ReLU (train_model.py:501-502): one tcgen05 launch on the space-to-depth bf16 input, which the
+        producing LayerNorm wrote (x_f32 None) or which is cast from the fp32 input here."""
         e, d = self.eng, self.s2f[name]
         h, w = e.H // d["lv"], e.W // d["lv"]
         B = self.ws["B"]
         xs = d["xs"][t]
-        e.L.call("pivp_cast_bf16", _ptr(x_f32), x_cs, 0, _ptr(xs), 4 * d["cb"], 0, B * 4 * h * w, d["cin"], 2 * h, 2 * w, 1, d["cb"], e._s())
+        if x_f32 is not None:
+            e.L.call("pivp_cast_bf16", _ptr(x_f32), x_cs, 0, _ptr(xs), 4 * d["cb"], 0, B * 4 * h * w, d["cin"], 2 * h, 2 * w, 1, d["cb"], e._s())
         e.L.call("pivp_tc_conv_taps", _ptr(xs), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
                  d["cout"], d["cout"], _ptr(e.p[name + "/b"]), 1, 0, _ptr(out), out_cs, 0, _ptr(out_bf16), ob_cs, 0, h, w, 1, 0, 0, e._s())
 

@@ -228,6 +228,38 @@ def test_lstm_gates_bwd_bf16_matches_fp32_kernel(pk, M, C, cin, first):
     assert rel(gates_b, gates_f) < 2 ** -8
 
 
+@pytest.mark.parametrize("B,H,W,C,cb", [(2, 32, 32, 32, 64), (3, 16, 16, 64, 64), (2, 8, 12, 16, 16)])
+def test_layernorm_s2d_bf16_output_equals_layernorm_then_cast(pk, B, H, W, C, cb):
+    """pivp_layernorm_fwd_s2d: the bf16 copy in the space-to-depth layout of the stride-2 convolution that follows (hidden2 -> enc1, hidden4 -> enc2,
+    train_model.py:597-599) == pivp_layernorm_fwd followed by pivp_cast_bf16(s2d), bit for bit; columns of the padded channel blocks stay untouched."""
+    L = pk.lib()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(21)
+    HW, n, M = H * W, H * W * C, B * H * W
+    x = torch.randn(M, C, device="cuda", generator=gen) * 2 + 0.3
+    gamma, beta = 1 + 0.2 * torch.randn(n, device="cuda", generator=gen), 0.2 * torch.randn(n, device="cuda", generator=gen)
+    ws = torch.empty(max(L.query("pivp_layernorm_workspace_bytes", B, n), 16), dtype=torch.uint8, device="cuda")
+    st1, st2 = torch.zeros(B, 2, device="cuda"), torch.zeros(B, 2, device="cuda")
+    y1, y2 = torch.empty(M, C, device="cuda"), torch.empty(M, C, device="cuda")
+    ref = torch.full((M // 4, 4 * cb), 3.0, dtype=torch.bfloat16, device="cuda")
+    got = ref.clone()
+    L.call("pivp_layernorm_fwd", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), B, HW, C, 1e-6, y1.data_ptr(), C, 0,
+           0, 0, 0, 0, 0, 0, 0, st1.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+    L.call("pivp_cast_bf16", y1.data_ptr(), C, 0, ref.data_ptr(), 4 * cb, 0, M, C, H, W, 1, cb, stream())
+    L.call("pivp_layernorm_fwd_s2d", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), B, HW, C, 1e-6, y2.data_ptr(), C, 0,
+           0, 0, 0, got.data_ptr(), 4 * cb, 0, 0, st2.data_ptr(), ws.data_ptr(), ws.numel(), W, cb, stream())
+    torch.cuda.synchronize()
+    if n % 4096:                                          # both calls ran the same two kernels: bit for bit
+        assert torch.equal(y1, y2) and torch.equal(st1, st2) and torch.equal(ref, got)
+    else:                                                 # the plain call ran the one-launch cluster kernel: same partials and merge order
+        assert rel(y2, y1) < 1e-6 and rel(st2, st1) < 1e-6 and rel(got, ref) < 2 ** -7
+    assert float(got.float().abs().max()) > 0
+    if cb > C:
+        assert bool((got.reshape(-1, 4, cb)[:, :, C:] == 3.0).all())
+    with pytest.raises(pk.PivpError):                     # odd map width
+        L.call("pivp_layernorm_fwd_s2d", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), B, HW, C, 1e-6, y2.data_ptr(), C, 0,
+               0, 0, 0, got.data_ptr(), 4 * cb, 0, 0, st2.data_ptr(), ws.data_ptr(), ws.numel(), W + 1, cb, stream())
+
+
 @pytest.mark.parametrize("B,HW,C,cin,last", [(3, 256, 64, 32, False), (2, 1024, 32, 32, True)])
 def test_layernorm_bwd_lstm_equals_separate_kernels(pk, B, HW, C, cin, last):
     """LayerNorm backward fused with the ConvLSTM gate backward == pivp_layernorm_bwd followed by pivp_lstm_gates_bwd_bf16."""
