@@ -151,6 +151,12 @@ int pivp_adam_step(float* p, const float* g, float* m, float* v, long n, int* st
  * backward: dx overwritten, dW [NH][64] and db [NH] accumulated into. */
 int pivp_heads_fwd(const float* x, int x_cs, int x_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
                    int B, int HW, void* stream);
+/* forward on relu(LayerNorm(x)) in one launch (norm_enc6 + ReLU `:601, 698` then the heads): x = the LayerNorm input, partial = the
+ * [B][HW*64/4096] (mean, M2) pairs written by pivp_tc_conv_taps_multi_ln, y = normalised rows kept for the backward, stats [B][2] =
+ * (mean, rstd) for pivp_layernorm_bwd.  HW must be a multiple of 128. */
+int pivp_heads_fwd_ln(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, const float* partial, float eps, float* stats,
+                      float* y, int y_cs, int y_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
+                      int B, int HW, void* stream);
 int pivp_heads_bwd(const float* x, int x_cs, int x_co, const float* W, const float* dy_a, int Na, const float* dy_b, int NH,
                    float* dx, int dx_cs, int dx_co, float* dW, float* db, int B, int HW, void* stream);
 

@@ -76,6 +76,9 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int s = 0; s < g.stages; ++s) { mbar_init(smem_u32(full + s), 1); mbar_init(smem_u32(empty + s), 1); }
         for (int p = 0; p < TC_MAXPH; ++p) mbar_init(smem_u32(accum_full + p), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // descriptor fetches overlap the set-up and the wait for the previous kernel instead of preceding the first operand load
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&map_a) : "memory");
+        for (int p = 0; p < nloop; ++p) asm volatile("prefetch.tensormap [%0];" ::"l"(&maps_b.m[blockIdx.z + p]) : "memory");
     }
     if (warp == 1) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)g.tmem_cols) : "memory");

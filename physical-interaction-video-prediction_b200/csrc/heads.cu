@@ -10,6 +10,7 @@
 // row per thread).  Arithmetic is packed fp32 (FFMA2).  NH (heads: 3+11 for CDNA/STP with 10 masks, 25+2 for DNA) is a template
 // parameter so every accumulator stays in a register.
 #include "common.cuh"
+#include <string.h>
 
 namespace pivp {
 namespace hd {
@@ -53,13 +54,79 @@ __device__ __forceinline__ void load_tile(const float* __restrict__ x, int cs, i
     }
 }
 
+// LayerNorm + ReLU applied while the tile is staged (pivp_heads_fwd_ln): x is the PRE-normalisation tensor (enc6's deconvolution output),
+// the (mean, M2) partials of the sample come from the deconvolution's epilogue, and the normalised tile is also written to y for the backward.
+struct LnIn {
+    const float* gamma; const float* beta;       // per element of a sample, [HW][64]; gamma == null: no LayerNorm (x is used as it is)
+    const float2* partial; int S;                // [B][S] pairs over 4096 values each
+    float eps;
+    float2* stats;                               // [B] (mean, rstd) saved for the LayerNorm backward
+    float* y; int y_cs, y_co;                    // normalised + ReLU output rows
+};
+
+// Chan merge of the S equal-sized chunk partials of sample b by one warp (same order as lnv::combine_warp); (mean, rstd) in every lane
+__device__ __forceinline__ float2 ln_combine(const float2* __restrict__ partial, long b, int S, float eps, int lane) {
+    float wsum = 0.f;
+    for (int s = lane; s < S; s += 32) wsum += partial[b * S + s].x * 4096.f;
+    const float n = 4096.f * (float)S;
+    const float mu = warp_sum(wsum) / n;
+    float m2 = 0.f;
+    for (int s = lane; s < S; s += 32) {
+        const float2 p = partial[b * S + s];
+        const float d = p.x - mu;
+        m2 += p.y + 4096.f * d * d;
+    }
+    m2 = warp_sum(m2);
+    return make_float2(mu, 1.f / sqrtf(m2 / n + eps));
+}
+
+template <int BATCH>
+__device__ __forceinline__ void load_tile_ln(const float* __restrict__ x, int cs, int co, long m0, long M, float* xs, const LnIn& ln, float2 st,
+                                             long e0) {
+    constexpr int NL = TP * (C / 4) / TP;
+#pragma unroll
+    for (int k0 = 0; k0 < NL; k0 += BATCH) {
+        float4 v[BATCH], ga[BATCH], be[BATCH];
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = threadIdx.x + (k0 + k) * TP, r = i >> 4, c4 = i & 15;
+            v[k] = ga[k] = be[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m0 + r < M) {
+                v[k] = __ldg(reinterpret_cast<const float4*>(x + (m0 + r) * cs + co) + c4);
+                ga[k] = __ldg(reinterpret_cast<const float4*>(ln.gamma + e0) + i);       // element (pixel r, channel 4 c4) of the sample = e0 + 4 i
+                be[k] = __ldg(reinterpret_cast<const float4*>(ln.beta + e0) + i);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < BATCH; ++k) {
+            const int i = threadIdx.x + (k0 + k) * TP, r = i >> 4, c4 = i & 15;
+            float4 o;
+            o.x = fmaxf((v[k].x - st.x) * st.y * ga[k].x + be[k].x, 0.f);
+            o.y = fmaxf((v[k].y - st.x) * st.y * ga[k].y + be[k].y, 0.f);
+            o.z = fmaxf((v[k].z - st.x) * st.y * ga[k].z + be[k].z, 0.f);
+            o.w = fmaxf((v[k].w - st.x) * st.y * ga[k].w + be[k].w, 0.f);
+            *reinterpret_cast<float4*>(xs + r * XP + 4 * c4) = o;
+            if (m0 + r < M) *reinterpret_cast<float4*>(ln.y + (m0 + r) * ln.y_cs + ln.y_co + 4 * c4) = o;
+        }
+    }
+}
+
 template <int NH>
 __global__ void __launch_bounds__(TP) heads_fwd_kernel(const float* __restrict__ x, int cs, int co, const float* __restrict__ Wt,
                                                        const float* __restrict__ bias, float* __restrict__ out_a, int Na,
-                                                       float* __restrict__ out_b, long M, int HW) {
+                                                       float* __restrict__ out_b, long M, int HW, LnIn ln) {
     pdl_enter();
     constexpr int NP = (NH + 3) / 4 * 4;                         // padded to float4
     __shared__ __align__(16) float xs[TP * XP];
+    __shared__ float2 st_s;
+    if (ln.gamma && threadIdx.x < 32) {                          // the tile lies inside one sample (HW is a multiple of the tile)
+        const long b = ((long)blockIdx.x * TP) / HW;
+        const float2 st = ln_combine(ln.partial, b, ln.S, ln.eps, threadIdx.x);
+        if (threadIdx.x == 0) {
+            st_s = st;
+            if (((long)blockIdx.x * TP) % HW == 0) ln.stats[b] = st;
+        }
+    }
     __shared__ __align__(16) float wt[C * NP];                   // W transposed: wt[c][n]
     {   // W rows are contiguous ([n][64]): 128-bit loads, all in flight together with the pixel tile and the bias
         constexpr int NW = (NP * (C / 4) + TP - 1) / TP;
@@ -79,7 +146,12 @@ __global__ void __launch_bounds__(TP) heads_fwd_kernel(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < NP / 2; ++j) acc[j] = make_float2(2 * j < NH ? __ldg(bias + 2 * j) : 0.f, 2 * j + 1 < NH ? __ldg(bias + 2 * j + 1) : 0.f);
     const long m0 = (long)blockIdx.x * TP;
-    load_tile<16>(x, cs, co, m0, M, xs);
+    if (ln.gamma) {
+        __syncthreads();                                         // st_s
+        load_tile_ln<8>(x, cs, co, m0, M, xs, ln, st_s, (m0 % HW) * C);
+    } else {
+        load_tile<16>(x, cs, co, m0, M, xs);
+    }
     __syncthreads();
     const float* xr = xs + threadIdx.x * XP;
 #pragma unroll 4
@@ -242,16 +314,37 @@ extern "C" {
 
 /* x: NHWC rows (stride x_cs, offset x_co, 64 channels); W: [NH][64] (enc7 rows then mask rows, the internal "head" layout);
  * out_a (B,Na,H,W) and out_b (B,NH-Na,H,W) NCHW planes.  NH in {14, 27}; other head counts -> PIVP_EUNSUPPORTED (use the conv path). */
-int pivp_heads_fwd(const float* x, int x_cs, int x_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
-                   int B, int HW, void* stream) {
+static int heads_fwd_impl(const float* x, int x_cs, int x_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
+                          int B, int HW, const hd::LnIn& ln, void* stream) {
     PIVP_REQUIRE(x && W && bias && out_a && out_b && B > 0 && HW > 0 && Na > 0 && Na < NH, "heads_fwd: bad argument");
     PIVP_REQUIRE(hd::a16(x) && x_cs % 4 == 0 && x_co % 4 == 0, "heads_fwd: rows must be 16-byte aligned");
     const long M = (long)B * HW;
     const unsigned grid = (unsigned)((M + hd::TP - 1) / hd::TP);
-    if (NH == 14) launch_k(hd::heads_fwd_kernel<14>, dim3(grid), dim3(hd::TP), 0, (cudaStream_t)stream, x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
-    else if (NH == 27) launch_k(hd::heads_fwd_kernel<27>, dim3(grid), dim3(hd::TP), 0, (cudaStream_t)stream, x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW);
+    if (NH == 14) launch_k(hd::heads_fwd_kernel<14>, dim3(grid), dim3(hd::TP), 0, (cudaStream_t)stream, x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW, ln);
+    else if (NH == 27) launch_k(hd::heads_fwd_kernel<27>, dim3(grid), dim3(hd::TP), 0, (cudaStream_t)stream, x, x_cs, x_co, W, bias, out_a, Na, out_b, M, HW, ln);
     else { set_error("heads_fwd: %d heads not instantiated (14 or 27)", NH); return PIVP_EUNSUPPORTED; }
     return check_launch("heads_fwd");
+}
+
+int pivp_heads_fwd(const float* x, int x_cs, int x_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
+                   int B, int HW, void* stream) {
+    hd::LnIn none;
+    memset(&none, 0, sizeof(none));
+    return heads_fwd_impl(x, x_cs, x_co, W, bias, out_a, Na, out_b, NH, B, HW, none, stream);
+}
+
+/* The heads on relu(LayerNorm(x)) in ONE launch (norm_enc6 + ReLU, train_model.py:601, 698, then enc7 / masks): x = the LayerNorm INPUT (enc6's
+ * deconvolution output), partial = the [B][HW*64/4096] (mean, M2) pairs the deconvolution's epilogue wrote (pivp_tc_conv_taps_multi_ln),
+ * gamma / beta [HW*64]; y receives the normalised rows (the backward reads them), stats [B] the (mean, rstd) pairs pivp_layernorm_bwd needs.
+ * Replaces pivp_layernorm_fwd(relu | 2) + pivp_heads_fwd.  HW must be a multiple of 128 and HW*64 of 4096. */
+int pivp_heads_fwd_ln(const float* x, int x_cs, int x_co, const float* gamma, const float* beta, const float* partial, float eps, float* stats,
+                      float* y, int y_cs, int y_co, const float* W, const float* bias, float* out_a, int Na, float* out_b, int NH,
+                      int B, int HW, void* stream) {
+    PIVP_REQUIRE(gamma && beta && partial && stats && y, "heads_fwd_ln: null pointer");
+    PIVP_REQUIRE(HW % hd::TP == 0 && ((long)HW * hd::C) % 4096 == 0, "heads_fwd_ln: HW must be a multiple of 128");
+    PIVP_REQUIRE(hd::a16(gamma) && hd::a16(beta) && hd::a16(y) && y_cs % 4 == 0 && y_co % 4 == 0, "heads_fwd_ln: rows must be 16-byte aligned");
+    hd::LnIn ln{gamma, beta, reinterpret_cast<const float2*>(partial), (int)((long)HW * hd::C / 4096), eps, reinterpret_cast<float2*>(stats), y, y_cs, y_co};
+    return heads_fwd_impl(x, x_cs, x_co, W, bias, out_a, Na, out_b, NH, B, HW, ln, stream);
 }
 
 /* dx is OVERWRITTEN; dW [NH][64] and db [NH] are ACCUMULATED into (atomics). */

@@ -11,6 +11,7 @@ time t: channels [0,Cin) = layer input x_t, channels [Cin,Cin+C) = h_{t-1}; the 
 h_t straight into ``xhL[t+1]``, so the reference's F.concat (train_model.py:262) never materialises.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -517,10 +518,17 @@ class Engine(object):
                 e6_stats = False
                 self._conv_dgrad(View(ws["cat6"][t], 64, 0, 64), B, H // 2, W // 2, p["enc6/W"], p["enc6/b"], 3, 2, 1,
                                  View(ws["e6pre"][t], 64, 0, 64), H, W, relu=0)
-            self._ln_fwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), B, HW[1], View(ws["e6"][t], 64, 0, 64), None, 1,
-                         ws["ln_stats"]["norm_enc6"][t], have_stats=e6_stats)
+            heads_ln = e6_stats and self.Nh in (14, 27) and os.environ.get("PIVP_HEADS_LN", "1") != "0"
+            if not heads_ln:
+                self._ln_fwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), B, HW[1], View(ws["e6"][t], 64, 0, 64), None, 1,
+                             ws["ln_stats"]["norm_enc6"][t], have_stats=e6_stats)
             # ---- heads (enc7 + masks 1x1), NCHW planes out
-            if self.Nh in (14, 27):       # fused heads: e6 read once, planes written directly (heads.cu)
+            if heads_ln:                  # norm_enc6 + ReLU applied while the heads kernel stages its tile (statistics from the enc6 epilogue)
+                L.call("pivp_heads_fwd_ln", _ptr(ws["e6pre"][t]), 64, 0, _ptr(p["norm_enc6/norm/gamma"]), _ptr(p["norm_enc6/norm/beta"]),
+                       _ptr(ws["ln_ws"]), 1e-6, _ptr(ws["ln_stats"]["norm_enc6"][t]), _ptr(ws["e6"][t]), 64, 0,
+                       _ptr(p["model/enc7/W"]), _ptr(p["model/enc7/b"]), _ptr(ws["enc7_pre"][t]), self.Ne, _ptr(ws["mask_pre"][t]), self.Nh,
+                       B, HW[1], s)
+            elif self.Nh in (14, 27):     # fused heads: e6 read once, planes written directly (heads.cu)
                 L.call("pivp_heads_fwd", _ptr(ws["e6"][t]), 64, 0, _ptr(p["model/enc7/W"]), _ptr(p["model/enc7/b"]),
                        _ptr(ws["enc7_pre"][t]), self.Ne, _ptr(ws["mask_pre"][t]), self.Nh, B, HW[1], s)
             else:

@@ -484,3 +484,37 @@ def test_tc_convlstm_with_fused_layernorm_equals_cell_then_layernorm(pk, B, H, W
         assert rel(b[6], a[6]) < 1e-5                              # (mean, rstd) saved for the backward pass
         c_prev = a[1]
     assert int(counter.min()) == int(counter.max()) == 3 * (H * W // 128) * (C // 32)
+
+
+@pytest.mark.parametrize("NH,Na,B,HW", [(14, 3, 2, 4096), (27, 25, 3, 256)])
+def test_heads_fwd_ln_equals_layernorm_then_heads(pk, NH, Na, B, HW):
+    """pivp_heads_fwd_ln (norm_enc6 + ReLU applied while the heads kernel stages its tile, statistics = (mean, M2) partials of 4096 values as the
+    enc6 epilogue writes them) == pivp_layernorm_fwd(relu) followed by pivp_heads_fwd (train_model.py:601, 698, 288, 527)."""
+    L = pk.lib()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(31)
+    C, M, n = 64, B * HW, HW * 64
+    R = lambda *sh: torch.randn(*sh, device="cuda", generator=gen)
+    x = R(M, C) * 1.5 + 0.2
+    gamma, beta = 1 + 0.2 * R(n), 0.2 * R(n)
+    Wh, bh = R(NH, C) / 8, 0.1 * R(NH)
+    ws = torch.empty(max(L.query("pivp_layernorm_workspace_bytes", B, n), 16), dtype=torch.uint8, device="cuda")
+    st1, st2 = torch.zeros(B, 2, device="cuda"), torch.zeros(B, 2, device="cuda")
+    y1, y2 = torch.empty(M, C, device="cuda"), torch.empty(M, C, device="cuda")
+    a1, b1 = torch.empty(B, Na, HW, device="cuda"), torch.empty(B, NH - Na, HW, device="cuda")
+    a2, b2 = torch.empty_like(a1), torch.empty_like(b1)
+    L.call("pivp_layernorm_fwd", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), B, HW, C, 1e-6, y1.data_ptr(), C, 0,
+           0, 0, 0, 0, 0, 0, 1, st1.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+    L.call("pivp_heads_fwd", y1.data_ptr(), C, 0, Wh.data_ptr(), bh.data_ptr(), a1.data_ptr(), Na, b1.data_ptr(), NH, B, HW, stream())
+    # partials of 4096 consecutive elements (any partition into 4096-value chunks merges to the same statistics)
+    xs = x.reshape(B, n // 4096, 4096).double()
+    mean = xs.mean(2)
+    part = torch.stack([mean, ((xs - mean[:, :, None]) ** 2).sum(2)], dim=2).float().contiguous()
+    L.call("pivp_heads_fwd_ln", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), part.data_ptr(), 1e-6, st2.data_ptr(),
+           y2.data_ptr(), C, 0, Wh.data_ptr(), bh.data_ptr(), a2.data_ptr(), Na, b2.data_ptr(), NH, B, HW, stream())
+    torch.cuda.synchronize()
+    assert rel(st2, st1) < 1e-5 and rel(y2, y1) < 1e-5
+    assert rel(a2, a1) < 1e-5 and rel(b2, b1) < 1e-5
+    assert float(y2.min()) == 0.0 and float(y2.max()) > 0
+    with pytest.raises(pk.PivpError):
+        L.call("pivp_heads_fwd_ln", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), part.data_ptr(), 1e-6, st2.data_ptr(),
+               y2.data_ptr(), C, 0, Wh.data_ptr(), bh.data_ptr(), a2.data_ptr(), Na, b2.data_ptr(), NH, B, HW + 64, stream())
