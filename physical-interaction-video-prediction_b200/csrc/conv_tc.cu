@@ -45,20 +45,23 @@ struct TcGeom {
 // blockIdx.z picks the weight tensor map and the geometry; the A tensor, tile counts and epilogue are common.
 constexpr int TC_MAXPH = 4;
 struct TcMapsB { CUtensorMap m[TC_MAXPH]; };
+struct TcMapsOut { CUtensorMap m[TC_MAXPH]; };   // per phase: the output seen as (channel, x', y', image) of the A grid (strides os pixels)
 struct TcGeomPack {
     TcGeom g[TC_MAXPH];
+    int out_bytes;   // > 0: the epilogue stages its tile in the first out_bytes of shared memory and writes it with TMA stores (maps_o)
     int nloop;       // 1: one phase per CTA (blockIdx.z picks it).  n > 1: every CTA walks phases 0..n-1 of its pixel tile, one TMEM
                      // accumulator of BN columns per phase (grid z = 1) -- a quarter of the CTAs, so a 64x64 deconvolution is ONE wave
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
-conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ TcMapsB maps_b, const __grid_constant__ TcGeomPack gp,
-                    TcEpilogue ep) {
+conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ TcMapsB maps_b, const __grid_constant__ TcMapsOut maps_o,
+                    const __grid_constant__ TcGeomPack gp, TcEpilogue ep) {
     const TcGeom& g = gp.g[blockIdx.z];            // fields common to all phases (tile geometry, Kc, BN, ring depth, TMEM columns)
     const int nloop = gp.nloop;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    // carve: [stages][A 16 KB | B BN*128] then barriers
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // carve: [output staging, out_bytes] [stages][A 16 KB | B BN*128] then barriers
+    uint8_t* smem_base = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* smem = smem_base + gp.out_bytes;        // the operand ring
     const uint32_t a_bytes = TC_BM * 128, b_bytes = (uint32_t)g.BN * 128, stage_bytes = a_bytes + b_bytes;
     uint64_t* bars = (uint64_t*)(smem + (size_t)g.stages * stage_bytes);
     uint64_t* full = bars;
@@ -165,11 +168,37 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             const long orow = ((long)bi * g.OH + iy * g.os + gq.oa) * g.OW + ix * g.os + gq.ob;
             // (the staged, coalesced write-out of tc_epilogue_staged was measured here too: +0.2 ms per step -- with 4 epilogue warps and
             // rows of <= 128 channels the extra shared-memory round trip costs more than the scattered 16-byte stores)
+            if (gp.out_bytes) {
+                // staged tile + TMA stores (one box of 32 fp32 columns x 128 pixels per store) into phase p's strided view of the output
+                float2* red = reinterpret_cast<float2*>(bias_s + g.BN) + p * 32;
+                if (p > 0) {                                                   // the previous phase's stores have read the staging tile
+                    if (warp == 2) { if (elect_one()) tma_store_wait_read(); __syncwarp(); }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                const uint32_t stage = smem_u32(smem_base);
+                if (ep.ln_partial) tc_epilogue_row_stage<true>(ep, trow + (uint32_t)(p * g.BN), g.BN, bias_s, stage, row, red, q, lane);
+                else tc_epilogue_row_stage<false>(ep, trow + (uint32_t)(p * g.BN), g.BN, bias_s, stage, row, red, q, lane);
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps: tile (and statistics) complete
+                if (warp == 2) {
+                    if (elect_one()) {
+                        const int tiles_x = g.W / g.TW, tiles_y = g.H / g.TH;
+                        const int tx = m_tile % tiles_x, ty = (m_tile / tiles_x) % tiles_y, tb = m_tile / (tiles_x * tiles_y);
+                        for (int b = 0; b < (g.BN >> 5); ++b)
+                            tma_store_4d(&maps_o.m[blockIdx.z + p], stage + (uint32_t)b * 16384u, ep.out_co + n0 + 32 * b, tx * g.TW, ty * g.TH, tb * g.TB);
+                        tma_store_commit();
+                        if (p == nloop - 1) tma_store_wait_read();             // shared memory must outlive the bulk reads
+                    }
+                    __syncwarp();
+                }
+            }
             if (ep.ln_partial) {
                 // statistics of the LayerNorm behind this deconvolution: one (mean, M2) pair per (tile, phase, 32-column group)
                 float2* red = reinterpret_cast<float2*>(bias_s + g.BN) + p * 32;
-                tc_epilogue_row_ln(ep, trow + (uint32_t)(p * g.BN), orow, n0, g.BN, bias_s, red, q, lane);
-                asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps
+                if (!gp.out_bytes) {
+                    tc_epilogue_row_ln(ep, trow + (uint32_t)(p * g.BN), orow, n0, g.BN, bias_s, red, q, lane);
+                    asm volatile("bar.sync 1, 128;" ::: "memory");             // the four epilogue warps
+                }
                 const int grp = (int)threadIdx.x - 64;
                 if (grp < (g.BN >> 5)) {
                     const float2 a = red[grp * 4], b = red[grp * 4 + 1], c = red[grp * 4 + 2], e = red[grp * 4 + 3];
@@ -182,7 +211,7 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     ep.ln_partial[(long)bi * ep.ln_S + ((long)(tile_in * nphases + (int)blockIdx.z + p)) * (g.N >> 5) + (n0 >> 5) + grp] =
                         make_float2(0.5f * (mab + mce), (sab + sce) + dd * dd * 1024.f);
                 }
-            } else {
+            } else if (!gp.out_bytes) {
                 tc_epilogue_row(ep, trow + (uint32_t)(p * g.BN), m, orow, n0, g.BN, n_tile, bias_s);
             }
         }
@@ -269,8 +298,13 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
     static const int fuse_env = getenv("PIVP_TC_TAPS_FUSE_PH") ? atoi(getenv("PIVP_TC_TAPS_FUSE_PH")) : 1;
     const bool fuse_ph = fuse_env && nph > 1 && ctas > 2 * 148 && nph * BN <= 256;
     if (fuse_ph) ctas /= nph;
+    // phases walked inside the CTA and a plain fp32 output: the epilogue stages each phase's tile and writes it with TMA stores
+    static const int tma_env = getenv("PIVP_TC_TAPS_TMA") ? atoi(getenv("PIVP_TC_TAPS_TMA")) : 1;
+    const bool tma_out = tma_env && fuse_ph && ep.mode == 0 && ep.out && !ep.out_bf16 && !ep.accumulate && !ep.atomic && BN % 32 == 0 &&
+                         !(reinterpret_cast<uintptr_t>(ep.out) & 15) && ep.out_cs % 4 == 0 && ep.out_co % 4 == 0;
+    const int out_bytes = tma_out ? (BN / 32) * 16384 : 0;
     const int env_ring = getenv("PIVP_TC_TAPS_RING_KB") ? atoi(getenv("PIVP_TC_TAPS_RING_KB")) : 0;
-    int stages = ((env_ring > 0 ? env_ring : ctas <= 148 ? 190 : 100) * 1024) / stage_bytes;
+    int stages = ((env_ring > 0 ? env_ring : ctas <= 148 ? 190 : tma_out ? 108 : 100) * 1024 - out_bytes) / stage_bytes;      // two CTAs per SM: <= ~112 KB each
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     TcGeomPack gp;                                 // by-value kernel parameters
@@ -307,12 +341,25 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
         if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(B%d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
     }
     gp.nloop = fuse_ph ? nph : 1;
+    gp.out_bytes = out_bytes;
+    TcMapsOut mo;
+    memset(&mo, 0, sizeof(mo));
+    if (tma_out) {
+        for (int p = 0; p < nph; ++p) {                    // phase p writes pixels (i * os + oa, j * os + ob): a strided view with its own base
+            const float* base = ep.out + ((long)ph[p].oa * OW + ph[p].ob) * ep.out_cs;
+            cuuint64_t dims[4] = {(cuuint64_t)ep.out_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+            cuuint64_t str[3] = {(cuuint64_t)os * ep.out_cs * 4, (cuuint64_t)os * OW * ep.out_cs * 4, (cuuint64_t)OH * OW * ep.out_cs * 4};
+            cuuint32_t box[4] = {32u, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
+            CUresult r = encode_tmap_ex(&mo.m[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, base, 4, dims, str, box);
+            if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(out%d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
+        }
+    }
     if (ep.ln_partial) {
         PIVP_REQUIRE(ep.mode == 0 && !ep.relu && !ep.accumulate && !ep.atomic && BN % 32 == 0 && N % 32 == 0 && (H * W) % TC_BM == 0 && TB == 1,
                      "%s: LayerNorm statistics need a plain store, 32-column groups and tiles inside one sample", who);
         ep.ln_S = (H * W / TC_BM) * nph * (N / 32);
     }
-    const size_t smem = 1024 + (size_t)stages * stage_bytes + (2 * stages + TC_MAXPH) * 8 + 16 + (size_t)BN * 4 + TC_MAXPH * 32 * sizeof(float2);
+    const size_t smem = 1024 + (size_t)out_bytes + (size_t)stages * stage_bytes + (2 * stages + TC_MAXPH) * 8 + 16 + (size_t)BN * 4 + TC_MAXPH * 32 * sizeof(float2);
     static PerDeviceOnce attr_once;            // the opt-in is per device
     if (attr_once.need()) {
         cudaError_t e = cudaFuncSetAttribute(conv_taps_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
@@ -320,7 +367,7 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
     }
     const long M = (long)B * H * W;
     dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN), (unsigned)(fuse_ph ? 1 : nph));
-    launch_k(conv_taps_tc_kernel, grid, dim3(TC_THREADS), smem, stream, map_a, mb, gp, ep);
+    launch_k(conv_taps_tc_kernel, grid, dim3(TC_THREADS), smem, stream, map_a, mb, mo, gp, ep);
     return check_launch(who);
 }
 

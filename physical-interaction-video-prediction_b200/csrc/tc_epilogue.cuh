@@ -177,6 +177,56 @@ __device__ __forceinline__ void tc_epilogue_row_ln(const TcEpilogue& ep, uint32_
     }
 }
 
+// Mode 0 through shared memory for a TMA store: the row's BN fp32 values (+bias, ReLU) go into BN / 32 staging tiles of 128 rows x 128 B laid
+// out as the output tensor map's boxes (128-byte swizzle), one 16 KB tile per 32 columns; a per-thread global store would put 16 bytes into each of
+// 32 different cache lines per instruction.  STATS: also the (mean, M2) pairs of tc_epilogue_row_ln (computed before the ReLU is applied: not combined).
+template <bool STATS>
+__device__ __forceinline__ void tc_epilogue_row_stage(const TcEpilogue& ep, uint32_t trow, int BN, const float* bias_s, uint32_t stage, int row,
+                                                      float2* red, int q, int lane) {
+    const uint32_t r128 = (uint32_t)row * 128u, rsw = (uint32_t)(row & 7);
+    for (int g0 = 0; g0 < BN; g0 += 32) {
+        float mean = 0.f, m2 = 0.f;
+        const uint32_t sb = stage + (uint32_t)(g0 >> 5) * 16384u + r128;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int c0 = g0 + 8 * k;
+            float v[8];
+            tc_ld8(trow + (uint32_t)c0, v);
+            tc_ld_wait();
+            if (ep.bias) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] += bias_s[c0 + i];
+            }
+            if (STATS) {
+                const float cm = (((v[0] + v[1]) + (v[2] + v[3])) + ((v[4] + v[5]) + (v[6] + v[7]))) * 0.125f;
+                float c2 = 0.f;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { const float d = v[i] - cm; c2 = fmaf(d, d, c2); }
+                const float d = cm - mean;
+                mean += d * (1.f / (float)(k + 1));
+                m2 += c2 + d * d * (8.f * (float)k / (float)(k + 1));
+            } else if (ep.relu) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            st_shared_v4(sb + (((uint32_t)(2 * k) ^ rsw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+            st_shared_v4(sb + (((uint32_t)(2 * k + 1) ^ rsw) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+        }
+        if (STATS) {
+            float cnt = 32.f;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float mo = __shfl_xor_sync(0xffffffffu, mean, o), m2o = __shfl_xor_sync(0xffffffffu, m2, o);
+                const float d = mo - mean;
+                m2 = (m2 + m2o) + d * d * (cnt * 0.5f);
+                mean = 0.5f * (mean + mo);
+                cnt *= 2.f;
+            }
+            if (lane == 0) red[(g0 >> 5) * 4 + q] = make_float2(mean, m2);
+        }
+    }
+}
+
 __device__ __forceinline__ void tc_epilogue_row(const TcEpilogue& ep, uint32_t trow, long m, long orow, int n0, int BN, int n_tile,
                                                 const float* bias_s) {
     if (ep.mode == 0) {
