@@ -49,13 +49,14 @@ struct TcMapsOut { CUtensorMap m[TC_MAXPH]; };   // per phase: the output seen a
 struct TcGeomPack {
     TcGeom g[TC_MAXPH];
     int out_bytes;   // > 0: the epilogue stages its tile in the first out_bytes of shared memory and writes it with TMA stores (maps_o)
+    int out_b_off;   // > 0: offset of the bf16 copy's staging tiles inside that region (maps_ob)
     int nloop;       // 1: one phase per CTA (blockIdx.z picks it).  n > 1: every CTA walks phases 0..n-1 of its pixel tile, one TMEM
                      // accumulator of BN columns per phase (grid z = 1) -- a quarter of the CTAs, so a 64x64 deconvolution is ONE wave
 };
 
 __global__ void __launch_bounds__(TC_THREADS, 2)
 conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ TcMapsB maps_b, const __grid_constant__ TcMapsOut maps_o,
-                    const __grid_constant__ TcGeomPack gp, TcEpilogue ep) {
+                    const __grid_constant__ TcMapsOut maps_ob, const __grid_constant__ TcGeomPack gp, TcEpilogue ep) {
     const TcGeom& g = gp.g[blockIdx.z];            // fields common to all phases (tile geometry, Kc, BN, ring depth, TMEM columns)
     const int nloop = gp.nloop;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -175,17 +176,20 @@ conv_taps_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                     if (warp == 2) { if (elect_one()) tma_store_wait_read(); __syncwarp(); }
                     asm volatile("bar.sync 1, 128;" ::: "memory");
                 }
-                const uint32_t stage = smem_u32(smem_base);
-                if (ep.ln_partial) tc_epilogue_row_stage<true>(ep, trow + (uint32_t)(p * g.BN), g.BN, bias_s, stage, row, red, q, lane);
-                else tc_epilogue_row_stage<false>(ep, trow + (uint32_t)(p * g.BN), g.BN, bias_s, stage, row, red, q, lane);
+                const uint32_t stage = smem_u32(smem_base), stage_b = gp.out_b_off ? stage + (uint32_t)gp.out_b_off : 0u;
+                if (ep.ln_partial) tc_epilogue_row_stage<true>(ep, trow + (uint32_t)(p * g.BN), g.BN, bias_s, stage, row, red, q, lane, stage_b);
+                else tc_epilogue_row_stage<false>(ep, trow + (uint32_t)(p * g.BN), g.BN, bias_s, stage, row, red, q, lane, stage_b);
                 fence_proxy_async();
                 asm volatile("bar.sync 1, 128;" ::: "memory");                 // the four epilogue warps: tile (and statistics) complete
                 if (warp == 2) {
                     if (elect_one()) {
                         const int tiles_x = g.W / g.TW, tiles_y = g.H / g.TH;
                         const int tx = m_tile % tiles_x, ty = (m_tile / tiles_x) % tiles_y, tb = m_tile / (tiles_x * tiles_y);
-                        for (int b = 0; b < (g.BN >> 5); ++b)
+                        for (int b = 0; b < (g.BN >> 5); ++b) {
                             tma_store_4d(&maps_o.m[blockIdx.z + p], stage + (uint32_t)b * 16384u, ep.out_co + n0 + 32 * b, tx * g.TW, ty * g.TH, tb * g.TB);
+                            if (stage_b)
+                                tma_store_4d(&maps_ob.m[blockIdx.z + p], stage_b + (uint32_t)b * 8192u, ep.ob_co + n0 + 32 * b, tx * g.TW, ty * g.TH, tb * g.TB);
+                        }
                         tma_store_commit();
                         if (p == nloop - 1) tma_store_wait_read();             // shared memory must outlive the bulk reads
                     }
@@ -302,11 +306,16 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
     // (PIVP_TC_TAPS_TMA: 0 = per-thread stores, 1 = only the launches that walk their phases inside the CTA, 2 = every eligible launch;
     //  measured on the b32 step: 7.05 / 7.00 / 6.95 ms)
     static const int tma_env = getenv("PIVP_TC_TAPS_TMA") ? atoi(getenv("PIVP_TC_TAPS_TMA")) : 2;
-    const bool tma_out = tma_env && (fuse_ph || tma_env >= 2) && ep.mode == 0 && ep.out && !ep.out_bf16 && !ep.accumulate && !ep.atomic && BN % 32 == 0 &&
+    const bool bf16_ok = !ep.out_bf16 || (tma_env >= 3 && !(reinterpret_cast<uintptr_t>(ep.out_bf16) & 15) && ep.ob_cs % 8 == 0 && ep.ob_co % 8 == 0);
+    const bool tma_out = tma_env && (fuse_ph || tma_env >= 2) && ep.mode == 0 && ep.out && bf16_ok && !ep.accumulate && !ep.atomic && BN % 32 == 0 &&
                          !(reinterpret_cast<uintptr_t>(ep.out) & 15) && ep.out_cs % 4 == 0 && ep.out_co % 4 == 0;
-    const int out_bytes = tma_out ? (BN / 32) * 16384 : 0;
+    // (two CTAs per SM share 227 KB: a staging area above 48 KB would leave the operand ring a single stage -- keep the per-thread stores there)
+    const int want_bytes = (BN / 32) * 16384 + (ep.out_bf16 ? (BN / 32) * 8192 : 0);
+    const bool tma_fits = ctas <= 148 || want_bytes <= 48 * 1024;
+    const int out_b_off = tma_out && tma_fits && ep.out_bf16 ? (BN / 32) * 16384 : 0;
+    const int out_bytes = tma_out && tma_fits ? want_bytes : 0;
     const int env_ring = getenv("PIVP_TC_TAPS_RING_KB") ? atoi(getenv("PIVP_TC_TAPS_RING_KB")) : 0;
-    int stages = ((env_ring > 0 ? env_ring : ctas <= 148 ? 190 : tma_out ? 108 : 100) * 1024 - out_bytes) / stage_bytes;      // two CTAs per SM: <= ~112 KB each
+    int stages = ((env_ring > 0 ? env_ring : ctas <= 148 ? 190 : out_bytes ? 108 : 100) * 1024 - out_bytes) / stage_bytes;      // two CTAs per SM: <= ~112 KB each
     if (stages > 8) stages = 8;
     if (stages < 2) stages = 2;
     TcGeomPack gp;                                 // by-value kernel parameters
@@ -344,9 +353,11 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
     }
     gp.nloop = fuse_ph ? nph : 1;
     gp.out_bytes = out_bytes;
-    TcMapsOut mo;
+    gp.out_b_off = out_b_off;
+    TcMapsOut mo, mob;
     memset(&mo, 0, sizeof(mo));
-    if (tma_out) {
+    memset(&mob, 0, sizeof(mob));
+    if (out_bytes) {
         for (int p = 0; p < nph; ++p) {                    // phase p writes pixels (i * os + oa, j * os + ob): a strided view with its own base
             const float* base = ep.out + ((long)ph[p].oa * OW + ph[p].ob) * ep.out_cs;
             cuuint64_t dims[4] = {(cuuint64_t)ep.out_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
@@ -354,6 +365,13 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
             cuuint32_t box[4] = {32u, (cuuint32_t)TW, (cuuint32_t)TH, (cuuint32_t)TB};
             CUresult r = encode_tmap_ex(&mo.m[p], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, base, 4, dims, str, box);
             if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(out%d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
+            if (ep.out_bf16) {
+                const __nv_bfloat16* bb = ep.out_bf16 + ((long)ph[p].oa * OW + ph[p].ob) * ep.ob_cs;
+                cuuint64_t dimb[4] = {(cuuint64_t)ep.ob_cs, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+                cuuint64_t strb[3] = {(cuuint64_t)os * ep.ob_cs * 2, (cuuint64_t)os * OW * ep.ob_cs * 2, (cuuint64_t)OH * OW * ep.ob_cs * 2};
+                r = encode_tmap_ex(&mob.m[p], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, CU_TENSOR_MAP_SWIZZLE_64B, bb, 4, dimb, strb, box);
+                if (r != CUDA_SUCCESS) { set_error("%s: cuTensorMapEncodeTiled(out_bf16 %d) failed (%d)", who, p, (int)r); return PIVP_ECUDA; }
+            }
         }
     }
     if (ep.ln_partial) {
@@ -369,7 +387,7 @@ static int launch_conv_taps_multi(const void* in_bf16, int in_cs, int B, int H, 
     }
     const long M = (long)B * H * W;
     dim3 grid((unsigned)(M / TC_BM), (unsigned)(N / BN), (unsigned)(fuse_ph ? 1 : nph));
-    launch_k(conv_taps_tc_kernel, grid, dim3(TC_THREADS), smem, stream, map_a, mb, mo, gp, ep);
+    launch_k(conv_taps_tc_kernel, grid, dim3(TC_THREADS), smem, stream, map_a, mb, mo, mob, gp, ep);
     return check_launch(who);
 }
 

@@ -180,10 +180,12 @@ __device__ __forceinline__ void tc_epilogue_row_ln(const TcEpilogue& ep, uint32_
 // Mode 0 through shared memory for a TMA store: the row's BN fp32 values (+bias, ReLU) go into BN / 32 staging tiles of 128 rows x 128 B laid
 // out as the output tensor map's boxes (128-byte swizzle), one 16 KB tile per 32 columns; a per-thread global store would put 16 bytes into each of
 // 32 different cache lines per instruction.  STATS: also the (mean, M2) pairs of tc_epilogue_row_ln (computed before the ReLU is applied: not combined).
+// stage_b != 0: also the bf16 copy, BN / 32 tiles of 128 rows x 64 B (64-byte swizzle) at stage_b.
 template <bool STATS>
 __device__ __forceinline__ void tc_epilogue_row_stage(const TcEpilogue& ep, uint32_t trow, int BN, const float* bias_s, uint32_t stage, int row,
-                                                      float2* red, int q, int lane) {
+                                                      float2* red, int q, int lane, uint32_t stage_b = 0) {
     const uint32_t r128 = (uint32_t)row * 128u, rsw = (uint32_t)(row & 7);
+    const uint32_t r64 = (uint32_t)row * 64u, rsw64 = (uint32_t)((row >> 1) & 3);
     for (int g0 = 0; g0 < BN; g0 += 32) {
         float mean = 0.f, m2 = 0.f;
         const uint32_t sb = stage + (uint32_t)(g0 >> 5) * 16384u + r128;
@@ -211,6 +213,10 @@ __device__ __forceinline__ void tc_epilogue_row_stage(const TcEpilogue& ep, uint
             }
             st_shared_v4(sb + (((uint32_t)(2 * k) ^ rsw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
             st_shared_v4(sb + (((uint32_t)(2 * k + 1) ^ rsw) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+            if (stage_b) {
+                const uint4 pk = pack8_bf16(v);
+                st_shared_v4(stage_b + (uint32_t)(g0 >> 5) * 8192u + r64 + (((uint32_t)k ^ rsw64) << 4), pk.x, pk.y, pk.z, pk.w);
+            }
         }
         if (STATS) {
             float cnt = 32.f;
