@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 bool wgrad_halo_supported(int H, int W, int Cx, int N4);
 size_t wgrad_halo_ws_bytes(int SB, int H, int W, int Cx, int N4);
 int launch_wgrad5x5_halo(const void* dg_bf16, int dg_cs, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* part,
-                         size_t ws_bytes, void* stream, const char* who);
+                         size_t ws_bytes, float* dW, void* stream, const char* who);
 
 }  // namespace pivp
 
@@ -380,8 +380,8 @@ int pivp_tc_wgrad5x5(const void* dg_bf16, const void* xh_bf16, int xh_cs, int SB
     PIVP_REQUIRE(N4 % 128 == 0 && xh_cs >= (Cx + 63) / 64 * 64, "tc_wgrad5x5: 4C must be a multiple of 128 and XH rows hold ceil(Cx/64)*64 channels");
     if (wgrad_halo_supported(H, W, Cx, N4)) {
         PIVP_REQUIRE(dg_bf16 && xh_bf16 && dW && workspace, "tc_wgrad5x5: null pointer");
-        const int splits = launch_wgrad5x5_halo(dg_bf16, N4, xh_bf16, xh_cs, SB, H, W, Cx, N4, (float*)workspace, ws_bytes, stream, "tc_wgrad5x5");
-        if (splits < 0) return splits;
+        const int splits = launch_wgrad5x5_halo(dg_bf16, N4, xh_bf16, xh_cs, SB, H, W, Cx, N4, (float*)workspace, ws_bytes, dW, stream, "tc_wgrad5x5");
+        if (splits <= 0) return splits;                // 0: the kernel added its partial tiles into dW itself (TMA reduce-add)
         const long n = (long)N4 * 25 * Cx, stride = (long)((N4 + 127) / 128 * 128) * 25 * Cx;
         launch_splitk_reduce((const float*)workspace, dW, n, stride, splits, stream);
         return check_launch("tc_wgrad5x5(reduce)");

@@ -14,6 +14,7 @@
 // to the split-K workspace exactly like conv_tc_wgrad.cu (same layout, same reduce kernel).
 #include "tc_common.cuh"
 #include <stdlib.h>
+#include <string.h>
 
 namespace pivp {
 namespace wgh {
@@ -31,10 +32,12 @@ struct Geom {
     int chunks, tpg, groups;                     // 64-channel chunks of XH, taps per group, tap groups
     int kb_total, kb_per_split;                  // K steps = 8x8 pixel blocks over all images
     int pair;                                    // most taps issued as one MMA of N = 64 * run columns (PIVP_TC_WGRAD_PAIR = 1, 2 or 4; default 4)
+    int tma_out;                                 // partial tiles leave as TMA reduce-adds straight into dW (no split-K workspace, no reduce kernel)
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
-wgrad5x5_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, Geom g, float* __restrict__ part) {
+wgrad5x5_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
+                     Geom g, float* __restrict__ part) {
     pdl_enter();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -148,6 +151,41 @@ wgrad5x5_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
         mbar_wait(smem_u32(accum_full), 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (g.tma_out) {
+            // dW (fp32 [n][tap][c], zeroed by cleargrads) += this CTA's partial tiles, added by the memory system: one TMA reduce-add per
+            // (tap, 32 channels) box of 128 n x 128 B.  The operand ring is dead (every MMA has retired): six staging buffers of two boxes
+            // rotate through it, a buffer is rewritten once the bulk group that read it has finished reading.
+            const int row = q * 32 + lane;
+            const uint32_t r128 = (uint32_t)row * 128u, rsw = (uint32_t)(row & 7);
+            const uint32_t stage0 = smem_u32(smem);
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const uint32_t sb = stage0 + (uint32_t)(tl % 6) * 32768u;
+                if (tl >= 6) {
+                    if (warp == 2) { if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 5;" ::: "memory"); __syncwarp(); }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                for (int c0 = 0; c0 < ncol; c0 += 8) {
+                    float v[8];
+                    tc_ld8(trow + (uint32_t)(tl * 64 + c0), v);
+                    tc_ld_wait();
+                    const uint32_t base = sb + (uint32_t)(c0 >> 5) * 16384u + r128;
+                    const uint32_t k4 = (uint32_t)((c0 & 31) >> 2);
+                    st_shared_v4(base + ((k4 ^ rsw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                    st_shared_v4(base + (((k4 + 1u) ^ rsw) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2) {
+                    if (elect_one()) {
+                        for (int b = 0; b < (ncol >> 5); ++b) tma_reduce_add_4d(&map_o, sb + (uint32_t)b * 16384u, chunk * 64 + 32 * b, tap0 + tl, n0, 0);
+                        tma_store_commit();
+                        if (tl == ntaps - 1) tma_store_wait_read();
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+        } else {
         float* dst_row = part + ((size_t)split * g.Mrows + n) * 25 * g.Cx + chunk * 64;
         for (int tl = 0; tl < ntaps; ++tl) {
             float* dst = dst_row + (size_t)(tap0 + tl) * g.Cx;
@@ -160,6 +198,7 @@ wgrad5x5_halo_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_con
             }
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -201,14 +240,25 @@ size_t wgrad_halo_ws_bytes(int SB, int H, int W, int Cx, int N4) {
     return (size_t)splits * g.Mrows * 25 * Cx * sizeof(float);
 }
 
-// returns the number of K splits written to `part` (>= 1), or a negative error code
+// returns the number of K splits written to `part` (>= 1; 0 when the partial tiles were reduce-added into dW directly), or a negative error code
 int launch_wgrad5x5_halo(const void* dg_bf16, int dg_cs, const void* xh_bf16, int xh_cs, int SB, int H, int W, int Cx, int N4, float* part,
-                         size_t ws_bytes, void* stream, const char* who) {
+                         size_t ws_bytes, float* dW, void* stream, const char* who) {
     using namespace wgh;
     Geom g;
     int splits;
     plan(Cx, N4, H, W, SB, &g, &splits);
-    PIVP_REQUIRE(ws_bytes >= (size_t)splits * g.Mrows * 25 * Cx * sizeof(float), "%s(halo): workspace too small", who);
+    // dW reachable by TMA (16-byte aligned, whole 32-channel boxes): the partial tiles are reduce-added into it directly, 0 splits returned
+    static const int tma_env = getenv("PIVP_TC_WGRAD_TMA") ? atoi(getenv("PIVP_TC_WGRAD_TMA")) : 1;
+    g.tma_out = tma_env && dW && Cx % 32 == 0 && !(reinterpret_cast<uintptr_t>(dW) & 15);
+    CUtensorMap map_o;
+    memset(&map_o, 0, sizeof(map_o));
+    if (g.tma_out) {
+        cuuint64_t dims[4] = {(cuuint64_t)Cx, 25, (cuuint64_t)N4, 1};
+        cuuint64_t str[3] = {(cuuint64_t)Cx * 4, (cuuint64_t)25 * Cx * 4, (cuuint64_t)N4 * 25 * Cx * 4};
+        cuuint32_t box[4] = {32, 1, 128, 1};
+        if (encode_tmap_ex(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, dW, 4, dims, str, box) != CUDA_SUCCESS) g.tma_out = 0;
+    }
+    PIVP_REQUIRE(g.tma_out || ws_bytes >= (size_t)splits * g.Mrows * 25 * Cx * sizeof(float), "%s(halo): workspace too small", who);
     PIVP_REQUIRE(dg_cs % 8 == 0 && xh_cs % 8 == 0, "%s(halo): rows must be 16-byte aligned", who);
     CUtensorMap map_a, map_b;
     {
@@ -232,9 +282,9 @@ int launch_wgrad5x5_halo(const void* dg_bf16, int dg_cs, const void* xh_bf16, in
         if (e != cudaSuccess) { set_error("%s(halo): cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
     }
     dim3 grid((unsigned)(g.Mrows / 128), (unsigned)(g.chunks * g.groups), (unsigned)splits);
-    launch_k(wgrad5x5_halo_kernel, dim3(grid), dim3(THREADS), smem, (cudaStream_t)stream, map_a, map_b, g, part);
+    launch_k(wgrad5x5_halo_kernel, dim3(grid), dim3(THREADS), smem, (cudaStream_t)stream, map_a, map_b, map_o, g, part);
     if (int e = check_launch(who)) return e;
-    return splits;
+    return g.tma_out ? 0 : splits;
 }
 
 }  // namespace pivp
