@@ -15,6 +15,8 @@
 //  * A ring (3 x 16 KB) and B ring (up to 8 slots) with full/empty mbarriers; one A tile feeds ntaps*4 MMAs.
 //  * grid = (4C/128, tap groups, K splits); every CTA stores its fp32 partial tile, a second kernel sums the splits into dW.
 #include "tc_common.cuh"
+#include <string.h>
+#include <stdlib.h>
 #include <stdlib.h>
 
 namespace pivp {
@@ -33,6 +35,7 @@ struct WgGeom {
     int Mrows;               // accumulator rows = ceil(N4/128)*128 (rows >= N4 are zero: TMA fills out-of-range channels)
     signed char dy[25], dx[25];
     short coff[25];          // channel offset of each tap inside the XH rows (space-to-depth phases)
+    int tma_out;             // partial tiles leave as TMA reduce-adds straight into dW (rows >= N4 are clipped by the tensor map)
 };
 
 // MN-major, 128-byte swizzle shared-memory matrix descriptor: LBO = byte distance between 64-element MN chunks,
@@ -48,7 +51,8 @@ __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t saddr, uint
 }
 
 __global__ void __launch_bounds__(WG_THREADS, 1)
-conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, WgGeom g, float* __restrict__ part) {
+conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const __grid_constant__ CUtensorMap map_o,
+                        WgGeom g, float* __restrict__ part) {
     pdl_enter();
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -158,6 +162,39 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
         mbar_wait(smem_u32(accum_full), 0);
         tc_fence_after();
         const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16);
+        if (g.tma_out) {
+            // dW += partial tile, added by the memory system (see conv_tc_wgrad_halo.cu): two staging buffers of Cx / 32 boxes in the dead rings
+            const int row = q * 32 + lane, nbox = g.Cx >> 5;
+            const uint32_t r128 = (uint32_t)row * 128u, rsw = (uint32_t)(row & 7);
+            const uint32_t stage0 = smem_u32(smem), buf_bytes = (uint32_t)nbox * 16384u;
+            for (int tl = 0; tl < ntaps; ++tl) {
+                const uint32_t sbuf = stage0 + (uint32_t)(tl & 1) * buf_bytes;
+                if (tl >= 2) {
+                    if (warp == 2) { if (elect_one()) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); __syncwarp(); }
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+                }
+                for (int c0 = 0; c0 < g.Cx; c0 += 8) {
+                    float v[8];
+                    tc_ld8(trow + (uint32_t)(tl * g.Cx + c0), v);
+                    tc_ld_wait();
+                    const uint32_t base = sbuf + (uint32_t)(c0 >> 5) * 16384u + r128;
+                    const uint32_t k4 = (uint32_t)((c0 & 31) >> 2);
+                    st_shared_v4(base + ((k4 ^ rsw) << 4), __float_as_uint(v[0]), __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                    st_shared_v4(base + (((k4 + 1u) ^ rsw) << 4), __float_as_uint(v[4]), __float_as_uint(v[5]), __float_as_uint(v[6]), __float_as_uint(v[7]));
+                }
+                fence_proxy_async();
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                if (warp == 2) {
+                    if (elect_one()) {
+                        for (int b = 0; b < nbox; ++b) tma_reduce_add_4d(&map_o, sbuf + (uint32_t)b * 16384u, 32 * b, tap0 + tl, n0, 0);
+                        tma_store_commit();
+                        if (tl == ntaps - 1) tma_store_wait_read();
+                    }
+                    __syncwarp();
+                }
+            }
+            tc_fence_before();
+        } else {
         float* dst_row = part + ((size_t)split * g.Mrows + n) * g.ntaps * g.Cx;
         for (int tl = 0; tl < ntaps; ++tl) {
             float* dst = dst_row + (size_t)(tap0 + tl) * g.Cx;
@@ -170,6 +207,7 @@ conv5x5_wgrad_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_
             }
         }
         tc_fence_before();
+        }
     }
     __syncthreads();
     if (warp == 1) {
@@ -339,11 +377,23 @@ static int launch_wgrad(const void* dg_bf16, int dg_cs, const void* xh_bf16, int
     int groups, splits;
     g.kb_total = (int)(ptot / 64);
     wgrad_plan(Cx, g.Mrows, ntaps, g.kb_total, &g.tpg, &groups, &splits, &g.kb_per_split);
-    PIVP_REQUIRE(ws_bytes >= (size_t)splits * g.Mrows * ntaps * Cx * sizeof(float), "%s: workspace too small", who);
     int bst = (150 * 1024) / (chunks * 8192);
     if (bst > 8) bst = 8;
     if (bst < 2) bst = 2;
     g.b_stages = bst;
+    // dW reachable by TMA and two staging buffers fit the (dead) operand rings: reduce-add the partial tiles into dW, no workspace, no reduce launch
+    static const int tma_env = getenv("PIVP_TC_WGRAD_TMA") ? atoi(getenv("PIVP_TC_WGRAD_TMA")) : 1;
+    const size_t ring_bytes = (size_t)WG_ASTAGES * 16384 + (size_t)bst * chunks * 8192;
+    g.tma_out = tma_env && Cx % 32 == 0 && !(reinterpret_cast<uintptr_t>(dW) & 15) && 2 * (size_t)(Cx / 32) * 16384 <= ring_bytes;
+    CUtensorMap map_o;
+    memset(&map_o, 0, sizeof(map_o));
+    if (g.tma_out) {
+        cuuint64_t dims[4] = {(cuuint64_t)Cx, (cuuint64_t)ntaps, (cuuint64_t)N4, 1};
+        cuuint64_t str[3] = {(cuuint64_t)Cx * 4, (cuuint64_t)ntaps * Cx * 4, (cuuint64_t)N4 * ntaps * Cx * 4};
+        cuuint32_t box[4] = {32, 1, 128, 1};
+        if (encode_tmap_ex(&map_o, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, CU_TENSOR_MAP_SWIZZLE_128B, dW, 4, dims, str, box) != CUDA_SUCCESS) g.tma_out = 0;
+    }
+    PIVP_REQUIRE(g.tma_out || ws_bytes >= (size_t)splits * g.Mrows * ntaps * Cx * sizeof(float), "%s: workspace too small", who);
     CUtensorMap map_a, map_b;
     {
         cuuint64_t dims[2] = {(cuuint64_t)N4, (cuuint64_t)ptot};
@@ -366,8 +416,9 @@ static int launch_wgrad(const void* dg_bf16, int dg_cs, const void* xh_bf16, int
         if (e != cudaSuccess) { set_error("%s: cudaFuncSetAttribute: %s", who, cudaGetErrorString(e)); return PIVP_ECUDA; }
     }
     dim3 grid((unsigned)(g.Mrows / 128), (unsigned)groups, (unsigned)splits);
-    launch_k(conv5x5_wgrad_tc_kernel, dim3(grid), dim3(WG_THREADS), smem, (cudaStream_t)stream, map_a, map_b, g, (float*)workspace);
+    launch_k(conv5x5_wgrad_tc_kernel, dim3(grid), dim3(WG_THREADS), smem, (cudaStream_t)stream, map_a, map_b, map_o, g, (float*)workspace);
     if (int e = check_launch(who)) return e;
+    if (g.tma_out) return PIVP_OK;
     const long n = (long)N4 * ntaps * Cx;
     const long stride = (long)g.Mrows * ntaps * Cx;
     launch_splitk_reduce((const float*)workspace, dW, n, stride, splits, stream);
