@@ -141,6 +141,9 @@ int pivp_linear_wgrad_steps(const float* dy, long dy_step, const float* x, long 
 int pivp_mse(const float* gen, const float* target, long n, float gscale, float* dgen, float* loss_slot, void* stream);
 /* scheduled_sample (train_model.py:73-122) as the per-sample select it reduces to */
 int pivp_sched_select(const float* gt, const float* gen, const int* take, float* out, int B, int per_sample, void* stream);
+/* the same select of (B, C, H*W) planes, also written as NHWC rows out_nhwc[(b*HW + p)*C + c] -- the layout enc0 (train_model.py:500) reads,
+ * so the layout change costs no launch of its own */
+int pivp_sched_select_nhwc(const float* gt, const float* gen, const int* take, float* out, float* out_nhwc, int B, int C, int HW, void* stream);
 /* Chainer 2.0.1 AdamRule (train_model.py:860-861; A.8). step[0] = number of updates done so far (device int, incremented). */
 int pivp_adam_step(float* p, const float* g, float* m, float* v, long n, int* step, float alpha, float beta1, float beta2, float eps,
                    float gscale, void* stream);

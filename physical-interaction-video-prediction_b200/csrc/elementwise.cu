@@ -814,6 +814,20 @@ __global__ void sched_select_kernel(const float* __restrict__ gt, const float* _
     if (i >= n) return;
     out[i] = take[i / per_sample] ? gt[i] : gen[i];
 }
+// the same select, also delivered as NHWC rows (the layout the first convolution reads): out_nhwc[(b * HW + p) * C + c] = out[(b * C + c) * HW + p]
+__global__ void sched_select_nhwc_kernel(const float* __restrict__ gt, const float* __restrict__ gen, const int* __restrict__ take,
+                                         float* __restrict__ out, float* __restrict__ out_nhwc, int C, int HW, long n) {
+    pdl_enter();
+    const long i = (long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const long bc = i / HW;
+    const int p = (int)(i - bc * HW);
+    const long b = bc / C;
+    const int c = (int)(bc - b * C);
+    const float v = take[b] ? gt[i] : gen[i];
+    out[i] = v;
+    out_nhwc[(b * HW + p) * C + c] = v;
+}
 
 // Chainer 2.0.1 AdamRule.  step[0] holds t-1 on entry; lr computed once per block.
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
@@ -1172,6 +1186,13 @@ int pivp_sched_select(const float* gt, const float* gen, const int* take, float*
     const long n = (long)B * per_sample;
     launch_k(sched_select_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, gt, gen, take, out, per_sample, n);
     return check_launch("sched_select");
+}
+
+int pivp_sched_select_nhwc(const float* gt, const float* gen, const int* take, float* out, float* out_nhwc, int B, int C, int HW, void* stream) {
+    PIVP_REQUIRE(gt && gen && take && out && out_nhwc && B > 0 && C > 0 && HW > 0, "sched_select_nhwc: bad argument");
+    const long n = (long)B * C * HW;
+    launch_k(sched_select_nhwc_kernel, dim3(nblk(n, 256)), dim3(256), 0, (cudaStream_t)stream, gt, gen, take, out, out_nhwc, C, HW, n);
+    return check_launch("sched_select_nhwc");
 }
 
 int pivp_adam_step(float* p, const float* g, float* m, float* v, long n, int* step, float alpha, float beta1, float beta2, float eps,

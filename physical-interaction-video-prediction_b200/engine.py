@@ -432,8 +432,9 @@ class Engine(object):
             elif feedself:
                 prev = ws["gen"][t - 1]
             else:
-                prev = ws["prev_buf"][t]
-                L.call("pivp_sched_select", _ptr(images[t]), _ptr(ws["gen"][t - 1]), _ptr(ws["take"][t]), _ptr(prev), B, 3 * H * W, s)
+                prev = ws["prev_buf"][t]             # the select also writes the NHWC rows enc0 reads (no nchw_to_nhwc launch on this path)
+                L.call("pivp_sched_select_nhwc", _ptr(images[t]), _ptr(ws["gen"][t - 1]), _ptr(ws["take"][t]), _ptr(prev),
+                       _ptr(ws["img_nhwc"][t]), B, 3, HW[1], s)
             self.prev.append(prev)
             # state predictor + smear (train_model.py:563-565, 676, 730): needs the action and the previous state only -> side branch 5;
             # it fills the smear columns of enc3's input, enc2 fills the others; joined in front of enc3
@@ -441,7 +442,8 @@ class Engine(object):
                 L.call("pivp_state_fwd", _ptr(actions[t]), _ptr(ws["cur"][t]), _ptr(p["current_state/W"]), _ptr(p["current_state/b"]),
                        _ptr(ws["sa"][t]), _ptr(ws["cur"][t + 1]), _ptr(ws["in3"][t]) if self.use_state else 0, self.cs3, 64,
                        HW[8], B, self._s())
-            L.call("pivp_nchw_to_nhwc", _ptr(prev), _ptr(ws["img_nhwc"][t]), 3, 0, B, 3, HW[1], s)
+            if t < self.ctx or feedself:
+                L.call("pivp_nchw_to_nhwc", _ptr(prev), _ptr(ws["img_nhwc"][t]), 3, 0, B, 3, HW[1], s)
             # ---- group 0: enc0 -> LN -> relu  (goes to lstm1's x slot and to the enc6 skip slot)
             self._conv_fwd(View(ws["img_nhwc"][t], 3, 0, 3), B, H, W, p["enc0/W"], p["enc0/b"], 32, 5, 2, 2,
                            View(ws["enc0_pre"][t], 32, 0, 32))

@@ -246,6 +246,14 @@ def test_sched_select_bit_exact(pk):
         np.random.seed(5)
         out = pk.scheduled_sample(cu(gt), cu(gen), B, n_gt)
         assert np.array_equal(out.cpu().numpy(), ref)
+        # the variant the training step uses: the same select plus its NHWC rows (what enc0 reads)
+        take = torch.from_numpy((ref.reshape(B, -1) == gt.reshape(B, -1)).all(1).astype(np.int32)).cuda()
+        o1, o2 = torch.empty(B, 3, 8, 8, device="cuda"), torch.empty(B, 8, 8, 3, device="cuda")
+        gt_d, gen_d = cu(gt), cu(gen)
+        pk.lib().call("pivp_sched_select_nhwc", gt_d.data_ptr(), gen_d.data_ptr(), take.data_ptr(), o1.data_ptr(), o2.data_ptr(), B, 3, 64,
+                      torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        assert np.array_equal(o1.cpu().numpy(), ref) and np.array_equal(o2.permute(0, 3, 1, 2).cpu().numpy(), ref)
 
 
 def test_adam_matches_chainer_rule(pk):
