@@ -327,7 +327,8 @@ static void wgrad_plan(int Cx, int Mrows, int ntaps_total, int kb_total, int* tp
     *tpg = (ntaps_total + *groups - 1) / *groups;
     *groups = (ntaps_total + *tpg - 1) / *tpg;
     const int tiles = (Mrows / 128) * (*groups);
-    int s = (2 * 148 + tiles - 1) / tiles;
+    static const int target = getenv("PIVP_TC_WGRAD_TAPS_CTAS") ? atoi(getenv("PIVP_TC_WGRAD_TAPS_CTAS")) : 0;      // 0: 2 x 148 rounded up
+    int s = target > 0 ? target / tiles : (2 * 148 + tiles - 1) / tiles;
     int smax = kb_total / 8;
     if (smax < 1) smax = 1;
     if (s > smax) s = smax;

@@ -216,7 +216,11 @@ static void plan(int Cx, int N4, int H, int W, int SB, Geom* g, int* splits) {
     static const int pair_env = getenv("PIVP_TC_WGRAD_PAIR") ? atoi(getenv("PIVP_TC_WGRAD_PAIR")) : 4;
     g->pair = pair_env < 1 ? 1 : pair_env > 4 ? 4 : pair_env;
     const int tiles = (g->Mrows / 128) * g->chunks * g->groups;
-    int s = (2 * 148 + tiles - 1) / tiles;
+    // K splits: one CTA per SM is resident -- ONE wave (split count rounded down to <= 148 CTAs).  With the partial tiles reduce-added by TMA a
+    // second wave only doubles the reduce traffic and the prologues (PIVP_TC_WGRAD_CTAS; measured per launch / per step: 148 -> 108 us, 6.80 ms;
+    // 296 -> 115 us, 6.87 ms; 444 -> 120 us, 6.92 ms; 128 / 160 / 192 -> 125 / 133 / 147 us; 0 = the old rule, 2 x 148 rounded up)
+    static const int target = getenv("PIVP_TC_WGRAD_CTAS") ? atoi(getenv("PIVP_TC_WGRAD_CTAS")) : 148;
+    int s = target > 0 ? target / tiles : (2 * 148 + tiles - 1) / tiles;
     int smax = g->kb_total / 8;
     if (smax < 1) smax = 1;
     if (s > smax) s = smax;
