@@ -91,6 +91,14 @@ int pivp_layernorm_fwd_s2d(const float* x, int x_cs, int x_co, const float* gamm
 int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                        const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
                        float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream);
+/* The same, with dx delivered as the bf16 space-to-depth GEMM operand of the transposed convolution BELOW this LayerNorm and that convolution's
+ * bias gradient accumulated (norm_enc6 -> enc6, train_model.py:507, 601 backward): ho_bf16 rows (b, y/2, x/2) of [B*H/2*W/2][ho_cs], column
+ * ho_co + ((y&1)*2 + (x&1)) * ho_cblk + c; ho_w = width of the normalised map; ho_db [C] += sum of dx over samples and pixels.  Replaces
+ * pivp_layernorm_bwd + pivp_grad_handover; dx may be NULL (the fp32 gradient is then never written).  ho_bf16 = NULL: pivp_layernorm_bwd. */
+int pivp_layernorm_bwd_handover(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+                                const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
+                                float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
+                                void* ho_bf16, int ho_cs, int ho_co, int ho_w, int ho_cblk, float* ho_db, void* stream);
 /* LayerNorm backward of a ConvLSTM output h_t fused with that layer's gate backward (tensor-core mode, bf16 gate storage): instead of
  * writing d h_t, each thread adds the recurrent d h_t (dh_b view, may be NULL) and produces the gate pre-activation gradients, written
  * bf16 over gates_bf16 (pivp_tc_conv5x5 flags bit 1); dc updated in place.  Replaces pivp_layernorm_bwd + pivp_lstm_gates_bwd_bf16. */

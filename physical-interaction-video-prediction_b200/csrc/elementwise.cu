@@ -868,7 +868,8 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
 int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu, float* dx, int dx_cs,
                int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st, void* gates_bf16,
-               const float* c_prev, const float* c_cur, const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid);
+               const float* c_prev, const float* c_cur, const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid,
+               void* ho_bf16, int ho_cs, int ho_co, int ho_w, int ho_cblk, float* ho_db);
 
 }  // namespace pivp
 
@@ -951,18 +952,24 @@ int pivp_layernorm_fwd(const float* x, int x_cs, int x_co, const float* gamma, c
                                   workspace, ws_bytes, 0, 0, stream);
 }
 
-int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
-                       const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
-                       float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream) {
-    PIVP_REQUIRE(x && g1 && gamma && beta && stats && dx && dgamma && dbeta && workspace, "layernorm_bwd: null pointer");
+int pivp_layernorm_bwd_handover(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+                                const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
+                                float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes,
+                                void* ho_bf16, int ho_cs, int ho_co, int ho_w, int ho_cblk, float* ho_db, void* stream) {
+    PIVP_REQUIRE(x && g1 && gamma && beta && stats && (dx || ho_bf16) && dgamma && dbeta && workspace, "layernorm_bwd: null pointer");
+    PIVP_REQUIRE(!ho_bf16 || (ho_db && ho_w > 0 && ho_w % 2 == 0 && HW % ho_w == 0 && (HW / ho_w) % 2 == 0 && ho_cblk >= C && ho_cblk % 4 == 0 &&
+                              ho_cs % 4 == 0 && ho_co % 4 == 0 && ho_cs >= ho_co + 4 * ho_cblk && !((uintptr_t)ho_bf16 & 7) && !((uintptr_t)ho_db & 15)),
+                 "layernorm_bwd: bad hand-over geometry");
     const int n = HW * C;
     int chunk;
     const int S = ln_split(n, &chunk);
     PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_bwd: workspace too small");
     PIVP_REQUIRE(B <= 4096, "layernorm_bwd: batch too large for the shared-memory totals");
     if (int r = ln_vec_bwd(x, x_cs, x_co, g1, g1_cs, g1_co, g2, g2_cs, g2_co, gamma, beta, stats, B, HW, C, relu, dx, dx_cs, dx_co, dgamma,
-                           dbeta, workspace, S, chunk, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, 0))
+                           dbeta, workspace, S, chunk, (cudaStream_t)stream, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, 0, ho_bf16, ho_cs, ho_co, ho_w,
+                           ho_cblk, ho_db))
         return r < 0 ? r : PIVP_OK;
+    PIVP_REQUIRE(!ho_bf16, "layernorm_bwd: the hand-over output needs the vectorised path (16-byte aligned views, C a multiple of 4 dividing 512)");
     launch_k(ln_bwd_stats_kernel, dim3(S, B), dim3(LN_T), 0, (cudaStream_t)stream, CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co},
                                                                         gamma, beta, (const float2*)stats, n, C, chunk, relu, (float2*)workspace);
     if (int e = check_launch("layernorm_bwd(stats)")) return e;
@@ -970,6 +977,14 @@ int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int 
         CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
         (const float2*)workspace, S, B, n, C, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta);
     return check_launch("layernorm_bwd(apply)");
+}
+
+int pivp_layernorm_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
+                       const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu,
+                       float* dx, int dx_cs, int dx_co, float* dgamma, float* dbeta, void* workspace, size_t ws_bytes, void* stream) {
+    PIVP_REQUIRE(dx, "layernorm_bwd: null pointer");
+    return pivp_layernorm_bwd_handover(x, x_cs, x_co, g1, g1_cs, g1_co, g2, g2_cs, g2_co, gamma, beta, stats, B, HW, C, relu, dx, dx_cs, dx_co, dgamma,
+                                       dbeta, workspace, ws_bytes, nullptr, 0, 0, 0, 0, nullptr, stream);
 }
 
 /* LayerNorm backward of a ConvLSTM output h_t fused with the gate backward of that layer (tensor-core mode, bf16 gate storage):
@@ -988,7 +1003,8 @@ int pivp_layernorm_bwd_lstm(const float* x, int x_cs, int x_co, const float* g1,
     const int S = ln_split(n, &chunk);
     PIVP_REQUIRE(ws_bytes >= (size_t)B * S * sizeof(float2), "layernorm_bwd_lstm: workspace too small");
     const int r = ln_vec_bwd(x, x_cs, x_co, g1, g1_cs, g1_co, g2, g2_cs, g2_co, gamma, beta, stats, B, HW, C, 0, (float*)c_cur /*unused*/, C, 0,
-                             dgamma, dbeta, workspace, S, chunk, (cudaStream_t)stream, gates_bf16, c_prev, c_cur, dh_b, dhb_cs, dhb_co, dc, dc_valid);
+                             dgamma, dbeta, workspace, S, chunk, (cudaStream_t)stream, gates_bf16, c_prev, c_cur, dh_b, dhb_cs, dhb_co, dc, dc_valid,
+                             nullptr, 0, 0, 0, 0, nullptr);
     if (r == 0) { set_error("layernorm_bwd_lstm: views must be 16-byte aligned with channel counts that are multiples of 4"); return PIVP_EUNSUPPORTED; }
     return r < 0 ? r : PIVP_OK;
 }

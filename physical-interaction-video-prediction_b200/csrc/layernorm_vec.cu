@@ -172,6 +172,13 @@ struct GateFuse {
     float* dc;                     // [M][C] in: d c_t from step t+1 (when dc_valid), out: d c_{t-1}
     int dc_valid;
 };
+// dx leaves as the bf16 space-to-depth GEMM operand of the transposed convolution below this LayerNorm, together with that convolution's bias
+// gradient (what grad_handover_kernel does in a launch of its own): norm_enc6 -> enc6 (train_model.py:507, 601 backward).  dst == null: not used.
+struct HandOver {
+    __nv_bfloat16* dst; int b_cs, b_co, w, cblk;   // row (b, y/2, x/2) of [B*H/2*W/2][b_cs], column b_co + ((y&1)*2 + (x&1)) * cblk + c
+    float* db;                                     // [C] += sum over samples and pixels of dx
+};
+
 __device__ __forceinline__ void unpack4(uint2 u, float (&v)[4]) {
     const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
     const float2 a = __bfloat1622float2(p[0]), b = __bfloat1622float2(p[1]);
@@ -223,9 +230,11 @@ __device__ __forceinline__ void gate_backward4(const GateFuse& gf, long m, int c
 __global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView g2, const float* __restrict__ gamma,
                                                        const float* __restrict__ beta, const float2* __restrict__ stats,
                                                        const float2* __restrict__ partial, int S, int B, int bchunk, Geo g, int n,
-                                                       int relu, View dx, float* __restrict__ dgamma, float* __restrict__ dbeta, GateFuse gf) {
+                                                       int relu, View dx, float* __restrict__ dgamma, float* __restrict__ dbeta, GateFuse gf,
+                                                       HandOver ho) {
     pdl_enter();
     extern __shared__ float4 tot[];              // [bchunk] : (mean, rstd, mean q, mean q*xhat)
+    __shared__ float4 cbs[TB];                   // hand-over: per-thread bias-gradient sums, reduced over the threads that share a channel quad
     const int b0 = blockIdx.y * bchunk, nb = min(bchunk, B - b0);
     for (int i = threadIdx.x; i < nb; i += TB) {
         float a = 0.f, c = 0.f;
@@ -235,12 +244,14 @@ __global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView 
     }
     __syncthreads();
     const int e = (blockIdx.x * TB + threadIdx.x) * 4;
-    if (e >= n) return;
+    if (e >= n && !ho.dst) return;               // (hand-over: n is a multiple of the CTA's 512 elements, every thread stays for the reduction)
     const int pix = g.cshift >= 0 ? (e >> g.cshift) : (e / g.C);
     const int ch = e - pix * g.C;
     const float4 ga = ld4(gamma + e);
     const float4 be = relu ? ld4(beta + e) : make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg, cb = dg;
+    const int py = ho.dst ? pix / ho.w : 0, px = pix - py * (ho.dst ? ho.w : 0);
+    const int hcol = ho.dst ? ho.b_co + ((py & 1) * 2 + (px & 1)) * ho.cblk + ch : 0;
 #pragma unroll 4
     for (int i = 0; i < nb; ++i) {
         const long row = (long)(b0 + i) * g.HW + pix;
@@ -255,10 +266,26 @@ __global__ void __launch_bounds__(TB) bwd_apply_kernel(CView x, CView g1, CView 
         d.z = (gq.z * ga.z - t.z - xh.z * t.w) * t.y;
         d.w = (gq.w * ga.w - t.z - xh.w * t.w) * t.y;
         if (gf.gates) gate_backward4(gf, row, ch, g.C, d);
-        else *reinterpret_cast<float4*>(dx.p + row * dx.cs + dx.co + ch) = d;
+        else if (ho.dst) {
+            const long brow = ((long)(b0 + i) * (g.HW / ho.w >> 1) + (py >> 1)) * (ho.w >> 1) + (px >> 1);
+            const float dv[4] = {d.x, d.y, d.z, d.w};
+            *reinterpret_cast<uint2*>(ho.dst + brow * ho.b_cs + hcol) = pack4(dv);
+            cb.x += d.x; cb.y += d.y; cb.z += d.z; cb.w += d.w;
+        } else *reinterpret_cast<float4*>(dx.p + row * dx.cs + dx.co + ch) = d;
     }
     atomicAdd(reinterpret_cast<float4*>(dgamma + e), dg);
     atomicAdd(reinterpret_cast<float4*>(dbeta + e), db);
+    if (ho.dst) {
+        // bias gradient: the CTA's 512 consecutive elements are 512 / C pixels x C channels -- thread t and t + C/4 hold the same channel quad
+        cbs[threadIdx.x] = cb;
+        __syncthreads();
+        const int q4 = g.C >> 2;                 // threads per pixel
+        if ((int)threadIdx.x < q4) {
+            float4 a = cbs[threadIdx.x];
+            for (int r = threadIdx.x + q4; r < TB; r += q4) { const float4 t = cbs[r]; a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w; }
+            atomicAdd(reinterpret_cast<float4*>(ho.db + 4 * threadIdx.x), a);
+        }
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------------------------
@@ -495,16 +522,19 @@ int ln_vec_fwd(const float* x, int x_cs, int x_co, const float* gamma, const flo
 int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, int g1_co, const float* g2, int g2_cs, int g2_co,
                const float* gamma, const float* beta, const float* stats, int B, int HW, int C, int relu, float* dx, int dx_cs,
                int dx_co, float* dgamma, float* dbeta, void* workspace, int S, int chunk, cudaStream_t st, void* gates_bf16,
-               const float* c_prev, const float* c_cur, const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid) {
+               const float* c_prev, const float* c_cur, const float* dh_b, int dhb_cs, int dhb_co, float* dc, int dc_valid,
+               void* ho_bf16, int ho_cs, int ho_co, int ho_w, int ho_cblk, float* ho_db) {
     using namespace lnv;
     GateFuse gf{(__nv_bfloat16*)gates_bf16, c_prev, c_cur, dh_b, dhb_cs, dhb_co, dc, dc_valid};
+    HandOver ho{(__nv_bfloat16*)ho_bf16, ho_cs, ho_co, ho_w, ho_cblk, ho_db};
     const int n = HW * C;
+    if (ho.dst && (n % (TB * 4) || (TB * 4) % C || C % 4 || TB % (C / 4))) return 0;      // hand-over: whole pixels per CTA (scalar path cannot do it: caller reports)
     if (disabled() || C % 4 || chunk % 4 || chunk > T * E4 * 4 || !view_ok(x, x_cs, x_co) || !view_ok(g1, g1_cs, g1_co) || !view_ok(g2, g2_cs, g2_co) ||
         !view_ok(dx, dx_cs, dx_co) || !a16(gamma) || !a16(beta) || !a16(dgamma) || !a16(dbeta))
         return 0;
     const Geo g = make_geo(HW, C);
     static const int fused_mode = getenv("PIVP_LN_BWD_FUSED") ? atoi(getenv("PIVP_LN_BWD_FUSED")) : 1;     // 0: two launches; k >= 1: one cluster launch, k samples per CTA
-    if (fused_mode > 0 && n % CHUNK_F == 0 && n / CHUNK_F <= 8) {
+    if (fused_mode > 0 && !ho.dst && n % CHUNK_F == 0 && n / CHUNK_F <= 8) {
         const int CL = n / CHUNK_F, bchunk = fused_mode < B ? fused_mode : B;
         auto go = [&](auto kern) {
             launch_cluster(kern, dim3(CL, (B + bchunk - 1) / bchunk), dim3(TF), (unsigned)CL, st,
@@ -528,7 +558,7 @@ int ln_vec_bwd(const float* x, int x_cs, int x_co, const float* g1, int g1_cs, i
     nby = (B + bchunk - 1) / bchunk;
     launch_k(bwd_apply_kernel, dim3(gx, nby), dim3(TB), (size_t)bchunk * sizeof(float4), st, 
         CView{x, x_cs, x_co}, CView{g1, g1_cs, g1_co}, CView{g2, g2_cs, g2_co}, gamma, beta, (const float2*)stats,
-        (const float2*)workspace, S, B, bchunk, g, n, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta, gf);
+        (const float2*)workspace, S, B, bchunk, g, n, relu, View{dx, dx_cs, dx_co}, dgamma, dbeta, gf, ho);
     if (int e = check_launch("layernorm_bwd(apply)")) return e;
     return 1;
 }

@@ -272,14 +272,17 @@ class Engine(object):
                     0 if y2 is None else y2.co, 0 if y_bf16 is None else y_bf16.ptr, 0 if y_bf16 is None else y_bf16.cs,
                     0 if y_bf16 is None else y_bf16.co, relu, _ptr(stats), _ptr(ws["ln_ws"]), ws["ln_ws"].numel(), s2d_w, s2d_cb, self._s())
 
-    def _ln_bwd(self, name, x, g1, g2, B, HW, relu, stats, dx, ln_ws=None):
+    def _ln_bwd(self, name, x, g1, g2, B, HW, relu, stats, dx, ln_ws=None, handover=None):
+        """``handover`` = (bf16 tensor, row stride, map width, channel block, bias-gradient tensor): dx leaves as the space-to-depth bf16 operand of
+        the transposed convolution below this LayerNorm plus that convolution's bias gradient (dx may then be None)."""
         ws = self.ws
         ln_ws = ws["ln_ws"] if ln_ws is None else ln_ws
-        self.L.call("pivp_layernorm_bwd", x.ptr, x.cs, x.co, g1.ptr, g1.cs, g1.co, 0 if g2 is None else g2.ptr,
+        ho = (0, 0, 0, 0, 0, 0) if handover is None else (_ptr(handover[0]), handover[1], 0, handover[2], handover[3], _ptr(handover[4]))
+        self.L.call("pivp_layernorm_bwd_handover", x.ptr, x.cs, x.co, g1.ptr, g1.cs, g1.co, 0 if g2 is None else g2.ptr,
                     0 if g2 is None else g2.cs, 0 if g2 is None else g2.co, _ptr(self.p[name + "/norm/gamma"]),
-                    _ptr(self.p[name + "/norm/beta"]), _ptr(stats), B, HW, x.C, relu, dx.ptr, dx.cs, dx.co,
-                    _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(ln_ws),
-                    ln_ws.numel(), self._s())
+                    _ptr(self.p[name + "/norm/beta"]), _ptr(stats), B, HW, x.C, relu, 0 if dx is None else dx.ptr, 0 if dx is None else dx.cs,
+                    0 if dx is None else dx.co, _ptr(self.g[name + "/norm/gamma"]), _ptr(self.g[name + "/norm/beta"]), _ptr(ln_ws),
+                    ln_ws.numel(), *ho, self._s())
 
     def _ln_lstm_bwd(self, name, li, t, x, g1, g2, B, HW, last, ln_ws=None):
         """LayerNorm backward of ConvLSTM layer li's output at step t, then the layer's gate / input-gradient backward.
@@ -651,11 +654,12 @@ class Engine(object):
             self._conv_wgrad(View(ws["e6"][t], 64, 0, 64), B, H, W, dhead, H, W, 1, 1, 0, g["model/enc7/W"], g["model/enc7/b"])
             self._conv_dgrad(dhead, B, H, W, p["model/enc7/W"], None, 1, 1, 0, View(ws["d_e6"], 64, 0, 64), H, W)
         # ---- norm_enc6 (+relu) and enc6 deconv
-        self._ln_bwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), View(ws["d_e6"], 64, 0, 64), None, B, HW[1], 1,
-                     ws["ln_stats"]["norm_enc6"][t], View(ws["d_e6pre"], 64, 0, 64), ln_ws=ws["ln_ws_head"])
         de6 = View(ws["d_e6pre"], 64, 0, 64)
-        if self.tc is not None:           # bias gradient + bf16 space-to-depth operand in one hand-over launch; weight gradient deferred
-            self.tc.deconv_bwd_fused("enc6", t, None, de6, None, g["enc6/b"], ws["d_cat6"][s3], 0)
+        ho = self.tc.deconv_handover("enc6", t, W, g["enc6/b"]) if (self.tc is not None and os.environ.get("PIVP_LN_HANDOVER", "1") != "0") else None
+        self._ln_bwd("norm_enc6", View(ws["e6pre"][t], 64, 0, 64), View(ws["d_e6"], 64, 0, 64), None, B, HW[1], 1,
+                     ws["ln_stats"]["norm_enc6"][t], None if ho is not None else de6, ln_ws=ws["ln_ws_head"], handover=ho)
+        if self.tc is not None:           # bias gradient + bf16 space-to-depth operand: from the LayerNorm backward itself (or one hand-over launch)
+            self.tc.deconv_bwd_fused("enc6", t, None, de6, None, g["enc6/b"], ws["d_cat6"][s3], 0, handover=ho is None)
         else:
             L.call("pivp_colsum", de6.ptr, 64, 0, Mr[1], 64, _ptr(g["enc6/b"]), s)
             self._conv_wgrad(de6, B, H, W, View(ws["cat6"][t], 64, 0, 64), H // 2, W // 2, 3, 2, 1, g["enc6/W"], None)

@@ -235,7 +235,13 @@ class TensorCorePlan(object):
         e.L.call("pivp_tc_conv_taps", _ptr(d["dys"][t]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
                  d["cin"], d["bn"], 0, 0, accumulate, _ptr(out), d["cin"], 0, 0, 0, 0, h, w, 1, 0, 0, e._s())
 
-    def deconv_bwd_fused(self, name, t, out, ga, gb, db, d_in, accumulate):
+    def deconv_handover(self, name, t, width, db):
+        """What Engine._ln_bwd(handover=...) needs to write the bf16 space-to-depth operand of deconvolution `name`'s backward itself:
+        (operand tensor of step t, its row stride, width of the big map, channel block, bias-gradient tensor)."""
+        d = self.dbw[name]
+        return d["dys"][t], 4 * d["cb"], width, d["cb"], db
+
+    def deconv_bwd_fused(self, name, t, out, ga, gb, db, d_in, accumulate, handover=True):
         """Backward of a stride-2 deconvolution fed by a ReLU (``out`` = its output view, or None for a plain gradient):
         ONE hand-over launch masks the gradient, accumulates the bias gradient and writes the space-to-depth bf16 operand
         (kept for the deferred weight gradient), then the 9-tap tcgen05 GEMM produces d_in."""
@@ -243,8 +249,9 @@ class TensorCorePlan(object):
         h, w = e.H // d["lv"], e.W // d["lv"]
         B = self.ws["B"]
         z = lambda v: (0, 0, 0) if v is None else (v.ptr, v.cs, v.co)
-        e.L.call("pivp_grad_handover", *z(out), *z(ga), *z(gb), 0, 0, 0, _ptr(d["dys"][t]), 4 * d["cb"], 0, 2 * h, 2 * w, 1, d["cb"],
-                 _ptr(db), B * 4 * h * w, d["cout"], e._s())
+        if handover:                         # else: the producer (LayerNorm backward) already wrote d["dys"][t] and the bias gradient
+            e.L.call("pivp_grad_handover", *z(out), *z(ga), *z(gb), 0, 0, 0, _ptr(d["dys"][t]), 4 * d["cb"], 0, 2 * h, 2 * w, 1, d["cb"],
+                     _ptr(db), B * 4 * h * w, d["cout"], e._s())
         e.L.call("pivp_tc_conv_taps", _ptr(d["dys"][t]), 4 * d["cb"], B, h, w, d["cb"], 9, d["dy"], d["dx"], d["co"], _ptr(d["wt"]),
                  d["cin"], d["bn"], 0, 0, accumulate, _ptr(d_in), d["cin"], 0, 0, 0, 0, h, w, 1, 0, 0, e._s())
 

@@ -518,3 +518,38 @@ def test_heads_fwd_ln_equals_layernorm_then_heads(pk, NH, Na, B, HW):
     with pytest.raises(pk.PivpError):
         L.call("pivp_heads_fwd_ln", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), part.data_ptr(), 1e-6, st2.data_ptr(),
                y2.data_ptr(), C, 0, Wh.data_ptr(), bh.data_ptr(), a2.data_ptr(), Na, b2.data_ptr(), NH, B, HW + 64, stream())
+
+
+@pytest.mark.parametrize("B,H,W,C,cb,relu", [(2, 64, 64, 64, 64, 1), (3, 16, 16, 32, 64, 0)])
+def test_layernorm_bwd_handover_equals_layernorm_bwd_then_handover(pk, B, H, W, C, cb, relu):
+    """pivp_layernorm_bwd_handover (dx written as the bf16 space-to-depth operand of the transposed convolution below + its bias gradient;
+    norm_enc6 -> enc6 backward, train_model.py:507, 601) == pivp_layernorm_bwd followed by pivp_grad_handover."""
+    L = pk.lib()
+    gen = torch.Generator(device="cuda"); gen.manual_seed(41)
+    HW, n, M = H * W, H * W * C, B * H * W
+    R = lambda *sh: torch.randn(*sh, device="cuda", generator=gen)
+    x, g1 = R(M, C) * 1.5 + 0.2, R(M, C)
+    gamma, beta = 1 + 0.2 * R(n), 0.2 * R(n)
+    ws = torch.empty(max(L.query("pivp_layernorm_workspace_bytes", B, n), 16), dtype=torch.uint8, device="cuda")
+    stats, y = torch.zeros(B, 2, device="cuda"), torch.empty(M, C, device="cuda")
+    L.call("pivp_layernorm_fwd", x.data_ptr(), C, 0, gamma.data_ptr(), beta.data_ptr(), B, HW, C, 1e-6, y.data_ptr(), C, 0,
+           0, 0, 0, 0, 0, 0, relu, stats.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+    dx = torch.empty(M, C, device="cuda")
+    dg1, db1, dg2, db2 = (torch.zeros(n, device="cuda") for _ in range(4))
+    cb1, cb2 = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    op1 = torch.full((M // 4, 4 * cb), 3.0, dtype=torch.bfloat16, device="cuda")
+    op2 = op1.clone()
+    L.call("pivp_layernorm_bwd", x.data_ptr(), C, 0, g1.data_ptr(), C, 0, 0, 0, 0, gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), B, HW, C, relu,
+           dx.data_ptr(), C, 0, dg1.data_ptr(), db1.data_ptr(), ws.data_ptr(), ws.numel(), stream())
+    L.call("pivp_grad_handover", 0, 0, 0, dx.data_ptr(), C, 0, 0, 0, 0, 0, 0, 0, op1.data_ptr(), 4 * cb, 0, H, W, 1, cb, cb1.data_ptr(), M, C, stream())
+    L.call("pivp_layernorm_bwd_handover", x.data_ptr(), C, 0, g1.data_ptr(), C, 0, 0, 0, 0, gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), B, HW, C,
+           relu, 0, 0, 0, dg2.data_ptr(), db2.data_ptr(), ws.data_ptr(), ws.numel(), op2.data_ptr(), 4 * cb, 0, W, cb, cb2.data_ptr(), stream())
+    torch.cuda.synchronize()
+    assert float(op1.float().abs().max()) > 0
+    assert rel(op2, op1) < 2 ** -7                         # same values up to the kernels' instruction selection, then one bf16 rounding
+    assert rel(dg2, dg1) < 1e-5 and rel(db2, db1) < 1e-5 and rel(cb2, cb1) < 1e-4
+    if cb > C:
+        assert bool((op2.reshape(-1, 4, cb)[:, :, C:] == 3.0).all())
+    with pytest.raises(pk.PivpError):                      # odd map width
+        L.call("pivp_layernorm_bwd_handover", x.data_ptr(), C, 0, g1.data_ptr(), C, 0, 0, 0, 0, gamma.data_ptr(), beta.data_ptr(), stats.data_ptr(), B, HW,
+               C, relu, 0, 0, 0, dg2.data_ptr(), db2.data_ptr(), ws.data_ptr(), ws.numel(), op2.data_ptr(), 4 * cb, 0, W + 1, cb, cb2.data_ptr(), stream())
